@@ -1,0 +1,203 @@
+/*
+ * theoremsearch.h — C ABI of libtheoremsearch.so (B200 / sm_100a).
+ *
+ * This is the drop-in boundary for TheoremSearch's retrieval hot path: "score a query
+ * embedding (or a batch) against the corpus of theorem/slogan embeddings, return the top-k
+ * theorem ids".  The reference has no FFI of its own; every entry point below names the
+ * reference expression it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - Plain C: pointers, sizes, ints.  No torch / C++ types cross this boundary.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All device
+ *     work is enqueued on it; no entry point synchronises the device unless it says so.
+ *   - Unless a name ends in `_host`, data pointers are DEVICE pointers owned by the caller.
+ *   - Return value: 0 = TS_OK, negative = error class; text via ts_last_error() (thread-local).
+ *   - The library owns only what hangs off a ts_index / ts_ctx handle.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     TS_ERR_CUDA.
+ *
+ * Result order everywhere: score descending, ties broken by LOWER row/id first
+ * (BASELINE.json north_star); entries past the number of eligible rows have score = -inf,
+ * id = -1.
+ */
+#ifndef THEOREMSEARCH_H_
+#define THEOREMSEARCH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define TS_API
+#else
+#define TS_API __attribute__((visibility("default")))
+#endif
+
+/* ---- enums ------------------------------------------------------------------------- */
+
+enum ts_status {
+    TS_OK = 0,
+    TS_ERR_BAD_ARG = -1,      /* null pointer, bad dtype, k out of range, dim mismatch ...   */
+    TS_ERR_CUDA = -2,         /* a CUDA runtime call failed (message has the cudaError text) */
+    TS_ERR_OOM = -3,          /* device or pinned-host allocation failed                     */
+    TS_ERR_UNSUPPORTED = -4,  /* valid request this build has no kernel for                  */
+    TS_ERR_CAPACITY = -5,     /* index full / workspace too small                            */
+    TS_ERR_STATE = -6         /* call order (e.g. ivf_search before ivf_build)               */
+};
+
+enum ts_dtype {
+    TS_F32 = 0,       /* IEEE binary32                                   */
+    TS_BF16 = 1,      /* bfloat16 (corpus storage for exact search)      */
+    TS_FP8_E4M3 = 2,  /* e4m3 + one fp32 scale per row (IVF list storage) */
+    TS_F16 = 3        /* IEEE binary16 (accepted as a source dtype only) */
+};
+
+#define TS_MAX_K 1024   /* largest k any search entry point accepts            */
+#define TS_MAX_DIM 2048 /* largest embedding dimension (reference uses 768/1024) */
+
+typedef struct ts_index ts_index; /* the corpus: quantised rows (+ ids, + IVF lists) on one GPU */
+typedef struct ts_ctx ts_ctx;     /* per-caller search context: workspace, pinned staging, stream */
+
+/* ---- library ----------------------------------------------------------------------- */
+
+/* Version of this ABI (bumped on any signature change). */
+TS_API int ts_abi_version(void);
+
+/* Last error message of the calling thread ("" if none). Never NULL. */
+TS_API const char* ts_last_error(void);
+
+/* Number of CUDA kernels this library has launched since load (all threads). bench.py reads
+ * it before/after the timed region to report "gpu_launches". */
+TS_API uint64_t ts_kernel_launches(void);
+
+/* ---- index: the corpus ---------------------------------------------------------------
+ * Replaces the reference's corpus containers: the `embeddings_db` tensor
+ * (test_app.py:129-130, app_showcase_model.py:52 `torch.load('corpus_embeddings.pt')`) and
+ * the pgvector table `theorem_embedding_qwen(slogan_id BIGINT, embedding vector(1024))`
+ * (rds_schema.sql:50-53). */
+
+/* Allocate an empty index for `capacity` rows of `dim` elements stored as `dtype`
+ * (TS_BF16 or TS_F32) on CUDA device `device`. */
+TS_API int ts_index_create(ts_index** out, int device, int dim, int dtype, int64_t capacity);
+
+/* Free the index and everything it owns. NULL is a no-op. */
+TS_API void ts_index_destroy(ts_index* index);
+
+/* Append `n` rows (device pointer, row-major [n, dim], `src_dtype` in {F32, BF16, F16}).
+ * normalize != 0: each row becomes x / max(||x||_2, 1e-12) before quantisation — the
+ * `F.normalize` inside sentence_transformers.util.cos_sim (test_app.py:76) and
+ * `model.encode(..., normalize_embeddings=True)` (ec2/generate_embeddings/embeddings.py:27,35).
+ * `ids` (device int64[n]) are the caller's row keys (slogan_id / theorem_id,
+ * rds_schema.sql:22,34); NULL = the row's position in the index.  Kernel K1. */
+TS_API int ts_index_add(ts_index* index, const void* rows, int src_dtype, int64_t n,
+                        int normalize, const int64_t* ids, void* stream);
+
+/* Same, rows/ids in HOST memory; staged through pinned buffers in chunks. Synchronises. */
+TS_API int ts_index_add_host(ts_index* index, const void* rows, int src_dtype, int64_t n,
+                             int normalize, const int64_t* ids);
+
+TS_API int64_t ts_index_size(const ts_index* index);     /* rows added so far */
+TS_API int64_t ts_index_capacity(const ts_index* index);
+TS_API int ts_index_dim(const ts_index* index);
+TS_API int ts_index_dtype(const ts_index* index);
+TS_API int ts_index_device(const ts_index* index);
+
+/* Copy stored rows [first, first+n) back, dequantised to fp32, into device buffer
+ * out[n, dim]. This is what parity tests feed the oracle ("same inputs"). */
+TS_API int ts_index_get_rows(const ts_index* index, int64_t first, int64_t n, float* out,
+                             void* stream);
+
+/* Raw device pointer / byte size of the stored corpus (for save/load and diagnostics). */
+TS_API const void* ts_index_data(const ts_index* index);
+TS_API size_t ts_index_row_bytes(const ts_index* index);
+
+/* ---- exact search --------------------------------------------------------------------
+ * Replaces `util.cos_sim(q, corpus)[0]` + `np.argsort(-scores)[:k]` (test_app.py:75-77),
+ * `torch.topk(scores, k=min(200, N), sorted=True)` (app_showcase_model.py:92-96),
+ * `util.cos_sim(q_emb, s_emb)` + `np.argsort(-sim_matrix, axis=1)` (compare_embeddings.py:61,105)
+ * and pgvector's `ORDER BY e.embedding <#> q LIMIT k` (streamlit_app.py:275-282). */
+
+/* Bytes of device workspace ts_search / ts_search_keys need for this (nq, k). */
+TS_API size_t ts_workspace_bytes(const ts_index* index, int nq, int k);
+
+/* Exact top-k. queries: device [nq, dim] of q_dtype (F32 or BF16); normalize_queries != 0
+ * L2-normalises them first (cos_sim semantics), 0 takes them as-is (pgvector `<#>` semantics).
+ * allow_mask: optional device bitmask, bit r of word r/32 set = row r is eligible (the SQL WHERE
+ * of streamlit_app.py:175-243 applied BEFORE ORDER BY/LIMIT); NULL = all rows.
+ * out_scores: device float[nq, k]; out_ids: device int64[nq, k] (caller ids, or rows if none).
+ * Dispatch: nq == 1 (and small nq) -> K2 bandwidth-bound scan; larger nq -> K3 tcgen05 GEMM. */
+TS_API int ts_search(ts_index* index, const void* queries, int q_dtype, int nq, int k,
+                     int normalize_queries, const uint32_t* allow_mask, float* out_scores,
+                     int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same scan, but stops before the id mapping and returns this GPU's candidates as packed
+ * 64-bit keys out_keys[nq, k] (see ts_pack_key): the payload of the cross-GPU all-gather. */
+TS_API int ts_search_keys(ts_index* index, const void* queries, int q_dtype, int nq, int k,
+                          int normalize_queries, const uint32_t* allow_mask, uint64_t* out_keys,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* K5: merge gathered per-shard candidates. keys: device [nshards, nq, k] packed keys, each
+ * [k] slice sorted descending (as ts_search_keys writes them). shard_base: device
+ * int64[nshards], global row of each shard's row 0 (NULL = zeros). id_map: optional device
+ * int64 table indexed by global row (NULL = ids are global rows). Writes the global top-k. */
+TS_API int ts_merge_topk(const uint64_t* keys, int nshards, int nq, int k,
+                         const int64_t* shard_base, const int64_t* id_map, float* out_scores,
+                         int64_t* out_ids, void* stream);
+
+/* Packed candidate key: high 32 bits = order-preserving image of the fp32 score, low 32 bits
+ * = 0xFFFFFFFF - row, so unsigned `max` == "higher score, then lower row". 0 = empty slot. */
+TS_API uint64_t ts_pack_key(float score, uint32_t row);
+TS_API void ts_unpack_key(uint64_t key, float* score, uint32_t* row);
+
+/* ---- search context: the host-buffer (end-to-end) path --------------------------------
+ * What a Streamlit callback actually does (streamlit_app.py:173,284-286): one host query
+ * vector in, k rows out.  A ctx owns a stream, pinned staging and workspace sized for
+ * (max_nq, max_k); one ctx per host thread makes concurrent searches on one index safe. */
+TS_API int ts_ctx_create(ts_ctx** out, ts_index* index, int max_nq, int max_k);
+TS_API void ts_ctx_destroy(ts_ctx* ctx);
+
+/* queries: HOST [nq, dim] fp32. out_scores / out_ids: HOST [nq, k]. allow_mask: DEVICE or NULL.
+ * H2D copy, search, D2H copy and a stream synchronise all happen inside the call. */
+TS_API int ts_search_host(ts_ctx* ctx, const float* queries, int nq, int k, int normalize_queries,
+                          const uint32_t* allow_mask, float* out_scores, int64_t* out_ids);
+
+/* Device time (ms, CUDA events on the ctx stream) of the dominant kernel of the last
+ * ts_search_host call when timing is enabled with ts_ctx_set_timing(ctx, 1); -1 otherwise. */
+TS_API int ts_ctx_set_timing(ts_ctx* ctx, int enabled);
+TS_API float ts_ctx_last_kernel_ms(const ts_ctx* ctx);
+
+/* ---- IVF-Flat (pgvector `ivfflat` equivalent; the reference never creates the index,
+ * rds_schema.sql has no CREATE INDEX — BASELINE.json config 5 asks for it) ------------- */
+
+/* Spherical k-means over `n_sample` device rows [n_sample, dim] fp32 -> nlist centroids. */
+TS_API int ts_ivf_train(ts_index* index, const float* sample, int64_t n_sample, int nlist,
+                        int iters, uint64_t seed, void* stream);
+/* Assign every stored row to its nearest centroid and build the inverted lists
+ * (row permutation + list offsets); list rows are stored as `list_dtype` (BF16 or FP8_E4M3). */
+TS_API int ts_ivf_build(ts_index* index, int list_dtype, void* stream);
+TS_API size_t ts_ivf_workspace_bytes(const ts_index* index, int nq, int k, int nprobe,
+                                     int rescore_k);
+/* ANN search: coarse top-nprobe centroids, scan those lists, keep rescore_k candidates,
+ * rescore them against the full-precision rows, return top-k. */
+TS_API int ts_ivf_search(ts_index* index, const void* queries, int q_dtype, int nq, int k,
+                         int nprobe, int rescore_k, int normalize_queries, float* out_scores,
+                         int64_t* out_ids, void* workspace, size_t workspace_bytes,
+                         void* stream);
+TS_API int ts_ivf_nlist(const ts_index* index);
+/* Copy list sizes (int64[nlist]) to a device buffer — for balance diagnostics. */
+TS_API int ts_ivf_list_sizes(const ts_index* index, int64_t* out, void* stream);
+
+/* ---- tuning / diagnostics (not part of the drop-in surface) -------------------------- */
+
+/* Set an internal tunable by name (e.g. "scan.ctas_per_sm", "scan.stages"); returns
+ * TS_ERR_BAD_ARG for unknown names. Used by the bench sweeps only. */
+TS_API int ts_set_tunable(const char* name, int value);
+TS_API int ts_get_tunable(const char* name, int* value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THEOREMSEARCH_H_ */

@@ -1,0 +1,68 @@
+"""Reference-shaped search API: the call shapes of TheoremSearch's retrieval path, backed by
+``libtheoremsearch.so``.
+
+Tensor level:
+  * ``build_index``      <- the corpus tensor of ``test_app.py:129-130`` / ``torch.load`` at
+                            ``app_showcase_model.py:52`` / the rows of ``theorem_embedding_qwen``.
+  * ``cos_sim_topk``     <- ``util.cos_sim(q, corpus)`` + ``argsort`` / ``torch.topk``
+                            (``test_app.py:76-77``, ``app_showcase_model.py:93-96``,
+                            ``compare_embeddings.py:61,105``).
+  * ``search_theorems``  <- ``test_app.py:67`` (same signature; returns rows instead of rendering).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .index import TheoremIndex
+
+
+def build_index(embeddings, ids=None, dtype: str = "bf16", normalize: bool = True,
+                device: int | str | torch.device = 0, capacity: Optional[int] = None) -> TheoremIndex:
+    """Corpus [N, D] (torch tensor on any device, or numpy) -> resident index.  ``normalize=True``
+    performs once, at build time, the ``F.normalize`` that ``util.cos_sim`` repeats on every
+    query (test_app.py:76) — and that the production writer already applies
+    (ec2/generate_embeddings/embeddings.py:27,35)."""
+    n, d = int(embeddings.shape[0]), int(embeddings.shape[1])
+    ix = TheoremIndex(d, capacity if capacity is not None else max(n, 1), dtype=dtype, device=device)
+    if n:
+        if isinstance(embeddings, torch.Tensor) and embeddings.is_cuda and embeddings.device != ix.device:
+            embeddings = embeddings.to(ix.device)
+        ix.add(embeddings, ids=ids, normalize=normalize)
+    return ix
+
+
+def cos_sim_topk(queries, corpus_index: TheoremIndex, k: int, normalize_queries: bool = True,
+                 allow_mask: Optional[torch.Tensor] = None):
+    """(scores float32 [Q, k], ids int64 [Q, k]) sorted by score desc then id asc.  A 1-D query
+    returns 1-D rows so ``idx.item()`` / ``scores[i].item()`` consumers (test_app.py:85-88) work."""
+    one_d = (queries.ndim if hasattr(queries, "ndim") else np.asarray(queries).ndim) == 1
+    scores, ids = corpus_index.search(queries, k, normalize=normalize_queries, allow_mask=allow_mask)
+    return (scores[0], ids[0]) if one_d else (scores, ids)
+
+
+def search_theorems(query, model, theorems_data, embeddings_db, k: int = 5):
+    """``test_app.py:67-88`` with the same arguments: encode the query with the caller's model,
+    score against the corpus, take the top 5.  ``embeddings_db`` is a ``TheoremIndex`` (or a
+    raw [N, D] tensor, indexed on the fly).  Returns one dict per hit —
+    ``{"rank", "index", "similarity", "theorem"}`` — where the reference rendered an expander."""
+    if not query:
+        return []
+    index = embeddings_db if isinstance(embeddings_db, TheoremIndex) else build_index(embeddings_db)
+    query_embedding = model.encode(query, convert_to_tensor=True)  # test_app.py:75
+    k = min(k, len(index))
+    if k == 0:
+        return []
+    scores, ids = cos_sim_topk(query_embedding.reshape(-1), index, k)
+    scores = scores.cpu()
+    ids = ids.cpu()
+    out = []
+    for rank in range(k):
+        idx = int(ids[rank].item())
+        if idx < 0:
+            break
+        out.append({"rank": rank + 1, "index": idx, "similarity": float(scores[rank].item()),
+                    "theorem": theorems_data[idx]})
+    return out

@@ -1,0 +1,141 @@
+// K1 — fused L2-normalise + cast (+ zero-pad rows to a 16-byte multiple).
+//
+// Replaces the trailing F.normalize of `model.encode(..., normalize_embeddings=True)`
+// (reference streamlit_app.py:173; ec2/generate_embeddings/embeddings.py:27,35) and the
+// F.normalize pair inside sentence_transformers.util.cos_sim (test_app.py:76), applied ONCE
+// when the corpus is written instead of on every query.
+//
+// Arithmetic (bit-defined, restated by oracle.normalize_f64):
+//   ss   = sum_i (double)x_i^2            (fp64 accumulate, lane-strided + butterfly)
+//   nrm  = max((float)sqrt(ss), 1e-12f)
+//   y_i  = x_i / nrm                      (IEEE fp32 division)
+//   out  = bf16_rn(y_i) | y_i
+// HBM-bound: reads 4*D, writes 2*D (bf16) bytes per row. One warp per row, grid-stride.
+#include "ts_common.cuh"
+
+namespace ts {
+
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p);
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
+    return __bfloat162float(*p);
+}
+template <>
+__device__ __forceinline__ float load_as_float<__half>(const __half* p) { return __half2float(*p); }
+
+template <typename T>
+__device__ __forceinline__ void store_from_float(T* p, float v);
+template <>
+__device__ __forceinline__ void store_from_float<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void store_from_float<__nv_bfloat16>(__nv_bfloat16* p, float v) {
+    *p = __float2bfloat16_rn(v);
+}
+
+// Each lane owns element pairs (2*lane, 2*lane+1) + 64*i so bf16 stores are 4-byte, 128 B/warp.
+template <typename SRC, typename DST>
+__global__ void __launch_bounds__(256) normalize_cast_kernel(const SRC* __restrict__ src, int64_t n,
+                                                             int dim, int dim_pad, int normalize,
+                                                             DST* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = warp0; row < n; row += nwarps) {
+        const SRC* x = src + row * (int64_t)dim;
+        DST* y = dst + row * (int64_t)dim_pad;
+        float inv_den = 1.0f;
+        if (normalize) {
+            double ss = 0.0;
+            for (int i = lane; i < dim; i += 32) {
+                double v = (double)load_as_float<SRC>(x + i);
+                ss = fma(v, v, ss);
+            }
+            ss = warp_sum(ss);
+            inv_den = fmaxf((float)sqrt(ss), 1e-12f);
+        }
+        for (int i = 2 * lane; i < dim_pad; i += 64) {
+            float a = (i < dim) ? load_as_float<SRC>(x + i) : 0.0f;
+            float b = (i + 1 < dim) ? load_as_float<SRC>(x + i + 1) : 0.0f;
+            if (normalize) {
+                a = __fdiv_rn(a, inv_den);
+                b = __fdiv_rn(b, inv_den);
+            }
+            store_from_float<DST>(y + i, a);
+            if (i + 1 < dim_pad) store_from_float<DST>(y + i + 1, b);
+        }
+    }
+}
+
+template <typename SRC>
+__global__ void __launch_bounds__(256) dequant_rows_kernel(const SRC* __restrict__ src, int64_t n,
+                                                           int dim, int dim_pad,
+                                                           float* __restrict__ dst) {
+    int64_t total = n * (int64_t)dim;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = t / dim;
+        int c = (int)(t - r * dim);
+        dst[t] = load_as_float<SRC>(src + r * (int64_t)dim_pad + c);
+    }
+}
+
+template <typename SRC>
+static int launch_nc(const void* src, int64_t n, int dim, int dim_pad, int normalize, void* dst,
+                     int dst_dtype, cudaStream_t s) {
+    if (n == 0) return TS_OK;
+    int64_t blocks64 = (n + 7) / 8;
+    int blocks = (int)(blocks64 > 148 * 32 ? 148 * 32 : blocks64);
+    if (dst_dtype == TS_BF16) {
+        normalize_cast_kernel<SRC, __nv_bfloat16><<<blocks, 256, 0, s>>>(
+            (const SRC*)src, n, dim, dim_pad, normalize, (__nv_bfloat16*)dst);
+    } else if (dst_dtype == TS_F32) {
+        normalize_cast_kernel<SRC, float><<<blocks, 256, 0, s>>>((const SRC*)src, n, dim, dim_pad,
+                                                                 normalize, (float*)dst);
+    } else {
+        set_error("normalize_cast: unsupported destination dtype %d", dst_dtype);
+        return TS_ERR_UNSUPPORTED;
+    }
+    TS_LAUNCH_CHECK();
+    return TS_OK;
+}
+
+int launch_normalize_cast(const void* src, int src_dtype, int64_t n, int dim, int dim_pad,
+                          int normalize, void* dst, int dst_dtype, cudaStream_t s) {
+    switch (src_dtype) {
+        case TS_F32: return launch_nc<float>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s);
+        case TS_BF16:
+            return launch_nc<__nv_bfloat16>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s);
+        case TS_F16: return launch_nc<__half>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s);
+        default:
+            set_error("normalize_cast: unsupported source dtype %d", src_dtype);
+            return TS_ERR_BAD_ARG;
+    }
+}
+
+int launch_prepare_queries(const void* q, int q_dtype, int nq, int dim, int dim_pad, int normalize,
+                           float* out_f32, cudaStream_t s) {
+    return launch_normalize_cast(q, q_dtype, nq, dim, dim_pad, normalize, out_f32, TS_F32, s);
+}
+
+int launch_dequant_rows(const void* src, int src_dtype, int64_t n, int dim, int dim_pad, float* dst,
+                        cudaStream_t s) {
+    if (n == 0) return TS_OK;
+    int64_t total = n * (int64_t)dim;
+    int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    if (src_dtype == TS_BF16)
+        dequant_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)src, n, dim,
+                                                                 dim_pad, dst);
+    else if (src_dtype == TS_F32)
+        dequant_rows_kernel<float><<<blocks, 256, 0, s>>>((const float*)src, n, dim, dim_pad, dst);
+    else {
+        set_error("dequant_rows: unsupported dtype %d", src_dtype);
+        return TS_ERR_UNSUPPORTED;
+    }
+    TS_LAUNCH_CHECK();
+    return TS_OK;
+}
+
+}  // namespace ts

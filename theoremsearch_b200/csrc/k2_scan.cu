@@ -1,0 +1,338 @@
+// K2 — single-query exact scan with the top-k fused into the scan (HBM-bandwidth bound).
+//
+// Replaces, per query, the reference's
+//     cosine_scores = util.cos_sim(query_embedding, embeddings_db)[0]      (test_app.py:76)
+//     top = np.argsort(-cosine_scores.cpu())[:5]                           (test_app.py:77)
+//     torch.topk(cosine_scores, k=min(200, N), sorted=True)                (app_showcase_model.py:96)
+//     ORDER BY e.embedding <#> q ASC LIMIT k                               (streamlit_app.py:281-282)
+// which re-normalise the corpus, materialise all N scores and fully sort them.
+//
+// Design (B200):
+//   * persistent grid, ctas_per_sm CTAs per SM, W warps each; every warp runs its OWN
+//     TMA pipeline: `stages` shared-memory slots, one mbarrier per slot; lane 0 issues
+//     cp.async.bulk (1-D TMA, whole rows are contiguous so no tensor map is needed) for the
+//     warp's next tile as soon as the warp has finished reading a slot. No block-wide
+//     barrier inside the scan loop.
+//   * a tile is R whole rows (~8 KB). Lanes read the slot with conflict-free 128-bit LDS
+//     (lane l takes bytes [16l, 16l+16) of each 512-byte chunk of a row), convert bf16->fp32
+//     with one shift/mask per element and FMA against the query held in registers as fp32.
+//   * the R per-row partial sums are reduced with a transposing butterfly (R-1 + log2(32/R)
+//     shuffles per tile instead of 5R).
+//   * top-k: each warp keeps a sorted list of 64-bit keys (score,row) in registers
+//     (WarpTopK); a candidate is inserted only if it beats the warp's current k-th key, which
+//     after warm-up is rare, so the steady state costs one compare + one ballot per tile.
+//     Scores never go to HBM: each CTA writes only its k best keys; K5 merges the CTA lists.
+//
+// Algorithmic bytes: N * row_bytes per query (+ D*4 query + nparts*k*8 candidates).
+#include "ts_common.cuh"
+
+namespace ts {
+
+struct ScanParams {
+    const uint8_t* data;      // [n_rows, row_bytes]
+    int64_t n_rows;
+    uint32_t row_bytes;       // dim_pad * elem size, multiple of 16
+    int dim_pad;
+    const float* queries;     // [nq, dim_pad] fp32, already normalised / zero padded
+    int k;
+    const uint32_t* mask;     // allow bitmask or nullptr
+    uint64_t* part_keys;      // [nq, nparts, k]
+    int stages;
+};
+
+template <int NCHUNK>
+struct RowsPerTile {
+    static constexpr int value = NCHUNK == 1 ? 16 : (NCHUNK == 2 ? 8 : (NCHUNK <= 4 ? 4 : 2));
+};
+
+// dot of one 16-byte chunk with the matching slice of q
+template <int ELEM>
+struct Chunk;
+template <>
+struct Chunk<2> {  // 8 bf16
+    static constexpr int N = 8;
+    __device__ static __forceinline__ float dot(const uint4& v, const float* q, float acc) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            acc = fmaf(__uint_as_float(w[i] << 16), q[2 * i], acc);
+            acc = fmaf(__uint_as_float(w[i] & 0xFFFF0000u), q[2 * i + 1], acc);
+        }
+        return acc;
+    }
+};
+template <>
+struct Chunk<4> {  // 4 fp32
+    static constexpr int N = 4;
+    __device__ static __forceinline__ float dot(const uint4& v, const float* q, float acc) {
+        acc = fmaf(__uint_as_float(v.x), q[0], acc);
+        acc = fmaf(__uint_as_float(v.y), q[1], acc);
+        acc = fmaf(__uint_as_float(v.z), q[2], acc);
+        acc = fmaf(__uint_as_float(v.w), q[3], acc);
+        return acc;
+    }
+};
+
+// Transposing reduction: in: a[r] = this lane's partial sum for row r of the tile.
+// out: a[0] = full sum for row `row_of_lane(lane)`, replicated over a group of 32/R lanes.
+template <int R>
+__device__ __forceinline__ void transpose_reduce(float (&a)[R], int lane) {
+    int o = 16;
+#pragma unroll
+    for (int r = R; r > 1; r >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < r / 2; ++i) {
+            float send = upper ? a[i] : a[i + r / 2];
+            float keep = upper ? a[i + r / 2] : a[i];
+            a[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, o);
+        }
+        o >>= 1;
+    }
+#pragma unroll
+    for (; o > 0; o >>= 1) a[0] += __shfl_xor_sync(0xFFFFFFFFu, a[0], o);
+}
+template <int R>
+__device__ __forceinline__ int row_of_lane(int lane) {
+    int row = 0, o = 16;
+#pragma unroll
+    for (int r = R; r > 1; r >>= 1) {
+        if (lane & o) row += r / 2;
+        o >>= 1;
+    }
+    return row;
+}
+
+template <int ELEM, int NCHUNK, int KPL>
+__global__ void __launch_bounds__(256, 1) scan_topk_kernel(const ScanParams p) {
+    constexpr int R = RowsPerTile<NCHUNK>::value;
+    constexpr int CN = Chunk<ELEM>::N;       // elements per 16-byte chunk
+    constexpr int GROUP = 32 / R;            // lanes that end up holding the same row's score
+    extern __shared__ __align__(128) uint8_t smem[];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int W = blockDim.x >> 5;
+    const int stages = p.stages;
+    const uint32_t tile_bytes = R * p.row_bytes;
+    const int qi = blockIdx.y;
+
+    uint8_t* my_slots = smem + (size_t)warp * stages * tile_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)W * stages * tile_bytes);
+    uint64_t* my_bars = bars + warp * stages;
+
+    if (lane == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&my_bars[s], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+
+    // query slice of this lane, fp32 in registers
+    float q[NCHUNK * CN];
+    {
+        const float* qv = p.queries + (size_t)qi * p.dim_pad;
+#pragma unroll
+        for (int j = 0; j < NCHUNK; ++j) {
+            const int e0 = (j * 32 + lane) * CN;
+#pragma unroll
+            for (int i = 0; i < CN; ++i) q[j * CN + i] = (e0 + i < p.dim_pad) ? __ldg(qv + e0 + i) : 0.f;
+        }
+    }
+
+    const int64_t num_tiles = (p.n_rows + R - 1) / R;
+    const int64_t gw = (int64_t)blockIdx.x * W + warp;
+    const int64_t tw = (int64_t)gridDim.x * W;
+    const uint64_t policy = l2_policy_evict_first();
+
+    auto issue = [&](int64_t tile, int s) {
+        const int64_t row0 = tile * R;
+        const int64_t rows = (p.n_rows - row0 < R) ? (p.n_rows - row0) : R;
+        const uint32_t bytes = (uint32_t)rows * p.row_bytes;
+        mbar_expect_tx(&my_bars[s], bytes);
+        tma_load_1d_hint(my_slots + (size_t)s * tile_bytes, p.data + (size_t)row0 * p.row_bytes, bytes,
+                         &my_bars[s], policy);
+    };
+
+    if (lane == 0) {
+        for (int s = 0; s < stages; ++s) {
+            const int64_t t = gw + (int64_t)s * tw;
+            if (t < num_tiles) issue(t, s);
+        }
+    }
+
+    WarpTopK<KPL> list;
+    list.clear();
+    uint64_t thr = 0ull;  // current k-th key of this warp's list (0 while it has < k entries)
+    const int k = p.k;
+    const int my_row = row_of_lane<R>(lane);
+    const bool leader = (lane & (GROUP - 1)) == 0;
+
+    int s = 0;
+    uint32_t parity = 0;
+    for (int64_t tile = gw; tile < num_tiles; tile += tw) {
+        const int64_t row0 = tile * R;
+        const int64_t row = row0 + my_row;
+        const bool in_range = row < p.n_rows;
+
+        // fetch the allow bit early so its latency hides behind the barrier wait + FMAs
+        bool allowed = in_range && leader;
+        if (p.mask != nullptr && allowed) allowed = (__ldg(p.mask + (row >> 5)) >> (row & 31)) & 1u;
+
+        mbar_wait(&my_bars[s], parity);
+
+        const uint8_t* slot = my_slots + (size_t)s * tile_bytes;
+        float acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.f;
+#pragma unroll
+        for (int j = 0; j < NCHUNK; ++j) {
+            const uint32_t off = (uint32_t)(j * 32 + lane) * 16u;
+            if (off < p.row_bytes) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    // rows past the end of a short last tile hold stale smem; masked below
+                    const uint4 v = *reinterpret_cast<const uint4*>(slot + (size_t)r * p.row_bytes + off);
+                    acc[r] = Chunk<ELEM>::dot(v, &q[j * CN], acc[r]);
+                }
+            }
+        }
+        __syncwarp();  // every lane is done reading the slot
+        if (lane == 0) {
+            const int64_t nt = tile + (int64_t)stages * tw;
+            if (nt < num_tiles) issue(nt, s);
+        }
+
+        transpose_reduce<R>(acc, lane);
+        const uint64_t key = allowed ? pack_key(acc[0], (uint32_t)row) : 0ull;
+        unsigned m = __ballot_sync(0xFFFFFFFFu, key > thr);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const uint64_t x = __shfl_sync(0xFFFFFFFFu, key, src);
+            if (x > thr) {
+                list.insert(x, lane);
+                thr = list.at(k - 1);
+            }
+        }
+        if (++s == stages) {
+            s = 0;
+            parity ^= 1u;
+        }
+    }
+
+    // ---- CTA merge: warps park their lists in smem (the pipeline has drained: every issued
+    // copy was waited on), warp 0 folds them into its own and writes the CTA's k best.
+    __syncthreads();
+    uint64_t* lists = reinterpret_cast<uint64_t*>(smem);  // [W][KPL*32]
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) lists[(size_t)warp * (KPL * 32) + j * 32 + lane] = list.key[j];
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < W; ++w) merge_sorted_into<KPL>(list, lists + (size_t)w * (KPL * 32), k, k, lane);
+        uint64_t* out = p.part_keys + ((size_t)qi * gridDim.x + blockIdx.x) * k;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+            const int pos = j * 32 + lane;
+            if (pos < k) out[pos] = list.key[j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+struct ScanConfig {
+    int grid, warps, stages;
+    size_t smem;
+};
+
+template <int ELEM, int NCHUNK>
+static ScanConfig scan_config(const ts_index* ix, int kpl) {
+    constexpr int R = RowsPerTile<NCHUNK>::value;
+    const Tunables& t = tunables();
+    const size_t tile_bytes = (size_t)R * ix->dim_pad * ELEM;
+    int stages = t.scan_stages < 2 ? 2 : t.scan_stages;
+    int ctas = t.scan_ctas_per_sm < 1 ? 1 : t.scan_ctas_per_sm;
+    int warps = t.scan_warps < 1 ? 1 : (t.scan_warps > 8 ? 8 : t.scan_warps);
+    const size_t budget = (size_t)(220 * 1024) / ctas - 1024;
+    while (warps > 1 && (size_t)warps * stages * tile_bytes + 8 * warps * stages > budget) --warps;
+    while (stages > 2 && (size_t)warps * stages * tile_bytes + 8 * warps * stages > budget) --stages;
+    size_t smem = (size_t)warps * stages * tile_bytes + 8 * (size_t)warps * stages;
+    const size_t list_bytes = (size_t)warps * kpl * 32 * 8;
+    if (smem < list_bytes) smem = list_bytes;
+    ScanConfig c;
+    c.grid = sm_count(ix->device) * ctas;
+    c.warps = warps;
+    c.stages = stages;
+    c.smem = smem;
+    return c;
+}
+
+template <int ELEM, int NCHUNK, int KPL>
+static int launch_one(const ts_index* ix, const ScanParams& p0, int nq, int nparts, cudaStream_t s,
+                      cudaEvent_t ev0, cudaEvent_t ev1) {
+    ScanConfig c = scan_config<ELEM, NCHUNK>(ix, KPL);
+    ScanParams p = p0;
+    p.stages = c.stages;
+    auto kern = scan_topk_kernel<ELEM, NCHUNK, KPL>;
+    TS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    if (ev0) TS_CHECK_CUDA(cudaEventRecord(ev0, s));
+    kern<<<dim3(nparts, nq), c.warps * 32, c.smem, s>>>(p);
+    TS_LAUNCH_CHECK();
+    if (ev1) TS_CHECK_CUDA(cudaEventRecord(ev1, s));
+    return TS_OK;
+}
+
+template <int ELEM, int NCHUNK>
+static int launch_k(const ts_index* ix, const ScanParams& p, int nq, int nparts, cudaStream_t s,
+                    cudaEvent_t ev0, cudaEvent_t ev1) {
+    if (p.k <= 32) return launch_one<ELEM, NCHUNK, 1>(ix, p, nq, nparts, s, ev0, ev1);
+    if (p.k <= 128) return launch_one<ELEM, NCHUNK, 4>(ix, p, nq, nparts, s, ev0, ev1);
+    if (p.k <= 256) return launch_one<ELEM, NCHUNK, 8>(ix, p, nq, nparts, s, ev0, ev1);
+    return launch_one<ELEM, NCHUNK, 32>(ix, p, nq, nparts, s, ev0, ev1);
+}
+
+int scan_nparts(const ts_index* ix) {
+    int ctas = tunables().scan_ctas_per_sm < 1 ? 1 : tunables().scan_ctas_per_sm;
+    return sm_count(ix->device) * ctas;
+}
+
+int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64_t n_rows,
+                     const float* queries_f32, int nq, int k, const uint32_t* allow_mask,
+                     uint64_t* part_keys, int nparts, cudaStream_t s, cudaEvent_t ev0,
+                     cudaEvent_t ev1) {
+    TS_REQUIRE(k >= 1 && k <= TS_MAX_K, TS_ERR_BAD_ARG, "scan: k=%d out of range [1, %d]", k, TS_MAX_K);
+    TS_REQUIRE(n_rows < (int64_t)0xFFFFFFFFll, TS_ERR_UNSUPPORTED, "scan: more than 2^32-1 rows per shard");
+    TS_REQUIRE(nparts == scan_nparts(ix), TS_ERR_BAD_ARG, "scan: workspace sized for another grid");
+    ScanParams p;
+    p.data = (const uint8_t*)data;
+    p.n_rows = n_rows;
+    p.dim_pad = ix->dim_pad;
+    p.queries = queries_f32;
+    p.k = k;
+    p.mask = allow_mask;
+    p.part_keys = part_keys;
+    p.stages = 0;
+    if (data_dtype == TS_BF16) {
+        p.row_bytes = (uint32_t)ix->dim_pad * 2;
+        const int nchunk = (ix->dim_pad + 255) / 256;
+        switch (nchunk) {
+            case 1: return launch_k<2, 1>(ix, p, nq, nparts, s, ev0, ev1);
+            case 2: return launch_k<2, 2>(ix, p, nq, nparts, s, ev0, ev1);
+            case 3: return launch_k<2, 3>(ix, p, nq, nparts, s, ev0, ev1);
+            case 4: return launch_k<2, 4>(ix, p, nq, nparts, s, ev0, ev1);
+            default:
+                if (nchunk <= 8) return launch_k<2, 8>(ix, p, nq, nparts, s, ev0, ev1);
+        }
+    } else if (data_dtype == TS_F32) {
+        p.row_bytes = (uint32_t)ix->dim_pad * 4;
+        const int nchunk = (ix->dim_pad + 127) / 128;
+        if (nchunk <= 2) return launch_k<4, 2>(ix, p, nq, nparts, s, ev0, ev1);
+        if (nchunk <= 4) return launch_k<4, 4>(ix, p, nq, nparts, s, ev0, ev1);
+        if (nchunk <= 6) return launch_k<4, 6>(ix, p, nq, nparts, s, ev0, ev1);
+        if (nchunk <= 8) return launch_k<4, 8>(ix, p, nq, nparts, s, ev0, ev1);
+        if (nchunk <= 16) return launch_k<4, 16>(ix, p, nq, nparts, s, ev0, ev1);
+    }
+    set_error("scan: no kernel for dtype %d dim %d", data_dtype, ix->dim);
+    return TS_ERR_UNSUPPORTED;
+}
+
+}  // namespace ts

@@ -1,0 +1,443 @@
+// C ABI of libtheoremsearch.so — see include/theoremsearch.h for the contract and the
+// reference call sites each entry point replaces.
+#include "ts_common.cuh"
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+namespace ts {
+
+static thread_local std::string t_error;
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    t_error = buf;
+}
+
+Tunables& tunables() {
+    static Tunables t;
+    return t;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            ok = false;
+            return;
+        }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// Workspace layout for exact search: [prepared queries fp32 | per-CTA candidate keys]
+struct SearchWs {
+    float* q_f32;
+    uint64_t* part_keys;
+    int nparts;
+    size_t bytes;
+};
+static SearchWs carve_ws(const ts_index* ix, int nq, int k, void* base) {
+    SearchWs w;
+    w.nparts = scan_nparts(ix);
+    size_t off = 0;
+    w.q_f32 = (float*)((char*)base + off);
+    off += align_up((size_t)nq * ix->dim_pad * sizeof(float), 256);
+    w.part_keys = (uint64_t*)((char*)base + off);
+    off += align_up((size_t)nq * w.nparts * k * sizeof(uint64_t), 256);
+    w.bytes = off;
+    return w;
+}
+
+static int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k,
+                       int normalize_queries, const uint32_t* allow_mask, uint64_t* out_keys,
+                       float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+                       cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1) {
+    TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "search: index is NULL");
+    TS_REQUIRE(nq >= 0, TS_ERR_BAD_ARG, "search: nq=%d", nq);
+    TS_REQUIRE(k >= 1 && k <= TS_MAX_K, TS_ERR_BAD_ARG, "search: k=%d out of range [1, %d]", k, TS_MAX_K);
+    TS_REQUIRE(q_dtype == TS_F32 || q_dtype == TS_BF16 || q_dtype == TS_F16, TS_ERR_BAD_ARG,
+               "search: query dtype %d", q_dtype);
+    if (nq == 0) return TS_OK;
+    TS_REQUIRE(queries != nullptr, TS_ERR_BAD_ARG, "search: queries is NULL");
+    TS_REQUIRE(workspace != nullptr, TS_ERR_BAD_ARG, "search: workspace is NULL");
+    DeviceGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "search: cannot select CUDA device %d", ix->device);
+    SearchWs w = carve_ws(ix, nq, k, workspace);
+    TS_REQUIRE(workspace_bytes >= w.bytes, TS_ERR_CAPACITY, "search: workspace %zu < %zu bytes",
+               workspace_bytes, w.bytes);
+    int rc = launch_prepare_queries(queries, q_dtype, nq, ix->dim, ix->dim_pad, normalize_queries,
+                                    w.q_f32, s);
+    if (rc) return rc;
+    rc = launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, w.part_keys,
+                          w.nparts, s, ev0, ev1);
+    if (rc) return rc;
+    return launch_merge(w.part_keys, w.nparts, nq, k, /*query_major=*/true, nullptr,
+                        ix->has_ids ? ix->ids : nullptr, out_keys, out_scores, out_ids, s);
+}
+
+}  // namespace ts
+
+using namespace ts;
+
+extern "C" {
+
+int ts_abi_version(void) { return 1; }
+
+const char* ts_last_error(void) { return t_error.c_str(); }
+
+uint64_t ts_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+
+uint64_t ts_pack_key(float score, uint32_t row) { return pack_key(score, row); }
+
+void ts_unpack_key(uint64_t key, float* score, uint32_t* row) {
+    if (score) *score = key ? key_score(key) : -INFINITY;
+    if (row) *row = key_row(key);
+}
+
+// ------------------------------------------------------------------------------------ index
+int ts_index_create(ts_index** out, int device, int dim, int dtype, int64_t capacity) {
+    TS_REQUIRE(out != nullptr, TS_ERR_BAD_ARG, "index_create: out is NULL");
+    *out = nullptr;
+    TS_REQUIRE(dim >= 1 && dim <= TS_MAX_DIM, TS_ERR_BAD_ARG, "index_create: dim=%d out of range [1, %d]",
+               dim, TS_MAX_DIM);
+    TS_REQUIRE(dtype == TS_BF16 || dtype == TS_F32, TS_ERR_BAD_ARG,
+               "index_create: storage dtype must be TS_BF16 or TS_F32 (got %d)", dtype);
+    TS_REQUIRE(capacity >= 0 && capacity < (int64_t)0xFFFFFFFFll, TS_ERR_BAD_ARG,
+               "index_create: capacity=%lld", (long long)capacity);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("index_create: no CUDA device (%s); libtheoremsearch has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return TS_ERR_CUDA;
+    }
+    TS_REQUIRE(device >= 0 && device < ndev, TS_ERR_BAD_ARG, "index_create: device %d of %d", device, ndev);
+    DeviceGuard g(device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "index_create: cannot select CUDA device %d", device);
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    TS_REQUIRE(major == 10, TS_ERR_UNSUPPORTED,
+               "index_create: device %d is sm_%d0; this library is built for sm_100a only", device, major);
+    ts_index* ix = new ts_index();
+    ix->device = device;
+    ix->dim = dim;
+    ix->dim_pad = (dim + 7) / 8 * 8;
+    ix->dtype = dtype;
+    ix->capacity = capacity;
+    size_t bytes = (size_t)std::max<int64_t>(capacity, 1) * ix->row_bytes();
+    e = cudaMalloc(&ix->data, bytes);
+    if (e != cudaSuccess) {
+        set_error("index_create: cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        delete ix;
+        cudaGetLastError();
+        return TS_ERR_OOM;
+    }
+    *out = ix;
+    return TS_OK;
+}
+
+void ts_index_destroy(ts_index* ix) {
+    if (!ix) return;
+    DeviceGuard g(ix->device);
+    cudaFree(ix->data);
+    cudaFree(ix->ids);
+    cudaFree(ix->centroids);
+    cudaFree(ix->centroids_bf16);
+    cudaFree(ix->list_offsets);
+    cudaFree(ix->list_rows);
+    cudaFree(ix->list_data);
+    cudaFree(ix->list_scales);
+    delete ix;
+}
+
+__global__ void iota_ids_kernel(int64_t* ids, int64_t first, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        ids[i] = first + i;
+}
+
+int ts_index_add(ts_index* ix, const void* rows, int src_dtype, int64_t n, int normalize,
+                 const int64_t* ids, void* stream) {
+    TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "index_add: index is NULL");
+    TS_REQUIRE(n >= 0, TS_ERR_BAD_ARG, "index_add: n=%lld", (long long)n);
+    if (n == 0) return TS_OK;
+    TS_REQUIRE(rows != nullptr, TS_ERR_BAD_ARG, "index_add: rows is NULL");
+    TS_REQUIRE(ix->size + n <= ix->capacity, TS_ERR_CAPACITY, "index_add: %lld + %lld rows exceed capacity %lld",
+               (long long)ix->size, (long long)n, (long long)ix->capacity);
+    DeviceGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "index_add: cannot select CUDA device %d", ix->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (ids != nullptr && !ix->has_ids) {
+        // first explicit ids: materialise the id table, rows added so far keep id = row
+        TS_CHECK_CUDA(cudaMalloc(&ix->ids, (size_t)std::max<int64_t>(ix->capacity, 1) * sizeof(int64_t)));
+        if (ix->size > 0) {
+            iota_ids_kernel<<<256, 256, 0, s>>>(ix->ids, 0, ix->size);
+            TS_LAUNCH_CHECK();
+        }
+        ix->has_ids = true;
+    }
+    if (ix->has_ids) {
+        if (ids != nullptr) {
+            TS_CHECK_CUDA(cudaMemcpyAsync(ix->ids + ix->size, ids, (size_t)n * sizeof(int64_t),
+                                          cudaMemcpyDeviceToDevice, s));
+        } else {
+            iota_ids_kernel<<<256, 256, 0, s>>>(ix->ids + ix->size, ix->size, n);
+            TS_LAUNCH_CHECK();
+        }
+    }
+    void* dst = (char*)ix->data + (size_t)ix->size * ix->row_bytes();
+    int rc = launch_normalize_cast(rows, src_dtype, n, ix->dim, ix->dim_pad, normalize, dst, ix->dtype, s);
+    if (rc) return rc;
+    ix->size += n;
+    ix->ivf_built = false;
+    return TS_OK;
+}
+
+int ts_index_add_host(ts_index* ix, const void* rows, int src_dtype, int64_t n, int normalize,
+                      const int64_t* ids) {
+    TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "index_add_host: index is NULL");
+    TS_REQUIRE(n >= 0, TS_ERR_BAD_ARG, "index_add_host: n=%lld", (long long)n);
+    if (n == 0) return TS_OK;
+    TS_REQUIRE(rows != nullptr, TS_ERR_BAD_ARG, "index_add_host: rows is NULL");
+    TS_REQUIRE(src_dtype == TS_F32 || src_dtype == TS_BF16 || src_dtype == TS_F16, TS_ERR_BAD_ARG,
+               "index_add_host: source dtype %d", src_dtype);
+    DeviceGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "index_add_host: cannot select CUDA device %d", ix->device);
+    const size_t src_row = (size_t)ix->dim * (src_dtype == TS_F32 ? 4 : 2);
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)((64u << 20) / src_row)));
+    void* d_rows = nullptr;
+    int64_t* d_ids = nullptr;
+    TS_CHECK_CUDA(cudaMalloc(&d_rows, (size_t)chunk * src_row));
+    if (ids) {
+        cudaError_t e = cudaMalloc(&d_ids, (size_t)chunk * sizeof(int64_t));
+        if (e != cudaSuccess) {
+            cudaFree(d_rows);
+            set_error("index_add_host: cudaMalloc ids failed: %s", cudaGetErrorString(e));
+            return TS_ERR_OOM;
+        }
+    }
+    int rc = TS_OK;
+    for (int64_t pos = 0; pos < n && rc == TS_OK; pos += chunk) {
+        const int64_t m = std::min(chunk, n - pos);
+        cudaError_t e = cudaMemcpy(d_rows, (const char*)rows + (size_t)pos * src_row, (size_t)m * src_row,
+                                   cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && ids)
+            e = cudaMemcpy(d_ids, ids + pos, (size_t)m * sizeof(int64_t), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            set_error("index_add_host: H2D copy failed: %s", cudaGetErrorString(e));
+            rc = TS_ERR_CUDA;
+            break;
+        }
+        rc = ts_index_add(ix, d_rows, src_dtype, m, normalize, ids ? d_ids : nullptr, nullptr);
+        if (rc == TS_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) {
+            set_error("index_add_host: kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = TS_ERR_CUDA;
+        }
+    }
+    cudaFree(d_rows);
+    cudaFree(d_ids);
+    return rc;
+}
+
+int64_t ts_index_size(const ts_index* ix) { return ix ? ix->size : -1; }
+int64_t ts_index_capacity(const ts_index* ix) { return ix ? ix->capacity : -1; }
+int ts_index_dim(const ts_index* ix) { return ix ? ix->dim : -1; }
+int ts_index_dtype(const ts_index* ix) { return ix ? ix->dtype : -1; }
+int ts_index_device(const ts_index* ix) { return ix ? ix->device : -1; }
+const void* ts_index_data(const ts_index* ix) { return ix ? ix->data : nullptr; }
+size_t ts_index_row_bytes(const ts_index* ix) { return ix ? ix->row_bytes() : 0; }
+
+int ts_index_get_rows(const ts_index* ix, int64_t first, int64_t n, float* out, void* stream) {
+    TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "index_get_rows: index is NULL");
+    TS_REQUIRE(first >= 0 && n >= 0 && first + n <= ix->size, TS_ERR_BAD_ARG,
+               "index_get_rows: [%lld, %lld) outside [0, %lld)", (long long)first, (long long)(first + n),
+               (long long)ix->size);
+    if (n == 0) return TS_OK;
+    TS_REQUIRE(out != nullptr, TS_ERR_BAD_ARG, "index_get_rows: out is NULL");
+    DeviceGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "index_get_rows: cannot select CUDA device %d", ix->device);
+    return launch_dequant_rows((const char*)ix->data + (size_t)first * ix->row_bytes(), ix->dtype, n, ix->dim,
+                               ix->dim_pad, out, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------ search
+size_t ts_workspace_bytes(const ts_index* ix, int nq, int k) {
+    if (!ix || nq < 0 || k < 1) return 0;
+    return carve_ws(ix, std::max(nq, 1), k, nullptr).bytes;
+}
+
+int ts_search(ts_index* ix, const void* queries, int q_dtype, int nq, int k, int normalize_queries,
+              const uint32_t* allow_mask, float* out_scores, int64_t* out_ids, void* workspace,
+              size_t workspace_bytes, void* stream) {
+    TS_REQUIRE(nq == 0 || (out_scores != nullptr && out_ids != nullptr), TS_ERR_BAD_ARG,
+               "search: output pointers are NULL");
+    return search_impl(ix, queries, q_dtype, nq, k, normalize_queries, allow_mask, nullptr, out_scores,
+                       out_ids, workspace, workspace_bytes, (cudaStream_t)stream, nullptr, nullptr);
+}
+
+int ts_search_keys(ts_index* ix, const void* queries, int q_dtype, int nq, int k, int normalize_queries,
+                   const uint32_t* allow_mask, uint64_t* out_keys, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+    TS_REQUIRE(nq == 0 || out_keys != nullptr, TS_ERR_BAD_ARG, "search_keys: out_keys is NULL");
+    return search_impl(ix, queries, q_dtype, nq, k, normalize_queries, allow_mask, out_keys, nullptr, nullptr,
+                       workspace, workspace_bytes, (cudaStream_t)stream, nullptr, nullptr);
+}
+
+int ts_merge_topk(const uint64_t* keys, int nshards, int nq, int k, const int64_t* shard_base,
+                  const int64_t* id_map, float* out_scores, int64_t* out_ids, void* stream) {
+    TS_REQUIRE(keys != nullptr || nq == 0, TS_ERR_BAD_ARG, "merge_topk: keys is NULL");
+    TS_REQUIRE(nq == 0 || (out_scores != nullptr && out_ids != nullptr), TS_ERR_BAD_ARG,
+               "merge_topk: output pointers are NULL");
+    return launch_merge(keys, nshards, nq, k, /*query_major=*/false, shard_base, id_map, nullptr, out_scores,
+                        out_ids, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------ ctx
+int ts_ctx_create(ts_ctx** out, ts_index* ix, int max_nq, int max_k) {
+    TS_REQUIRE(out != nullptr, TS_ERR_BAD_ARG, "ctx_create: out is NULL");
+    *out = nullptr;
+    TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "ctx_create: index is NULL");
+    TS_REQUIRE(max_nq >= 1 && max_k >= 1 && max_k <= TS_MAX_K, TS_ERR_BAD_ARG, "ctx_create: max_nq=%d max_k=%d",
+               max_nq, max_k);
+    DeviceGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "ctx_create: cannot select CUDA device %d", ix->device);
+    ts_ctx* c = new ts_ctx();
+    c->index = ix;
+    c->max_nq = max_nq;
+    c->max_k = max_k;
+    c->workspace_bytes = ts_workspace_bytes(ix, max_nq, max_k);
+    const size_t qb = (size_t)max_nq * ix->dim * sizeof(float);
+    const size_t sb = (size_t)max_nq * max_k * sizeof(float);
+    const size_t ib = (size_t)max_nq * max_k * sizeof(int64_t);
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_queries, qb);
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_scores, sb);
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_ids, ib);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_queries, qb);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_scores, sb);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_ids, ib);
+    if (e == cudaSuccess) e = cudaMalloc(&c->workspace, c->workspace_bytes);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e != cudaSuccess) {
+        set_error("ctx_create: allocation failed: %s", cudaGetErrorString(e));
+        ts_ctx_destroy(c);
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? TS_ERR_OOM : TS_ERR_CUDA;
+    }
+    *out = c;
+    return TS_OK;
+}
+
+void ts_ctx_destroy(ts_ctx* c) {
+    if (!c) return;
+    DeviceGuard g(c->index ? c->index->device : 0);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFreeHost(c->h_queries);
+    cudaFreeHost(c->h_scores);
+    cudaFreeHost(c->h_ids);
+    cudaFree(c->d_queries);
+    cudaFree(c->d_scores);
+    cudaFree(c->d_ids);
+    cudaFree(c->workspace);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int ts_ctx_set_timing(ts_ctx* c, int enabled) {
+    TS_REQUIRE(c != nullptr, TS_ERR_BAD_ARG, "ctx_set_timing: ctx is NULL");
+    c->timing = enabled != 0;
+    c->last_ms = -1.f;
+    return TS_OK;
+}
+
+float ts_ctx_last_kernel_ms(const ts_ctx* c) { return c ? c->last_ms : -1.f; }
+
+int ts_search_host(ts_ctx* c, const float* queries, int nq, int k, int normalize_queries,
+                   const uint32_t* allow_mask, float* out_scores, int64_t* out_ids) {
+    TS_REQUIRE(c != nullptr, TS_ERR_BAD_ARG, "search_host: ctx is NULL");
+    TS_REQUIRE(nq >= 0 && nq <= c->max_nq, TS_ERR_CAPACITY, "search_host: nq=%d exceeds ctx max_nq=%d", nq,
+               c->max_nq);
+    TS_REQUIRE(k >= 1 && k <= c->max_k, TS_ERR_CAPACITY, "search_host: k=%d exceeds ctx max_k=%d", k, c->max_k);
+    if (nq == 0) return TS_OK;
+    TS_REQUIRE(queries && out_scores && out_ids, TS_ERR_BAD_ARG, "search_host: NULL buffer");
+    ts_index* ix = c->index;
+    DeviceGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "search_host: cannot select CUDA device %d", ix->device);
+    const size_t qb = (size_t)nq * ix->dim * sizeof(float);
+    memcpy(c->h_queries, queries, qb);
+    TS_CHECK_CUDA(cudaMemcpyAsync(c->d_queries, c->h_queries, qb, cudaMemcpyHostToDevice, c->stream));
+    int rc = search_impl(ix, c->d_queries, TS_F32, nq, k, normalize_queries, allow_mask, nullptr, c->d_scores,
+                         c->d_ids, c->workspace, c->workspace_bytes, c->stream, c->timing ? c->ev0 : nullptr,
+                         c->timing ? c->ev1 : nullptr);
+    if (rc) return rc;
+    const size_t n = (size_t)nq * k;
+    TS_CHECK_CUDA(cudaMemcpyAsync(c->h_scores, c->d_scores, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    TS_CHECK_CUDA(cudaMemcpyAsync(c->h_ids, c->d_ids, n * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    TS_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(out_scores, c->h_scores, n * sizeof(float));
+    memcpy(out_ids, c->h_ids, n * sizeof(int64_t));
+    if (c->timing) TS_CHECK_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    return TS_OK;
+}
+
+// ------------------------------------------------------------------------------------ IVF (K4)
+int ts_ivf_train(ts_index*, const float*, int64_t, int, int, uint64_t, void*) {
+    set_error("ivf_train: IVF-Flat kernels are not built yet");
+    return TS_ERR_UNSUPPORTED;
+}
+int ts_ivf_build(ts_index*, int, void*) {
+    set_error("ivf_build: IVF-Flat kernels are not built yet");
+    return TS_ERR_UNSUPPORTED;
+}
+size_t ts_ivf_workspace_bytes(const ts_index*, int, int, int, int) { return 0; }
+int ts_ivf_search(ts_index*, const void*, int, int, int, int, int, int, float*, int64_t*, void*, size_t, void*) {
+    set_error("ivf_search: IVF-Flat kernels are not built yet");
+    return TS_ERR_UNSUPPORTED;
+}
+int ts_ivf_nlist(const ts_index* ix) { return ix ? ix->nlist : -1; }
+int ts_ivf_list_sizes(const ts_index*, int64_t*, void*) {
+    set_error("ivf_list_sizes: IVF-Flat kernels are not built yet");
+    return TS_ERR_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------ tunables
+static int* tunable_slot(const char* name) {
+    Tunables& t = tunables();
+    if (!name) return nullptr;
+    if (!strcmp(name, "scan.ctas_per_sm")) return &t.scan_ctas_per_sm;
+    if (!strcmp(name, "scan.warps")) return &t.scan_warps;
+    if (!strcmp(name, "scan.stages")) return &t.scan_stages;
+    if (!strcmp(name, "scan.tile_bytes")) return &t.scan_tile_bytes;
+    if (!strcmp(name, "batch.min_nq")) return &t.batch_min_nq;
+    return nullptr;
+}
+int ts_set_tunable(const char* name, int value) {
+    int* s = tunable_slot(name);
+    TS_REQUIRE(s != nullptr, TS_ERR_BAD_ARG, "set_tunable: unknown tunable '%s'", name ? name : "(null)");
+    *s = value;
+    return TS_OK;
+}
+int ts_get_tunable(const char* name, int* value) {
+    int* s = tunable_slot(name);
+    TS_REQUIRE(s != nullptr && value != nullptr, TS_ERR_BAD_ARG, "get_tunable: unknown tunable '%s'",
+               name ? name : "(null)");
+    *value = *s;
+    return TS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,296 @@
+// Shared device/host helpers for libtheoremsearch (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/theoremsearch.h"
+
+namespace ts {
+
+// ---------------------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define TS_CHECK_CUDA(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            ts::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),        \
+                          __FILE__, __LINE__);                                           \
+            return (_e == cudaErrorMemoryAllocation) ? TS_ERR_OOM : TS_ERR_CUDA;         \
+        }                                                                                \
+    } while (0)
+
+#define TS_REQUIRE(cond, code, ...)       \
+    do {                                  \
+        if (!(cond)) {                    \
+            ts::set_error(__VA_ARGS__);   \
+            return (code);                \
+        }                                 \
+    } while (0)
+
+// Every kernel launch goes through this so ts_kernel_launches() is an honest count.
+#define TS_LAUNCH_CHECK()                                   \
+    do {                                                    \
+        ts::g_launches.fetch_add(1, std::memory_order_relaxed); \
+        TS_CHECK_CUDA(cudaGetLastError());                  \
+    } while (0)
+
+inline int sm_count(int device) {
+    static int cached[64] = {0};
+    if (device >= 0 && device < 64 && cached[device]) return cached[device];
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+    if (device >= 0 && device < 64) cached[device] = n;
+    return n;
+}
+
+// ---------------------------------------------------------------------------- tunables
+struct Tunables {
+    int scan_ctas_per_sm = 1;   // persistent CTAs per SM for K2
+    int scan_warps = 8;         // consumer warps per CTA
+    int scan_stages = 3;        // TMA ring depth per warp
+    int scan_tile_bytes = 8192; // bytes per TMA bulk copy (whole rows)
+    int batch_min_nq = 2;       // nq >= this goes to the batched path (when available)
+};
+Tunables& tunables();
+
+// ---------------------------------------------------------------------------- keys
+// key = orderable_u32(score) << 32 | (0xFFFFFFFF - row). Unsigned max == (score desc, row asc).
+// 0 is reserved for "empty".
+__host__ __device__ __forceinline__ uint32_t orderable_from_float(float f) {
+#ifdef __CUDA_ARCH__
+    if (f != f) return 1u;
+    f = f + 0.0f;  // -0.0 -> +0.0
+    uint32_t u = __float_as_uint(f);
+#else
+    if (f != f) return 1u;
+    f = f + 0.0f;
+    uint32_t u;
+    memcpy(&u, &f, 4);
+#endif
+    uint32_t hi = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return hi ? hi : 1u;
+}
+__host__ __device__ __forceinline__ float float_from_orderable(uint32_t hi) {
+    uint32_t u = (hi & 0x80000000u) ? (hi & 0x7FFFFFFFu) : ~hi;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t pack_key(float score, uint32_t row) {
+    return ((uint64_t)orderable_from_float(score) << 32) | (uint64_t)(0xFFFFFFFFu - row);
+}
+__host__ __device__ __forceinline__ uint32_t key_row(uint64_t key) {
+    return 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+}
+__host__ __device__ __forceinline__ float key_score(uint64_t key) {
+    return float_from_orderable((uint32_t)(key >> 32));
+}
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------- warp top-k list
+// A descending list of KPL*32 keys held across one warp: position p = j*32 + lane lives in
+// slot j of lane `lane`. Slot values are unique keys or 0 (empty, sorts last).
+template <int KPL>
+struct WarpTopK {
+    uint64_t key[KPL];
+
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) key[j] = 0ull;
+    }
+
+    // The key at list position `pos` (warp-uniform pos), broadcast to every lane.
+    __device__ __forceinline__ uint64_t at(int pos) const {
+        uint64_t v = 0ull;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j)
+            if (j == (pos >> 5)) v = key[j];
+        return __shfl_sync(0xFFFFFFFFu, v, pos & 31);
+    }
+
+    // Insert x (warp-uniform, x != any present key). Entries below x shift down one
+    // position; the last one falls off.
+    __device__ __forceinline__ void insert(uint64_t x, int lane) {
+        uint64_t carry = ~0ull;  // "previous position" of position 0: +inf, never < x
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+            uint64_t up = __shfl_up_sync(0xFFFFFFFFu, key[j], 1);
+            uint64_t last = __shfl_sync(0xFFFFFFFFu, key[j], 31);
+            uint64_t prev = (lane == 0) ? carry : up;
+            uint64_t mine = key[j];
+            key[j] = (mine > x) ? mine : ((prev > x) ? x : prev);
+            carry = last;
+        }
+    }
+};
+
+// Insert the (descending-sorted) list src[0..n) into `list`, stopping at the first element
+// that no longer beats the list's current k-th entry. All lanes call with the same args.
+template <int KPL>
+__device__ __forceinline__ void merge_sorted_into(WarpTopK<KPL>& list, const uint64_t* src, int n,
+                                                  int k, int lane) {
+    uint64_t thr = list.at(k - 1);
+    for (int i = 0; i < n; ++i) {
+        uint64_t x = src[i];
+        if (x <= thr) break;  // sorted: nothing after it can enter either (0 = empty too)
+        list.insert(x, lane);
+        thr = list.at(k - 1);
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------- mbarrier / TMA (1-D bulk)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared bulk copy (TMA engine, no tensor map): bytes % 16 == 0, both 16B aligned.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d_hint(void* smem_dst, const void* gmem_src,
+                                                 uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+#endif  // __CUDACC__
+
+}  // namespace ts
+
+// ---------------------------------------------------------------------------- handles
+struct ts_index {
+    int device = 0;
+    int dim = 0;          // logical embedding dimension
+    int dim_pad = 0;      // stored elements per row (multiple of 8 -> 16-byte rows)
+    int dtype = TS_BF16;  // storage dtype of `data`
+    int64_t capacity = 0;
+    int64_t size = 0;
+    void* data = nullptr;     // [capacity, dim_pad] of dtype
+    int64_t* ids = nullptr;   // [capacity] caller ids; valid only when has_ids
+    bool has_ids = false;
+
+    // IVF-Flat state (K4)
+    int nlist = 0;
+    float* centroids = nullptr;         // [nlist, dim_pad] fp32 unit vectors
+    __nv_bfloat16* centroids_bf16 = nullptr;  // same, bf16, what the coarse scan reads
+    int64_t* list_offsets = nullptr;    // [nlist + 1] into the permuted row order
+    uint32_t* list_rows = nullptr;      // [size] original row of each permuted position
+    void* list_data = nullptr;          // [size, dim_pad] permuted rows in list_dtype
+    float* list_scales = nullptr;       // [size] per-row scale (fp8 only)
+    int list_dtype = TS_BF16;
+    bool ivf_built = false;
+
+    size_t elem_bytes() const { return dtype == TS_F32 ? 4 : 2; }
+    size_t row_bytes() const { return (size_t)dim_pad * elem_bytes(); }
+};
+
+struct ts_ctx {
+    ts_index* index = nullptr;
+    int max_nq = 0, max_k = 0;
+    cudaStream_t stream = nullptr;
+    float* h_queries = nullptr;   // pinned [max_nq, dim]
+    float* h_scores = nullptr;    // pinned [max_nq, max_k]
+    int64_t* h_ids = nullptr;     // pinned [max_nq, max_k]
+    float* d_queries = nullptr;
+    float* d_scores = nullptr;
+    int64_t* d_ids = nullptr;
+    void* workspace = nullptr;
+    size_t workspace_bytes = 0;
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = -1.f;
+};
+
+// internal kernel entry points (one per .cu)
+namespace ts {
+int launch_normalize_cast(const void* src, int src_dtype, int64_t n, int dim, int dim_pad,
+                          int normalize, void* dst, int dst_dtype, cudaStream_t s);
+int launch_dequant_rows(const void* src, int src_dtype, int64_t n, int dim, int dim_pad, float* dst,
+                        cudaStream_t s);
+int launch_prepare_queries(const void* q, int q_dtype, int nq, int dim, int dim_pad, int normalize,
+                           float* out_f32, cudaStream_t s);
+// K2: per-CTA candidate lists part_keys[nq][nparts][k]; returns nparts through *nparts_out
+int scan_nparts(const ts_index* ix);
+int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64_t n_rows,
+                     const float* queries_f32, int nq, int k, const uint32_t* allow_mask,
+                     uint64_t* part_keys, int nparts, cudaStream_t s, cudaEvent_t ev0,
+                     cudaEvent_t ev1);
+// K5: lists[nlists][nq][k] (list-major) or [nq][nlists][k] (query-major) -> top-k
+int launch_merge(const uint64_t* keys, int nlists, int nq, int k, bool query_major,
+                 const int64_t* list_base, const int64_t* id_map, uint64_t* out_keys,
+                 float* out_scores, int64_t* out_ids, cudaStream_t s);
+}  // namespace ts

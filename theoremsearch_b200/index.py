@@ -1,0 +1,258 @@
+"""``TheoremIndex`` — the corpus of theorem/slogan embeddings resident in one B200's HBM.
+
+Host-side mirror of the reference's corpus containers: the ``embeddings_db`` tensor of
+``test_app.py:129-130`` / ``app_showcase_model.py:52`` and the pgvector table
+``theorem_embedding_qwen`` (``rds_schema.sql:50-53``).  All arithmetic happens in
+``libtheoremsearch.so``; torch is used only for device buffers and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import TS_BF16, TS_F16, TS_F32, check, lib
+
+_TORCH_TO_TS = {torch.float32: TS_F32, torch.bfloat16: TS_BF16, torch.float16: TS_F16}
+_NAME_TO_TS = {"bf16": TS_BF16, "bfloat16": TS_BF16, "f32": TS_F32, "fp32": TS_F32, "float32": TS_F32}
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise _lib.TheoremSearchError(
+            -2, "no CUDA device visible; theoremsearch_b200 has no CPU fallback (B200 / sm_100a only)")
+
+
+def pack_allow_mask(allow: np.ndarray | torch.Tensor, device: torch.device | str | None = None) -> torch.Tensor:
+    """Boolean row mask [N] -> the uint32 bitmask K2 consumes (bit r of word r//32), as an
+    int32 torch tensor (same bits) on ``device``.  Mirrors the SQL WHERE of
+    ``streamlit_app.py:175-243`` being applied before ``ORDER BY ... LIMIT``."""
+    a = np.asarray(allow.cpu() if isinstance(allow, torch.Tensor) else allow).astype(bool)
+    n = a.shape[0]
+    words = (n + 31) // 32
+    padded = np.zeros(words * 32, dtype=bool)
+    padded[:n] = a
+    bits = np.packbits(padded.reshape(words, 32), axis=1, bitorder="little").view(np.uint32).reshape(words)
+    t = torch.from_numpy(bits.view(np.int32).copy())
+    return t.to(device) if device is not None else t
+
+
+class TheoremIndex:
+    """Exact-search index over L2-normalised embeddings stored as bf16 (or fp32) rows."""
+
+    def __init__(self, dim: int, capacity: int, dtype: str = "bf16", device: int | str | torch.device = 0):
+        _require_cuda()
+        dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if dev.type != "cuda":
+            raise _lib.TheoremSearchError(-1, f"TheoremIndex lives on a CUDA device, not {dev}")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        self.dim = int(dim)
+        self.dtype = dtype
+        h = C.c_void_p()
+        check(lib.ts_index_create(C.byref(h), self.device.index, self.dim, _NAME_TO_TS[dtype], int(capacity)))
+        self._h = h
+        self._ws: dict[tuple[int, int], torch.Tensor] = {}
+        self._ctx: dict[tuple[int, int], C.c_void_p] = {}
+
+    # -------------------------------------------------------------------------------- lifecycle
+    def close(self) -> None:
+        for ctx in self._ctx.values():
+            lib.ts_ctx_destroy(ctx)
+        self._ctx.clear()
+        if getattr(self, "_h", None):
+            lib.ts_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        return int(lib.ts_index_size(self._h))
+
+    @property
+    def capacity(self) -> int:
+        return int(lib.ts_index_capacity(self._h))
+
+    @property
+    def row_bytes(self) -> int:
+        return int(lib.ts_index_row_bytes(self._h))
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    # -------------------------------------------------------------------------------- building
+    def add(self, rows, ids=None, normalize: bool = True) -> "TheoremIndex":
+        """Append rows [n, dim]. CUDA tensors are consumed in place (K1 on the current stream);
+        numpy arrays / CPU tensors go through the chunked host path. ``ids``: int64 [n]."""
+        if isinstance(rows, torch.Tensor) and rows.is_cuda:
+            if rows.device != self.device:
+                raise _lib.TheoremSearchError(-1, f"rows on {rows.device}, index on {self.device}")
+            if rows.dim() != 2 or rows.shape[1] != self.dim:
+                raise _lib.TheoremSearchError(-1, f"rows must be [n, {self.dim}], got {tuple(rows.shape)}")
+            if rows.dtype not in _TORCH_TO_TS:
+                rows = rows.to(torch.float32)
+            rows = rows.contiguous()
+            id_ptr = None
+            if ids is not None:
+                ids = torch.as_tensor(ids, dtype=torch.int64, device=self.device).contiguous()
+                id_ptr = ids.data_ptr()
+            check(lib.ts_index_add(self._h, rows.data_ptr(), _TORCH_TO_TS[rows.dtype], rows.shape[0],
+                                   int(normalize), id_ptr, _stream_ptr(self.device)))
+            # the kernel reads `rows`/`ids` asynchronously: keep them alive until the stream drains
+            torch.cuda.current_stream(self.device).synchronize()
+            return self
+        arr = rows.detach().cpu() if isinstance(rows, torch.Tensor) else rows
+        if isinstance(arr, torch.Tensor):
+            if arr.dtype not in _TORCH_TO_TS:
+                arr = arr.to(torch.float32)
+            code = _TORCH_TO_TS[arr.dtype]
+            arr = arr.contiguous()
+            n, d, ptr = arr.shape[0], arr.shape[1], arr.data_ptr()
+        else:
+            arr = np.ascontiguousarray(np.asarray(arr, dtype=np.float32))
+            if arr.ndim != 2:
+                raise _lib.TheoremSearchError(-1, f"rows must be 2-D, got shape {arr.shape}")
+            code = TS_F32
+            n, d, ptr = arr.shape[0], arr.shape[1], arr.ctypes.data
+        if d != self.dim:
+            raise _lib.TheoremSearchError(-1, f"rows must be [n, {self.dim}], got [{n}, {d}]")
+        id_arr = None
+        if ids is not None:
+            id_arr = np.ascontiguousarray(np.asarray(ids, dtype=np.int64))
+            if id_arr.shape != (n,):
+                raise _lib.TheoremSearchError(-1, f"ids must be [{n}], got {id_arr.shape}")
+        check(lib.ts_index_add_host(self._h, ptr, code, n, int(normalize),
+                                    id_arr.ctypes.data if id_arr is not None else None))
+        return self
+
+    def get_rows(self, first: int = 0, n: Optional[int] = None) -> torch.Tensor:
+        """Stored rows dequantised to fp32 (device tensor) — the oracle's 'same inputs'."""
+        n = len(self) - first if n is None else n
+        out = torch.empty((n, self.dim), dtype=torch.float32, device=self.device)
+        check(lib.ts_index_get_rows(self._h, first, n, out.data_ptr(), _stream_ptr(self.device)))
+        return out
+
+    # -------------------------------------------------------------------------------- searching
+    def _workspace(self, nq: int, k: int) -> torch.Tensor:
+        need = int(lib.ts_workspace_bytes(self._h, nq, k))
+        key = (nq, k)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._ws = {key: ws}  # keep one workspace; shapes rarely alternate
+        return ws
+
+    def _prep_queries(self, queries) -> torch.Tensor:
+        q = queries if isinstance(queries, torch.Tensor) else torch.as_tensor(np.asarray(queries))
+        if q.dim() == 1:
+            q = q.unsqueeze(0)
+        if q.dim() != 2 or q.shape[1] != self.dim:
+            raise _lib.TheoremSearchError(-1, f"queries must be [nq, {self.dim}], got {tuple(q.shape)}")
+        if q.dtype not in _TORCH_TO_TS:
+            q = q.to(torch.float32)
+        return q.to(self.device).contiguous()
+
+    def search(self, queries, k: int, normalize: bool = True, allow_mask: Optional[torch.Tensor] = None):
+        """Exact top-k on device tensors. Returns (scores float32 [nq, k], ids int64 [nq, k]),
+        score descending, ties -> lower row; padded with (-inf, -1)."""
+        q = self._prep_queries(queries)
+        nq = q.shape[0]
+        scores = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        ws = self._workspace(nq, k)
+        mask_ptr = self._mask_ptr(allow_mask)
+        check(lib.ts_search(self._h, q.data_ptr(), _TORCH_TO_TS[q.dtype], nq, int(k), int(normalize), mask_ptr,
+                            scores.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(),
+                            _stream_ptr(self.device)))
+        q.record_stream(torch.cuda.current_stream(self.device))
+        return scores, ids
+
+    def search_keys(self, queries, k: int, normalize: bool = True, allow_mask: Optional[torch.Tensor] = None):
+        """This shard's candidates as packed 64-bit keys (int64 tensor holding the uint64 bits)
+        [nq, k] — the all-gather payload of the sharded path."""
+        q = self._prep_queries(queries)
+        nq = q.shape[0]
+        keys = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        ws = self._workspace(nq, k)
+        check(lib.ts_search_keys(self._h, q.data_ptr(), _TORCH_TO_TS[q.dtype], nq, int(k), int(normalize),
+                                 self._mask_ptr(allow_mask), keys.data_ptr(), ws.data_ptr(), ws.numel(),
+                                 _stream_ptr(self.device)))
+        q.record_stream(torch.cuda.current_stream(self.device))
+        return keys
+
+    def _mask_ptr(self, allow_mask):
+        if allow_mask is None:
+            return None
+        words = (len(self) + 31) // 32
+        if (not allow_mask.is_cuda or allow_mask.device != self.device or allow_mask.dtype != torch.int32
+                or allow_mask.numel() < words or not allow_mask.is_contiguous()):
+            raise _lib.TheoremSearchError(
+                -1, f"allow_mask must be a contiguous int32 CUDA tensor of >= {words} words on {self.device} "
+                    "(see pack_allow_mask)")
+        return allow_mask.data_ptr()
+
+    def _get_ctx(self, nq: int, k: int) -> C.c_void_p:
+        for (mq, mk), ctx in self._ctx.items():
+            if nq <= mq and k <= mk:
+                return ctx
+        ctx = C.c_void_p()
+        check(lib.ts_ctx_create(C.byref(ctx), self._h, max(nq, 1), max(k, 1)))
+        self._ctx[(max(nq, 1), max(k, 1))] = ctx
+        return ctx
+
+    def search_host(self, queries: np.ndarray, k: int, normalize: bool = True,
+                    allow_mask: Optional[torch.Tensor] = None, timing: bool = False):
+        """End-to-end call with HOST buffers (what a UI callback does): numpy fp32 queries in,
+        numpy (scores [nq, k], ids [nq, k]) out; H2D, search, D2H and the synchronise happen
+        inside the C call (``ts_search_host``)."""
+        q = np.ascontiguousarray(np.asarray(queries, dtype=np.float32))
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.shape[1] != self.dim:
+            raise _lib.TheoremSearchError(-1, f"queries must be [nq, {self.dim}], got {q.shape}")
+        nq = q.shape[0]
+        ctx = self._get_ctx(nq, k)
+        if timing:
+            check(lib.ts_ctx_set_timing(ctx, 1))
+        scores = np.empty((nq, k), dtype=np.float32)
+        ids = np.empty((nq, k), dtype=np.int64)
+        check(lib.ts_search_host(ctx, q.ctypes.data, nq, int(k), int(normalize), self._mask_ptr(allow_mask),
+                                 scores.ctypes.data, ids.ctypes.data))
+        if timing:
+            self.last_kernel_ms = float(lib.ts_ctx_last_kernel_ms(ctx))
+        return scores, ids
+
+
+def merge_topk(keys: torch.Tensor, k: int, shard_base: Optional[Sequence[int] | torch.Tensor] = None,
+               id_map: Optional[torch.Tensor] = None):
+    """K5 on gathered candidates: keys int64 [nshards, nq, k] (packed uint64 bits) ->
+    (scores [nq, k], ids [nq, k]) with rows rebased by ``shard_base``."""
+    _require_cuda()
+    if keys.dim() != 3 or keys.dtype != torch.int64 or not keys.is_cuda:
+        raise _lib.TheoremSearchError(-1, "keys must be an int64 CUDA tensor [nshards, nq, k]")
+    keys = keys.contiguous()
+    nshards, nq, kk = keys.shape
+    if kk != k:
+        raise _lib.TheoremSearchError(-1, f"keys last dim {kk} != k {k}")
+    dev = keys.device
+    base = None
+    if shard_base is not None:
+        base = torch.as_tensor(shard_base, dtype=torch.int64).to(dev).contiguous()
+    scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.ts_merge_topk(keys.data_ptr(), nshards, nq, k, base.data_ptr() if base is not None else None,
+                                id_map.data_ptr() if id_map is not None else None, scores.data_ptr(),
+                                ids.data_ptr(), _stream_ptr(dev)))
+    return scores, ids

@@ -1,0 +1,62 @@
+"""Row-sharded corpus across the GPUs of one box (one process per GPU, ``torch.distributed``).
+
+New surface with no reference counterpart (the reference has no distributed code at all,
+SURVEY §2); specified by BASELINE.json: GPU g holds rows [g*N/G, (g+1)*N/G), every GPU scans its
+shard for the (replicated) queries, ONE all-gather of the k x 8-byte packed (score,row) keys
+goes over NVLink, and K5 merges the G lists on every rank.  No corpus bytes cross NVLink.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+from .index import TheoremIndex, merge_topk
+
+
+def shard_bounds(n_rows: int, world_size: int) -> list[tuple[int, int]]:
+    """Contiguous shards [g*N/G, (g+1)*N/G)."""
+    return [((g * n_rows) // world_size, ((g + 1) * n_rows) // world_size) for g in range(world_size)]
+
+
+class ShardedIndex:
+    """One rank's view of a row-sharded corpus.
+
+    ``local`` holds this rank's rows; ``n_total`` is the global row count.  ``local_search`` and
+    ``merge`` default to the CUDA path (``TheoremIndex.search_keys`` / K5); tests on the gloo
+    backend inject CPU stand-ins for those two to exercise the host logic (bounds, gather
+    layout, rebasing) without a GPU.
+    """
+
+    def __init__(self, local: Optional[TheoremIndex], n_total: int, group=None,
+                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None,
+                 id_map: Optional[torch.Tensor] = None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.n_total = int(n_total)
+        self.bounds = shard_bounds(self.n_total, self.world)
+        self.lo, self.hi = self.bounds[self.rank]
+        self.local = local
+        self._local_search = local_search or (lambda q, k, normalize, allow_mask:
+                                              local.search_keys(q, k, normalize=normalize, allow_mask=allow_mask))
+        self._merge = merge or merge_topk
+        self.id_map = id_map
+        self._base = None
+
+    def shard_base(self, device) -> torch.Tensor:
+        if self._base is None or self._base.device != torch.device(device):
+            self._base = torch.tensor([lo for lo, _ in self.bounds], dtype=torch.int64, device=device)
+        return self._base
+
+    def search(self, queries: torch.Tensor, k: int, normalize: bool = True,
+               allow_mask: Optional[torch.Tensor] = None):
+        """Replicated queries [nq, D] -> global (scores [nq, k], ids [nq, k]) on every rank."""
+        keys = self._local_search(queries, k, normalize, allow_mask)          # [nq, k] packed keys
+        if self.world == 1:
+            gathered = keys.unsqueeze(0)
+        else:
+            gathered = torch.empty((self.world,) + tuple(keys.shape), dtype=keys.dtype, device=keys.device)
+            dist.all_gather_into_tensor(gathered, keys.contiguous(), group=self.group)
+        return self._merge(gathered, k, shard_base=self.shard_base(keys.device), id_map=self.id_map)
