@@ -1,0 +1,127 @@
+"""Host-side logic of the drop-in boundary (filters -> mask, result rows, citation re-rank, showcase
+post-filter) against goldens produced by the reference's own functions. The scorer is the test-only
+OracleIndex (no GPU here); tests/test_gpu_store.py runs the same goldens through the CUDA index."""
+import datetime
+
+import numpy as np
+import pytest
+
+import theoremsearch_b200 as ts
+from theoremsearch_b200 import store as st
+from tests.helpers import BASE_FILTERS, OracleIndex, TableModel, golden_store_rows, load_golden, unpack_allow_mask
+
+
+def test_search_rows_match_reference_run():
+    g = load_golden("streamlit_rows")
+    store = st.TheoremStore(golden_store_rows(g), OracleIndex(np.array(g["embeddings"], np.float32)))
+    model = TableModel({k: np.array(v, np.float32) for k, v in g["queries"].items()})
+    for res in g["results"]:
+        filters = dict(BASE_FILTERS, top_k=res["top_k"], citation_weight=res["citation_weight"])
+        got = store.search(res["query"], model, filters)
+        want = res["results"]
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            assert list(a.keys()) == list(b.keys())          # the 16 keys, in the reference's order
+            for key in a:
+                if key in ("similarity", "score"):
+                    assert a[key] == pytest.approx(b[key], abs=2e-6), key
+                else:
+                    assert a[key] == b[key], key
+
+
+def test_showcase_post_filter_matches_reference_run():
+    g = load_golden("showcase_search")
+    index = OracleIndex(np.array(g["corpus"], np.float32))
+    # the reference normalises inside cos_sim on every call; OracleIndex does it in search_host(normalize=True)
+    index.rows = __import__("oracle.oracle", fromlist=["x"]).normalize_f64(index.rows)
+    model = TableModel({k: np.array(v, np.float32) for k, v in g["queries"].items()})
+    for res in g["results"]:
+        filters = dict(g["filter_sets"][res["filters"]])
+        filters["citation_range"] = tuple(filters["citation_range"])
+        got = st.search_showcase(res["query"], model, g["theorems"], index, filters)
+        assert [int(h["info"]["paper_url"][-5:]) for h in got] == [h["index"] for h in res["hits"]]
+        assert np.allclose([h["similarity"] for h in got], [h["similarity"] for h in res["hits"]], atol=2e-6)
+
+
+def _mini_store():
+    D = datetime.datetime
+    rows = [
+        # paper_id title authors link last_updated summary journal_ref cat cats citations tid name body slogan
+        ("p0", "Optimal Transport I", ["Ann", "Bob"], "https://arxiv.org/abs/2401.00001", D(2024, 1, 2), "", None, "math.AP", [], 10, 1, "Theorem 1", "b", "s"),
+        ("p1", "Schemes", ["Cat"], "https://stacks.math.columbia.edu/tag/0001", None, "", None, "math.AG", [], None, 2, "Lemma 2.3", "b", "s"),
+        ("p2", "Graphs", ["Bob"], "https://ARXIV.org/abs/1905.12345", D(2019, 5, 1), "", "J. Comb.", "math.CO", [], 0, 3, "Proposition A", "b", "s"),
+        ("p3", "No link", ["Dan"], None, D(2020, 1, 1), "", None, "math.CO", [], 5, 4, None, "b", "s"),
+        ("p4", "Transport II", ["Eve"], "https://arxiv.org/abs/2001.00002", None, "", None, "math.AP", [], 300, 5, "Main Corollary", "b", "s"),
+    ]
+    emb = np.eye(5, 8, dtype=np.float32)
+    return st.TheoremStore(rows, OracleIndex(emb))
+
+
+def test_where_clause_three_valued_logic():
+    s = _mini_store()
+    f = dict(BASE_FILTERS)
+    assert s.build_allow(f).tolist() == [True, True, True, False, True]          # NULL link fails both source tests
+    assert s.build_allow(dict(f, sources=["arXiv"])).tolist() == [True, False, True, False, True]   # ILIKE is case-insensitive
+    assert s.build_allow(dict(f, sources=["Stacks Project"])).tolist() == [False, True, False, False, False]
+    assert s.build_allow(dict(f, authors=["Bob", "Zed"])).tolist() == [True, False, True, False, False]
+    assert s.build_allow(dict(f, tags=["math.AP"])).tolist() == [True, False, False, False, True]
+    # year: arXiv rows need a year in range (NULL date fails), non-arXiv rows pass
+    assert s.build_allow(dict(f, year_range=(2019, 2024))).tolist() == [True, True, True, False, False]
+    assert s.build_allow(dict(f, year_range=(2020, 2024))).tolist() == [True, True, False, False, False]
+    assert s.build_allow(dict(f, journal_status="Journal Article")).tolist() == [False, False, True, False, False]
+    assert s.build_allow(dict(f, journal_status="Preprint Only")).tolist() == [True, False, False, False, True]
+    assert s.build_allow(dict(f, types=["lemma", "corollary"])).tolist() == [False, True, False, False, True]
+    assert s.build_allow(dict(f, paper_filter={"ids": {"1905.12345"}, "titles": {"transport"}})).tolist() == \
+        [True, False, True, False, True]
+    assert s.build_allow(dict(f, citation_range=(1, 100))).tolist() == [True, True, False, False, False]
+    assert s.build_allow(dict(f, citation_range=(1, 100), include_unknown_citations=False)).tolist() == \
+        [True, False, False, False, False]
+
+
+def test_filters_apply_before_limit():
+    s = _mini_store()
+    model = TableModel({"q": np.array([0.1, 0.9, 0.5, 0.4, 0.3, 0, 0, 0], np.float32)})
+    f = dict(BASE_FILTERS, top_k=2, citation_weight=0.0, sources=["arXiv"])
+    got = s.search("q", model, f)
+    assert [r["theorem_id"] for r in got] == [3, 5]        # row 1 (best) is filtered out BEFORE the limit
+    # reference quirk kept: the SQL filter is ILIKE (case-insensitive, :181) but the row's "source" is a
+    # case-sensitive Python `"arxiv.org" in link` (:293) -> an upper-case host passes the arXiv filter yet
+    # is labelled Stacks Project.
+    assert got[0]["source"] == "Stacks Project" and got[0]["type"] == "proposition" and got[0]["journal_published"] is True
+    assert got[1]["source"] == "arXiv"
+    assert got[1]["type"] == "corollary" and got[1]["year"] is None
+    assert s.search("q", model, dict(f, sources=[])) == []
+    # similarity is 1 + cosine (streamlit_app.py:275)
+    qn = model.table["q"] / np.linalg.norm(model.table["q"])
+    assert got[0]["similarity"] == pytest.approx(1.0 + qn[2], abs=1e-6)
+
+
+def test_citation_weight_reranks_pool():
+    s = _mini_store()
+    model = TableModel({"q": np.array([0.5, 0.5, 0.5, 0.5, 0.49, 0, 0, 0], np.float32)})
+    f = dict(BASE_FILTERS, top_k=3, citation_weight=0.1)
+    got = s.search("q", model, f)
+    # ln(300) lifts row 4 to the top, ln(10) row 0 next; citations 0 / NULL add nothing
+    assert [r["theorem_id"] for r in got] == [5, 1, 2]
+    assert got[0]["score"] == pytest.approx(got[0]["similarity"] + 0.1 * np.log(300.0))
+    assert got[2]["score"] == got[2]["similarity"]
+
+
+def test_latest_slogan_rows_distinct_on():
+    # (theorem_id, slogan_id) per embedding row -> keep the highest slogan_id of each theorem
+    assert st.latest_slogan_rows([(7, 1), (3, 2), (7, 5), (3, 1), (9, 4)]) == [1, 2, 4]
+
+
+def test_allow_mask_bit_layout():
+    allow = np.zeros(70, dtype=bool)
+    allow[[0, 31, 32, 69]] = True
+    m = ts.pack_allow_mask(allow)
+    w = m.numpy().view(np.uint32)
+    assert w.tolist() == [0x80000001, 0x00000001, 1 << 5]
+    assert np.array_equal(unpack_allow_mask(m, 70), allow)
+
+
+def test_infer_type_and_pool_size():
+    assert st.infer_type("Lemma 3.1") == "lemma" and st.infer_type(None) == "theorem"
+    assert st.infer_type("Remark") == "theorem" and st.infer_type("Main Theorem (Corollary)") == "theorem"
+    assert st.pool_size(1) == 50 and st.pool_size(5) == 50 and st.pool_size(20) == 200

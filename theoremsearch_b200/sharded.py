@@ -57,6 +57,7 @@ class ShardedIndex:
         if self.world == 1:
             gathered = keys.unsqueeze(0)
         else:
-            gathered = torch.empty((self.world,) + tuple(keys.shape), dtype=keys.dtype, device=keys.device)
-            dist.all_gather_into_tensor(gathered, keys.contiguous(), group=self.group)
+            flat = torch.empty(self.world * keys.numel(), dtype=keys.dtype, device=keys.device)
+            dist.all_gather_into_tensor(flat, keys.contiguous().view(-1), group=self.group)
+            gathered = flat.view((self.world,) + tuple(keys.shape))               # [G, nq, k], shard-major
         return self._merge(gathered, k, shard_base=self.shard_base(keys.device), id_map=self.id_map)

@@ -1,0 +1,233 @@
+"""App-level search: ``streamlit_app.search_and_display`` (reference ``streamlit_app.py:165-399``)
+minus the rendering, over an in-memory table instead of RDS.
+
+The reference runs one SQL statement: paper ⨝ theorem ⨝ latest_slogan ⨝ theorem_embedding_qwen,
+``WHERE <filters>``, ``ORDER BY e.embedding <#> q ASC LIMIT k`` (:253-286) — or, with a citation
+weight, a ``max(50, 10k)`` candidate pool re-ranked by ``similarity + w*ln(citations)``
+(:316-364).  Here the joined table is ``TheoremStore.rows`` (one row per theorem, carrying its
+latest slogan — the ``DISTINCT ON (theorem_id) ... ORDER BY slogan_id DESC`` of :254-259 is
+applied when the store is built), the WHERE clause becomes an allow-bitmask consumed INSIDE the
+scan kernel (so LIMIT k is exact among eligible rows, as in SQL), and the ORDER BY/LIMIT is K2.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Optional, Sequence
+
+import numpy as np
+
+from .index import pack_allow_mask
+
+ALLOWED_TYPES = ["theorem", "lemma", "proposition", "corollary"]  # streamlit_app.py:40-42
+
+# column order of the reference's SELECT (streamlit_app.py:261-274)
+COLUMNS = ("paper_id", "title", "authors", "link", "last_updated", "summary", "journal_ref",
+           "primary_category", "categories", "citations", "theorem_id", "theorem_name", "theorem_body",
+           "theorem_slogan")
+
+
+def infer_type(name: Optional[str]) -> str:
+    """streamlit_app.py:61-68."""
+    if not name:
+        return "theorem"
+    lower = name.lower()
+    for t in ALLOWED_TYPES:
+        if t in lower:
+            return t
+    return "theorem"
+
+
+def pool_size(top_k: int) -> int:
+    """streamlit_app.py:317."""
+    return max(50, int(top_k) * 10)
+
+
+def latest_slogan_rows(slogans: Sequence[tuple[int, int]]) -> list[int]:
+    """``SELECT DISTINCT ON (theorem_id) ... ORDER BY theorem_id, slogan_id DESC``
+    (streamlit_app.py:254-259): input (theorem_id, slogan_id) per embedding row, output the
+    positions of the rows to keep (the highest slogan_id of each theorem), in theorem_id order."""
+    best: dict[int, tuple[int, int]] = {}
+    for pos, (tid, sid) in enumerate(slogans):
+        if tid not in best or sid > best[tid][0]:
+            best[tid] = (sid, pos)
+    return [best[t][1] for t in sorted(best)]
+
+
+class TheoremStore:
+    """The joined paper/theorem/slogan table plus the embedding index over the same rows.
+
+    ``rows[i]`` is a tuple in ``COLUMNS`` order and describes index row ``i``.  ``index`` needs
+    ``search_host(queries, k, normalize, allow_mask)`` and ``device`` (a ``TheoremIndex``)."""
+
+    def __init__(self, rows: Sequence[Sequence[Any]], index):
+        self.rows = [tuple(r) for r in rows]
+        self.index = index
+        n = len(self.rows)
+        col = {c: [r[j] for r in self.rows] for j, c in enumerate(COLUMNS)}
+        link_l = [(l or "").lower() for l in col["link"]]
+        self._has_link = np.array([l is not None for l in col["link"]], dtype=bool)
+        self._is_arxiv = np.array(["arxiv.org" in l for l in link_l], dtype=bool)
+        self._link_l = link_l
+        self._title_l = [(t or "").lower() if t is not None else None for t in col["title"]]
+        self._authors = [set(a or ()) for a in col["authors"]]
+        self._category = col["primary_category"]
+        self._year = np.array([(d.year if d is not None else -1) for d in col["last_updated"]], dtype=np.int64)
+        self._has_journal = np.array([j is not None for j in col["journal_ref"]], dtype=bool)
+        self._name_l = [(nm.lower() if nm is not None else None) for nm in col["theorem_name"]]
+        self._cit_known = np.array([c is not None for c in col["citations"]], dtype=bool)
+        self._cit = np.array([(c if c is not None else 0) for c in col["citations"]], dtype=np.int64)
+        assert n == len(self._cit)
+
+    def __len__(self) -> int:
+        return len(self.rows)
+
+    # ---------------------------------------------------------------------------- WHERE
+    def build_allow(self, filters: dict) -> np.ndarray:
+        """The WHERE clause of streamlit_app.py:175-243 as a boolean row mask (SQL three-valued
+        logic: a NULL operand makes the predicate not-true)."""
+        n = len(self.rows)
+        allow = np.ones(n, dtype=bool)
+        arxiv = self._is_arxiv & self._has_link
+        not_arxiv = (~self._is_arxiv) & self._has_link
+        sources = filters.get("sources") or []
+        if sources:                                                            # :179-186
+            m = np.zeros(n, dtype=bool)
+            hit = False
+            if "arXiv" in sources:
+                m |= arxiv
+                hit = True
+            if "Stacks Project" in sources:
+                m |= not_arxiv
+                hit = True
+            if hit:
+                allow &= m
+        if filters.get("authors"):                                             # :189-191  p.authors && %s
+            want = set(filters["authors"])
+            allow &= np.array([bool(a & want) for a in self._authors], dtype=bool)
+        if filters.get("tags"):                                                # :194-196
+            want = set(filters["tags"])
+            allow &= np.array([c in want for c in self._category], dtype=bool)
+        if filters.get("year_range"):                                          # :199-205
+            y0, y1 = filters["year_range"]
+            allow &= (arxiv & (self._year >= y0) & (self._year <= y1)) | not_arxiv
+        js = filters.get("journal_status", "All")                              # :208-212
+        if js == "Journal Article":
+            allow &= arxiv & self._has_journal
+        elif js == "Preprint Only":
+            allow &= arxiv & ~self._has_journal
+        pf = filters.get("paper_filter") or {"ids": set(), "titles": set()}    # :215-227
+        ids = [str(i).lower() for i in pf.get("ids", ())]
+        titles = [str(t).lower() for t in pf.get("titles", ())]
+        if ids or titles:
+            m = np.zeros(n, dtype=bool)
+            if ids:
+                m |= np.array([h and any(i in l for i in ids) for h, l in zip(self._has_link, self._link_l)], dtype=bool)
+            if titles:
+                m |= np.array([t is not None and any(s in t for s in titles) for t in self._title_l], dtype=bool)
+            allow &= m
+        if filters.get("types"):                                               # :230-233
+            want = [str(t).lower() for t in filters["types"]]
+            allow &= np.array([nm is not None and any(t in nm for t in want) for nm in self._name_l], dtype=bool)
+        low, high = filters["citation_range"]                                  # :236-245
+        between = self._cit_known & (self._cit >= low) & (self._cit <= high)
+        if filters["include_unknown_citations"]:
+            allow &= between | ~self._cit_known
+        else:
+            allow &= between
+        return allow
+
+    # ---------------------------------------------------------------------------- rows
+    def result_row(self, i: int, similarity: float, score: float) -> dict:
+        """The 16-key dict of streamlit_app.py:297-314 / :379-396."""
+        (paper_id, title, authors, link, last_updated, _summary, journal_ref, primary_category, _categories,
+         citations, theorem_id, theorem_name, theorem_body, theorem_slogan) = self.rows[i]
+        link_str = link or ""
+        return {
+            "paper_id": paper_id,
+            "authors": authors,
+            "paper_title": title,
+            "paper_url": link,
+            "year": last_updated.year if last_updated else None,
+            "primary_category": primary_category,
+            "source": "arXiv" if "arxiv.org" in link_str else "Stacks Project",
+            "type": infer_type(theorem_name or ""),
+            "journal_published": bool(journal_ref),
+            "citations": citations,
+            "theorem_id": theorem_id,
+            "theorem_name": theorem_name,
+            "theorem_slogan": theorem_slogan,
+            "theorem_body": theorem_body,
+            "similarity": float(similarity),
+            "score": float(score),
+        }
+
+    # ---------------------------------------------------------------------------- search
+    def search(self, query, model, filters: dict) -> list[dict]:
+        """``search_and_display(query, model, filters)`` up to (not including) rendering."""
+        if not filters["sources"]:                                             # :166-168
+            return []
+        citation_weight = float(filters["citation_weight"])                    # :170
+        query_vec = model.encode(query or "", normalize_embeddings=True, convert_to_numpy=True)  # :173
+        query_vec = np.asarray(query_vec, dtype=np.float32).reshape(-1)
+        top_k = int(filters["top_k"])
+        allow = self.build_allow(filters)
+        mask = None if bool(allow.all()) else pack_allow_mask(allow, self.index.device)
+        n_ok = int(allow.sum())
+        if n_ok == 0 or top_k <= 0:
+            return []
+        if citation_weight == 0.0:                                             # :252-314
+            k = min(top_k, n_ok)
+            scores, rows = self.index.search_host(query_vec, k, normalize=False, allow_mask=mask)
+            out = []
+            for s, r in zip(scores[0], rows[0]):
+                if r < 0:
+                    break
+                sim = 1.0 + float(s)                                           # :275  1.0 - (e <#> q)
+                out.append(self.result_row(int(r), sim, sim))
+            return out
+        pool = min(pool_size(top_k), n_ok)                                     # :317
+        scores, rows = self.index.search_host(query_vec, pool, normalize=False, allow_mask=mask)
+        cand = [(1.0 + float(s), int(r)) for s, r in zip(scores[0], rows[0]) if r >= 0]
+        weighted = []
+        for sim, r in cand:                                                    # :351-360
+            c = self.rows[r][9]
+            weighted.append(sim + citation_weight * (math.log(float(c)) if (c is not None and c > 0) else 0.0))
+        order = sorted(range(len(cand)), key=lambda j: (-weighted[j], -cand[j][0], j))[:top_k]   # :362-363
+        return [self.result_row(cand[j][1], cand[j][0], weighted[j]) for j in order]
+
+
+def search_showcase(query, model, theorems_data, embeddings_db, filters: dict, pool: int = 200) -> list[dict]:
+    """``app_showcase_model.search_and_display`` (reference :82-129) up to rendering: take the
+    top ``min(200, N)`` by cosine, then POST-filter that pool in rank order until ``top_k``
+    survive.  Kept for drop-in fidelity; ``TheoremStore.search`` pre-filters instead (exact)."""
+    if not query or not filters["sources"]:
+        return []
+    query_emb = model.encode(query, convert_to_tensor=True)                    # :92
+    q = np.asarray(query_emb.detach().cpu().numpy() if hasattr(query_emb, "detach") else query_emb,
+                   dtype=np.float32).reshape(-1)
+    k = min(pool, len(theorems_data))                                          # :96
+    scores, idxs = embeddings_db.search_host(q, k, normalize=True)
+    out = []
+    for s, idx in zip(scores[0], idxs[0]):
+        if idx < 0:
+            break
+        item = theorems_data[int(idx)]
+        type_match = not filters["types"] or item["type"].lower() in filters["types"]
+        tag_match = not filters["tags"] or item["primary_math_tag"] in filters["tags"]
+        author_match = not filters["authors"] or any(a in item["authors"] for a in filters["authors"])
+        source_match = item["source"] in filters["sources"]
+        citation_match = filters["citation_range"][0] <= item["citations"] <= filters["citation_range"][1]
+        year_match = True
+        if filters["year_range"] and item["source"] == "arXiv":
+            year_match = filters["year_range"][0] <= item.get("year", 0) <= filters["year_range"][1]
+        journal_match = True
+        if item["source"] == "arXiv":
+            if filters["journal_status"] == "Journal Article":
+                journal_match = item.get("journal_published", False)
+            elif filters["journal_status"] == "Preprint Only":
+                journal_match = not item.get("journal_published", False)
+        if all([type_match, tag_match, author_match, source_match, year_match, citation_match, journal_match]):
+            out.append({"info": item, "similarity": float(s)})
+        if len(out) >= filters["top_k"]:
+            break
+    return out
