@@ -93,9 +93,9 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const MergeParams p) {
     }
 }
 
-int launch_merge(const uint64_t* keys, int nlists, int nq, int k, bool query_major,
-                 const int64_t* list_base, const int64_t* id_map, uint64_t* out_keys,
-                 float* out_scores, int64_t* out_ids, cudaStream_t s) {
+int launch_merge_strided(const uint64_t* keys, int nlists, int nq, int k, int64_t stride_list,
+                         int64_t stride_query, const int64_t* list_base, const int64_t* id_map,
+                         uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t s) {
     TS_REQUIRE(k >= 1 && k <= TS_MAX_K, TS_ERR_BAD_ARG, "merge: k=%d out of range [1, %d]", k, TS_MAX_K);
     TS_REQUIRE(nlists >= 1 && nq >= 0, TS_ERR_BAD_ARG, "merge: nlists=%d nq=%d", nlists, nq);
     if (nq == 0) return TS_OK;
@@ -104,13 +104,8 @@ int launch_merge(const uint64_t* keys, int nlists, int nq, int k, bool query_maj
     p.nlists = nlists;
     p.nq = nq;
     p.k = k;
-    if (query_major) {  // [nq][nlists][k]
-        p.stride_query = (int64_t)nlists * k;
-        p.stride_list = k;
-    } else {  // [nlists][nq][k]
-        p.stride_list = (int64_t)nq * k;
-        p.stride_query = k;
-    }
+    p.stride_list = stride_list;
+    p.stride_query = stride_query;
     p.list_base = list_base;
     p.id_map = id_map;
     p.out_keys = out_keys;
@@ -129,6 +124,17 @@ int launch_merge(const uint64_t* keys, int nlists, int nq, int k, bool query_maj
     }
     TS_LAUNCH_CHECK();
     return TS_OK;
+}
+
+int launch_merge(const uint64_t* keys, int nlists, int nq, int k, bool query_major,
+                 const int64_t* list_base, const int64_t* id_map, uint64_t* out_keys,
+                 float* out_scores, int64_t* out_ids, cudaStream_t s) {
+    if (query_major)  // [nq][nlists][k]
+        return launch_merge_strided(keys, nlists, nq, k, k, (int64_t)nlists * k, list_base, id_map, out_keys,
+                                    out_scores, out_ids, s);
+    // [nlists][nq][k]
+    return launch_merge_strided(keys, nlists, nq, k, (int64_t)nq * k, k, list_base, id_map, out_keys, out_scores,
+                                out_ids, s);
 }
 
 }  // namespace ts

@@ -61,6 +61,11 @@ static SearchWs carve_ws(const ts_index* ix, int nq, int k, void* base) {
     return w;
 }
 
+// nq >= batch.min_nq on a bf16 corpus goes to K3 (tcgen05 GEMM); everything else to K2.
+static bool use_batched(const ts_index* ix, int nq) {
+    return ix->dtype == TS_BF16 && nq >= tunables().batch_min_nq && ix->size > 0;
+}
+
 static int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k,
                        int normalize_queries, const uint32_t* allow_mask, uint64_t* out_keys,
                        float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
@@ -75,6 +80,9 @@ static int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, i
     TS_REQUIRE(workspace != nullptr, TS_ERR_BAD_ARG, "search: workspace is NULL");
     DeviceGuard g(ix->device);
     TS_REQUIRE(g.ok, TS_ERR_CUDA, "search: cannot select CUDA device %d", ix->device);
+    if (use_batched(ix, nq))
+        return launch_batched_search(ix, queries, q_dtype, nq, k, normalize_queries, allow_mask, out_keys,
+                                     out_scores, out_ids, workspace, workspace_bytes, s, ev0, ev1);
     SearchWs w = carve_ws(ix, nq, k, workspace);
     TS_REQUIRE(workspace_bytes >= w.bytes, TS_ERR_CAPACITY, "search: workspace %zu < %zu bytes",
                workspace_bytes, w.bytes);
@@ -275,7 +283,9 @@ int ts_index_get_rows(const ts_index* ix, int64_t first, int64_t n, float* out, 
 // ------------------------------------------------------------------------------------ search
 size_t ts_workspace_bytes(const ts_index* ix, int nq, int k) {
     if (!ix || nq < 0 || k < 1) return 0;
-    return carve_ws(ix, std::max(nq, 1), k, nullptr).bytes;
+    const size_t scan = carve_ws(ix, std::max(nq, 1), k, nullptr).bytes;
+    const size_t batched = ix->dtype == TS_BF16 ? batched_workspace_bytes(ix, std::max(nq, 1), k) : 0;
+    return std::max(scan, batched);
 }
 
 int ts_search(ts_index* ix, const void* queries, int q_dtype, int nq, int k, int normalize_queries,
@@ -424,6 +434,9 @@ static int* tunable_slot(const char* name) {
     if (!strcmp(name, "scan.stages")) return &t.scan_stages;
     if (!strcmp(name, "scan.tile_bytes")) return &t.scan_tile_bytes;
     if (!strcmp(name, "batch.min_nq")) return &t.batch_min_nq;
+    if (!strcmp(name, "batch.cap")) return &t.batch_cap;
+    if (!strcmp(name, "batch.first_chunk")) return &t.batch_first_chunk;
+    if (!strcmp(name, "batch.growth")) return &t.batch_growth;
     return nullptr;
 }
 int ts_set_tunable(const char* name, int value) {

@@ -61,7 +61,10 @@ struct Tunables {
     int scan_warps = 8;         // consumer warps per CTA
     int scan_stages = 3;        // TMA ring depth per warp
     int scan_tile_bytes = 8192; // bytes per TMA bulk copy (whole rows)
-    int batch_min_nq = 2;       // nq >= this goes to the batched path (when available)
+    int batch_min_nq = 4;       // nq >= this goes to the batched tcgen05 path (bf16 corpus)
+    int batch_cap = 3072;       // K3 candidate slots per query per chunk
+    int batch_first_chunk = 1024;  // rows of the first K3 chunk (every row passes thr = -inf)
+    int batch_growth = 3;       // next chunk = growth x rows already seen
 };
 Tunables& tunables();
 
@@ -293,4 +296,13 @@ int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64
 int launch_merge(const uint64_t* keys, int nlists, int nq, int k, bool query_major,
                  const int64_t* list_base, const int64_t* id_map, uint64_t* out_keys,
                  float* out_scores, int64_t* out_ids, cudaStream_t s);
+int launch_merge_strided(const uint64_t* keys, int nlists, int nq, int k, int64_t stride_list,
+                         int64_t stride_query, const int64_t* list_base, const int64_t* id_map,
+                         uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t s);
+// K3: batched tcgen05 GEMM + fused top-k
+size_t batched_workspace_bytes(const ts_index* ix, int nq, int k);
+int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, int nq, int k, int normalize,
+                          const uint32_t* allow_mask, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
+                          void* workspace, size_t workspace_bytes, cudaStream_t s, cudaEvent_t ev0,
+                          cudaEvent_t ev1);
 }  // namespace ts
