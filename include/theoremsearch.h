@@ -197,6 +197,12 @@ TS_API int ts_ivf_list_sizes(const ts_index* index, int64_t* out, void* stream);
 TS_API int ts_set_tunable(const char* name, int value);
 TS_API int ts_get_tunable(const char* name, int* value);
 
+/* How many queries of the most recent batched (K3) search failed the exactness certificate or
+ * overflowed their candidate buffer and were therefore re-scanned by the exact K2 path.
+ * Synchronises the device; -1 if no batched search has run. Valid until the caller frees or
+ * reuses that search's workspace. */
+TS_API int ts_debug_last_batched_fixups(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,6 +1,7 @@
 """GPU parity tests for the batched path (K3: tcgen05/TMEM GEMM + fused top-k epilogue, K3b
-compaction), through the C ABI.  Oracle: fp64 scores of the SAME inputs the tensor cores see
-(bf16 corpus rows, bf16-rounded normalised queries), (score desc, row asc) order."""
+compaction, K3c fp32 re-score + exactness certificate, K2 fix-up), through the C ABI.
+Oracle: fp64 scores of the same inputs (bf16 corpus rows, fp32 normalised queries) — the batched
+path must return exactly what the single-query path returns."""
 import numpy as np
 import pytest
 import torch
@@ -17,8 +18,8 @@ def ts():
     return ts
 
 
-def prepared_bf16(q_raw):
-    return oracle.bf16_round(oracle.normalize_f64(q_raw))
+def prepared(q_raw):
+    return oracle.normalize_f64(q_raw)
 
 
 @pytest.mark.parametrize("n,d,nq,k", [
@@ -32,7 +33,7 @@ def test_batched_matches_oracle(ts, n, d, nq, k):
     q_raw = oracle.synthetic_queries(nq, d, seed=300 + nq)
     assert nq >= ts.get_tunable("batch.min_nq")
     s, i = index.search(torch.from_numpy(q_raw), k, normalize=True)
-    check_against_oracle(ts, index, prepared_bf16(q_raw), k, s, i)
+    check_against_oracle(ts, index, prepared(q_raw), k, s, i)
 
 
 def test_batched_with_mask_and_ids(ts):
@@ -47,7 +48,7 @@ def test_batched_with_mask_and_ids(ts):
         allow = rng.random(n) < frac
         mask = ts.pack_allow_mask(allow, index.device)
         s, i = index.search(torch.from_numpy(q_raw), k, allow_mask=mask)
-        check_against_oracle(ts, index, prepared_bf16(q_raw), k, s, i, ids=ids, allow=allow)
+        check_against_oracle(ts, index, prepared(q_raw), k, s, i, ids=ids, allow=allow)
 
 
 def test_batched_duplicates_tie_rule(ts):
@@ -64,16 +65,65 @@ def test_batched_duplicates_tie_rule(ts):
     assert len(set(s[2].tolist())) == 1
 
 
-def test_batched_equals_looped_single_query_on_bf16_queries(ts):
-    """Same inputs through K2 (one query at a time, fp32 FMA) and K3 (tensor cores): same ids."""
-    n, d, nq, k = 30000, 1024, 24, 10
+@pytest.mark.parametrize("n,d,nq,k", [(30000, 1024, 24, 10), (30000, 768, 70, 100), (5000, 200, 9, 33)])
+def test_batched_is_bitwise_the_single_query_path(ts, n, d, nq, k):
+    """K3 (tensor cores + re-score) and K2 (one query at a time): identical ids AND identical score bits."""
     rows = unit_rows(n, d, seed=29)
     index = ts.build_index(rows, dtype="bf16", normalize=False)
-    q = torch.from_numpy(prepared_bf16(oracle.synthetic_queries(nq, d, seed=6)))
-    s3, i3 = index.search(q, k, normalize=False)
+    q = torch.from_numpy(oracle.synthetic_queries(nq, d, seed=6))
+    s3, i3 = index.search(q, k)
     s2 = torch.empty_like(s3)
     i2 = torch.empty_like(i3)
     for j in range(nq):
-        s2[j], i2[j] = (x[0] for x in index.search(q[j], k, normalize=False))
+        s2[j], i2[j] = (x[0] for x in index.search(q[j], k))
     assert torch.equal(i2, i3)
-    assert torch.allclose(s2, s3, atol=2e-6)
+    assert torch.equal(s2, s3)
+
+
+def test_random_data_is_certified_without_fixups(ts):
+    rows = unit_rows(200000, 256, seed=31)
+    index = ts.build_index(rows, dtype="bf16", normalize=False)
+    q = oracle.synthetic_queries(300, 256, seed=8)
+    s, i = index.search(torch.from_numpy(q), 10)
+    assert ts.last_batched_fixups() == 0
+    check_against_oracle(ts, index, prepared(q), 10, s, i)
+
+
+def test_near_duplicate_cluster_fails_certificate_and_is_fixed_up(ts):
+    """300 rows within 1e-4 of each other at the top of one query's ranking: the bf16-query GEMM
+    cannot separate them, the certificate must refuse, and the K2 re-scan must make it exact."""
+    n, d, nq, k = 20000, 1024, 16, 10
+    rows = unit_rows(n, d, seed=37)
+    q_raw = oracle.synthetic_queries(nq, d, seed=11)
+    qn = oracle.normalize_f64(q_raw)
+    rng = np.random.default_rng(0)
+    cluster = rng.choice(n, size=300, replace=False)
+    for r in cluster:
+        v = 0.9 * qn[3] + 0.436 * oracle.normalize_f64(rng.standard_normal(d).astype(np.float32))[0] * 1.0
+        rows[r] = oracle.normalize_f64(v + 1e-4 * rng.standard_normal(d).astype(np.float32))[0]
+    # make the cluster REALLY tight in score: same direction, tiny jitter
+    base = oracle.normalize_f64(0.9 * qn[3] + 0.1 * rows[cluster[0]])[0]
+    for r in cluster:
+        rows[r] = oracle.normalize_f64(base + 2e-5 * rng.standard_normal(d).astype(np.float32))[0]
+    index = ts.build_index(rows, dtype="bf16", normalize=False)
+    s, i = index.search(torch.from_numpy(q_raw), k)
+    fix = ts.last_batched_fixups()
+    assert fix >= 1
+    check_against_oracle(ts, index, prepared(q_raw), k, s, i)
+    s1, i1 = index.search(torch.from_numpy(q_raw[3]), k)
+    assert torch.equal(i[3], i1[0]) and torch.equal(s[3], s1[0])
+
+
+def test_ascending_order_overflows_buffers_and_is_fixed_up(ts):
+    """Rows sorted by ascending score for query 0: every row beats the running threshold, the
+    candidate buffer overflows, the query is flagged and re-scanned exactly."""
+    n, d, nq, k = 40000, 256, 8, 10
+    rows = unit_rows(n, d, seed=41)
+    q_raw = oracle.synthetic_queries(nq, d, seed=12)
+    qn = oracle.normalize_f64(q_raw)
+    order = np.argsort(oracle.bf16_round(rows) @ qn[0])
+    rows = rows[order]
+    index = ts.build_index(rows, dtype="bf16", normalize=False)
+    s, i = index.search(torch.from_numpy(q_raw), k)
+    assert ts.last_batched_fixups() >= 1
+    check_against_oracle(ts, index, prepared(q_raw), k, s, i)

@@ -79,6 +79,7 @@ SIGNATURES = {
     "ts_ivf_list_sizes": (_i, [_p, _p, _p]),
     "ts_set_tunable": (_i, [C.c_char_p, _i]),
     "ts_get_tunable": (_i, [C.c_char_p, C.POINTER(_i)]),
+    "ts_debug_last_batched_fixups": (_i, []),
 }
 
 
@@ -120,6 +121,10 @@ def get_tunable(name: str) -> int:
     v = _i(0)
     check(lib.ts_get_tunable(name.encode(), C.byref(v)))
     return v.value
+
+
+def last_batched_fixups() -> int:
+    return int(lib.ts_debug_last_batched_fixups())
 
 
 def pack_key(score: float, row: int) -> int:

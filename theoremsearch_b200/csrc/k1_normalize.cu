@@ -36,10 +36,16 @@ __device__ __forceinline__ void store_from_float<__nv_bfloat16>(__nv_bfloat16* p
 }
 
 // Each lane owns element pairs (2*lane, 2*lane+1) + 64*i so bf16 stores are 4-byte, 128 B/warp.
+__device__ __forceinline__ float stored_value(float v, float*) { return v; }
+__device__ __forceinline__ float stored_value(float v, __nv_bfloat16*) {
+    return __bfloat162float(__float2bfloat16_rn(v));
+}
+
 template <typename SRC, typename DST>
 __global__ void __launch_bounds__(256) normalize_cast_kernel(const SRC* __restrict__ src, int64_t n,
                                                              int dim, int dim_pad, int normalize,
-                                                             DST* __restrict__ dst) {
+                                                             DST* __restrict__ dst,
+                                                             float* __restrict__ max_norm2) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -56,6 +62,7 @@ __global__ void __launch_bounds__(256) normalize_cast_kernel(const SRC* __restri
             ss = warp_sum(ss);
             inv_den = fmaxf((float)sqrt(ss), 1e-12f);
         }
+        float qs = 0.f;  // squared norm of the row AS STORED (bounds |<dq, row>| in K3's certificate)
         for (int i = 2 * lane; i < dim_pad; i += 64) {
             float a = (i < dim) ? load_as_float<SRC>(x + i) : 0.0f;
             float b = (i + 1 < dim) ? load_as_float<SRC>(x + i + 1) : 0.0f;
@@ -65,6 +72,13 @@ __global__ void __launch_bounds__(256) normalize_cast_kernel(const SRC* __restri
             }
             store_from_float<DST>(y + i, a);
             if (i + 1 < dim_pad) store_from_float<DST>(y + i + 1, b);
+            const float sa = stored_value(a, (DST*)nullptr), sb = stored_value(b, (DST*)nullptr);
+            qs = fmaf(sa, sa, fmaf(sb, sb, qs));
+        }
+        if (max_norm2 != nullptr) {
+            qs = warp_sum(qs);
+            // non-negative floats order like their bit patterns; NaN/Inf rows poison the bound on purpose
+            if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(max_norm2), __float_as_uint(qs));
         }
     }
 }
@@ -84,16 +98,16 @@ __global__ void __launch_bounds__(256) dequant_rows_kernel(const SRC* __restrict
 
 template <typename SRC>
 static int launch_nc(const void* src, int64_t n, int dim, int dim_pad, int normalize, void* dst,
-                     int dst_dtype, cudaStream_t s) {
+                     int dst_dtype, cudaStream_t s, float* max_norm2) {
     if (n == 0) return TS_OK;
     int64_t blocks64 = (n + 7) / 8;
     int blocks = (int)(blocks64 > 148 * 32 ? 148 * 32 : blocks64);
     if (dst_dtype == TS_BF16) {
         normalize_cast_kernel<SRC, __nv_bfloat16><<<blocks, 256, 0, s>>>(
-            (const SRC*)src, n, dim, dim_pad, normalize, (__nv_bfloat16*)dst);
+            (const SRC*)src, n, dim, dim_pad, normalize, (__nv_bfloat16*)dst, max_norm2);
     } else if (dst_dtype == TS_F32) {
         normalize_cast_kernel<SRC, float><<<blocks, 256, 0, s>>>((const SRC*)src, n, dim, dim_pad,
-                                                                 normalize, (float*)dst);
+                                                                 normalize, (float*)dst, max_norm2);
     } else {
         set_error("normalize_cast: unsupported destination dtype %d", dst_dtype);
         return TS_ERR_UNSUPPORTED;
@@ -103,12 +117,12 @@ static int launch_nc(const void* src, int64_t n, int dim, int dim_pad, int norma
 }
 
 int launch_normalize_cast(const void* src, int src_dtype, int64_t n, int dim, int dim_pad,
-                          int normalize, void* dst, int dst_dtype, cudaStream_t s) {
+                          int normalize, void* dst, int dst_dtype, cudaStream_t s, float* max_norm2) {
     switch (src_dtype) {
-        case TS_F32: return launch_nc<float>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s);
+        case TS_F32: return launch_nc<float>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
         case TS_BF16:
-            return launch_nc<__nv_bfloat16>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s);
-        case TS_F16: return launch_nc<__half>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s);
+            return launch_nc<__nv_bfloat16>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
+        case TS_F16: return launch_nc<__half>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
         default:
             set_error("normalize_cast: unsupported source dtype %d", src_dtype);
             return TS_ERR_BAD_ARG;

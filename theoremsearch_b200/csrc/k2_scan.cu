@@ -24,6 +24,8 @@
 //     Scores never go to HBM: each CTA writes only its k best keys; K5 merges the CTA lists.
 //
 // Algorithmic bytes: N * row_bytes per query (+ D*4 query + nparts*k*8 candidates).
+#include <algorithm>
+
 #include "ts_common.cuh"
 
 namespace ts {
@@ -36,8 +38,11 @@ struct ScanParams {
     const float* queries;     // [nq, dim_pad] fp32, already normalised / zero padded
     int k;
     const uint32_t* mask;     // allow bitmask or nullptr
-    uint64_t* part_keys;      // [nq, nparts, k]
+    uint64_t* part_keys;      // [work item, nparts, k]
     int stages;
+    int nq;                   // work items when qcount == nullptr (work item w scans query w)
+    const int* qlist;         // fix-up mode: work item w scans query qlist[w] ...
+    const int* qcount;        // ... for w < *qcount (device-side count; 0 = every CTA exits at once)
 };
 
 template <int NCHUNK>
@@ -103,9 +108,8 @@ __device__ __forceinline__ int row_of_lane(int lane) {
     return row;
 }
 
-template <int ELEM, int NCHUNK, int KPL>
-__global__ void __launch_bounds__(256, 1) scan_topk_kernel(const ScanParams p) {
-    constexpr int R = RowsPerTile<NCHUNK>::value;
+template <int ELEM, int NCHUNK, int KPL, int R>
+__global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
     constexpr int CN = Chunk<ELEM>::N;       // elements per 16-byte chunk
     constexpr int GROUP = 32 / R;            // lanes that end up holding the same row's score
     extern __shared__ __align__(128) uint8_t smem[];
@@ -115,7 +119,6 @@ __global__ void __launch_bounds__(256, 1) scan_topk_kernel(const ScanParams p) {
     const int W = blockDim.x >> 5;
     const int stages = p.stages;
     const uint32_t tile_bytes = R * p.row_bytes;
-    const int qi = blockIdx.y;
 
     uint8_t* my_slots = smem + (size_t)warp * stages * tile_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)W * stages * tile_bytes);
@@ -126,6 +129,30 @@ __global__ void __launch_bounds__(256, 1) scan_topk_kernel(const ScanParams p) {
         fence_mbar_init();
     }
     __syncwarp();
+
+    const int64_t num_tiles = (p.n_rows + R - 1) / R;
+    const int64_t gw = (int64_t)blockIdx.x * W + warp;
+    const int64_t tw = (int64_t)gridDim.x * W;
+    const uint64_t policy = l2_policy_evict_first();
+    const int k = p.k;
+    const int my_row = row_of_lane<R>(lane);
+    const bool leader = (lane & (GROUP - 1)) == 0;
+
+    auto issue = [&](int64_t tile, int s) {
+        const int64_t row0 = tile * R;
+        const int64_t rows = (p.n_rows - row0 < R) ? (p.n_rows - row0) : R;
+        const uint32_t bytes = (uint32_t)rows * p.row_bytes;
+        mbar_expect_tx(&my_bars[s], bytes);
+        tma_load_1d_hint(my_slots + (size_t)s * tile_bytes, p.data + (size_t)row0 * p.row_bytes, bytes,
+                         &my_bars[s], policy);
+    };
+
+    // ring position persists across work items (mbarrier phases cannot be rewound)
+    int s = 0;
+    uint32_t parity = 0;
+    const int nwork = p.qcount ? *p.qcount : p.nq;
+    for (int wi = blockIdx.y; wi < nwork; wi += gridDim.y) {
+    const int qi = p.qlist ? p.qlist[wi] : wi;
 
     // query slice of this lane, fp32 in registers
     float q[NCHUNK * CN];
@@ -139,36 +166,19 @@ __global__ void __launch_bounds__(256, 1) scan_topk_kernel(const ScanParams p) {
         }
     }
 
-    const int64_t num_tiles = (p.n_rows + R - 1) / R;
-    const int64_t gw = (int64_t)blockIdx.x * W + warp;
-    const int64_t tw = (int64_t)gridDim.x * W;
-    const uint64_t policy = l2_policy_evict_first();
-
-    auto issue = [&](int64_t tile, int s) {
-        const int64_t row0 = tile * R;
-        const int64_t rows = (p.n_rows - row0 < R) ? (p.n_rows - row0) : R;
-        const uint32_t bytes = (uint32_t)rows * p.row_bytes;
-        mbar_expect_tx(&my_bars[s], bytes);
-        tma_load_1d_hint(my_slots + (size_t)s * tile_bytes, p.data + (size_t)row0 * p.row_bytes, bytes,
-                         &my_bars[s], policy);
-    };
-
     if (lane == 0) {
-        for (int s = 0; s < stages; ++s) {
-            const int64_t t = gw + (int64_t)s * tw;
-            if (t < num_tiles) issue(t, s);
+        int ss = s;
+        for (int i = 0; i < stages; ++i) {
+            const int64_t t = gw + (int64_t)i * tw;
+            if (t < num_tiles) issue(t, ss);
+            if (++ss == stages) ss = 0;
         }
     }
 
     WarpTopK<KPL> list;
     list.clear();
     uint64_t thr = 0ull;  // current k-th key of this warp's list (0 while it has < k entries)
-    const int k = p.k;
-    const int my_row = row_of_lane<R>(lane);
-    const bool leader = (lane & (GROUP - 1)) == 0;
 
-    int s = 0;
-    uint32_t parity = 0;
     for (int64_t tile = gw; tile < num_tiles; tile += tw) {
         const int64_t row0 = tile * R;
         const int64_t row = row0 + my_row;
@@ -229,13 +239,15 @@ __global__ void __launch_bounds__(256, 1) scan_topk_kernel(const ScanParams p) {
     __syncthreads();
     if (warp == 0) {
         for (int w = 1; w < W; ++w) merge_sorted_into<KPL>(list, lists + (size_t)w * (KPL * 32), k, k, lane);
-        uint64_t* out = p.part_keys + ((size_t)qi * gridDim.x + blockIdx.x) * k;
+        uint64_t* out = p.part_keys + ((size_t)wi * gridDim.x + blockIdx.x) * k;
 #pragma unroll
         for (int j = 0; j < KPL; ++j) {
             const int pos = j * 32 + lane;
             if (pos < k) out[pos] = list.key[j];
         }
     }
+    __syncthreads();  // the list area aliases the TMA slots of the next work item
+    }  // work items
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -244,14 +256,13 @@ struct ScanConfig {
     size_t smem;
 };
 
-template <int ELEM, int NCHUNK>
+template <int ELEM, int NCHUNK, int R>
 static ScanConfig scan_config(const ts_index* ix, int kpl) {
-    constexpr int R = RowsPerTile<NCHUNK>::value;
     const Tunables& t = tunables();
     const size_t tile_bytes = (size_t)R * ix->dim_pad * ELEM;
     int stages = t.scan_stages < 2 ? 2 : t.scan_stages;
     int ctas = t.scan_ctas_per_sm < 1 ? 1 : t.scan_ctas_per_sm;
-    int warps = t.scan_warps < 1 ? 1 : (t.scan_warps > 8 ? 8 : t.scan_warps);
+    int warps = t.scan_warps < 1 ? 1 : (t.scan_warps > 16 ? 16 : t.scan_warps);
     const size_t budget = (size_t)(220 * 1024) / ctas - 1024;
     while (warps > 1 && (size_t)warps * stages * tile_bytes + 8 * warps * stages > budget) --warps;
     while (stages > 2 && (size_t)warps * stages * tile_bytes + 8 * warps * stages > budget) --stages;
@@ -266,19 +277,37 @@ static ScanConfig scan_config(const ts_index* ix, int kpl) {
     return c;
 }
 
-template <int ELEM, int NCHUNK, int KPL>
-static int launch_one(const ts_index* ix, const ScanParams& p0, int nq, int nparts, cudaStream_t s,
-                      cudaEvent_t ev0, cudaEvent_t ev1) {
-    ScanConfig c = scan_config<ELEM, NCHUNK>(ix, KPL);
+template <int ELEM, int NCHUNK, int KPL, int R>
+static int launch_r(const ts_index* ix, const ScanParams& p0, int nq, int nparts, cudaStream_t s,
+                    cudaEvent_t ev0, cudaEvent_t ev1) {
+    ScanConfig c = scan_config<ELEM, NCHUNK, R>(ix, KPL);
     ScanParams p = p0;
     p.stages = c.stages;
-    auto kern = scan_topk_kernel<ELEM, NCHUNK, KPL>;
+    auto kern = scan_topk_kernel<ELEM, NCHUNK, KPL, R>;
     TS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
     if (ev0) TS_CHECK_CUDA(cudaEventRecord(ev0, s));
-    kern<<<dim3(nparts, nq), c.warps * 32, c.smem, s>>>(p);
+    kern<<<dim3(nparts, p.qcount ? std::min(nq, 8) : nq), c.warps * 32, c.smem, s>>>(p);
     TS_LAUNCH_CHECK();
     if (ev1) TS_CHECK_CUDA(cudaEventRecord(ev1, s));
     return TS_OK;
+}
+
+// rows per TMA tile: the default aims at ~8 KB; "scan.tile_rows" (2/4/8/16) overrides it for the
+// common k <= 32 kernels (the large-k instances keep the default to bound compile time).
+template <int ELEM, int NCHUNK, int KPL>
+static int launch_one(const ts_index* ix, const ScanParams& p, int nq, int nparts, cudaStream_t s,
+                      cudaEvent_t ev0, cudaEvent_t ev1) {
+    constexpr int RD = RowsPerTile<NCHUNK>::value;
+    if constexpr (KPL == 1) {
+        switch (tunables().scan_tile_rows) {
+            case 2: return launch_r<ELEM, NCHUNK, KPL, 2>(ix, p, nq, nparts, s, ev0, ev1);
+            case 4: return launch_r<ELEM, NCHUNK, KPL, 4>(ix, p, nq, nparts, s, ev0, ev1);
+            case 8: return launch_r<ELEM, NCHUNK, KPL, 8>(ix, p, nq, nparts, s, ev0, ev1);
+            case 16: return launch_r<ELEM, NCHUNK, KPL, 16>(ix, p, nq, nparts, s, ev0, ev1);
+            default: break;
+        }
+    }
+    return launch_r<ELEM, NCHUNK, KPL, RD>(ix, p, nq, nparts, s, ev0, ev1);
 }
 
 template <int ELEM, int NCHUNK>
@@ -298,7 +327,7 @@ int scan_nparts(const ts_index* ix) {
 int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64_t n_rows,
                      const float* queries_f32, int nq, int k, const uint32_t* allow_mask,
                      uint64_t* part_keys, int nparts, cudaStream_t s, cudaEvent_t ev0,
-                     cudaEvent_t ev1) {
+                     cudaEvent_t ev1, const int* qlist, const int* qcount) {
     TS_REQUIRE(k >= 1 && k <= TS_MAX_K, TS_ERR_BAD_ARG, "scan: k=%d out of range [1, %d]", k, TS_MAX_K);
     TS_REQUIRE(n_rows < (int64_t)0xFFFFFFFFll, TS_ERR_UNSUPPORTED, "scan: more than 2^32-1 rows per shard");
     TS_REQUIRE(nparts == scan_nparts(ix), TS_ERR_BAD_ARG, "scan: workspace sized for another grid");
@@ -311,6 +340,9 @@ int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64
     p.mask = allow_mask;
     p.part_keys = part_keys;
     p.stages = 0;
+    p.nq = nq;
+    p.qlist = qlist;
+    p.qcount = qcount;
     if (data_dtype == TS_BF16) {
         p.row_bytes = (uint32_t)ix->dim_pad * 2;
         const int nchunk = (ix->dim_pad + 255) / 256;

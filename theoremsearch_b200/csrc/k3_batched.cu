@@ -54,7 +54,8 @@ struct BatchParams {
     int nq, k, cap;
     int num_k_blocks;
     int num_m_blocks, num_n_blocks;
-    const float* thr;             // [num_n_blocks * BN] running k-th best score per query (-inf initially)
+    int bn;                       // queries per n-block actually used (multiple of 32, <= BN): UMMA N, TMA box rows
+    const float* thr;             // [num_n_blocks * bn] running k-th best score per query (-inf initially)
     uint32_t* count;              // [nq] candidates appended in this chunk
     uint64_t* cand;               // [nq][k + cap]: [0,k) sorted best so far, [k, k+cap) appended
     const uint32_t* mask;         // allow bitmask or nullptr
@@ -167,9 +168,9 @@ batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const int row0 = (int)(p.row_begin + (int64_t)m_blk * BM);
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait_wd(&empty[stage], phase ^ 1u);
-                    mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
+                    mbar_expect_tx(&full[stage], A_BYTES + (uint32_t)p.bn * (BK * 2));
                     tma_load_2d(smem_a + (size_t)stage * A_BYTES, &tmap_a, kb * BK, row0, &full[stage], pol_a);
-                    tma_load_2d(smem_b + (size_t)stage * B_BYTES, &tmap_b, kb * BK, n_blk * BN, &full[stage], pol_b);
+                    tma_load_2d(smem_b + (size_t)stage * B_BYTES, &tmap_b, kb * BK, n_blk * p.bn, &full[stage], pol_b);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1u;
@@ -181,7 +182,7 @@ batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         // ===================== MMA issuer =====================
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) |
                                    ((uint32_t)(BM >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
@@ -222,10 +223,10 @@ batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
             const int m_blk = t / p.num_n_blocks, n_blk = t % p.num_n_blocks;
-            const int q0 = n_blk * BN;
+            const int q0 = n_blk * p.bn;
             float* thr_t = thr_s + acc * BN;
-            thr_t[ep_tid] = p.thr[q0 + ep_tid];
-            thr_t[ep_tid + EPI_THREADS] = p.thr[q0 + ep_tid + EPI_THREADS];
+            if (ep_tid < p.bn) thr_t[ep_tid] = p.thr[q0 + ep_tid];
+            if (ep_tid + EPI_THREADS < p.bn) thr_t[ep_tid + EPI_THREADS] = p.thr[q0 + ep_tid + EPI_THREADS];
             asm volatile("bar.sync 1, 128;" ::: "memory");
 
             const int64_t row = p.row_begin + (int64_t)m_blk * BM + row_in_tile;
@@ -236,7 +237,7 @@ batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             tcgen05_fence_after();
             const uint32_t taddr0 = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < p.bn / 32; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c * 32), v);
                 tmem_ld_wait();
@@ -335,6 +336,130 @@ __global__ void init_batch_state_kernel(uint64_t* cand, uint32_t* count, float* 
     }
 }
 
+// ---------------------------------------------------------------------------------- query rounding
+// q32 (normalised fp32, what K2 dots with) -> bf16 copy for the tensor cores, plus
+// qerr[q] = ||q32 - bf16(q32)||_2: by Cauchy-Schwarz |<q32,c> - <q16,c>| <= qerr * ||c||.
+__global__ void __launch_bounds__(256) round_queries_kernel(const float* __restrict__ q32, int nq, int dim_pad,
+                                                            __nv_bfloat16* __restrict__ q16, float* __restrict__ qerr) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    float e2 = 0.f;
+    for (int i = lane; i < dim_pad; i += 32) {
+        const float v = q32[(size_t)q * dim_pad + i];
+        const __nv_bfloat16 b = __float2bfloat16_rn(v);
+        q16[(size_t)q * dim_pad + i] = b;
+        const float d = v - __bfloat162float(b);
+        e2 = fmaf(d, d, e2);
+    }
+    e2 = warp_sum(e2);
+    if (lane == 0) qerr[q] = sqrtf(e2) * 1.0001f + 1e-30f;
+}
+
+// ---------------------------------------------------------------------------------- K3c rescore + certify
+// One CTA per query. The GEMM ranked candidates with bf16-ROUNDED queries; the exact path (K2)
+// scores with the fp32 query. Re-score the kp best candidates with the fp32 query using K2's exact
+// summation order (so both paths return bit-identical scores), sort, keep k, and CERTIFY the
+// result: every row the GEMM left out has bf16-query score <= b (the kp-th kept one), hence
+// fp32-query score <= b + qerr*max||row||; if the k-th rescored score beats that bound the top-k is
+// provably the exact one, otherwise (or if a candidate buffer overflowed) the query is flagged and
+// re-scanned by K2.
+__global__ void __launch_bounds__(256) rescore_certify_kernel(uint64_t* cand, size_t cand_stride, int kp, int k,
+                                                              const float* __restrict__ q32,
+                                                              const uint8_t* __restrict__ corpus, uint32_t row_bytes,
+                                                              int dim_pad, const float* __restrict__ qerr,
+                                                              const float* __restrict__ max_norm2,
+                                                              const uint32_t* __restrict__ overflow,
+                                                              int* __restrict__ flags) {
+    extern __shared__ uint64_t rs_buf[];   // [P] rescored keys
+    const int q = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t* mine = cand + (size_t)q * cand_stride;
+    int P = 1;
+    while (P < kp) P <<= 1;
+    const uint64_t worst_kept = mine[kp - 1];   // 0 when fewer than kp rows were eligible at all
+    const float* qv = q32 + (size_t)q * dim_pad;
+    for (int j = warp; j < P; j += 8) {
+        uint64_t key = (j < kp) ? mine[j] : 0ull;
+        if (key != 0ull) {
+            const uint32_t row = key_row(key);
+            const uint8_t* r = corpus + (size_t)row * row_bytes;
+            float acc = 0.f;
+            for (uint32_t off = (uint32_t)lane * 16u; off < row_bytes; off += 512u) {   // K2's chunk order
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(r + off));
+                const float4 qa = __ldg(reinterpret_cast<const float4*>(qv + off / 2));
+                const float4 qb = __ldg(reinterpret_cast<const float4*>(qv + off / 2 + 4));
+                acc = fmaf(__uint_as_float(v.x << 16), qa.x, acc);
+                acc = fmaf(__uint_as_float(v.x & 0xFFFF0000u), qa.y, acc);
+                acc = fmaf(__uint_as_float(v.y << 16), qa.z, acc);
+                acc = fmaf(__uint_as_float(v.y & 0xFFFF0000u), qa.w, acc);
+                acc = fmaf(__uint_as_float(v.z << 16), qb.x, acc);
+                acc = fmaf(__uint_as_float(v.z & 0xFFFF0000u), qb.y, acc);
+                acc = fmaf(__uint_as_float(v.w << 16), qb.z, acc);
+                acc = fmaf(__uint_as_float(v.w & 0xFFFF0000u), qb.w, acc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);   // == K2's reduce tree
+            key = pack_key(acc, row);
+        }
+        if (lane == 0) rs_buf[j] = key;
+    }
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int st = size >> 1; st > 0; st >>= 1) {
+            for (int i = threadIdx.x; i < P / 2; i += blockDim.x) {
+                const int lo = 2 * i - (i & (st - 1));
+                const int hi = lo + st;
+                const bool desc = (lo & size) == 0;
+                const uint64_t a = rs_buf[lo], b = rs_buf[hi];
+                if ((a < b) == desc) {
+                    rs_buf[lo] = b;
+                    rs_buf[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < k; i += blockDim.x) mine[i] = rs_buf[i];
+    if (threadIdx.x == 0) {
+        bool ok = overflow[q] == 0;
+        if (ok && worst_kept != 0ull) {
+            const uint64_t kth = rs_buf[k - 1];
+            const float bound = key_score(worst_kept) + qerr[q] * sqrtf(*max_norm2) + 2e-6f;
+            ok = kth != 0ull && key_score(kth) > bound;   // NaN bound -> not certified -> re-scan
+        }
+        flags[q] = ok ? 0 : 1;
+    }
+}
+
+// Compact the flagged queries into a work list for the K2 fix-up pass (single CTA, ballot scan).
+__global__ void __launch_bounds__(1024) build_fix_list_kernel(const int* __restrict__ flags, int nq,
+                                                              int* __restrict__ list, int* __restrict__ count) {
+    __shared__ int base;
+    __shared__ int warp_tot[32];
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int start = 0; start < nq; start += blockDim.x) {
+        const int q = start + threadIdx.x;
+        const bool f = q < nq && flags[q] != 0;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, f);
+        if (lane == 0) warp_tot[warp] = __popc(m);
+        __syncthreads();
+        int off = base;
+        for (int w = 0; w < warp; ++w) off += warp_tot[w];
+        if (f) list[off + __popc(m & ((1u << lane) - 1u))] = q;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_tot[w];
+            base += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base;
+}
+
 // ---------------------------------------------------------------------------------- host side
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -363,15 +488,43 @@ static int make_tmap_bf16_rows(CUtensorMap* map, const void* base, uint64_t rows
     return TS_OK;
 }
 
+// candidates kept per query by the GEMM stage: k plus a margin that makes the exactness
+// certificate succeed (the gap between the k-th and kp-th score must exceed the bf16 query
+// rounding bound ~1.1e-3; doubling k gives ~5e-3 on 10M random unit rows).
+static int batched_kp(int k) { return std::max(2 * k, k + 64); }
+// candidate slots per query per chunk: the tunable, raised so that it holds >= 3 chunks' worth of
+// expected survivors for large k, within the 8192-key compaction sort.
+static int batched_cap(int kp) { return std::min(std::max(tunables().batch_cap, 3 * kp), 8192 - kp); }
+// chunk growth: expected survivors per query per chunk ~ growth * kp must stay well below cap.
+static int batched_growth(int kp, int cap) { return std::max(1, std::min(tunables().batch_growth, cap / (2 * kp))); }
+
+// diagnostics: where the last batched search left its fix-up count (device memory in the caller's workspace)
+static const int* g_last_fix_count = nullptr;
+static int g_last_fix_device = 0;
+int debug_last_batched_fixups() {
+    if (!g_last_fix_count) return -1;
+    int prev = 0, v = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(g_last_fix_device);
+    if (cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpy(&v, g_last_fix_count, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+        v = -1;
+    cudaSetDevice(prev);
+    return v;
+}
+
 size_t batched_workspace_bytes(const ts_index* ix, int nq, int k) {
-    const Tunables& t = tunables();
-    const int nq_pad = (nq + k3::BN - 1) / k3::BN * k3::BN;
+    const int nq_pad = (nq + k3::BN - 1) / k3::BN * k3::BN + k3::BN;
+    const int kp = batched_kp(k);
+    const int nparts = scan_nparts(ix);
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
     size_t b = 0;
-    b += ((size_t)nq * ix->dim_pad * 2 + 255) / 256 * 256;           // bf16 queries
-    b += ((size_t)nq_pad * 4 + 255) / 256 * 256;                     // thr
-    b += ((size_t)nq_pad * 4 + 255) / 256 * 256;                     // count
-    b += ((size_t)nq_pad * 4 + 255) / 256 * 256;                     // overflow flags
-    b += ((size_t)nq * ((size_t)k + t.batch_cap) * 8 + 255) / 256 * 256;  // candidates
+    b += al((size_t)nq * ix->dim_pad * 4);                   // fp32 normalised queries
+    b += al((size_t)nq * ix->dim_pad * 2);                   // bf16 queries
+    b += al((size_t)nq_pad * 4) * 4;                         // thr, count, overflow, qerr
+    b += al((size_t)nq * 4) * 2 + 256;                       // flags, fix list, fix count
+    b += al((size_t)nq * ((size_t)kp + batched_cap(kp)) * 8);  // candidates
+    b += al((size_t)nq * nparts * k * 8);                    // K2 fix-up partial lists (worst case: every query)
     return b;
 }
 
@@ -381,31 +534,46 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
     using namespace k3;
     TS_REQUIRE(ix->dtype == TS_BF16, TS_ERR_UNSUPPORTED, "batched: corpus must be stored as bf16");
     const Tunables& t = tunables();
-    const int cap = t.batch_cap;
+    const int k_out = k;          // what the caller asked for
+    k = batched_kp(k_out);        // what the GEMM stage keeps per query (kp)
+    const int cap = batched_cap(k);
+    const int growth = batched_growth(k, cap);
+    const int nparts = scan_nparts(ix);
     TS_REQUIRE(workspace_bytes >= batched_workspace_bytes(ix, nq, k), TS_ERR_CAPACITY,
                "batched: workspace %zu < %zu bytes", workspace_bytes, batched_workspace_bytes(ix, nq, k));
-    const int nq_pad = (nq + BN - 1) / BN * BN;
+    const int nq_pad = (nq + BN - 1) / BN * BN + BN;
+    // n-blocks: as few as possible, equal width, width a multiple of 32 (UMMA N % 16, epilogue reads 32 columns)
+    const int num_n_blocks = (nq + BN - 1) / BN;
+    const int bn = ((nq + num_n_blocks - 1) / num_n_blocks + 31) / 32 * 32;
     char* w = (char*)workspace;
     auto take = [&](size_t bytes) {
         char* p = w;
         w += (bytes + 255) / 256 * 256;
         return p;
     };
+    float* q32 = (float*)take((size_t)nq * ix->dim_pad * 4);
     __nv_bfloat16* q16 = (__nv_bfloat16*)take((size_t)nq * ix->dim_pad * 2);
     float* thr = (float*)take((size_t)nq_pad * 4);
     uint32_t* count = (uint32_t*)take((size_t)nq_pad * 4);
     uint32_t* overflow = (uint32_t*)take((size_t)nq_pad * 4);
+    float* qerr = (float*)take((size_t)nq_pad * 4);
+    int* flags = (int*)take((size_t)nq * 4);
+    int* fix_list = (int*)take((size_t)nq * 4);
+    int* fix_count = (int*)take(256);
     uint64_t* cand = (uint64_t*)take((size_t)nq * ((size_t)k + cap) * 8);
+    uint64_t* fix_parts = (uint64_t*)take((size_t)nq * nparts * k_out * 8);
 
-    int rc = launch_normalize_cast(queries, q_dtype, nq, ix->dim, ix->dim_pad, normalize, q16, TS_BF16, s);
+    int rc = launch_prepare_queries(queries, q_dtype, nq, ix->dim, ix->dim_pad, normalize, q32, s);
     if (rc) return rc;
+    round_queries_kernel<<<(nq + 7) / 8, 256, 0, s>>>(q32, nq, ix->dim_pad, q16, qerr);
+    TS_LAUNCH_CHECK();
     init_batch_state_kernel<<<256, 256, 0, s>>>(cand, count, thr, overflow, nq, nq_pad, k, cap);
     TS_LAUNCH_CHECK();
 
     CUtensorMap tmap_a, tmap_b;
     rc = make_tmap_bf16_rows(&tmap_a, ix->data, (uint64_t)ix->size, (uint64_t)ix->dim_pad, ix->row_bytes(), BM);
     if (rc) return rc;
-    rc = make_tmap_bf16_rows(&tmap_b, q16, (uint64_t)nq, (uint64_t)ix->dim_pad, (uint64_t)ix->dim_pad * 2, BN);
+    rc = make_tmap_bf16_rows(&tmap_b, q16, (uint64_t)nq, (uint64_t)ix->dim_pad, (uint64_t)ix->dim_pad * 2, bn);
     if (rc) return rc;
 
     static bool attr_set = false;
@@ -419,14 +587,15 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
     int P = 1;
     while (P < k + cap) P <<= 1;
     const size_t sort_smem = (size_t)P * 8;
-    TS_REQUIRE(sort_smem <= 64 * 1024, TS_ERR_UNSUPPORTED, "batched: k + cap = %d too large for the compaction sort", k + cap);
+    TS_REQUIRE(sort_smem <= 64 * 1024, TS_ERR_UNSUPPORTED, "batched: kp + cap = %d too large for the compaction sort", k + cap);
 
     BatchParams p;
     p.nq = nq;
     p.k = k;
     p.cap = cap;
     p.num_k_blocks = (ix->dim_pad + BK - 1) / BK;
-    p.num_n_blocks = nq_pad / BN;
+    p.num_n_blocks = num_n_blocks;
+    p.bn = bn;
     p.thr = thr;
     p.count = count;
     p.cand = cand;
@@ -440,7 +609,7 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
     int64_t pos = 0;
     if (ev0) TS_CHECK_CUDA(cudaEventRecord(ev0, s));
     while (pos < ix->size) {
-        int64_t chunk = (pos == 0) ? first : pos * (int64_t)t.batch_growth;
+        int64_t chunk = (pos == 0) ? first : pos * (int64_t)growth;
         chunk = (chunk + BM - 1) / BM * BM;
         const int64_t end = std::min<int64_t>(ix->size, pos + chunk);
         p.row_begin = pos;
@@ -455,10 +624,29 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
         pos = end;
     }
     if (ev1) TS_CHECK_CUDA(cudaEventRecord(ev1, s));
-    // cand[q][0..k) now holds each query's sorted top-k keys: emit scores / ids (or keys)
-    rc = launch_merge_strided(cand, 1, nq, k, /*stride_list=*/0, /*stride_query=*/(int64_t)k + cap, nullptr,
-                              ix->has_ids ? ix->ids : nullptr, out_keys, out_scores, out_ids, s);
-    return rc;
+    // cand[q][0..kp): best kp by bf16-query score. Re-score with the fp32 query, keep k_out, certify.
+    const size_t cstride = (size_t)k + cap;
+    int PR = 1;
+    while (PR < k) PR <<= 1;
+    rescore_certify_kernel<<<nq, 256, (size_t)PR * 8, s>>>(cand, cstride, k, k_out, q32, (const uint8_t*)ix->data,
+                                                           (uint32_t)ix->row_bytes(), ix->dim_pad, qerr, ix->max_norm2,
+                                                           overflow, flags);
+    TS_LAUNCH_CHECK();
+    // Fix-up: queries that could not be certified (or overflowed) are re-scanned exactly by K2.
+    // The work list lives on the device; with nothing flagged these launches exit immediately.
+    build_fix_list_kernel<<<1, 1024, 0, s>>>(flags, nq, fix_list, fix_count);
+    TS_LAUNCH_CHECK();
+    g_last_fix_count = fix_count;
+    g_last_fix_device = ix->device;
+    rc = launch_scan_topk(ix, ix->data, ix->dtype, ix->size, q32, nq, k_out, allow_mask, fix_parts, nparts, s, nullptr,
+                          nullptr, fix_list, fix_count);
+    if (rc) return rc;
+    rc = launch_merge_strided(fix_parts, nparts, nq, k_out, /*stride_list=*/k_out, /*stride_query=*/(int64_t)nparts * k_out,
+                              nullptr, nullptr, cand, nullptr, nullptr, s, fix_list, fix_count, (int64_t)cstride);
+    if (rc) return rc;
+    // cand[q][0..k_out) now holds each query's exact sorted top-k keys: emit scores / ids (or keys)
+    return launch_merge_strided(cand, 1, nq, k_out, /*stride_list=*/0, /*stride_query=*/(int64_t)cstride, nullptr,
+                                ix->has_ids ? ix->ids : nullptr, out_keys, out_scores, out_ids, s);
 }
 
 }  // namespace ts

@@ -9,6 +9,8 @@
 // register-resident WarpTopK stops at the first element that does not beat its current k-th
 // key; 8 warps fold disjoint subsets of the lists, then warp 0 folds the 8 warp lists.
 // Latency-bound (a few microseconds); the payload is nlists*k*8 bytes per query.
+#include <algorithm>
+
 #include "ts_common.cuh"
 
 namespace ts {
@@ -19,9 +21,12 @@ struct MergeParams {
     int64_t stride_list, stride_query;  // element (l, q, i) at keys[l*stride_list + q*stride_query + i]
     const int64_t* list_base;           // [nlists] row offset added to each list's rows, or null
     const int64_t* id_map;              // row -> caller id, or null
-    uint64_t* out_keys;                 // [nq, k] or null
+    uint64_t* out_keys;                 // [nq, out_stride] or null
     float* out_scores;                  // [nq, k] or null
     int64_t* out_ids;                   // [nq, k] or null
+    int64_t out_stride;                 // elements between consecutive queries in out_keys
+    const int* qlist;                   // fix-up mode: work item w reads lists of item w, writes query qlist[w]
+    const int* qcount;                  // ... for w < *qcount
 };
 
 __device__ __forceinline__ uint64_t rebase_key(uint64_t key, int64_t base) {
@@ -36,8 +41,10 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const MergeParams p) {
     uint64_t(*lists)[KPL * 32] = reinterpret_cast<uint64_t(*)[KPL * 32]>(merge_smem);  // [8][KPL*32]
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int qi = blockIdx.x;
     const int k = p.k;
+    const int nwork = p.qcount ? *p.qcount : p.nq;
+    for (int qi = blockIdx.x; qi < nwork; qi += gridDim.x) {
+    const int qo = p.qlist ? p.qlist[qi] : qi;   // output row
 
     WarpTopK<KPL> list;
     list.clear();
@@ -72,15 +79,15 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const MergeParams p) {
 #pragma unroll
     for (int j = 0; j < KPL; ++j) lists[warp][j * 32 + lane] = list.key[j];
     __syncthreads();
-    if (warp != 0) return;
+    if (warp == 0) {
     for (int w = 1; w < 8; ++w) merge_sorted_into<KPL>(list, lists[w], k, k, lane);
 #pragma unroll
     for (int j = 0; j < KPL; ++j) {
         const int pos = j * 32 + lane;
         if (pos >= k) continue;
         const uint64_t key = list.key[j];
-        const size_t o = (size_t)qi * k + pos;
-        if (p.out_keys) p.out_keys[o] = key;
+        const size_t o = (size_t)qo * k + pos;
+        if (p.out_keys) p.out_keys[(size_t)qo * p.out_stride + pos] = key;
         if (p.out_scores) p.out_scores[o] = key ? key_score(key) : -INFINITY;
         if (p.out_ids) {
             int64_t id = -1;
@@ -91,11 +98,15 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const MergeParams p) {
             p.out_ids[o] = id;
         }
     }
+    }
+    __syncthreads();
+    }  // work items
 }
 
 int launch_merge_strided(const uint64_t* keys, int nlists, int nq, int k, int64_t stride_list,
                          int64_t stride_query, const int64_t* list_base, const int64_t* id_map,
-                         uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t s) {
+                         uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t s,
+                         const int* qlist, const int* qcount, int64_t out_stride) {
     TS_REQUIRE(k >= 1 && k <= TS_MAX_K, TS_ERR_BAD_ARG, "merge: k=%d out of range [1, %d]", k, TS_MAX_K);
     TS_REQUIRE(nlists >= 1 && nq >= 0, TS_ERR_BAD_ARG, "merge: nlists=%d nq=%d", nlists, nq);
     if (nq == 0) return TS_OK;
@@ -111,16 +122,20 @@ int launch_merge_strided(const uint64_t* keys, int nlists, int nq, int k, int64_
     p.out_keys = out_keys;
     p.out_scores = out_scores;
     p.out_ids = out_ids;
+    p.out_stride = out_stride ? out_stride : k;
+    p.qlist = qlist;
+    p.qcount = qcount;
+    const int grid = qcount ? std::min(nq, 64) : nq;
     if (k <= 32) {
-        merge_topk_kernel<1><<<nq, 256, 8 * 32 * 8, s>>>(p);
+        merge_topk_kernel<1><<<grid, 256, 8 * 32 * 8, s>>>(p);
     } else if (k <= 128) {
-        merge_topk_kernel<4><<<nq, 256, 8 * 128 * 8, s>>>(p);
+        merge_topk_kernel<4><<<grid, 256, 8 * 128 * 8, s>>>(p);
     } else if (k <= 256) {
-        merge_topk_kernel<8><<<nq, 256, 8 * 256 * 8, s>>>(p);
+        merge_topk_kernel<8><<<grid, 256, 8 * 256 * 8, s>>>(p);
     } else {
         TS_CHECK_CUDA(cudaFuncSetAttribute(merge_topk_kernel<32>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 8));
-        merge_topk_kernel<32><<<nq, 256, 8 * 1024 * 8, s>>>(p);
+        merge_topk_kernel<32><<<grid, 256, 8 * 1024 * 8, s>>>(p);
     }
     TS_LAUNCH_CHECK();
     return TS_OK;

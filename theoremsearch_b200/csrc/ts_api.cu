@@ -153,6 +153,15 @@ int ts_index_create(ts_index** out, int device, int dim, int dtype, int64_t capa
         cudaGetLastError();
         return TS_ERR_OOM;
     }
+    e = cudaMalloc(&ix->max_norm2, sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(ix->max_norm2, 0, sizeof(float));
+    if (e != cudaSuccess) {
+        set_error("index_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+        cudaFree(ix->data);
+        delete ix;
+        cudaGetLastError();
+        return TS_ERR_OOM;
+    }
     *out = ix;
     return TS_OK;
 }
@@ -161,6 +170,7 @@ void ts_index_destroy(ts_index* ix) {
     if (!ix) return;
     DeviceGuard g(ix->device);
     cudaFree(ix->data);
+    cudaFree(ix->max_norm2);
     cudaFree(ix->ids);
     cudaFree(ix->centroids);
     cudaFree(ix->centroids_bf16);
@@ -206,7 +216,8 @@ int ts_index_add(ts_index* ix, const void* rows, int src_dtype, int64_t n, int n
         }
     }
     void* dst = (char*)ix->data + (size_t)ix->size * ix->row_bytes();
-    int rc = launch_normalize_cast(rows, src_dtype, n, ix->dim, ix->dim_pad, normalize, dst, ix->dtype, s);
+    int rc = launch_normalize_cast(rows, src_dtype, n, ix->dim, ix->dim_pad, normalize, dst, ix->dtype, s,
+                                   ix->max_norm2);
     if (rc) return rc;
     ix->size += n;
     ix->ivf_built = false;
@@ -432,13 +443,15 @@ static int* tunable_slot(const char* name) {
     if (!strcmp(name, "scan.ctas_per_sm")) return &t.scan_ctas_per_sm;
     if (!strcmp(name, "scan.warps")) return &t.scan_warps;
     if (!strcmp(name, "scan.stages")) return &t.scan_stages;
-    if (!strcmp(name, "scan.tile_bytes")) return &t.scan_tile_bytes;
+    if (!strcmp(name, "scan.tile_rows")) return &t.scan_tile_rows;
     if (!strcmp(name, "batch.min_nq")) return &t.batch_min_nq;
     if (!strcmp(name, "batch.cap")) return &t.batch_cap;
     if (!strcmp(name, "batch.first_chunk")) return &t.batch_first_chunk;
     if (!strcmp(name, "batch.growth")) return &t.batch_growth;
     return nullptr;
 }
+int ts_debug_last_batched_fixups(void) { return debug_last_batched_fixups(); }
+
 int ts_set_tunable(const char* name, int value) {
     int* s = tunable_slot(name);
     TS_REQUIRE(s != nullptr, TS_ERR_BAD_ARG, "set_tunable: unknown tunable '%s'", name ? name : "(null)");

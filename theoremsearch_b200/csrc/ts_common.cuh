@@ -59,8 +59,8 @@ inline int sm_count(int device) {
 struct Tunables {
     int scan_ctas_per_sm = 1;   // persistent CTAs per SM for K2
     int scan_warps = 8;         // consumer warps per CTA
-    int scan_stages = 3;        // TMA ring depth per warp
-    int scan_tile_bytes = 8192; // bytes per TMA bulk copy (whole rows)
+    int scan_stages = 2;        // TMA ring depth per warp (2 measured best on B200: sweep in profiles/)
+    int scan_tile_rows = 0;     // rows per TMA bulk copy; 0 = default (~8 KB tiles)
     int batch_min_nq = 4;       // nq >= this goes to the batched tcgen05 path (bf16 corpus)
     int batch_cap = 3072;       // K3 candidate slots per query per chunk
     int batch_first_chunk = 1024;  // rows of the first K3 chunk (every row passes thr = -inf)
@@ -245,6 +245,7 @@ struct ts_index {
     void* data = nullptr;     // [capacity, dim_pad] of dtype
     int64_t* ids = nullptr;   // [capacity] caller ids; valid only when has_ids
     bool has_ids = false;
+    float* max_norm2 = nullptr;  // device scalar: max squared L2 norm over stored (quantised) rows
 
     // IVF-Flat state (K4)
     int nlist = 0;
@@ -281,7 +282,8 @@ struct ts_ctx {
 // internal kernel entry points (one per .cu)
 namespace ts {
 int launch_normalize_cast(const void* src, int src_dtype, int64_t n, int dim, int dim_pad,
-                          int normalize, void* dst, int dst_dtype, cudaStream_t s);
+                          int normalize, void* dst, int dst_dtype, cudaStream_t s,
+                          float* max_norm2 = nullptr);
 int launch_dequant_rows(const void* src, int src_dtype, int64_t n, int dim, int dim_pad, float* dst,
                         cudaStream_t s);
 int launch_prepare_queries(const void* q, int q_dtype, int nq, int dim, int dim_pad, int normalize,
@@ -291,16 +293,18 @@ int scan_nparts(const ts_index* ix);
 int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64_t n_rows,
                      const float* queries_f32, int nq, int k, const uint32_t* allow_mask,
                      uint64_t* part_keys, int nparts, cudaStream_t s, cudaEvent_t ev0,
-                     cudaEvent_t ev1);
+                     cudaEvent_t ev1, const int* qlist = nullptr, const int* qcount = nullptr);
 // K5: lists[nlists][nq][k] (list-major) or [nq][nlists][k] (query-major) -> top-k
 int launch_merge(const uint64_t* keys, int nlists, int nq, int k, bool query_major,
                  const int64_t* list_base, const int64_t* id_map, uint64_t* out_keys,
                  float* out_scores, int64_t* out_ids, cudaStream_t s);
 int launch_merge_strided(const uint64_t* keys, int nlists, int nq, int k, int64_t stride_list,
                          int64_t stride_query, const int64_t* list_base, const int64_t* id_map,
-                         uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t s);
+                         uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t s,
+                         const int* qlist = nullptr, const int* qcount = nullptr, int64_t out_stride = 0);
 // K3: batched tcgen05 GEMM + fused top-k
 size_t batched_workspace_bytes(const ts_index* ix, int nq, int k);
+int debug_last_batched_fixups();
 int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, int nq, int k, int normalize,
                           const uint32_t* allow_mask, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
                           void* workspace, size_t workspace_bytes, cudaStream_t s, cudaEvent_t ev0,
