@@ -75,7 +75,13 @@ def cmd_sweep_scan(a):
     q = synthetic.make_queries(64, a.dim, dev)
     pk = peaks()
     nbytes = a.rows * a.dim * 2
-    for ctas, warps, stages, rows in itertools.product((1, 2), (6, 8, 12, 16), (2, 3), (2, 4, 8)):
+    grid = list(itertools.product((1, 2), (6, 8, 12, 16), (2, 3), (2, 4, 8)))
+    iters = 40
+    if a.fine:   # the near-optimal region, more iterations, interleaved twice to expose drift
+        grid = [(1, 12, 2, 2), (1, 10, 2, 2), (1, 14, 2, 2), (1, 16, 2, 2), (1, 6, 2, 4), (1, 7, 2, 4), (1, 8, 2, 4),
+                (2, 6, 2, 2), (2, 8, 2, 2), (2, 3, 2, 4), (2, 4, 2, 4), (1, 3, 2, 8), (1, 4, 2, 8)] * 2
+        iters = 150
+    for ctas, warps, stages, rows in grid:
         if ctas * warps > 16 or ctas * warps * stages * rows * a.dim * 2 > 200 * 1024:
             continue
         ts.set_tunable("scan.tile_rows", rows)
@@ -84,7 +90,7 @@ def cmd_sweep_scan(a):
         ts.set_tunable("scan.stages", stages)
         it = iter(itertools.cycle(range(64)))
         try:
-            ms = timed(lambda: index.search(q[next(it)], a.k), 5, 40)
+            ms = timed(lambda: index.search(q[next(it)], a.k), 5, iters)
         except ts.TheoremSearchError as e:
             print(json.dumps({"bench": "sweep-scan", "ctas": ctas, "warps": warps, "stages": stages, "rows": rows,
                               "error": str(e)}))
@@ -114,6 +120,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--tunable", nargs=2, action="append", metavar=("NAME", "VALUE"))
+    ap.add_argument("--fine", action="store_true")
     a = ap.parse_args()
     if a.k is None:
         a.k = 100 if a.cmd == "batched" else 10

@@ -45,8 +45,11 @@ constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
 constexpr int THREADS = 192;
 constexpr int EPI_THREADS = 128;
+constexpr int STG_CAP = 256;           // survivors an epilogue warp stages in smem before flushing to HBM
 constexpr size_t SMEM_TILES = (size_t)STAGES * (A_BYTES + B_BYTES);
-constexpr size_t SMEM_BYTES = SMEM_TILES + ACC_STAGES * BN * sizeof(float) + 16 * sizeof(uint64_t) + 1024;
+constexpr size_t SMEM_STAGING = 4 * (size_t)STG_CAP * (sizeof(uint64_t) + sizeof(uint32_t));
+constexpr size_t SMEM_BYTES =
+    SMEM_TILES + ACC_STAGES * BN * sizeof(float) + 16 * sizeof(uint64_t) + SMEM_STAGING + 1024;
 }  // namespace k3
 
 struct BatchParams {
@@ -109,6 +112,11 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ uint32_t tmem_ld_32x32b_x1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    return r;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------- K3 kernel
@@ -127,6 +135,8 @@ batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint64_t* tmem_full = bars + 2 * STAGES;  // [ACC_STAGES]
     uint64_t* tmem_empty = tmem_full + ACC_STAGES;
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+    uint64_t* stg_keys_all = bars + 16;                                             // [4][STG_CAP]
+    uint32_t* stg_q_all = reinterpret_cast<uint32_t*>(stg_keys_all + 4 * STG_CAP);  // [4][STG_CAP]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -214,10 +224,28 @@ batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
     } else {
         // ===================== epilogue: threshold filter + append =====================
+        // Survivors are staged per warp in smem with ballot/popc slot assignment (no atomics, no
+        // divergence-serialised round trips) and flushed to the per-query HBM buffers 32 at a
+        // time, so the global atomicAdd latencies overlap instead of adding up.
         const int ep_tid = threadIdx.x - 64;              // 0..127
+        const int ew = warp - 2;                          // epilogue warp 0..3
         const int lane_base = 32 * (warp & 3);            // TMEM lanes this warp may touch
         const int row_in_tile = lane_base + lane;
         const size_t cand_stride = (size_t)p.k + p.cap;
+        uint64_t* stg_keys = stg_keys_all + ew * STG_CAP;
+        uint32_t* stg_q = stg_q_all + ew * STG_CAP;
+        const uint32_t lt_mask = (1u << lane) - 1u;
+        int staged = 0;                                   // warp-uniform
+        auto flush = [&]() {
+            __syncwarp();
+            for (int e = lane; e < staged; e += 32) {
+                const uint32_t q = stg_q[e];
+                const uint32_t pos = atomicAdd(p.count + q, 1u);
+                if (pos < (uint32_t)p.cap) p.cand[(size_t)q * cand_stride + p.k + pos] = stg_keys[e];
+            }
+            __syncwarp();
+            staged = 0;
+        };
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -249,21 +277,39 @@ batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     any |= (__uint_as_float(v[4 * j + 0]) > th.x) | (__uint_as_float(v[4 * j + 1]) > th.y) |
                            (__uint_as_float(v[4 * j + 2]) > th.z) | (__uint_as_float(v[4 * j + 3]) > th.w);
                 }
-                if (any && row_ok) {
+                if (__any_sync(0xFFFFFFFFu, any && row_ok)) {
+                    // rare path. Per-lane 32-bit pass mask (straight-line), OR-reduced over the warp to the
+                    // set of columns that have a survivor anywhere; each such column is re-read from TMEM
+                    // (one register per lane, no dynamic register indexing) and compacted with a ballot.
+                    unsigned pm = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float s = __uint_as_float(v[j]);
-                        if (s > thr_t[c * 32 + j]) {
-                            const int q = q0 + c * 32 + j;  // q < nq guaranteed: padded queries have thr = +inf
-                            const uint32_t pos = atomicAdd(p.count + q, 1u);
-                            if (pos < (uint32_t)p.cap) p.cand[(size_t)q * cand_stride + p.k + pos] = pack_key(s, (uint32_t)row);
+                    for (int j = 0; j < 32; ++j)
+                        pm |= (__uint_as_float(v[j]) > thr_t[c * 32 + j]) ? (1u << j) : 0u;   // padded queries: thr = +inf
+                    if (!row_ok) pm = 0;
+                    unsigned cols = __reduce_or_sync(0xFFFFFFFFu, pm);
+                    while (cols) {
+                        const int j = __ffs(cols) - 1;
+                        cols &= cols - 1;
+                        const float sc = __uint_as_float(tmem_ld_32x32b_x1(taddr0 + (uint32_t)(c * 32 + j)));
+                        tmem_ld_wait();
+                        const bool pass = (pm >> j) & 1u;
+                        const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+                        if (pass) {
+                            const int slot = staged + __popc(m & lt_mask);
+                            stg_keys[slot] = pack_key(sc, (uint32_t)row);
+                            stg_q[slot] = (uint32_t)(q0 + c * 32 + j);
                         }
+                        staged += __popc(m);
+                        if (staged > STG_CAP - 32) flush();
                     }
                 }
             }
+            // accumulator drained: hand the TMEM stage back before doing any HBM work
             tcgen05_fence_before();
             mbar_arrive(&tmem_empty[acc]);
+            if (staged >= STG_CAP / 2) flush();
         }
+        flush();
     }
 
     tcgen05_fence_before();
@@ -539,8 +585,8 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
     const int cap = batched_cap(k);
     const int growth = batched_growth(k, cap);
     const int nparts = scan_nparts(ix);
-    TS_REQUIRE(workspace_bytes >= batched_workspace_bytes(ix, nq, k), TS_ERR_CAPACITY,
-               "batched: workspace %zu < %zu bytes", workspace_bytes, batched_workspace_bytes(ix, nq, k));
+    TS_REQUIRE(workspace_bytes >= batched_workspace_bytes(ix, nq, k_out), TS_ERR_CAPACITY,
+               "batched: workspace %zu < %zu bytes", workspace_bytes, batched_workspace_bytes(ix, nq, k_out));
     const int nq_pad = (nq + BN - 1) / BN * BN + BN;
     // n-blocks: as few as possible, equal width, width a multiple of 32 (UMMA N % 16, epilogue reads 32 columns)
     const int num_n_blocks = (nq + BN - 1) / BN;
