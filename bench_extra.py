@@ -56,9 +56,12 @@ def cmd_batched(a):
     q = synthetic.make_queries(a.nq, a.dim, dev)
     for name, val in (a.tunable or []):
         ts.set_tunable(name, int(val))
+    from bench import ClockSampler
     l0 = ts.kernel_launches()
-    ms = timed(lambda: index.search(q, a.k), a.warmup, a.iters)
+    with ClockSampler(0) as clocks:
+        ms = timed(lambda: index.search(q, a.k), a.warmup, a.iters)
     launches = (ts.kernel_launches() - l0) // (a.warmup + a.iters)
+    fix = ts.last_batched_fixups()
     flops = 2.0 * a.nq * a.rows * a.dim
     pk = peaks()
     tf = flops / (ms * 1e-3) / 1e12
@@ -66,7 +69,8 @@ def cmd_batched(a):
                       "queries_per_s": a.nq / (ms * 1e-3), "tflops": tf,
                       "frac_of_measured_bf16_burst": tf / pk["bf16_tflops"],
                       "frac_of_measured_bf16_sustained": tf / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
-                      "launches_per_batch": launches, "tunables": a.tunable}))
+                      "launches_per_batch": launches, "tunables": a.tunable, "fixups": fix, "iters": a.iters,
+                      "clocks": clocks.summary()}))
 
 
 def cmd_sweep_scan(a):

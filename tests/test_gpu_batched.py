@@ -127,3 +127,26 @@ def test_ascending_order_overflows_buffers_and_is_fixed_up(ts):
     s, i = index.search(torch.from_numpy(q_raw), k)
     assert ts.last_batched_fixups() >= 1
     check_against_oracle(ts, index, prepared(q_raw), k, s, i)
+
+
+@pytest.mark.parametrize("n,d,nq,k", [
+    (5000, 1024, 100, 10), (20000, 1024, 64, 100), (4097, 768, 33, 10), (3000, 100, 16, 5),
+    (40000, 256, 257, 20), (127, 1024, 5, 10), (129, 512, 600, 1), (70000, 1024, 1000, 10),
+])
+def test_cta_pair_kernel_matches_oracle(ts, n, d, nq, k):
+    """Force the cta_group::2 (CTA pair) GEMM for every batch size, including odd tile counts."""
+    old = ts.get_tunable("batch.pair_min_nq")
+    old_pair = ts.get_tunable("batch.cta_pair")
+    ts.set_tunable("batch.pair_min_nq", 1)
+    ts.set_tunable("batch.cta_pair", 1)
+    try:
+        rows = unit_rows(n, d, seed=n + d + 2)
+        index = ts.build_index(rows, dtype="bf16", normalize=False)
+        q_raw = oracle.synthetic_queries(nq, d, seed=400 + nq)
+        s, i = index.search(torch.from_numpy(q_raw), k)
+        fix = ts.last_batched_fixups()
+        check_against_oracle(ts, index, prepared(q_raw), k, s, i)
+        assert fix <= max(2, nq // 50), f"{fix} of {nq} queries needed the K2 fix-up: the pair GEMM is mis-scoring"
+    finally:
+        ts.set_tunable("batch.pair_min_nq", old)
+        ts.set_tunable("batch.cta_pair", old_pair)

@@ -49,7 +49,7 @@ constexpr int STG_CAP = 256;           // survivors an epilogue warp stages in s
 constexpr size_t SMEM_TILES = (size_t)STAGES * (A_BYTES + B_BYTES);
 constexpr size_t SMEM_STAGING = 4 * (size_t)STG_CAP * (sizeof(uint64_t) + sizeof(uint32_t));
 constexpr size_t SMEM_BYTES =
-    SMEM_TILES + ACC_STAGES * BN * sizeof(float) + 16 * sizeof(uint64_t) + SMEM_STAGING + 1024;
+    SMEM_TILES + ACC_STAGES * BN * sizeof(float) + 18 * sizeof(uint64_t) + SMEM_STAGING + 1024;
 }  // namespace k3
 
 struct BatchParams {
@@ -120,68 +120,143 @@ __device__ __forceinline__ uint32_t tmem_ld_32x32b_x1(uint32_t taddr) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------- K3 kernel
+// PAIR = false: one CTA per tile, tcgen05 cta_group::1, tile = 128 corpus rows x bn queries.
+// PAIR = true : a cluster of two CTAs (one TPC) per tile, cta_group::2, tile = 256 corpus rows x bn
+//               queries. Each CTA stages its own 128 corpus rows and HALF of the query block; the
+//               tensor cores of both SMs read both halves, so operand traffic from L2 per SM drops
+//               from (128 + bn) to (128 + bn/2) rows per k-block. CTA rank 0 (leader) issues the MMAs;
+//               completion is multicast to both CTAs' mbarriers; each CTA runs the epilogue on the 128
+//               accumulator rows that live in its own TMEM.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                                 uint64_t policy) {
+    // bit 24 of a shared::cluster address selects the odd CTA of the pair: clearing it makes the
+    // transaction bytes land on the LEADER's barrier from either CTA
+    const uint32_t bar_addr = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_addr), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar) {   // arrive on this barrier in BOTH CTAs
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(cta)
+        : "memory");
+}
+
+template <bool PAIR>
 __global__ void __launch_bounds__(k3::THREADS, 1)
 batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const BatchParams p) {
     using namespace k3;
+    constexpr int NST = PAIR ? 6 : STAGES;                 // smem ring depth
+    constexpr int BSLOT = PAIR ? B_BYTES / 2 : B_BYTES;    // bytes reserved per stage for this CTA's part of B
+    constexpr int TILE_ROWS = PAIR ? 2 * BM : BM;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + (size_t)STAGES * A_BYTES;
+    uint8_t* smem_b = smem + (size_t)NST * A_BYTES;
+    static_assert((size_t)NST * (A_BYTES + BSLOT) == SMEM_TILES, "ring must fill the tile area exactly");
     float* thr_s = reinterpret_cast<float*>(smem + SMEM_TILES);                   // [ACC_STAGES][BN]
     uint64_t* bars = reinterpret_cast<uint64_t*>(thr_s + ACC_STAGES * BN);
-    uint64_t* full = bars;                    // [STAGES]
-    uint64_t* empty = bars + STAGES;          // [STAGES]
-    uint64_t* tmem_full = bars + 2 * STAGES;  // [ACC_STAGES]
-    uint64_t* tmem_empty = tmem_full + ACC_STAGES;
-    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
-    uint64_t* stg_keys_all = bars + 16;                                             // [4][STG_CAP]
+    uint64_t* full = bars;                    // [NST]   (PAIR: only the leader's are used)
+    uint64_t* empty = bars + 6;               // [NST]
+    uint64_t* tmem_full = bars + 12;          // [ACC_STAGES]
+    uint64_t* tmem_empty = bars + 14;         // [ACC_STAGES] (PAIR: only the leader's are used)
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 16);
+    uint64_t* stg_keys_all = bars + 18;                                             // [4][STG_CAP]
     uint32_t* stg_q_all = reinterpret_cast<uint32_t*>(stg_keys_all + 4 * STG_CAP);  // [4][STG_CAP]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;    // tile-scheduling unit (CTA or CTA pair)
+    const int nunits = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int num_tiles = p.num_m_blocks * p.num_n_blocks;
 
+    if constexpr (PAIR) cluster_sync_all();   // both CTAs resident before the paired TMEM allocation
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < NST; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
         for (int s = 0; s < ACC_STAGES; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], EPI_THREADS);
+            mbar_init(&tmem_empty[s], PAIR ? 2 * EPI_THREADS : EPI_THREADS);
         }
         fence_mbar_init();
     }
-    if (warp == 1) {  // TMEM owner: allocate all 512 columns (1 CTA per SM by launch bounds + smem)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
-                     "n"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (warp == 1) {  // TMEM owner: all 512 columns (1 CTA per SM by launch bounds + smem)
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
+                         "n"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
+                         "n"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (every CTA loads its own rows / its half of B) =====================
         if (lane == 0) {
             const uint64_t pol_a = l2_policy_evict_first();  // corpus tile: streamed (L2 holds it for the n-blocks in flight)
             const uint64_t pol_b = l2_policy_evict_last();   // query block: re-read by every corpus tile
+            const uint32_t b_rows = PAIR ? (uint32_t)p.bn / 2 : (uint32_t)p.bn;
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = unit; t < num_tiles; t += nunits) {
                 const int m_blk = t / p.num_n_blocks, n_blk = t % p.num_n_blocks;
-                const int row0 = (int)(p.row_begin + (int64_t)m_blk * BM);
+                const int row0 = (int)(p.row_begin + (int64_t)m_blk * TILE_ROWS + (int64_t)cta_rank * BM);
+                const int b0 = n_blk * p.bn + (int)(cta_rank * b_rows);
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait_wd(&empty[stage], phase ^ 1u);
-                    mbar_expect_tx(&full[stage], A_BYTES + (uint32_t)p.bn * (BK * 2));
-                    tma_load_2d(smem_a + (size_t)stage * A_BYTES, &tmap_a, kb * BK, row0, &full[stage], pol_a);
-                    tma_load_2d(smem_b + (size_t)stage * B_BYTES, &tmap_b, kb * BK, n_blk * p.bn, &full[stage], pol_b);
-                    if (++stage == STAGES) {
+                    if constexpr (PAIR) {
+                        if (leader) mbar_expect_tx(&full[stage], 2u * (A_BYTES + b_rows * (BK * 2)));
+                        tma_load_2d_pair(smem_a + (size_t)stage * A_BYTES, &tmap_a, kb * BK, row0, &full[stage], pol_a);
+                        tma_load_2d_pair(smem_b + (size_t)stage * BSLOT, &tmap_b, kb * BK, b0, &full[stage], pol_b);
+                    } else {
+                        mbar_expect_tx(&full[stage], A_BYTES + b_rows * (BK * 2));
+                        tma_load_2d(smem_a + (size_t)stage * A_BYTES, &tmap_a, kb * BK, row0, &full[stage], pol_a);
+                        tma_load_2d(smem_b + (size_t)stage * BSLOT, &tmap_b, kb * BK, b0, &full[stage], pol_b);
+                    }
+                    if (++stage == NST) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -189,15 +264,15 @@ batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (one thread; in PAIR mode only in the leader CTA) =====================
+        if (lane == 0 && leader) {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) |
-                                   ((uint32_t)(BM >> 4) << 24);
+                                   ((uint32_t)(TILE_ROWS >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            for (int t = unit; t < num_tiles; t += nunits, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
                 mbar_wait_wd(&tmem_empty[acc], acc_phase ^ 1u);
@@ -207,15 +282,23 @@ batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     mbar_wait_wd(&full[stage], phase);
                     tcgen05_fence_after();
                     const uint64_t da = umma_smem_desc(smem_a + (size_t)stage * A_BYTES);
-                    const uint64_t db = umma_smem_desc(smem_b + (size_t)stage * B_BYTES);
+                    const uint64_t db = umma_smem_desc(smem_b + (size_t)stage * BSLOT);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // +32 bytes per UMMA_K step inside the 128-byte swizzle span (address field is >>4)
-                        umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        if constexpr (PAIR)
+                            umma_bf16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        else
+                            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
                     }
-                    tcgen05_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
-                    if (kb == p.num_k_blocks - 1) tcgen05_commit(&tmem_full[acc]);
-                    if (++stage == STAGES) {
+                    if constexpr (PAIR) {
+                        tcgen05_commit_pair(&empty[stage]);  // smem slot reusable in BOTH CTAs once these MMAs retire
+                        if (kb == p.num_k_blocks - 1) tcgen05_commit_pair(&tmem_full[acc]);
+                    } else {
+                        tcgen05_commit(&empty[stage]);
+                        if (kb == p.num_k_blocks - 1) tcgen05_commit(&tmem_full[acc]);
+                    }
+                    if (++stage == NST) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -230,7 +313,7 @@ batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int ep_tid = threadIdx.x - 64;              // 0..127
         const int ew = warp - 2;                          // epilogue warp 0..3
         const int lane_base = 32 * (warp & 3);            // TMEM lanes this warp may touch
-        const int row_in_tile = lane_base + lane;
+        const int row_in_tile = (int)cta_rank * BM + lane_base + lane;
         const size_t cand_stride = (size_t)p.k + p.cap;
         uint64_t* stg_keys = stg_keys_all + ew * STG_CAP;
         uint32_t* stg_q = stg_q_all + ew * STG_CAP;
@@ -247,7 +330,7 @@ batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             staged = 0;
         };
         int it = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        for (int t = unit; t < num_tiles; t += nunits, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
             const int m_blk = t / p.num_n_blocks, n_blk = t % p.num_n_blocks;
@@ -257,7 +340,7 @@ batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             if (ep_tid + EPI_THREADS < p.bn) thr_t[ep_tid + EPI_THREADS] = p.thr[q0 + ep_tid + EPI_THREADS];
             asm volatile("bar.sync 1, 128;" ::: "memory");
 
-            const int64_t row = p.row_begin + (int64_t)m_blk * BM + row_in_tile;
+            const int64_t row = p.row_begin + (int64_t)m_blk * TILE_ROWS + row_in_tile;
             bool row_ok = row < p.row_end;
             if (row_ok && p.mask != nullptr) row_ok = (__ldg(p.mask + (row >> 5)) >> (row & 31)) & 1u;
 
@@ -304,19 +387,25 @@ batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     }
                 }
             }
-            // accumulator drained: hand the TMEM stage back before doing any HBM work
+            // accumulator drained: hand the TMEM stage back (to the leader's MMA thread) before any HBM work
             tcgen05_fence_before();
-            mbar_arrive(&tmem_empty[acc]);
+            if (PAIR && !leader)
+                mbar_arrive_remote(&tmem_empty[acc], 0);
+            else
+                mbar_arrive(&tmem_empty[acc]);
             if (staged >= STG_CAP / 2) flush();
         }
         flush();
     }
 
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        if constexpr (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
 }
 
@@ -619,13 +708,19 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
     CUtensorMap tmap_a, tmap_b;
     rc = make_tmap_bf16_rows(&tmap_a, ix->data, (uint64_t)ix->size, (uint64_t)ix->dim_pad, ix->row_bytes(), BM);
     if (rc) return rc;
-    rc = make_tmap_bf16_rows(&tmap_b, q16, (uint64_t)nq, (uint64_t)ix->dim_pad, (uint64_t)ix->dim_pad * 2, bn);
+    // CTA pairs pay off once the batch is tensor-bound; small batches (HBM-bound) keep single CTAs, which
+    // spread the corpus stream over all 148 SMs' TMA queues.
+    const bool pair = t.batch_cta_pair != 0 && nq >= t.batch_pair_min_nq;
+    rc = make_tmap_bf16_rows(&tmap_b, q16, (uint64_t)nq, (uint64_t)ix->dim_pad, (uint64_t)ix->dim_pad * 2,
+                             pair ? bn / 2 : bn);
     if (rc) return rc;
 
     static bool attr_set = false;
     if (!attr_set) {
-        TS_CHECK_CUDA(cudaFuncSetAttribute(batched_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)SMEM_BYTES));
+        TS_CHECK_CUDA(cudaFuncSetAttribute(batched_gemm_topk_kernel<false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        TS_CHECK_CUDA(cudaFuncSetAttribute(batched_gemm_topk_kernel<true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         TS_CHECK_CUDA(cudaFuncSetAttribute(compact_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            64 * 1024));
         attr_set = true;
@@ -650,20 +745,39 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
 
     // chunk schedule: first chunk fills the buffers (every row passes thr = -inf), then chunks
     // grow by `batch_growth` x the rows already seen, so expected survivors per query stay ~growth*k.
-    int64_t first = std::min<int64_t>((int64_t)(cap / 2) / BM * BM, (int64_t)t.batch_first_chunk / BM * BM);
-    if (first < BM) first = BM;
+    int64_t first = std::min<int64_t>((int64_t)(cap / 2) / (2 * BM) * (2 * BM),
+                                      (int64_t)t.batch_first_chunk / (2 * BM) * (2 * BM));
+    if (first < 2 * BM) first = 2 * BM;
     int64_t pos = 0;
     if (ev0) TS_CHECK_CUDA(cudaEventRecord(ev0, s));
     while (pos < ix->size) {
         int64_t chunk = (pos == 0) ? first : pos * (int64_t)growth;
-        chunk = (chunk + BM - 1) / BM * BM;
+        chunk = (chunk + 2 * BM - 1) / (2 * BM) * (2 * BM);
         const int64_t end = std::min<int64_t>(ix->size, pos + chunk);
         p.row_begin = pos;
         p.row_end = end;
-        p.num_m_blocks = (int)((end - pos + BM - 1) / BM);
+        const int tile_rows = pair ? 2 * BM : BM;
+        p.num_m_blocks = (int)((end - pos + tile_rows - 1) / tile_rows);
         const int tiles = p.num_m_blocks * p.num_n_blocks;
-        const int grid = tiles < sms ? tiles : sms;
-        batched_gemm_topk_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(tmap_a, tmap_b, p);
+        if (pair) {
+            const int pairs = std::min(tiles, sms / 2);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2 * pairs);
+            cfg.blockDim = dim3(THREADS);
+            cfg.dynamicSmemBytes = SMEM_BYTES;
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            TS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, batched_gemm_topk_kernel<true>, tmap_a, tmap_b, p));
+        } else {
+            const int grid = tiles < sms ? tiles : sms;
+            batched_gemm_topk_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>(tmap_a, tmap_b, p);
+        }
         TS_LAUNCH_CHECK();
         compact_candidates_kernel<<<nq, 256, sort_smem, s>>>(cand, count, thr, overflow, k, cap);
         TS_LAUNCH_CHECK();
