@@ -26,7 +26,7 @@
 // Algorithmic bytes: N * row_bytes per query (+ D*4 query + nparts*k*8 candidates).
 #include <algorithm>
 
-#include "ts_common.cuh"
+#include "merge_device.cuh"
 
 namespace ts {
 
@@ -43,7 +43,21 @@ struct ScanParams {
     int nq;                   // work items when qcount == nullptr (work item w scans query w)
     const int* qlist;         // fix-up mode: work item w scans query qlist[w] ...
     const int* qcount;        // ... for w < *qcount (device-side count; 0 = every CTA exits at once)
+    // fused query preparation: when q_raw != nullptr the kernel normalises the caller's query itself
+    // (bit-identical to K1's arithmetic) instead of reading a prepared fp32 copy from `queries`
+    const void* q_raw;        // [nq, dim] of q_dtype
+    int q_dtype, q_normalize, dim;
+    // fused final merge: when tickets != nullptr the last CTA of a work item to finish merges the
+    // grid's per-CTA lists and writes the final result (fin.keys / nlists / strides are filled in-kernel)
+    uint32_t* tickets;        // [work items], zero on entry, left zero on exit
+    MergeParams fin;
 };
+
+__device__ __forceinline__ float load_query_elem(const void* base, int dtype, size_t idx) {
+    if (dtype == TS_F32) return __ldg(reinterpret_cast<const float*>(base) + idx);
+    if (dtype == TS_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+    return __half2float(reinterpret_cast<const __half*>(base)[idx]);
+}
 
 template <int NCHUNK>
 struct RowsPerTile {
@@ -154,9 +168,18 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
     for (int wi = blockIdx.y; wi < nwork; wi += gridDim.y) {
     const int qi = p.qlist ? p.qlist[wi] : wi;
 
+    if (lane == 0) {   // get the corpus stream going before anything else
+        int ss = s;
+        for (int i = 0; i < stages; ++i) {
+            const int64_t t = gw + (int64_t)i * tw;
+            if (t < num_tiles) issue(t, ss);
+            if (++ss == stages) ss = 0;
+        }
+    }
+
     // query slice of this lane, fp32 in registers
     float q[NCHUNK * CN];
-    {
+    if (p.q_raw == nullptr) {
         const float* qv = p.queries + (size_t)qi * p.dim_pad;
 #pragma unroll
         for (int j = 0; j < NCHUNK; ++j) {
@@ -164,14 +187,29 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
 #pragma unroll
             for (int i = 0; i < CN; ++i) q[j * CN + i] = (e0 + i < p.dim_pad) ? __ldg(qv + e0 + i) : 0.f;
         }
-    }
-
-    if (lane == 0) {
-        int ss = s;
-        for (int i = 0; i < stages; ++i) {
-            const int64_t t = gw + (int64_t)i * tw;
-            if (t < num_tiles) issue(t, ss);
-            if (++ss == stages) ss = 0;
+    } else {
+        // K1's arithmetic, replicated per warp (4 KB from L2): ||x|| accumulated in fp64 with lane i
+        // taking elements i, i+32, ... then the butterfly; fp32 division by max((float)sqrt, 1e-12).
+        const size_t qoff = (size_t)qi * p.dim;
+        float den = 1.0f;
+        if (p.q_normalize) {
+            double ss = 0.0;
+            for (int i = lane; i < p.dim; i += 32) {
+                const double v = (double)load_query_elem(p.q_raw, p.q_dtype, qoff + i);
+                ss = fma(v, v, ss);
+            }
+            ss = warp_sum(ss);
+            den = fmaxf((float)sqrt(ss), 1e-12f);
+        }
+#pragma unroll
+        for (int j = 0; j < NCHUNK; ++j) {
+            const int e0 = (j * 32 + lane) * CN;
+#pragma unroll
+            for (int i = 0; i < CN; ++i) {
+                float v = (e0 + i < p.dim) ? load_query_elem(p.q_raw, p.q_dtype, qoff + e0 + i) : 0.f;
+                if (p.q_normalize) v = __fdiv_rn(v, den);
+                q[j * CN + i] = v;
+            }
         }
     }
 
@@ -245,8 +283,30 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
             const int pos = j * 32 + lane;
             if (pos < k) out[pos] = list.key[j];
         }
+        if (p.tickets != nullptr) __threadfence();   // publish this CTA's list before taking a ticket
     }
     __syncthreads();  // the list area aliases the TMA slots of the next work item
+    if (p.tickets != nullptr) {
+        // ---- fused final merge: the last CTA of this work item to arrive folds all gridDim.x lists
+        __shared__ int s_is_last;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const uint32_t t = atomicAdd(p.tickets + wi, 1u);
+            s_is_last = (t == gridDim.x - 1);
+            if (s_is_last) p.tickets[wi] = 0u;   // self-cleaning: the next launch finds zeros
+        }
+        __syncthreads();
+        if (s_is_last) {
+            __threadfence();
+            MergeParams mp = p.fin;
+            mp.keys = p.part_keys;
+            mp.nlists = gridDim.x;
+            mp.k = k;
+            mp.stride_list = k;
+            mp.stride_query = (int64_t)gridDim.x * k;
+            merge_lists<KPL>(mp, wi, qi, lists, W);
+        }
+    }
     }  // work items
 }
 
@@ -327,7 +387,7 @@ int scan_nparts(const ts_index* ix) {
 int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64_t n_rows,
                      const float* queries_f32, int nq, int k, const uint32_t* allow_mask,
                      uint64_t* part_keys, int nparts, cudaStream_t s, cudaEvent_t ev0,
-                     cudaEvent_t ev1, const int* qlist, const int* qcount) {
+                     cudaEvent_t ev1, const int* qlist, const int* qcount, const ScanFused* fused) {
     TS_REQUIRE(k >= 1 && k <= TS_MAX_K, TS_ERR_BAD_ARG, "scan: k=%d out of range [1, %d]", k, TS_MAX_K);
     TS_REQUIRE(n_rows < (int64_t)0xFFFFFFFFll, TS_ERR_UNSUPPORTED, "scan: more than 2^32-1 rows per shard");
     TS_REQUIRE(nparts == scan_nparts(ix), TS_ERR_BAD_ARG, "scan: workspace sized for another grid");
@@ -343,6 +403,24 @@ int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64
     p.nq = nq;
     p.qlist = qlist;
     p.qcount = qcount;
+    p.q_raw = nullptr;
+    p.q_dtype = TS_F32;
+    p.q_normalize = 0;
+    p.dim = ix->dim;
+    p.tickets = nullptr;
+    memset(&p.fin, 0, sizeof(p.fin));
+    if (fused != nullptr) {
+        p.q_raw = fused->q_raw;
+        p.q_dtype = fused->q_dtype;
+        p.q_normalize = fused->q_normalize;
+        p.tickets = fused->tickets;
+        p.fin.nq = nq;
+        p.fin.id_map = fused->id_map;
+        p.fin.out_keys = fused->out_keys;
+        p.fin.out_scores = fused->out_scores;
+        p.fin.out_ids = fused->out_ids;
+        p.fin.out_stride = k;
+    }
     if (data_dtype == TS_BF16) {
         p.row_bytes = (uint32_t)ix->dim_pad * 2;
         const int nchunk = (ix->dim_pad + 255) / 256;

@@ -46,6 +46,7 @@ struct DeviceGuard {
 struct SearchWs {
     float* q_f32;
     uint64_t* part_keys;
+    uint32_t* tickets;
     int nparts;
     size_t bytes;
 };
@@ -57,6 +58,8 @@ static SearchWs carve_ws(const ts_index* ix, int nq, int k, void* base) {
     off += align_up((size_t)nq * ix->dim_pad * sizeof(float), 256);
     w.part_keys = (uint64_t*)((char*)base + off);
     off += align_up((size_t)nq * w.nparts * k * sizeof(uint64_t), 256);
+    w.tickets = (uint32_t*)((char*)base + off);
+    off += align_up((size_t)nq * sizeof(uint32_t), 256);
     w.bytes = off;
     return w;
 }
@@ -86,14 +89,21 @@ static int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, i
     SearchWs w = carve_ws(ix, nq, k, workspace);
     TS_REQUIRE(workspace_bytes >= w.bytes, TS_ERR_CAPACITY, "search: workspace %zu < %zu bytes",
                workspace_bytes, w.bytes);
-    int rc = launch_prepare_queries(queries, q_dtype, nq, ix->dim, ix->dim_pad, normalize_queries,
-                                    w.q_f32, s);
-    if (rc) return rc;
-    rc = launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, w.part_keys,
-                          w.nparts, s, ev0, ev1);
-    if (rc) return rc;
-    return launch_merge(w.part_keys, w.nparts, nq, k, /*query_major=*/true, nullptr,
-                        ix->has_ids ? ix->ids : nullptr, out_keys, out_scores, out_ids, s);
+    // One kernel does everything: each warp normalises the query itself, the scan keeps per-warp
+    // top-k lists, and the last CTA to finish merges the 148 per-CTA lists and maps rows to ids.
+    // The only other stream operation is zeroing the nq ticket counters.
+    TS_CHECK_CUDA(cudaMemsetAsync(w.tickets, 0, (size_t)nq * sizeof(uint32_t), s));
+    ScanFused f;
+    f.q_raw = queries;
+    f.q_dtype = q_dtype;
+    f.q_normalize = normalize_queries;
+    f.tickets = w.tickets;
+    f.id_map = ix->has_ids ? ix->ids : nullptr;
+    f.out_keys = out_keys;
+    f.out_scores = out_scores;
+    f.out_ids = out_ids;
+    return launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, w.part_keys, w.nparts,
+                            s, ev0, ev1, nullptr, nullptr, &f);
 }
 
 }  // namespace ts

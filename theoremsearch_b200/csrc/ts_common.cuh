@@ -292,12 +292,23 @@ int launch_dequant_rows(const void* src, int src_dtype, int64_t n, int dim, int 
                         cudaStream_t s);
 int launch_prepare_queries(const void* q, int q_dtype, int nq, int dim, int dim_pad, int normalize,
                            float* out_f32, cudaStream_t s);
-// K2: per-CTA candidate lists part_keys[nq][nparts][k]; returns nparts through *nparts_out
+// K2: per-CTA candidate lists part_keys[nq][nparts][k]
 int scan_nparts(const ts_index* ix);
+// Optional fused stages of K2: in-kernel query normalisation and in-kernel final merge.
+struct ScanFused {
+    const void* q_raw;      // caller's queries [nq, dim] (nullptr: read prepared fp32 queries instead)
+    int q_dtype, q_normalize;
+    uint32_t* tickets;      // [nq] zeroed counters (nullptr: no fused merge, only part_keys are written)
+    const int64_t* id_map;
+    uint64_t* out_keys;     // any of the three may be nullptr
+    float* out_scores;
+    int64_t* out_ids;
+};
 int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64_t n_rows,
                      const float* queries_f32, int nq, int k, const uint32_t* allow_mask,
                      uint64_t* part_keys, int nparts, cudaStream_t s, cudaEvent_t ev0,
-                     cudaEvent_t ev1, const int* qlist = nullptr, const int* qcount = nullptr);
+                     cudaEvent_t ev1, const int* qlist = nullptr, const int* qcount = nullptr,
+                     const ScanFused* fused = nullptr);
 // K5: lists[nlists][nq][k] (list-major) or [nq][nlists][k] (query-major) -> top-k
 int launch_merge(const uint64_t* keys, int nlists, int nq, int k, bool query_major,
                  const int64_t* list_base, const int64_t* id_map, uint64_t* out_keys,
