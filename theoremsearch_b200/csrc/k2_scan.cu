@@ -27,6 +27,7 @@
 #include <algorithm>
 
 #include "merge_device.cuh"
+#include "scan_device.cuh"
 
 namespace ts {
 
@@ -57,69 +58,6 @@ __device__ __forceinline__ float load_query_elem(const void* base, int dtype, si
     if (dtype == TS_F32) return __ldg(reinterpret_cast<const float*>(base) + idx);
     if (dtype == TS_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
     return __half2float(reinterpret_cast<const __half*>(base)[idx]);
-}
-
-template <int NCHUNK>
-struct RowsPerTile {
-    static constexpr int value = NCHUNK == 1 ? 16 : (NCHUNK == 2 ? 8 : (NCHUNK <= 4 ? 4 : 2));
-};
-
-// dot of one 16-byte chunk with the matching slice of q
-template <int ELEM>
-struct Chunk;
-template <>
-struct Chunk<2> {  // 8 bf16
-    static constexpr int N = 8;
-    __device__ static __forceinline__ float dot(const uint4& v, const float* q, float acc) {
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            acc = fmaf(__uint_as_float(w[i] << 16), q[2 * i], acc);
-            acc = fmaf(__uint_as_float(w[i] & 0xFFFF0000u), q[2 * i + 1], acc);
-        }
-        return acc;
-    }
-};
-template <>
-struct Chunk<4> {  // 4 fp32
-    static constexpr int N = 4;
-    __device__ static __forceinline__ float dot(const uint4& v, const float* q, float acc) {
-        acc = fmaf(__uint_as_float(v.x), q[0], acc);
-        acc = fmaf(__uint_as_float(v.y), q[1], acc);
-        acc = fmaf(__uint_as_float(v.z), q[2], acc);
-        acc = fmaf(__uint_as_float(v.w), q[3], acc);
-        return acc;
-    }
-};
-
-// Transposing reduction: in: a[r] = this lane's partial sum for row r of the tile.
-// out: a[0] = full sum for row `row_of_lane(lane)`, replicated over a group of 32/R lanes.
-template <int R>
-__device__ __forceinline__ void transpose_reduce(float (&a)[R], int lane) {
-    int o = 16;
-#pragma unroll
-    for (int r = R; r > 1; r >>= 1) {
-        const bool upper = (lane & o) != 0;
-#pragma unroll
-        for (int i = 0; i < r / 2; ++i) {
-            float send = upper ? a[i] : a[i + r / 2];
-            float keep = upper ? a[i + r / 2] : a[i];
-            a[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, o);
-        }
-        o >>= 1;
-    }
-#pragma unroll
-    for (; o > 0; o >>= 1) a[0] += __shfl_xor_sync(0xFFFFFFFFu, a[0], o);
-}
-template <int R>
-__device__ __forceinline__ int row_of_lane(int lane) {
-    int row = 0, o = 16;
-#pragma unroll
-    for (int r = R; r > 1; r >>= 1) {
-        if (lane & o) row += r / 2;
-        o >>= 1;
-    }
-    return row;
 }
 
 template <int ELEM, int NCHUNK, int KPL, int R>
