@@ -170,25 +170,56 @@ TS_API int ts_ctx_set_timing(ts_ctx* ctx, int enabled);
 TS_API float ts_ctx_last_kernel_ms(const ts_ctx* ctx);
 
 /* ---- IVF-Flat (pgvector `ivfflat` equivalent; the reference never creates the index,
- * rds_schema.sql has no CREATE INDEX — BASELINE.json config 5 asks for it) ------------- */
+ * rds_schema.sql has no CREATE INDEX, so production runs the exact scan of
+ * streamlit_app.py:275-282 — BASELINE.json config 5 asks for the ANN variant) ----------
+ * Semantics restated from pgvector's ivfflat: k-means centroids over a sample, every row
+ * filed under its nearest centroid (inner product on unit vectors), a query ranks only the
+ * rows of its `nprobe` nearest lists.  The corpus must be stored as TS_BF16. */
 
-/* Spherical k-means over `n_sample` device rows [n_sample, dim] fp32 -> nlist centroids. */
+/* Spherical k-means (`iters` Lloyd iterations from `nlist` distinct seeded sample rows)
+ * -> nlist unit centroids.  sample: device fp32 [n_sample, dim] (normalised internally), or
+ * NULL = train on every (size/n_sample)-th STORED row in place (n_sample <= 0: all rows).
+ * Kernel K4a (tcgen05 GEMM + fused arg-max) does the assignment step. Synchronises. */
 TS_API int ts_ivf_train(ts_index* index, const float* sample, int64_t n_sample, int nlist,
                         int iters, uint64_t seed, void* stream);
-/* Assign every stored row to its nearest centroid and build the inverted lists
- * (row permutation + list offsets); list rows are stored as `list_dtype` (BF16 or FP8_E4M3). */
+/* Install centroids computed elsewhere (device fp32 [nlist, dim], taken as given) — how the
+ * ranks of a sharded index share one coarse quantiser (train on rank 0, broadcast). */
+TS_API int ts_ivf_set_centroids(ts_index* index, const float* centroids, int nlist, void* stream);
+/* Copy the centroids to a device buffer float[nlist, dim]. */
+TS_API int ts_ivf_get_centroids(const ts_index* index, float* out, void* stream);
+/* Assign every stored row to its nearest centroid (ties -> lower list) and build the
+ * inverted lists: rows permuted into (list, ascending row) order, stored as `list_dtype`:
+ * TS_BF16 (verbatim) or TS_FP8_E4M3 (e4m3 + one fp32 scale per row, scale = max|x|/448).
+ * Synchronises. */
 TS_API int ts_ivf_build(ts_index* index, int list_dtype, void* stream);
 TS_API size_t ts_ivf_workspace_bytes(const ts_index* index, int nq, int k, int nprobe,
                                      int rescore_k);
-/* ANN search: coarse top-nprobe centroids, scan those lists, keep rescore_k candidates,
- * rescore them against the full-precision rows, return top-k. */
+/* ANN search: exact top-nprobe centroids per query (K2/K3 over the centroid table), scan of
+ * those lists keeping max(k, rescore_k) candidates by list-precision score (K4b), exact
+ * re-score of the candidates against the stored bf16 rows with the fp32 query (K4c; returned
+ * scores are bit-identical to ts_search's for the same rows), top-k out.  Same output
+ * conventions as ts_search. nprobe is clamped to min(nlist, TS_MAX_K). */
 TS_API int ts_ivf_search(ts_index* index, const void* queries, int q_dtype, int nq, int k,
                          int nprobe, int rescore_k, int normalize_queries, float* out_scores,
                          int64_t* out_ids, void* workspace, size_t workspace_bytes,
                          void* stream);
+/* Same, returning packed keys out_keys[nq, k] (score, local row): the all-gather payload of
+ * the sharded IVF path, merged by ts_merge_topk. */
+TS_API int ts_ivf_search_keys(ts_index* index, const void* queries, int q_dtype, int nq, int k,
+                              int nprobe, int rescore_k, int normalize_queries,
+                              uint64_t* out_keys, void* workspace, size_t workspace_bytes,
+                              void* stream);
 TS_API int ts_ivf_nlist(const ts_index* index);
 /* Copy list sizes (int64[nlist]) to a device buffer — for balance diagnostics. */
 TS_API int ts_ivf_list_sizes(const ts_index* index, int64_t* out, void* stream);
+/* Copy the list layout to device buffers: offsets int64[nlist+1] (list l occupies positions
+ * [offsets[l], offsets[l+1])) and rows int64[size] (corpus row at each position). Either may
+ * be NULL. What parity tests feed the oracle. */
+TS_API int ts_ivf_get_lists(const ts_index* index, int64_t* offsets_out, int64_t* rows_out,
+                            void* stream);
+/* List rows at positions [first, first+n) dequantised to fp32 into device out[n, dim]. */
+TS_API int ts_ivf_get_list_data(const ts_index* index, int64_t first, int64_t n, float* out,
+                                void* stream);
 
 /* ---- tuning / diagnostics (not part of the drop-in surface) -------------------------- */
 

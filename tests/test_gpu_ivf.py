@@ -1,0 +1,235 @@
+"""GPU parity tests for the IVF-Flat path (K4a assignment GEMM, list build + e4m3 quantisation,
+K4b list scan, K4c re-score), through the C ABI.  Oracle: oracle.ivf_assign / oracle.ivf_search /
+oracle.quantize_fp8_e4m3 fed with the index's OWN centroids and stored rows ("same inputs").
+
+Bars: list layout and e4m3 quantisation bit-exact; assignment equal to the fp64 arg-max except
+where the two best centroids are closer than ASSIGN_EPS (fp32 tensor-core accumulation);
+bf16-list search equal to the oracle's exact top-k over the probed lists (same tie window as the
+exact path); fp8-list search: returned scores exact (re-scored) and recall vs the oracle's
+probed-list top-k >= 0.99 (BASELINE.json reports IVF as recall@10)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 1e-5
+TIE_EPS = 2e-6
+ASSIGN_EPS = 2e-5
+
+
+@pytest.fixture(scope="module")
+def ts():
+    import theoremsearch_b200 as ts
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return ts
+
+
+def clustered_rows(n, d, ncenters, sigma, seed):
+    rng = np.random.default_rng(seed)
+    centers = rng.standard_normal((ncenters, d)).astype(np.float32)
+    centers /= np.linalg.norm(centers, axis=1, keepdims=True)
+    which = rng.integers(0, ncenters, n)
+    x = centers[which] + sigma * rng.standard_normal((n, d)).astype(np.float32) / np.sqrt(d)
+    return x.astype(np.float32)
+
+
+def built(ts, rows, nlist, list_dtype, iters=4, seed=3, ids=None):
+    index = ts.build_index(rows, dtype="bf16", normalize=True, ids=ids)
+    index.ivf_train(nlist, iters=iters, seed=seed)
+    index.ivf_build(list_dtype)
+    return index
+
+
+def layout(index):
+    off, rows = index.ivf_lists()
+    return off.cpu().numpy(), rows.cpu().numpy()
+
+
+def assignment_from_lists(off, rows, n):
+    assign = np.empty(n, dtype=np.int64)
+    for l in range(len(off) - 1):
+        assign[rows[off[l]:off[l + 1]]] = l
+    return assign
+
+
+@pytest.mark.parametrize("n,d,nlist", [(5000, 1024, 37), (3000, 768, 256), (2000, 100, 300), (700, 64, 5)])
+def test_assignment_and_list_layout(ts, n, d, nlist):
+    x = clustered_rows(n, d, 50, 0.7, seed=n + d)
+    index = built(ts, x, nlist, "bf16")
+    assert index.nlist == nlist
+    off, rows = layout(index)
+    # layout: offsets ascending from 0 to n, rows a permutation, ascending inside each list
+    assert off[0] == 0 and off[-1] == n and np.all(np.diff(off) >= 0)
+    assert np.array_equal(np.sort(rows), np.arange(n))
+    for l in range(nlist):
+        seg = rows[off[l]:off[l + 1]]
+        assert np.all(np.diff(seg) > 0)
+    assert np.array_equal(index.ivf_list_sizes().cpu().numpy(), np.diff(off))
+    # assignment: nearest centroid of the bf16 centroid table the GEMM reads
+    stored = index.get_rows().cpu().numpy()
+    cent = oracle.bf16_round(index.ivf_centroids().cpu().numpy())
+    s = stored.astype(np.float64) @ cent.astype(np.float64).T
+    want = np.argmax(s, axis=1)
+    got = assignment_from_lists(off, rows, n)
+    bad = np.nonzero(got != want)[0]
+    for r in bad:   # only near-ties may differ
+        assert s[r, want[r]] - s[r, got[r]] <= ASSIGN_EPS, (r, got[r], want[r], s[r, want[r]], s[r, got[r]])
+    assert bad.size <= max(2, n // 200)
+    # centroids are unit vectors (spherical k-means)
+    cn = np.linalg.norm(index.ivf_centroids().cpu().numpy().astype(np.float64), axis=1)
+    assert np.max(np.abs(cn - 1.0)) < 1e-2
+
+
+@pytest.mark.parametrize("d", [1024, 768, 100])
+def test_fp8_list_quantisation_bit_exact(ts, d):
+    x = clustered_rows(3000, d, 20, 0.8, seed=d)
+    x[17] = 0.0   # all-zero row: scale 1, all zeros
+    index = built(ts, x, 16, "fp8")
+    off, rows = layout(index)
+    stored = index.get_rows().cpu().numpy()
+    want, _ = oracle.quantize_fp8_e4m3(stored[rows])
+    got = index.ivf_list_data().cpu().numpy()
+    assert np.array_equal(got, want)
+    # bf16 lists hold the stored rows verbatim
+    index.ivf_build("bf16")
+    off, rows = layout(index)
+    assert np.array_equal(index.ivf_list_data().cpu().numpy(), stored[rows])
+
+
+def oracle_probed_topk(index, q_prepared, k, nprobe, skip_eps=1e-6):
+    """oracle.ivf_search per query on the index's own centroids/lists. Returns list of
+    (scores, ids) or None where the probe set itself sits on a near-tie."""
+    stored = index.get_rows().cpu().numpy()
+    cent = oracle.bf16_round(index.ivf_centroids().cpu().numpy())
+    off, rows = layout(index)
+    assign = assignment_from_lists(off, rows, stored.shape[0])
+    out = []
+    for q in q_prepared:
+        cs = np.sort(cent.astype(np.float64) @ q.astype(np.float64))[::-1]
+        if nprobe < len(cs) and cs[nprobe - 1] - cs[nprobe] < skip_eps:
+            out.append(None)
+            continue
+        out.append(oracle.ivf_search(q, stored, cent, assign, k, nprobe))
+    return out, stored
+
+
+@pytest.mark.parametrize("n,d,nlist,nprobe,k", [(6000, 1024, 64, 8, 10), (4000, 768, 40, 5, 20), (3000, 96, 100, 100, 5),
+                                               (2500, 1024, 30, 1, 10), (5000, 256, 33, 7, 100)])
+def test_bf16_lists_match_oracle_over_probed_lists(ts, n, d, nlist, nprobe, k):
+    x = clustered_rows(n, d, 40, 0.9, seed=7 * n)
+    index = built(ts, x, nlist, "bf16")
+    q = oracle.normalize_f64(clustered_rows(12, d, 40, 0.9, seed=7 * n))   # same centres: realistic queries
+    s, i = index.ivf_search(torch.from_numpy(q), k, nprobe=nprobe, rescore_k=k, normalize=False)
+    s, i = s.cpu().numpy(), i.cpu().numpy()
+    refs, stored = oracle_probed_topk(index, q, k, nprobe)
+    checked = 0
+    for qi, ref in enumerate(refs):
+        if ref is None:
+            continue
+        checked += 1
+        rs, ri = ref
+        valid = ri >= 0
+        assert np.array_equal(i[qi] >= 0, valid)
+        g, r = i[qi][valid], ri[valid]
+        alls = stored.astype(np.float64) @ q[qi].astype(np.float64)
+        if not np.array_equal(g, r):
+            assert len(set(g.tolist())) == g.size
+            assert np.all(np.abs(alls[g] - alls[r]) <= TIE_EPS), (qi, g, r)
+        assert np.max(np.abs(s[qi][valid] - alls[g]), initial=0.0) <= SCORE_TOL
+    assert checked >= 8
+
+
+def test_probing_every_list_is_exact_search(ts):
+    x = clustered_rows(8000, 1024, 30, 1.0, seed=5)
+    index = built(ts, x, 48, "bf16")
+    q = torch.from_numpy(oracle.synthetic_queries(9, 1024))
+    s_e, i_e = index.search(q, 10)
+    s_a, i_a = index.ivf_search(q, 10, nprobe=48, rescore_k=10)
+    assert torch.equal(i_e, i_a)
+    assert torch.equal(s_e, s_a)   # re-scored in K2's summation order: bit-identical
+
+
+def test_fp8_lists_recall_and_exact_scores(ts):
+    n, d, nlist, nprobe, k = 30000, 1024, 64, 8, 10
+    x = clustered_rows(n, d, 200, 0.9, seed=21)
+    index = built(ts, x, nlist, "fp8")
+    q = oracle.normalize_f64(clustered_rows(40, d, 200, 0.9, seed=21))
+    s, i = index.ivf_search(torch.from_numpy(q), k, nprobe=nprobe, rescore_k=100, normalize=False)
+    s, i = s.cpu().numpy(), i.cpu().numpy()
+    refs, stored = oracle_probed_topk(index, q, k, nprobe)
+    hits = tot = 0
+    for qi, ref in enumerate(refs):
+        alls = stored.astype(np.float64) @ q[qi].astype(np.float64)
+        g = i[qi]
+        assert np.all(g >= 0) and len(set(g.tolist())) == k
+        assert np.max(np.abs(s[qi] - alls[g])) <= SCORE_TOL        # scores are the exact (re-scored) ones
+        assert np.all(np.diff(s[qi]) <= 0)
+        if ref is None:
+            continue
+        hits += len(set(g.tolist()) & set(ref[1].tolist()))
+        tot += k
+    assert hits / tot >= 0.99, hits / tot
+    # and against the unrestricted exact search the probe budget decides: report, loosely bounded
+    _, i_exact = index.search(torch.from_numpy(q), k, normalize=False)
+    assert oracle.recall_at_k(i, i_exact.cpu().numpy()) >= 0.6
+
+
+@pytest.mark.parametrize("list_dtype", ["bf16", "fp8"])
+def test_batched_queries_equal_single_queries(ts, list_dtype):
+    x = clustered_rows(20000, 1024, 100, 0.9, seed=33)
+    index = built(ts, x, 128, list_dtype)
+    q = torch.from_numpy(oracle.normalize_f64(clustered_rows(70, 1024, 100, 0.9, seed=33)))
+    s_b, i_b = index.ivf_search(q, 10, nprobe=16, rescore_k=64)     # coarse step on the tcgen05 path
+    for qi in range(0, 70, 7):
+        s_1, i_1 = index.ivf_search(q[qi], 10, nprobe=16, rescore_k=64)   # coarse step on the scan path
+        assert torch.equal(i_b[qi], i_1[0]) and torch.equal(s_b[qi], s_1[0])
+
+
+def test_empty_lists_ids_and_keys(ts):
+    base = clustered_rows(40, 128, 4, 0.2, seed=1)
+    x = np.repeat(base, 25, axis=0)                  # 1000 rows, only 40 distinct -> many empty lists
+    ids = np.arange(1000, dtype=np.int64) * 3 + 11
+    index = built(ts, x, 200, "fp8", ids=ids)
+    off, rows = layout(index)
+    assert (np.diff(off) == 0).sum() >= 100
+    q = torch.from_numpy(oracle.normalize_f64(base[:5]))
+    s, i = index.ivf_search(q, 30, nprobe=200, rescore_k=200, normalize=False)
+    s_e, i_e = index.search(q, 30, normalize=False)
+    assert torch.equal(s, s_e) and torch.equal(i, i_e)       # duplicates: ties -> lower row, via caller ids
+    keys = index.ivf_search_keys(q, 30, nprobe=200, rescore_k=200, normalize=False)
+    s_m, i_m = ts.merge_topk(keys.unsqueeze(0), 30)
+    assert torch.equal(s_m, s)
+    assert torch.equal(i_m * 3 + 11, i)
+    # fewer eligible rows than k: padding
+    s2, i2 = index.ivf_search(q[:1], 50, nprobe=1, rescore_k=50, normalize=False)
+    n_in_list = int((i2[0] >= 0).sum())
+    assert 0 < n_in_list <= 50
+    assert torch.all(torch.isneginf(s2[0][n_in_list:])) and torch.all(i2[0][n_in_list:] == -1)
+
+
+def test_shared_centroids_and_state_errors(ts):
+    x = clustered_rows(4000, 256, 30, 0.8, seed=9)
+    a = built(ts, x, 32, "bf16")
+    b = ts.build_index(x, dtype="bf16", normalize=True)
+    with pytest.raises(ts.TheoremSearchError) as e:
+        b.ivf_search(torch.zeros(1, 256), 5)
+    assert e.value.code == -6
+    with pytest.raises(ts.TheoremSearchError) as e:
+        b.ivf_build("bf16")
+    assert e.value.code == -6
+    b.ivf_set_centroids(a.ivf_centroids())
+    b.ivf_build("bf16")
+    for u, v in zip(layout(a), layout(b)):
+        assert np.array_equal(u, v)
+    # explicit sample training
+    c = ts.build_index(x, dtype="bf16", normalize=True, capacity=4010)
+    c.ivf_train(32, sample=torch.from_numpy(x[::2]).cuda(), iters=3, seed=1)
+    c.ivf_build("fp8")
+    assert int(c.ivf_list_sizes().sum()) == 4000
+    # adding rows invalidates the lists
+    c.add(x[:10])
+    with pytest.raises(ts.TheoremSearchError):
+        c.ivf_search(torch.zeros(1, 256), 5)

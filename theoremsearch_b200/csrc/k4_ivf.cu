@@ -1,0 +1,1201 @@
+// K4 — IVF-Flat (the pgvector `ivfflat` equivalent BASELINE.json config 5 asks for).
+//
+// The reference never creates the index (rds_schema.sql has no CREATE INDEX, so production runs the
+// exact seq-scan of streamlit_app.py:275-282); pgvector's ivfflat semantics are what is restated:
+// k-means centroids over a sample, every row filed under its nearest centroid, a query probes the
+// `nprobe` nearest lists and ranks only their rows.
+//
+// Kernels
+//   K4a assign_argmax_kernel   rows x centroids bf16 GEMM on tcgen05/TMEM with the arg-max over
+//                              centroids fused into the epilogue (thread <-> row, columns <-> centroids,
+//                              so the running maximum is thread-local). Tensor-bound: 2*N*nlist*D FLOPs.
+//                              Used by k-means (sample rows) and by the build (all rows).
+//   update_centroids_kernel    spherical k-means update: one CTA per centroid sums its rows in ascending
+//                              row order (deterministic, no atomics), normalises, re-seeds empty lists.
+//   gather_quantize_kernel     build: rows permuted into list order, stored e4m3 with one fp32 scale per
+//                              row (scale = max|x|/448) or as bf16.
+//   K4b list_scan_kernel       search: the probed lists of one query form one virtual row sequence that is
+//                              split evenly over all warps of `parts` CTAs; per-warp 1-D TMA pipelines,
+//                              the same dot/transposing-reduce/WarpTopK body as K2, last CTA merges.
+//                              HBM-bound: (rows in probed lists) * row_bytes per query.
+//   K4c ivf_rescore_kernel     the rescore_k survivors are re-scored against the full-precision corpus
+//                              rows with the fp32 query in K2's summation order (so returned scores are
+//                              bit-identical to the exact path's), sorted, top-k emitted.
+// The coarse step (top-nprobe centroids) is the exact-search path itself (K2 / K3) run over the
+// centroid table.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <vector>
+
+#include "merge_device.cuh"
+#include "scan_device.cuh"
+#include "umma_device.cuh"
+
+namespace ts {
+
+namespace k4 {
+using namespace umma;
+constexpr int STAGES = 4;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
+constexpr int THREADS = 192;
+constexpr int EPI_THREADS = 128;
+constexpr size_t SMEM_TILES = (size_t)STAGES * (A_BYTES + B_BYTES);
+constexpr size_t SMEM_BYTES = SMEM_TILES + 16 * sizeof(uint64_t) + 1024;
+}  // namespace k4
+
+struct AssignParams {
+    int64_t n_rows;
+    int nlist;
+    int num_k_blocks, num_m_blocks, num_n_blocks;
+    int bn;              // centroids per n-block (multiple of 32, <= 256)
+    uint32_t* assign;    // [n_rows] nearest centroid (ties -> lower centroid)
+    float* best;         // [n_rows] its score, or nullptr
+};
+
+// ---------------------------------------------------------------------------------- K4a
+__global__ void __launch_bounds__(k4::THREADS, 1)
+assign_argmax_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const AssignParams p) {
+    using namespace k4;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + (size_t)STAGES * A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_TILES);
+    uint64_t* full = bars;              // [STAGES]
+    uint64_t* empty = bars + 4;         // [STAGES]
+    uint64_t* tmem_full = bars + 8;     // [ACC_STAGES]
+    uint64_t* tmem_empty = bars + 10;   // [ACC_STAGES]
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < ACC_STAGES; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], EPI_THREADS);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
+                     "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    // A CTA owns whole m-blocks (128 rows) and walks every centroid block for them, so the running
+    // arg-max never leaves the epilogue thread's registers.
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint64_t pol_a = l2_policy_evict_first();
+            const uint64_t pol_b = l2_policy_evict_last();   // the centroid table is re-read by every m-block
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int mb = blockIdx.x; mb < p.num_m_blocks; mb += gridDim.x) {
+                for (int nb = 0; nb < p.num_n_blocks; ++nb) {
+                    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                        mbar_wait_wd(&empty[stage], phase ^ 1u);
+                        mbar_expect_tx(&full[stage], A_BYTES + (uint32_t)p.bn * (BK * 2));
+                        tma_load_2d(smem_a + (size_t)stage * A_BYTES, &tmap_a, kb * BK, mb * BM, &full[stage], pol_a);
+                        tma_load_2d(smem_b + (size_t)stage * B_BYTES, &tmap_b, kb * BK, nb * p.bn, &full[stage], pol_b);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) |
+                                   ((uint32_t)(BM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int mb = blockIdx.x; mb < p.num_m_blocks; mb += gridDim.x) {
+                for (int nb = 0; nb < p.num_n_blocks; ++nb, ++it) {
+                    const int acc = it & 1;
+                    const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                    mbar_wait_wd(&tmem_empty[acc], acc_phase ^ 1u);
+                    tcgen05_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                        mbar_wait_wd(&full[stage], phase);
+                        tcgen05_fence_after();
+                        const uint64_t da = umma_smem_desc(smem_a + (size_t)stage * A_BYTES);
+                        const uint64_t db = umma_smem_desc(smem_b + (size_t)stage * B_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        tcgen05_commit(&empty[stage]);
+                        if (kb == p.num_k_blocks - 1) tcgen05_commit(&tmem_full[acc]);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        const int lane_base = 32 * (warp & 3);
+        int it = 0;
+        for (int mb = blockIdx.x; mb < p.num_m_blocks; mb += gridDim.x) {
+            float best = -INFINITY;
+            uint32_t best_idx = 0;
+            for (int nb = 0; nb < p.num_n_blocks; ++nb, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                const int c0 = nb * p.bn;
+                const int valid = (p.nlist - c0 < p.bn) ? (p.nlist - c0) : p.bn;   // real centroids in this block
+                mbar_wait_wd(&tmem_full[acc], acc_phase);
+                tcgen05_fence_after();
+                const uint32_t taddr0 = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+                for (int c = 0; c * 32 < valid; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c * 32), v);
+                    tmem_ld_wait();
+                    if (c * 32 + 32 <= valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float f = __uint_as_float(v[j]);
+                            if (f > best) {   // strict: the lower centroid keeps a tie
+                                best = f;
+                                best_idx = (uint32_t)(c0 + c * 32 + j);
+                            }
+                        }
+                    } else {   // ragged tail: columns >= valid are zero-filled padding, not centroids
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float f = __uint_as_float(v[j]);
+                            if (c * 32 + j < valid && f > best) {
+                                best = f;
+                                best_idx = (uint32_t)(c0 + c * 32 + j);
+                            }
+                        }
+                    }
+                }
+                tcgen05_fence_before();
+                mbar_arrive(&tmem_empty[acc]);
+            }
+            const int64_t row = (int64_t)mb * BM + lane_base + lane;
+            if (row < p.n_rows) {
+                p.assign[row] = best_idx;
+                if (p.best != nullptr) p.best[row] = best;
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// rows: bf16, `row_stride` bytes apart (a strided view of the corpus is a valid sample); centroids: bf16
+// [nlist, dim_pad] contiguous.
+static int launch_assign(int device, const void* rows, int64_t n_rows, size_t row_stride, const __nv_bfloat16* cent,
+                         int nlist, int dim_pad, uint32_t* assign, float* best, cudaStream_t s) {
+    using namespace k4;
+    if (n_rows == 0) return TS_OK;
+    TS_REQUIRE(n_rows < (int64_t)1 << 31, TS_ERR_UNSUPPORTED, "ivf assign: more than 2^31-1 rows");
+    CUtensorMap tmap_a, tmap_b;
+    int rc = make_tmap_bf16_rows(&tmap_a, rows, (uint64_t)n_rows, (uint64_t)dim_pad, row_stride, BM);
+    if (rc) return rc;
+    AssignParams p;
+    p.n_rows = n_rows;
+    p.nlist = nlist;
+    p.num_k_blocks = (dim_pad + BK - 1) / BK;
+    p.num_m_blocks = (int)((n_rows + BM - 1) / BM);
+    p.num_n_blocks = (nlist + BN - 1) / BN;
+    p.bn = ((nlist + p.num_n_blocks - 1) / p.num_n_blocks + 31) / 32 * 32;
+    p.assign = assign;
+    p.best = best;
+    rc = make_tmap_bf16_rows(&tmap_b, cent, (uint64_t)nlist, (uint64_t)dim_pad, (uint64_t)dim_pad * 2, (uint32_t)p.bn);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TS_CHECK_CUDA(cudaFuncSetAttribute(assign_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)SMEM_BYTES));
+        attr_set = true;
+    }
+    const int grid = std::min(p.num_m_blocks, sm_count(device));
+    assign_argmax_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(tmap_a, tmap_b, p);
+    TS_LAUNCH_CHECK();
+    return TS_OK;
+}
+
+// ---------------------------------------------------------------------------------- k-means pieces
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// centroid c starts as sample row c*step + hash % step: nlist distinct rows spread over the sample
+__global__ void __launch_bounds__(256) init_centroids_kernel(const uint8_t* __restrict__ rows, size_t row_stride,
+                                                             int64_t n_rows, int nlist, int dim_pad, uint64_t seed,
+                                                             float* __restrict__ cent, __nv_bfloat16* __restrict__ cent16) {
+    const int c = blockIdx.x;
+    const int64_t step = n_rows / nlist;
+    const int64_t r = (int64_t)c * step + (int64_t)(splitmix64(seed ^ (uint64_t)c) % (uint64_t)step);
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(rows + (size_t)r * row_stride);
+    for (int i = threadIdx.x; i < dim_pad; i += blockDim.x) {
+        cent[(size_t)c * dim_pad + i] = __bfloat162float(src[i]);
+        cent16[(size_t)c * dim_pad + i] = src[i];
+    }
+}
+
+__global__ void iota_u32_kernel(uint32_t* out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (uint32_t)i;
+}
+
+// offsets[c] = first position in the ascending `sorted_assign` whose list id is >= c  (c in [0, nlist])
+__global__ void list_offsets_kernel(const uint32_t* __restrict__ sorted_assign, int64_t n, int nlist,
+                                    int64_t* __restrict__ offsets) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > nlist) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (sorted_assign[mid] < (uint32_t)c) lo = mid + 1; else hi = mid;
+    }
+    offsets[c] = lo;
+}
+
+// One CTA per centroid: sum of its member rows (ascending row order), normalised. Empty or
+// degenerate lists are re-seeded from a pseudo-random sample row.
+__global__ void __launch_bounds__(256) update_centroids_kernel(const uint8_t* __restrict__ rows, size_t row_stride,
+                                                               int64_t n_rows, const uint32_t* __restrict__ members,
+                                                               const int64_t* __restrict__ offsets, int dim_pad,
+                                                               uint64_t seed, float* __restrict__ cent,
+                                                               __nv_bfloat16* __restrict__ cent16) {
+    constexpr int MAXC = TS_MAX_DIM / 256;   // columns per thread
+    __shared__ float red[8];
+    __shared__ float s_norm;
+    const int c = blockIdx.x;
+    const int64_t b = offsets[c], e = offsets[c + 1];
+    float sum[MAXC];
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) sum[i] = 0.f;
+#pragma unroll 4
+    for (int64_t m = b; m < e; ++m) {
+        const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(rows + (size_t)members[m] * row_stride);
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            const int col = threadIdx.x + 256 * i;
+            if (col < dim_pad) sum[i] += __bfloat162float(src[col]);
+        }
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) ss = fmaf(sum[i], sum[i], ss);
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        s_norm = sqrtf(t);
+    }
+    __syncthreads();
+    const float nrm = s_norm;
+    const bool reseed = !(nrm > 1e-20f);   // empty list, cancelling members, or NaN
+    const __nv_bfloat16* alt = nullptr;
+    if (reseed)
+        alt = reinterpret_cast<const __nv_bfloat16*>(
+            rows + (size_t)(splitmix64(seed ^ (0xABCDull << 32) ^ (uint64_t)c) % (uint64_t)n_rows) * row_stride);
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int col = threadIdx.x + 256 * i;
+        if (col < dim_pad) {
+            const float v = reseed ? __bfloat162float(alt[col]) : __fdiv_rn(sum[i], nrm);
+            cent[(size_t)c * dim_pad + col] = v;
+            cent16[(size_t)c * dim_pad + col] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+// max ||centroid_bf16||^2 (the exactness certificate of the batched coarse search needs the bound)
+__global__ void __launch_bounds__(256) max_norm2_bf16_kernel(const __nv_bfloat16* __restrict__ rows, int n, int dim_pad,
+                                                             float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n) return;
+    float s = 0.f;
+    for (int i = lane; i < dim_pad; i += 32) {
+        const float v = __bfloat162float(rows[(size_t)r * dim_pad + i]);
+        s = fmaf(v, v, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(s));
+}
+
+// ---------------------------------------------------------------------------------- build: permute + quantise
+// One warp per list position: fetch the corpus row filed there, store it as e4m3 with a per-row scale
+// (scale = max|x| / 448, 1 for an all-zero row; q = e4m3_rn(x / scale), saturating) or as bf16.
+template <int LIST_ELEM>
+__global__ void __launch_bounds__(256) gather_quantize_kernel(const uint8_t* __restrict__ corpus, uint32_t src_row_bytes,
+                                                              const uint32_t* __restrict__ list_rows, int64_t n,
+                                                              int dim_pad, uint32_t dst_row_bytes,
+                                                              uint8_t* __restrict__ dst, float* __restrict__ scales) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    for (int64_t pos = w0; pos < n; pos += (int64_t)gridDim.x * 8) {
+        const uint8_t* src = corpus + (size_t)list_rows[pos] * src_row_bytes;
+        uint8_t* out = dst + (size_t)pos * dst_row_bytes;
+        if constexpr (LIST_ELEM == 2) {
+            for (uint32_t off = lane * 16u; off < dst_row_bytes; off += 512u)
+                *reinterpret_cast<uint4*>(out + off) = __ldg(reinterpret_cast<const uint4*>(src + off));
+        } else {
+            float amax = 0.f;
+            for (uint32_t off = lane * 16u; off < src_row_bytes; off += 512u) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + off));
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    amax = fmaxf(amax, fabsf(__uint_as_float(w[i] << 16)));
+                    amax = fmaxf(amax, fabsf(__uint_as_float(w[i] & 0xFFFF0000u)));
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, o));
+            const float scale = amax > 0.f ? __fdiv_rn(amax, 448.0f) : 1.0f;
+            if (lane == 0) scales[pos] = scale;
+            // 16 output bytes per lane per step = 16 elements = 32 source bytes
+            for (uint32_t ob = lane * 16u; ob < dst_row_bytes; ob += 512u) {
+                uint32_t packed[4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t sb = ob * 2u + h * 16u;
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (sb < src_row_bytes) v = __ldg(reinterpret_cast<const uint4*>(src + sb));
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i += 2) {
+                        const float a0 = __fdiv_rn(__uint_as_float(w[i] << 16), scale);
+                        const float a1 = __fdiv_rn(__uint_as_float(w[i] & 0xFFFF0000u), scale);
+                        const float a2 = __fdiv_rn(__uint_as_float(w[i + 1] << 16), scale);
+                        const float a3 = __fdiv_rn(__uint_as_float(w[i + 1] & 0xFFFF0000u), scale);
+                        const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a0, a1), __NV_SATFINITE, __NV_E4M3);
+                        const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(a2, a3), __NV_SATFINITE, __NV_E4M3);
+                        packed[h * 2 + i / 2] = lo | (hi << 16);
+                    }
+                }
+                *reinterpret_cast<uint4*>(out + ob) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+        }
+    }
+}
+
+// dequantise list positions [first, first+n) to fp32 [n, dim] (tests / diagnostics)
+__global__ void dequant_list_kernel(const uint8_t* __restrict__ data, uint32_t row_bytes, int list_dtype,
+                                    const float* __restrict__ scales, int64_t first, int64_t n, int dim,
+                                    float* __restrict__ out) {
+    const int64_t total = n * (int64_t)dim;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / dim;
+        const int c = (int)(t - r * dim);
+        const uint8_t* row = data + (size_t)(first + r) * row_bytes;
+        float v;
+        if (list_dtype == TS_BF16) {
+            v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(row)[c]);
+        } else {
+            const __half_raw h = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)row[c], __NV_E4M3);
+            v = __half2float(*reinterpret_cast<const __half*>(&h)) * scales[first + r];
+        }
+        out[t] = v;
+    }
+}
+
+__global__ void widen_u32_kernel(const uint32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (int64_t)in[i];
+}
+__global__ void list_sizes_kernel(const int64_t* __restrict__ offsets, int nlist, int64_t* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < nlist) out[c] = offsets[c + 1] - offsets[c];
+}
+
+// ---------------------------------------------------------------------------------- K4b list scan
+struct ListScanParams {
+    const uint8_t* list_data;     // [n, row_bytes] rows in list order
+    uint32_t row_bytes;           // multiple of 16
+    int dim_pad;                  // valid fp32 query elements
+    const float* scales;          // [n] per-row scale (fp8 lists) or nullptr
+    const int64_t* list_offsets;  // [nlist + 1]
+    const uint64_t* probes;       // [nq, nprobe] packed (score, list) keys from the coarse step; 0 = none
+    int nprobe;
+    const float* queries;         // [nq, dim_pad] fp32 normalised
+    int k;                        // candidates kept per query (rescore_k)
+    uint64_t* part_keys;          // [nq][gridDim.x][k]
+    uint32_t* tickets;            // [nq] zero on entry, left zero
+    uint64_t* out_keys;           // [nq][k] merged candidates, key row = list POSITION
+    int stages;
+};
+
+template <int ELEM, int NCHUNK, int KPL, int R>
+__global__ void __launch_bounds__(512, 1) list_scan_kernel(const ListScanParams p) {
+    constexpr int CN = Chunk<ELEM>::N;
+    constexpr int GROUP = 32 / R;
+    extern __shared__ __align__(128) uint8_t smem[];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int W = blockDim.x >> 5;
+    const int stages = p.stages;
+    const uint32_t tile_bytes = R * p.row_bytes;
+    const int qi = blockIdx.y;
+    const int nprobe = p.nprobe;
+
+    uint8_t* my_slots = smem + (size_t)warp * stages * tile_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)W * stages * tile_bytes);
+    uint64_t* my_bars = bars + warp * stages;
+    // probed-list table: first position, length, tiles before this list
+    int64_t* s_start = reinterpret_cast<int64_t*>(bars + W * stages);
+    int* s_len = reinterpret_cast<int*>(s_start + nprobe);
+    int* s_tpref = s_len + nprobe;   // [nprobe + 1]
+
+    if (lane == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&my_bars[s], 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        int carry = 0;
+        for (int j0 = 0; j0 < nprobe; j0 += 32) {
+            const int j = j0 + lane;
+            int len = 0;
+            int64_t start = 0;
+            if (j < nprobe) {
+                const uint64_t key = p.probes[(size_t)qi * nprobe + j];
+                if (key != 0ull) {
+                    const uint32_t l = key_row(key);
+                    start = p.list_offsets[l];
+                    len = (int)(p.list_offsets[l + 1] - start);
+                }
+                s_start[j] = start;
+                s_len[j] = len;
+            }
+            int t = (len + R - 1) / R;
+            int inc = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= o) inc += u;
+            }
+            if (j < nprobe) s_tpref[j] = carry + inc - t;
+            carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
+        if (lane == 0) s_tpref[nprobe] = carry;
+    }
+    __syncthreads();
+
+    const int64_t T = s_tpref[nprobe];
+    const int64_t g = (int64_t)blockIdx.x * W + warp;
+    const int64_t G = (int64_t)gridDim.x * W;
+    const int t0 = (int)(T * g / G), t1 = (int)(T * (g + 1) / G);
+    const uint64_t policy = l2_policy_evict_first();
+    const int k = p.k;
+    const int my_row = row_of_lane<R>(lane);
+    const bool leader = (lane & (GROUP - 1)) == 0;
+
+    // cursor: (list slot j, tile tt inside it); both cursors start at tile t0
+    int jc = 0;
+    if (t0 < t1) {
+        int lo = 0, hi = nprobe - 1;   // largest j with s_tpref[j] <= t0
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_tpref[mid] <= t0) lo = mid; else hi = mid - 1;
+        }
+        jc = lo;
+        while (s_tpref[jc + 1] <= t0) ++jc;   // skip empty lists that share the prefix value
+    }
+    int tc = t0 - s_tpref[jc];
+    int ji = jc, ti = tc;
+    auto advance = [&](int& j, int& tt) {
+        ++tt;
+        while (j < nprobe && tt >= s_tpref[j + 1] - s_tpref[j]) {
+            ++j;
+            tt = 0;
+        }
+    };
+    auto issue = [&](int j, int tt, int s) {
+        const int64_t pos0 = s_start[j] + (int64_t)tt * R;
+        const int left = s_len[j] - tt * R;
+        const uint32_t bytes = (uint32_t)(left < R ? left : R) * p.row_bytes;
+        mbar_expect_tx(&my_bars[s], bytes);
+        tma_load_1d_hint(my_slots + (size_t)s * tile_bytes, p.list_data + (size_t)pos0 * p.row_bytes, bytes, &my_bars[s],
+                         policy);
+    };
+    {
+        int it = t0;
+        for (int s = 0; s < stages && it < t1; ++s, ++it) {
+            if (lane == 0) issue(ji, ti, s);
+            advance(ji, ti);
+        }
+    }
+
+    float q[NCHUNK * CN];
+    {
+        const float* qv = p.queries + (size_t)qi * p.dim_pad;
+#pragma unroll
+        for (int j = 0; j < NCHUNK; ++j) {
+            const int e0 = (j * 32 + lane) * CN;
+#pragma unroll
+            for (int i = 0; i < CN; ++i) q[j * CN + i] = (e0 + i < p.dim_pad) ? __ldg(qv + e0 + i) : 0.f;
+        }
+    }
+
+    WarpTopK<KPL> list;
+    list.clear();
+    uint64_t thr = 0ull;
+    int s = 0;
+    uint32_t parity = 0;
+    for (int t = t0; t < t1; ++t) {
+        const int left = s_len[jc] - tc * R;
+        const int64_t pos = s_start[jc] + (int64_t)tc * R + my_row;
+        const bool mine = leader && my_row < left;
+        float scale = 1.0f;
+        if (ELEM == 1 && mine) scale = __ldg(p.scales + pos);
+
+        mbar_wait(&my_bars[s], parity);
+        const uint8_t* slot = my_slots + (size_t)s * tile_bytes;
+        float acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.f;
+#pragma unroll
+        for (int j = 0; j < NCHUNK; ++j) {
+            const uint32_t off = (uint32_t)(j * 32 + lane) * 16u;
+            if (off < p.row_bytes) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(slot + (size_t)r * p.row_bytes + off);
+                    acc[r] = Chunk<ELEM>::dot(v, &q[j * CN], acc[r]);
+                }
+            }
+        }
+        __syncwarp();
+        if (t + stages < t1) {
+            if (lane == 0) issue(ji, ti, s);
+            advance(ji, ti);
+        }
+        advance(jc, tc);
+
+        transpose_reduce<R>(acc, lane);
+        const uint64_t key = mine ? pack_key(acc[0] * scale, (uint32_t)pos) : 0ull;
+        unsigned m = __ballot_sync(0xFFFFFFFFu, key > thr);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const uint64_t x = __shfl_sync(0xFFFFFFFFu, key, src);
+            if (x > thr) {
+                list.insert(x, lane);
+                thr = list.at(k - 1);
+            }
+        }
+        if (++s == stages) {
+            s = 0;
+            parity ^= 1u;
+        }
+    }
+
+    __syncthreads();
+    uint64_t* lists = reinterpret_cast<uint64_t*>(smem);  // [W][KPL*32], aliases the drained slots
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) lists[(size_t)warp * (KPL * 32) + j * 32 + lane] = list.key[j];
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < W; ++w) merge_sorted_into<KPL>(list, lists + (size_t)w * (KPL * 32), k, k, lane);
+        uint64_t* out = p.part_keys + ((size_t)qi * gridDim.x + blockIdx.x) * k;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+            const int pos = j * 32 + lane;
+            if (pos < k) out[pos] = list.key[j];
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    __shared__ int s_is_last;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t t = atomicAdd(p.tickets + qi, 1u);
+        s_is_last = (t == gridDim.x - 1);
+        if (s_is_last) p.tickets[qi] = 0u;
+    }
+    __syncthreads();
+    if (s_is_last) {
+        __threadfence();
+        MergeParams mp;
+        mp.keys = p.part_keys;
+        mp.nlists = gridDim.x;
+        mp.nq = gridDim.y;
+        mp.k = k;
+        mp.stride_list = k;
+        mp.stride_query = (int64_t)gridDim.x * k;
+        mp.list_base = nullptr;
+        mp.id_map = nullptr;
+        mp.out_keys = p.out_keys;
+        mp.out_scores = nullptr;
+        mp.out_ids = nullptr;
+        mp.out_stride = k;
+        mp.qlist = nullptr;
+        mp.qcount = nullptr;
+        merge_lists<KPL>(mp, qi, qi, lists, W);
+    }
+}
+
+struct ListScanConfig {
+    int warps, stages;
+    size_t smem;
+};
+
+template <int ELEM, int NCHUNK, int KPL, int R>
+static int launch_list_scan_r(const ts_index* ix, ListScanParams p, int nq, int parts, cudaStream_t s) {
+    const Tunables& t = tunables();
+    const size_t tile_bytes = (size_t)R * p.row_bytes;
+    int stages = t.scan_stages < 2 ? 2 : t.scan_stages;
+    int warps = t.scan_warps < 1 ? 1 : (t.scan_warps > 16 ? 16 : t.scan_warps);
+    const size_t table = (size_t)p.nprobe * 16 + 16;   // s_start, s_len, s_tpref
+    const size_t budget = (size_t)(220 * 1024) - 1024 - table;
+    while (warps > 1 && (size_t)warps * stages * tile_bytes + 8 * warps * stages > budget) --warps;
+    size_t smem = (size_t)warps * stages * tile_bytes + 8 * (size_t)warps * stages + table;
+    const size_t list_bytes = (size_t)warps * KPL * 32 * 8;
+    if (smem < list_bytes) smem = list_bytes;
+    p.stages = stages;
+    auto kern = list_scan_kernel<ELEM, NCHUNK, KPL, R>;
+    TS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(parts, nq), warps * 32, smem, s>>>(p);
+    TS_LAUNCH_CHECK();
+    (void)ix;
+    return TS_OK;
+}
+
+template <int ELEM, int NCHUNK>
+static int launch_list_scan_k(const ts_index* ix, const ListScanParams& p, int nq, int parts, cudaStream_t s) {
+    constexpr int R = (ELEM == 1) ? (NCHUNK == 1 ? 16 : (NCHUNK == 2 ? 8 : 4)) : RowsPerTile<NCHUNK>::value;
+    if (p.k <= 32) return launch_list_scan_r<ELEM, NCHUNK, 1, R>(ix, p, nq, parts, s);
+    if (p.k <= 128) return launch_list_scan_r<ELEM, NCHUNK, 4, R>(ix, p, nq, parts, s);
+    if (p.k <= 256) return launch_list_scan_r<ELEM, NCHUNK, 8, R>(ix, p, nq, parts, s);
+    return launch_list_scan_r<ELEM, NCHUNK, 32, R>(ix, p, nq, parts, s);
+}
+
+static int launch_list_scan(const ts_index* ix, const ListScanParams& p, int nq, int parts, cudaStream_t s) {
+    const int nchunk = (int)((p.row_bytes + 511) / 512);
+    if (ix->list_dtype == TS_FP8_E4M3) {
+        if (nchunk <= 1) return launch_list_scan_k<1, 1>(ix, p, nq, parts, s);
+        if (nchunk <= 2) return launch_list_scan_k<1, 2>(ix, p, nq, parts, s);
+        if (nchunk <= 4) return launch_list_scan_k<1, 4>(ix, p, nq, parts, s);
+    } else {
+        switch (nchunk) {
+            case 1: return launch_list_scan_k<2, 1>(ix, p, nq, parts, s);
+            case 2: return launch_list_scan_k<2, 2>(ix, p, nq, parts, s);
+            case 3: return launch_list_scan_k<2, 3>(ix, p, nq, parts, s);
+            case 4: return launch_list_scan_k<2, 4>(ix, p, nq, parts, s);
+            default:
+                if (nchunk <= 8) return launch_list_scan_k<2, 8>(ix, p, nq, parts, s);
+        }
+    }
+    set_error("ivf list scan: no kernel for list dtype %d dim %d", ix->list_dtype, ix->dim);
+    return TS_ERR_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------- K4c rescore
+// One CTA per query: candidates (list positions) -> corpus rows -> exact fp32-query scores in K2's
+// summation order -> bitonic sort -> top-k.
+template <int ELEM>
+__global__ void __launch_bounds__(256) ivf_rescore_kernel(const uint64_t* __restrict__ cand, int kc, int k,
+                                                          const uint32_t* __restrict__ list_rows,
+                                                          const float* __restrict__ q32,
+                                                          const uint8_t* __restrict__ corpus, uint32_t row_bytes,
+                                                          int dim_pad, const int64_t* __restrict__ id_map,
+                                                          uint64_t* __restrict__ out_keys, float* __restrict__ out_scores,
+                                                          int64_t* __restrict__ out_ids) {
+    constexpr int CN = Chunk<ELEM>::N;
+    extern __shared__ uint64_t rs_buf[];
+    const int q = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int P = 1;
+    while (P < kc) P <<= 1;
+    const float* qv = q32 + (size_t)q * dim_pad;
+    for (int j = warp; j < P; j += 8) {
+        uint64_t key = (j < kc) ? cand[(size_t)q * kc + j] : 0ull;
+        if (key != 0ull) {
+            const uint32_t row = list_rows[key_row(key)];
+            const uint8_t* r = corpus + (size_t)row * row_bytes;
+            float acc = 0.f;
+            for (uint32_t off = (uint32_t)lane * 16u; off < row_bytes; off += 512u) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(r + off));
+                float ql[CN];
+#pragma unroll
+                for (int i = 0; i < CN; ++i) ql[i] = __ldg(qv + off / ELEM + i);
+                acc = Chunk<ELEM>::dot(v, ql, acc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+            key = pack_key(acc, row);
+        }
+        if (lane == 0) rs_buf[j] = key;
+    }
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int st = size >> 1; st > 0; st >>= 1) {
+            for (int i = threadIdx.x; i < P / 2; i += blockDim.x) {
+                const int lo = 2 * i - (i & (st - 1));
+                const int hi = lo + st;
+                const bool desc = (lo & size) == 0;
+                const uint64_t a = rs_buf[lo], b = rs_buf[hi];
+                if ((a < b) == desc) {
+                    rs_buf[lo] = b;
+                    rs_buf[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const uint64_t key = (i < P) ? rs_buf[i] : 0ull;
+        const size_t o = (size_t)q * k + i;
+        if (out_keys) out_keys[o] = key;
+        if (out_scores) out_scores[o] = key ? key_score(key) : -INFINITY;
+        if (out_ids) {
+            int64_t id = -1;
+            if (key) {
+                const uint32_t row = key_row(key);
+                id = id_map ? id_map[row] : (int64_t)row;
+            }
+            out_ids[o] = id;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- host: state
+static void ivf_free_lists(ts_index* ix) {
+    cudaFree(ix->list_offsets);
+    cudaFree(ix->list_rows);
+    cudaFree(ix->list_data);
+    cudaFree(ix->list_scales);
+    ix->list_offsets = nullptr;
+    ix->list_rows = nullptr;
+    ix->list_data = nullptr;
+    ix->list_scales = nullptr;
+    ix->ivf_built = false;
+}
+static void ivf_free_centroids(ts_index* ix) {
+    cudaFree(ix->centroids);
+    cudaFree(ix->centroids_bf16);
+    cudaFree(ix->centroid_max_norm2);
+    ix->centroids = nullptr;
+    ix->centroids_bf16 = nullptr;
+    ix->centroid_max_norm2 = nullptr;
+    ix->nlist = 0;
+}
+static int ivf_alloc_centroids(ts_index* ix, int nlist) {
+    ivf_free_lists(ix);
+    ivf_free_centroids(ix);
+    TS_CHECK_CUDA(cudaMalloc(&ix->centroids, (size_t)nlist * ix->dim_pad * sizeof(float)));
+    TS_CHECK_CUDA(cudaMalloc(&ix->centroids_bf16, (size_t)nlist * ix->dim_pad * sizeof(__nv_bfloat16)));
+    TS_CHECK_CUDA(cudaMalloc(&ix->centroid_max_norm2, sizeof(float)));
+    ix->nlist = nlist;
+    return TS_OK;
+}
+static int ivf_finish_centroids(ts_index* ix, cudaStream_t s) {
+    TS_CHECK_CUDA(cudaMemsetAsync(ix->centroid_max_norm2, 0, sizeof(float), s));
+    max_norm2_bf16_kernel<<<(ix->nlist + 7) / 8, 256, 0, s>>>(ix->centroids_bf16, ix->nlist, ix->dim_pad,
+                                                              ix->centroid_max_norm2);
+    TS_LAUNCH_CHECK();
+    return TS_OK;
+}
+
+struct DevGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DevGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+        else if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DevGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// temp device buffers of the train/build calls (build-time only; searches never allocate)
+struct TempBufs {
+    std::vector<void*> ptrs;
+    ~TempBufs() {
+        for (void* p : ptrs) cudaFree(p);
+    }
+    template <typename T>
+    int get(T** out, size_t count) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e != cudaSuccess) {
+            set_error("ivf: cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+            cudaGetLastError();
+            return TS_ERR_OOM;
+        }
+        ptrs.push_back(p);
+        *out = (T*)p;
+        return TS_OK;
+    }
+};
+
+// assign -> (members sorted by (list, row), offsets). Stable LSD radix sort on the list id keeps rows ascending.
+static int sort_by_list(const uint32_t* assign, int64_t n, int nlist, uint32_t* sorted_assign, uint32_t* rows_in,
+                        uint32_t* members, int64_t* offsets, TempBufs& tmp, cudaStream_t s) {
+    TS_REQUIRE(n < (int64_t)1 << 31, TS_ERR_UNSUPPORTED, "ivf: more than 2^31-1 rows in one sort");
+    iota_u32_kernel<<<1024, 256, 0, s>>>(rows_in, n);
+    TS_LAUNCH_CHECK();
+    int end_bit = 1;
+    while ((1 << end_bit) < nlist) ++end_bit;
+    size_t tbytes = 0;
+    TS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tbytes, assign, sorted_assign, rows_in, members, (int)n, 0,
+                                                  end_bit, s));
+    uint8_t* t = nullptr;
+    int rc = tmp.get(&t, tbytes);
+    if (rc) return rc;
+    TS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(t, tbytes, assign, sorted_assign, rows_in, members, (int)n, 0, end_bit,
+                                                  s));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    list_offsets_kernel<<<(nlist + 1 + 255) / 256, 256, 0, s>>>(sorted_assign, n, nlist, offsets);
+    TS_LAUNCH_CHECK();
+    return TS_OK;
+}
+
+}  // namespace ts
+
+using namespace ts;
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------ train
+int ts_ivf_train(ts_index* ix, const float* sample, int64_t n_sample, int nlist, int iters, uint64_t seed,
+                 void* stream) {
+    TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "ivf_train: index is NULL");
+    TS_REQUIRE(nlist >= 1 && nlist <= (1 << 20), TS_ERR_BAD_ARG, "ivf_train: nlist=%d out of range [1, 2^20]", nlist);
+    TS_REQUIRE(iters >= 0 && iters <= 1000, TS_ERR_BAD_ARG, "ivf_train: iters=%d", iters);
+    DevGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_train: cannot select CUDA device %d", ix->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    TempBufs tmp;
+    const uint8_t* rows = nullptr;
+    size_t row_stride = 0;
+    int64_t n = 0;
+    if (sample != nullptr) {
+        TS_REQUIRE(n_sample >= nlist, TS_ERR_BAD_ARG, "ivf_train: %lld sample rows < nlist %d", (long long)n_sample, nlist);
+        __nv_bfloat16* buf = nullptr;
+        int rc = tmp.get(&buf, (size_t)n_sample * ix->dim_pad);
+        if (rc) return rc;
+        rc = launch_normalize_cast(sample, TS_F32, n_sample, ix->dim, ix->dim_pad, 1, buf, TS_BF16, s);
+        if (rc) return rc;
+        rows = (const uint8_t*)buf;
+        row_stride = (size_t)ix->dim_pad * 2;
+        n = n_sample;
+    } else {
+        // sample = every (size / n_sample)-th stored row, read in place through a strided tensor map
+        TS_REQUIRE(ix->dtype == TS_BF16, TS_ERR_UNSUPPORTED, "ivf_train: training on stored rows needs a bf16 index");
+        TS_REQUIRE(ix->size >= nlist, TS_ERR_BAD_ARG, "ivf_train: %lld stored rows < nlist %d", (long long)ix->size, nlist);
+        if (n_sample <= 0 || n_sample > ix->size) n_sample = ix->size;
+        if (n_sample < nlist) n_sample = nlist;
+        const int64_t stride = ix->size / n_sample;
+        rows = (const uint8_t*)ix->data;
+        row_stride = (size_t)stride * ix->row_bytes();
+        n = n_sample;
+    }
+    int rc = ivf_alloc_centroids(ix, nlist);
+    if (rc) return rc;
+    init_centroids_kernel<<<nlist, 256, 0, s>>>(rows, row_stride, n, nlist, ix->dim_pad, seed, ix->centroids,
+                                                ix->centroids_bf16);
+    TS_LAUNCH_CHECK();
+    uint32_t *assign = nullptr, *sorted_assign = nullptr, *iota = nullptr, *members = nullptr;
+    int64_t* offsets = nullptr;
+    if ((rc = tmp.get(&assign, (size_t)n)) || (rc = tmp.get(&sorted_assign, (size_t)n)) || (rc = tmp.get(&iota, (size_t)n)) ||
+        (rc = tmp.get(&members, (size_t)n)) || (rc = tmp.get(&offsets, (size_t)nlist + 1)))
+        return rc;
+    for (int it = 0; it < iters; ++it) {
+        rc = launch_assign(ix->device, rows, n, row_stride, ix->centroids_bf16, nlist, ix->dim_pad, assign, nullptr, s);
+        if (rc) return rc;
+        rc = sort_by_list(assign, n, nlist, sorted_assign, iota, members, offsets, tmp, s);
+        if (rc) return rc;
+        update_centroids_kernel<<<nlist, 256, 0, s>>>(rows, row_stride, n, members, offsets, ix->dim_pad,
+                                                      splitmix64(seed + 1 + (uint64_t)it), ix->centroids,
+                                                      ix->centroids_bf16);
+        TS_LAUNCH_CHECK();
+    }
+    rc = ivf_finish_centroids(ix, s);
+    if (rc) return rc;
+    TS_CHECK_CUDA(cudaStreamSynchronize(s));   // temporaries are freed on return
+    return TS_OK;
+}
+
+int ts_ivf_set_centroids(ts_index* ix, const float* centroids, int nlist, void* stream) {
+    TS_REQUIRE(ix != nullptr && centroids != nullptr, TS_ERR_BAD_ARG, "ivf_set_centroids: NULL argument");
+    TS_REQUIRE(nlist >= 1 && nlist <= (1 << 20), TS_ERR_BAD_ARG, "ivf_set_centroids: nlist=%d", nlist);
+    DevGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_set_centroids: cannot select CUDA device %d", ix->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = ivf_alloc_centroids(ix, nlist);
+    if (rc) return rc;
+    rc = launch_normalize_cast(centroids, TS_F32, nlist, ix->dim, ix->dim_pad, 0, ix->centroids, TS_F32, s);
+    if (rc) return rc;
+    rc = launch_normalize_cast(centroids, TS_F32, nlist, ix->dim, ix->dim_pad, 0, ix->centroids_bf16, TS_BF16, s);
+    if (rc) return rc;
+    return ivf_finish_centroids(ix, s);
+}
+
+int ts_ivf_get_centroids(const ts_index* ix, float* out, void* stream) {
+    TS_REQUIRE(ix != nullptr && out != nullptr, TS_ERR_BAD_ARG, "ivf_get_centroids: NULL argument");
+    TS_REQUIRE(ix->nlist > 0, TS_ERR_STATE, "ivf_get_centroids: no centroids (call ts_ivf_train first)");
+    DevGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_get_centroids: cannot select CUDA device %d", ix->device);
+    return launch_dequant_rows(ix->centroids, TS_F32, ix->nlist, ix->dim, ix->dim_pad, out, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------ build
+int ts_ivf_build(ts_index* ix, int list_dtype, void* stream) {
+    TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "ivf_build: index is NULL");
+    TS_REQUIRE(ix->nlist > 0, TS_ERR_STATE, "ivf_build: no centroids (call ts_ivf_train or ts_ivf_set_centroids first)");
+    TS_REQUIRE(list_dtype == TS_BF16 || list_dtype == TS_FP8_E4M3, TS_ERR_BAD_ARG,
+               "ivf_build: list dtype must be TS_BF16 or TS_FP8_E4M3 (got %d)", list_dtype);
+    TS_REQUIRE(ix->dtype == TS_BF16, TS_ERR_UNSUPPORTED, "ivf_build: the corpus must be stored as bf16");
+    DevGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_build: cannot select CUDA device %d", ix->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    ivf_free_lists(ix);
+    const int64_t n = ix->size;
+    const uint32_t lrow = list_dtype == TS_BF16 ? (uint32_t)ix->row_bytes() : (uint32_t)((ix->dim + 15) / 16 * 16);
+    TempBufs tmp;
+    uint32_t *assign = nullptr, *sorted_assign = nullptr, *iota = nullptr;
+    int rc;
+    if ((rc = tmp.get(&assign, (size_t)n)) || (rc = tmp.get(&sorted_assign, (size_t)n)) || (rc = tmp.get(&iota, (size_t)n)))
+        return rc;
+    TS_CHECK_CUDA(cudaMalloc(&ix->list_offsets, ((size_t)ix->nlist + 1) * sizeof(int64_t)));
+    TS_CHECK_CUDA(cudaMalloc(&ix->list_rows, std::max<size_t>((size_t)n, 1) * sizeof(uint32_t)));
+    TS_CHECK_CUDA(cudaMalloc(&ix->list_data, std::max<size_t>((size_t)n, 1) * lrow));
+    if (list_dtype == TS_FP8_E4M3)
+        TS_CHECK_CUDA(cudaMalloc(&ix->list_scales, std::max<size_t>((size_t)n, 1) * sizeof(float)));
+    ix->list_dtype = list_dtype;
+    ix->list_row_bytes = lrow;
+    rc = launch_assign(ix->device, ix->data, n, ix->row_bytes(), ix->centroids_bf16, ix->nlist, ix->dim_pad, assign,
+                       nullptr, s);
+    if (rc) return rc;
+    rc = sort_by_list(assign, n, ix->nlist, sorted_assign, iota, ix->list_rows, ix->list_offsets, tmp, s);
+    if (rc) return rc;
+    if (n > 0) {
+        const int blocks = (int)std::min<int64_t>((n + 7) / 8, 148 * 16);
+        if (list_dtype == TS_BF16)
+            gather_quantize_kernel<2><<<blocks, 256, 0, s>>>((const uint8_t*)ix->data, (uint32_t)ix->row_bytes(),
+                                                             ix->list_rows, n, ix->dim_pad, lrow, (uint8_t*)ix->list_data,
+                                                             nullptr);
+        else
+            gather_quantize_kernel<1><<<blocks, 256, 0, s>>>((const uint8_t*)ix->data, (uint32_t)ix->row_bytes(),
+                                                             ix->list_rows, n, ix->dim_pad, lrow, (uint8_t*)ix->list_data,
+                                                             ix->list_scales);
+        TS_LAUNCH_CHECK();
+    }
+    TS_CHECK_CUDA(cudaStreamSynchronize(s));
+    ix->ivf_built = true;
+    return TS_OK;
+}
+
+int ts_ivf_nlist(const ts_index* ix) { return ix ? ix->nlist : -1; }
+
+int ts_ivf_list_sizes(const ts_index* ix, int64_t* out, void* stream) {
+    TS_REQUIRE(ix != nullptr && out != nullptr, TS_ERR_BAD_ARG, "ivf_list_sizes: NULL argument");
+    TS_REQUIRE(ix->ivf_built, TS_ERR_STATE, "ivf_list_sizes: lists are not built (call ts_ivf_build)");
+    DevGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_list_sizes: cannot select CUDA device %d", ix->device);
+    list_sizes_kernel<<<(ix->nlist + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ix->list_offsets, ix->nlist, out);
+    TS_LAUNCH_CHECK();
+    return TS_OK;
+}
+
+int ts_ivf_get_lists(const ts_index* ix, int64_t* offsets_out, int64_t* rows_out, void* stream) {
+    TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "ivf_get_lists: index is NULL");
+    TS_REQUIRE(ix->ivf_built, TS_ERR_STATE, "ivf_get_lists: lists are not built (call ts_ivf_build)");
+    DevGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_get_lists: cannot select CUDA device %d", ix->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (offsets_out)
+        TS_CHECK_CUDA(cudaMemcpyAsync(offsets_out, ix->list_offsets, ((size_t)ix->nlist + 1) * sizeof(int64_t),
+                                      cudaMemcpyDeviceToDevice, s));
+    if (rows_out && ix->size > 0) {
+        widen_u32_kernel<<<1024, 256, 0, s>>>(ix->list_rows, ix->size, rows_out);
+        TS_LAUNCH_CHECK();
+    }
+    return TS_OK;
+}
+
+int ts_ivf_get_list_data(const ts_index* ix, int64_t first, int64_t n, float* out, void* stream) {
+    TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "ivf_get_list_data: index is NULL");
+    TS_REQUIRE(ix->ivf_built, TS_ERR_STATE, "ivf_get_list_data: lists are not built (call ts_ivf_build)");
+    TS_REQUIRE(first >= 0 && n >= 0 && first + n <= ix->size, TS_ERR_BAD_ARG, "ivf_get_list_data: [%lld, %lld) outside [0, %lld)",
+               (long long)first, (long long)(first + n), (long long)ix->size);
+    if (n == 0) return TS_OK;
+    TS_REQUIRE(out != nullptr, TS_ERR_BAD_ARG, "ivf_get_list_data: out is NULL");
+    DevGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_get_list_data: cannot select CUDA device %d", ix->device);
+    const int64_t total = n * (int64_t)ix->dim;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+    dequant_list_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)ix->list_data, ix->list_row_bytes,
+                                                                  ix->list_dtype, ix->list_scales, first, n, ix->dim, out);
+    TS_LAUNCH_CHECK();
+    return TS_OK;
+}
+
+// ------------------------------------------------------------------------------------ search
+}  // extern "C"
+
+namespace ts {
+
+static inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
+
+static ts_index centroid_view(const ts_index* ix) {
+    ts_index v;
+    v.device = ix->device;
+    v.dim = ix->dim;
+    v.dim_pad = ix->dim_pad;
+    v.dtype = TS_BF16;
+    v.capacity = ix->nlist;
+    v.size = ix->nlist;
+    v.data = ix->centroids_bf16;
+    v.max_norm2 = ix->centroid_max_norm2;
+    return v;
+}
+
+static int ivf_parts(const ts_index* ix, int nq) {
+    const int sms = sm_count(ix->device);
+    return std::max(1, std::min(sms, (2 * sms + nq - 1) / std::max(nq, 1)));
+}
+
+struct IvfWs {
+    float* q32;
+    uint64_t* probes;
+    void* coarse;
+    size_t coarse_bytes;
+    uint64_t* part_keys;
+    uint32_t* tickets;
+    uint64_t* cand;
+    size_t bytes;
+};
+static IvfWs carve_ivf(const ts_index* ix, int nq, int kc, int nprobe, void* base) {
+    IvfWs w;
+    const ts_index view = centroid_view(ix);
+    size_t off = 0;
+    auto take = [&](size_t b) {
+        char* p = (char*)base + off;
+        off += al256(b);
+        return (void*)p;
+    };
+    w.q32 = (float*)take((size_t)nq * ix->dim_pad * 4);
+    w.probes = (uint64_t*)take((size_t)nq * nprobe * 8);
+    w.coarse_bytes = ts_workspace_bytes(&view, nq, nprobe);
+    w.coarse = take(w.coarse_bytes);
+    w.part_keys = (uint64_t*)take((size_t)nq * ivf_parts(ix, nq) * kc * 8);
+    w.tickets = (uint32_t*)take((size_t)nq * 4);
+    w.cand = (uint64_t*)take((size_t)nq * kc * 8);
+    w.bytes = off;
+    return w;
+}
+
+static int ivf_search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k, int nprobe, int rescore_k,
+                           int normalize, uint64_t* out_keys, float* out_scores, int64_t* out_ids, void* workspace,
+                           size_t workspace_bytes, cudaStream_t s) {
+    TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "ivf_search: index is NULL");
+    TS_REQUIRE(ix->ivf_built, TS_ERR_STATE, "ivf_search: lists are not built (call ts_ivf_train + ts_ivf_build)");
+    TS_REQUIRE(nq >= 0, TS_ERR_BAD_ARG, "ivf_search: nq=%d", nq);
+    TS_REQUIRE(k >= 1 && k <= TS_MAX_K, TS_ERR_BAD_ARG, "ivf_search: k=%d out of range [1, %d]", k, TS_MAX_K);
+    TS_REQUIRE(nprobe >= 1, TS_ERR_BAD_ARG, "ivf_search: nprobe=%d", nprobe);
+    TS_REQUIRE(rescore_k <= TS_MAX_K, TS_ERR_BAD_ARG, "ivf_search: rescore_k=%d exceeds %d", rescore_k, TS_MAX_K);
+    TS_REQUIRE(q_dtype == TS_F32 || q_dtype == TS_BF16 || q_dtype == TS_F16, TS_ERR_BAD_ARG, "ivf_search: query dtype %d",
+               q_dtype);
+    if (nq == 0) return TS_OK;
+    TS_REQUIRE(queries != nullptr && workspace != nullptr, TS_ERR_BAD_ARG, "ivf_search: NULL buffer");
+    nprobe = std::min(std::min(nprobe, ix->nlist), TS_MAX_K);
+    const int kc = std::max(k, rescore_k);
+    DevGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_search: cannot select CUDA device %d", ix->device);
+    IvfWs w = carve_ivf(ix, nq, kc, nprobe, workspace);
+    TS_REQUIRE(workspace_bytes >= w.bytes, TS_ERR_CAPACITY, "ivf_search: workspace %zu < %zu bytes", workspace_bytes,
+               w.bytes);
+    // 1. coarse: exact top-nprobe over the centroid table (K2 for a few queries, K3 for a batch)
+    ts_index view = centroid_view(ix);
+    int rc = search_impl(&view, queries, q_dtype, nq, nprobe, normalize, nullptr, w.probes, nullptr, nullptr, w.coarse,
+                         w.coarse_bytes, s, nullptr, nullptr);
+    if (rc) return rc;
+    // 2. scan the probed lists, keep kc candidates per query
+    rc = launch_prepare_queries(queries, q_dtype, nq, ix->dim, ix->dim_pad, normalize, w.q32, s);
+    if (rc) return rc;
+    TS_CHECK_CUDA(cudaMemsetAsync(w.tickets, 0, (size_t)nq * sizeof(uint32_t), s));
+    ListScanParams p;
+    p.list_data = (const uint8_t*)ix->list_data;
+    p.row_bytes = ix->list_row_bytes;
+    p.dim_pad = ix->dim_pad;
+    p.scales = ix->list_scales;
+    p.list_offsets = ix->list_offsets;
+    p.probes = w.probes;
+    p.nprobe = nprobe;
+    p.queries = w.q32;
+    p.k = kc;
+    p.part_keys = w.part_keys;
+    p.tickets = w.tickets;
+    p.out_keys = w.cand;
+    p.stages = 0;
+    rc = launch_list_scan(ix, p, nq, ivf_parts(ix, nq), s);
+    if (rc) return rc;
+    // 3. exact re-score of the survivors against the stored corpus rows
+    int P = 1;
+    while (P < kc) P <<= 1;
+    ivf_rescore_kernel<2><<<nq, 256, (size_t)P * 8, s>>>(w.cand, kc, k, ix->list_rows, w.q32, (const uint8_t*)ix->data,
+                                                         (uint32_t)ix->row_bytes(), ix->dim_pad,
+                                                         ix->has_ids ? ix->ids : nullptr, out_keys, out_scores, out_ids);
+    TS_LAUNCH_CHECK();
+    return TS_OK;
+}
+
+}  // namespace ts
+
+extern "C" {
+
+size_t ts_ivf_workspace_bytes(const ts_index* ix, int nq, int k, int nprobe, int rescore_k) {
+    if (!ix || ix->nlist <= 0 || nq < 0 || k < 1 || nprobe < 1) return 0;
+    nprobe = std::min(std::min(nprobe, ix->nlist), TS_MAX_K);
+    return carve_ivf(ix, std::max(nq, 1), std::max(k, rescore_k), nprobe, nullptr).bytes;
+}
+
+int ts_ivf_search(ts_index* ix, const void* queries, int q_dtype, int nq, int k, int nprobe, int rescore_k,
+                  int normalize_queries, float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+    TS_REQUIRE(nq == 0 || (out_scores != nullptr && out_ids != nullptr), TS_ERR_BAD_ARG,
+               "ivf_search: output pointers are NULL");
+    return ivf_search_impl(ix, queries, q_dtype, nq, k, nprobe, rescore_k, normalize_queries, nullptr, out_scores,
+                           out_ids, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int ts_ivf_search_keys(ts_index* ix, const void* queries, int q_dtype, int nq, int k, int nprobe, int rescore_k,
+                       int normalize_queries, uint64_t* out_keys, void* workspace, size_t workspace_bytes, void* stream) {
+    TS_REQUIRE(nq == 0 || out_keys != nullptr, TS_ERR_BAD_ARG, "ivf_search_keys: out_keys is NULL");
+    return ivf_search_impl(ix, queries, q_dtype, nq, k, nprobe, rescore_k, normalize_queries, out_keys, nullptr, nullptr,
+                           workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -69,7 +69,7 @@ static bool use_batched(const ts_index* ix, int nq) {
     return ix->dtype == TS_BF16 && nq >= tunables().batch_min_nq && ix->size > 0;
 }
 
-static int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k,
+int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k,
                        int normalize_queries, const uint32_t* allow_mask, uint64_t* out_keys,
                        float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
                        cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1) {
@@ -188,6 +188,7 @@ void ts_index_destroy(ts_index* ix) {
     cudaFree(ix->list_rows);
     cudaFree(ix->list_data);
     cudaFree(ix->list_scales);
+    cudaFree(ix->centroid_max_norm2);
     delete ix;
 }
 
@@ -424,26 +425,6 @@ int ts_search_host(ts_ctx* c, const float* queries, int nq, int k, int normalize
     memcpy(out_ids, c->h_ids, n * sizeof(int64_t));
     if (c->timing) TS_CHECK_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
     return TS_OK;
-}
-
-// ------------------------------------------------------------------------------------ IVF (K4)
-int ts_ivf_train(ts_index*, const float*, int64_t, int, int, uint64_t, void*) {
-    set_error("ivf_train: IVF-Flat kernels are not built yet");
-    return TS_ERR_UNSUPPORTED;
-}
-int ts_ivf_build(ts_index*, int, void*) {
-    set_error("ivf_build: IVF-Flat kernels are not built yet");
-    return TS_ERR_UNSUPPORTED;
-}
-size_t ts_ivf_workspace_bytes(const ts_index*, int, int, int, int) { return 0; }
-int ts_ivf_search(ts_index*, const void*, int, int, int, int, int, int, float*, int64_t*, void*, size_t, void*) {
-    set_error("ivf_search: IVF-Flat kernels are not built yet");
-    return TS_ERR_UNSUPPORTED;
-}
-int ts_ivf_nlist(const ts_index* ix) { return ix ? ix->nlist : -1; }
-int ts_ivf_list_sizes(const ts_index*, int64_t*, void*) {
-    set_error("ivf_list_sizes: IVF-Flat kernels are not built yet");
-    return TS_ERR_UNSUPPORTED;
 }
 
 // ------------------------------------------------------------------------------------ tunables

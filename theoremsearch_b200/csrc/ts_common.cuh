@@ -260,6 +260,8 @@ struct ts_index {
     void* list_data = nullptr;          // [size, dim_pad] permuted rows in list_dtype
     float* list_scales = nullptr;       // [size] per-row scale (fp8 only)
     int list_dtype = TS_BF16;
+    uint32_t list_row_bytes = 0;        // bytes per row of list_data (multiple of 16)
+    float* centroid_max_norm2 = nullptr;  // device scalar: max ||centroid_bf16||^2
     bool ivf_built = false;
 
     size_t elem_bytes() const { return dtype == TS_F32 ? 4 : 2; }
@@ -285,6 +287,10 @@ struct ts_ctx {
 
 // internal kernel entry points (one per .cu)
 namespace ts {
+// exact search over `ix` (K2 or K3 by batch size); exactly one of out_keys / (out_scores, out_ids) is used
+int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k, int normalize_queries,
+                const uint32_t* allow_mask, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
+                void* workspace, size_t workspace_bytes, cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1);
 int launch_normalize_cast(const void* src, int src_dtype, int64_t n, int dim, int dim_pad,
                           int normalize, void* dst, int dst_dtype, cudaStream_t s,
                           float* max_norm2 = nullptr);

@@ -234,6 +234,98 @@ class TheoremIndex:
         return scores, ids
 
 
+    # -------------------------------------------------------------------------------- IVF-Flat (K4)
+    def ivf_train(self, nlist: int, sample: Optional[torch.Tensor] = None, n_sample: int = 0, iters: int = 10,
+                  seed: int = 0) -> "TheoremIndex":
+        """Spherical k-means -> ``nlist`` centroids (pgvector ivfflat's training step).  ``sample``:
+        CUDA fp32 [n, dim], or None to train on every (len/n_sample)-th stored row in place."""
+        ptr, n = None, int(n_sample)
+        if sample is not None:
+            sample = sample.to(self.device, torch.float32).contiguous()
+            if sample.dim() != 2 or sample.shape[1] != self.dim:
+                raise _lib.TheoremSearchError(-1, f"sample must be [n, {self.dim}], got {tuple(sample.shape)}")
+            ptr, n = sample.data_ptr(), sample.shape[0]
+        check(lib.ts_ivf_train(self._h, ptr, n, int(nlist), int(iters), int(seed), _stream_ptr(self.device)))
+        return self
+
+    def ivf_set_centroids(self, centroids: torch.Tensor) -> "TheoremIndex":
+        c = centroids.to(self.device, torch.float32).contiguous()
+        if c.dim() != 2 or c.shape[1] != self.dim:
+            raise _lib.TheoremSearchError(-1, f"centroids must be [nlist, {self.dim}], got {tuple(c.shape)}")
+        check(lib.ts_ivf_set_centroids(self._h, c.data_ptr(), c.shape[0], _stream_ptr(self.device)))
+        torch.cuda.current_stream(self.device).synchronize()
+        return self
+
+    @property
+    def nlist(self) -> int:
+        return int(lib.ts_ivf_nlist(self._h))
+
+    def ivf_centroids(self) -> torch.Tensor:
+        out = torch.empty((self.nlist, self.dim), dtype=torch.float32, device=self.device)
+        check(lib.ts_ivf_get_centroids(self._h, out.data_ptr(), _stream_ptr(self.device)))
+        return out
+
+    def ivf_build(self, list_dtype: str = "fp8") -> "TheoremIndex":
+        """File every stored row under its nearest centroid; lists stored as e4m3 (+ per-row scale) or bf16."""
+        code = {"fp8": _lib.TS_FP8_E4M3, "fp8_e4m3": _lib.TS_FP8_E4M3, "e4m3": _lib.TS_FP8_E4M3, "bf16": TS_BF16}[list_dtype]
+        check(lib.ts_ivf_build(self._h, code, _stream_ptr(self.device)))
+        self._ws = {}
+        return self
+
+    def ivf_lists(self):
+        """(offsets int64 [nlist+1], rows int64 [len]): list l holds corpus rows rows[offsets[l]:offsets[l+1]]."""
+        off = torch.empty(self.nlist + 1, dtype=torch.int64, device=self.device)
+        rows = torch.empty(len(self), dtype=torch.int64, device=self.device)
+        check(lib.ts_ivf_get_lists(self._h, off.data_ptr(), rows.data_ptr(), _stream_ptr(self.device)))
+        return off, rows
+
+    def ivf_list_sizes(self) -> torch.Tensor:
+        out = torch.empty(self.nlist, dtype=torch.int64, device=self.device)
+        check(lib.ts_ivf_list_sizes(self._h, out.data_ptr(), _stream_ptr(self.device)))
+        return out
+
+    def ivf_list_data(self, first: int = 0, n: Optional[int] = None) -> torch.Tensor:
+        """List rows at positions [first, first+n) dequantised to fp32 (what the list scan scores)."""
+        n = len(self) - first if n is None else n
+        out = torch.empty((n, self.dim), dtype=torch.float32, device=self.device)
+        check(lib.ts_ivf_get_list_data(self._h, first, n, out.data_ptr(), _stream_ptr(self.device)))
+        return out
+
+    def _ivf_workspace(self, nq: int, k: int, nprobe: int, rescore_k: int) -> torch.Tensor:
+        need = int(lib.ts_ivf_workspace_bytes(self._h, nq, k, nprobe, rescore_k))
+        key = ("ivf", nq, k, nprobe, rescore_k)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+            self._ws = {key: ws}
+        return ws
+
+    def ivf_search(self, queries, k: int, nprobe: int = 32, rescore_k: int = 100, normalize: bool = True):
+        """ANN top-k: probe the ``nprobe`` nearest lists, keep ``rescore_k`` candidates by list-precision
+        score, re-score them exactly.  Returns (scores [nq, k], ids [nq, k]) like :meth:`search`."""
+        q = self._prep_queries(queries)
+        nq = q.shape[0]
+        scores = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        ws = self._ivf_workspace(nq, k, nprobe, rescore_k)
+        check(lib.ts_ivf_search(self._h, q.data_ptr(), _TORCH_TO_TS[q.dtype], nq, int(k), int(nprobe), int(rescore_k),
+                                int(normalize), scores.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(),
+                                _stream_ptr(self.device)))
+        q.record_stream(torch.cuda.current_stream(self.device))
+        return scores, ids
+
+    def ivf_search_keys(self, queries, k: int, nprobe: int = 32, rescore_k: int = 100, normalize: bool = True):
+        q = self._prep_queries(queries)
+        nq = q.shape[0]
+        keys = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        ws = self._ivf_workspace(nq, k, nprobe, rescore_k)
+        check(lib.ts_ivf_search_keys(self._h, q.data_ptr(), _TORCH_TO_TS[q.dtype], nq, int(k), int(nprobe),
+                                     int(rescore_k), int(normalize), keys.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     _stream_ptr(self.device)))
+        q.record_stream(torch.cuda.current_stream(self.device))
+        return keys
+
+
 def merge_topk(keys: torch.Tensor, k: int, shard_base: Optional[Sequence[int] | torch.Tensor] = None,
                id_map: Optional[torch.Tensor] = None):
     """K5 on gathered candidates: keys int64 [nshards, nq, k] (packed uint64 bits) ->
