@@ -5,6 +5,8 @@ configs and tuning sweeps.  Each sub-command prints one JSON line per measuremen
   python bench_extra.py batched   [--rows 10000000 --nq 4096 --k 100]     configs[2]: K3 tcgen05 GEMM + top-k
   python bench_extra.py sweep-scan [--rows 10000000]                      K2 tunables sweep
   python bench_extra.py small-batch [--rows 10000000]                     nq = 1..256 latency curve
+  python bench_extra.py ivf [--rows 40000000 --nlist 16384 --nprobe 32 --rescore 100 --data clustered]
+                                                                          configs[4] shape: IVF-Flat fp8 + rescore
 """
 from __future__ import annotations
 
@@ -114,9 +116,107 @@ def cmd_small_batch(a):
                           "corpus_gbs": a.rows * a.dim * 2 / (ms * 1e-3) / 1e9}))
 
 
+def timed_graph(fn, warmup, iters):
+    """Device time per call with the launch sequence replayed from a CUDA graph (no host launch cost)."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    for _ in range(warmup):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def recall_at_k(got: torch.Tensor, exact: torch.Tensor) -> float:
+    hits = (got.unsqueeze(2) == exact.unsqueeze(1)).any(dim=2).sum().item()
+    return hits / exact.numel()
+
+
+def cmd_ivf(a):
+    import time
+    dev = torch.device("cuda", 0)
+    pk = peaks()
+    index = ts.TheoremIndex(a.dim, a.rows, dtype="bf16", device=dev)
+    if a.data == "clustered":
+        centers = synthetic.fill_index_clustered(index, a.rows, a.centers or a.nlist, a.sigma, seed=0)
+        q_all = synthetic.make_clustered_queries(max(a.nq, a.nq_recall), centers, a.sigma)
+    else:
+        synthetic.fill_index(index, 0, a.rows, seed=0)
+        q_all = synthetic.make_queries(max(a.nq, a.nq_recall), a.dim, dev)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    index.ivf_train(a.nlist, n_sample=a.train_sample, iters=a.train_iters, seed=0)
+    torch.cuda.synchronize()
+    t1 = time.time()
+    index.ivf_build(a.list_dtype)
+    torch.cuda.synchronize()
+    t2 = time.time()
+    sizes = index.ivf_list_sizes().to(torch.float64)
+    out = {"bench": "ivf", "rows": a.rows, "dim": a.dim, "data": a.data, "nlist": a.nlist, "nprobe": a.nprobe,
+           "rescore_k": a.rescore, "k": a.k, "list_dtype": a.list_dtype, "train_sample": a.train_sample,
+           "train_iters": a.train_iters, "train_s": t1 - t0, "build_s": t2 - t1,
+           "list_rows_min_mean_max": [sizes.min().item(), sizes.mean().item(), sizes.max().item()],
+           "empty_lists": int((sizes == 0).sum().item())}
+    # recall@k against the exact path on the same index
+    qr = q_all[:a.nq_recall]
+    _, exact_ids = index.search(qr, a.k)
+    _, ivf_ids = index.ivf_search(qr, a.k, nprobe=a.nprobe, rescore_k=a.rescore)
+    out["recall_at_k"] = recall_at_k(ivf_ids, exact_ids)
+    out["recall_queries"] = a.nq_recall
+    for np_ in a.recall_sweep:
+        _, ids2 = index.ivf_search(qr, a.k, nprobe=np_, rescore_k=a.rescore)
+        out[f"recall_nprobe_{np_}"] = recall_at_k(ids2, exact_ids)
+    # bytes the list scan must read per query: rows of the probed lists x list row bytes (+ 4 B scale)
+    cent = index.ivf_centroids()
+    qn = torch.nn.functional.normalize(qr, dim=1)
+    probe = (qn @ cent.T).topk(min(a.nprobe, a.nlist), dim=1).indices
+    rows_probed = sizes[probe].sum(dim=1)
+    row_bytes = a.dim * (1 if a.list_dtype == "fp8" else 2) + (4 if a.list_dtype == "fp8" else 0)
+    out["rows_probed_mean"] = rows_probed.mean().item()
+    out["frac_of_corpus_probed"] = rows_probed.mean().item() / a.rows
+    scan_bytes = rows_probed.mean().item() * row_bytes
+    coarse_bytes = a.nlist * a.dim * 2
+    out["algorithmic_bytes_per_query"] = {"list_scan": scan_bytes, "coarse": coarse_bytes,
+                                          "rescore": a.rescore * a.dim * 2}
+    # single-query latency: eager (host launch cost included) and graph-replayed (device only)
+    q1 = [q_all[i:i + 1].contiguous() for i in range(64)]
+    it = iter(itertools.cycle(range(64)))
+    ms_eager = timed(lambda: index.ivf_search(q1[next(it)], a.k, nprobe=a.nprobe, rescore_k=a.rescore), 10, 200)
+    qs = q_all[:1].clone()
+    ms_graph = timed_graph(lambda: index.ivf_search(qs, a.k, nprobe=a.nprobe, rescore_k=a.rescore), 10, 200)
+    out["single_query_ms_eager"] = ms_eager
+    out["single_query_ms_graph"] = ms_graph
+    out["single_query_qps_graph"] = 1e3 / ms_graph
+    out["single_query_gbs_all_stages"] = (scan_bytes + coarse_bytes) / (ms_graph * 1e-3) / 1e9
+    ms_exact = timed(lambda: index.search(q1[next(it)], a.k), 3, 20)
+    out["exact_single_query_ms"] = ms_exact
+    # batched throughput
+    qb = q_all[:a.nq].contiguous()
+    ms_b = timed(lambda: index.ivf_search(qb, a.k, nprobe=a.nprobe, rescore_k=a.rescore), 2, 5)
+    out["batch_nq"] = a.nq
+    out["batch_ms"] = ms_b
+    out["batch_qps"] = a.nq / (ms_b * 1e-3)
+    out["batch_list_scan_gbs"] = a.nq * scan_bytes / (ms_b * 1e-3) / 1e9
+    out["batch_frac_of_measured_hbm"] = out["batch_list_scan_gbs"] / pk["hbm_gbs"]
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("cmd", choices=["batched", "sweep-scan", "small-batch"])
+    ap.add_argument("cmd", choices=["batched", "sweep-scan", "small-batch", "ivf"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--dim", type=int, default=1024)
     ap.add_argument("--nq", type=int, default=4096)
@@ -125,10 +225,21 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--tunable", nargs=2, action="append", metavar=("NAME", "VALUE"))
     ap.add_argument("--fine", action="store_true")
+    ap.add_argument("--nlist", type=int, default=16384)
+    ap.add_argument("--nprobe", type=int, default=32)
+    ap.add_argument("--rescore", type=int, default=100)
+    ap.add_argument("--list-dtype", default="fp8", choices=["fp8", "bf16"])
+    ap.add_argument("--data", default="clustered", choices=["clustered", "gaussian"])
+    ap.add_argument("--centers", type=int, default=0)
+    ap.add_argument("--sigma", type=float, default=1.0)
+    ap.add_argument("--train-sample", type=int, default=2_000_000)
+    ap.add_argument("--train-iters", type=int, default=10)
+    ap.add_argument("--nq-recall", type=int, default=1000)
+    ap.add_argument("--recall-sweep", type=int, nargs="*", default=[])
     a = ap.parse_args()
     if a.k is None:
         a.k = 100 if a.cmd == "batched" else 10
-    {"batched": cmd_batched, "sweep-scan": cmd_sweep_scan, "small-batch": cmd_small_batch}[a.cmd](a)
+    {"batched": cmd_batched, "sweep-scan": cmd_sweep_scan, "small-batch": cmd_small_batch, "ivf": cmd_ivf}[a.cmd](a)
 
 
 if __name__ == "__main__":

@@ -38,3 +38,31 @@ def fill_index(index: TheoremIndex, first_row: int, n_rows: int, seed: int = 0, 
 def make_queries(nq: int, dim: int, device, seed: int = QUERY_SEED) -> torch.Tensor:
     gen = torch.Generator(device=device).manual_seed(seed)
     return torch.randn((nq, dim), generator=gen, dtype=torch.float32, device=device)
+
+
+def fill_index_clustered(index: TheoremIndex, n_rows: int, n_centers: int, sigma: float = 1.0, seed: int = 0,
+                         sub_rows: int = 1 << 18) -> torch.Tensor:
+    """Clustered synthetic corpus (i.i.d. Gaussian rows have no list structure, so IVF recall
+    on them is a pessimistic bound): row = centre[c] + sigma * N(0, I/dim), c uniform.  Returns the unit
+    centres [n_centers, dim] so queries can be drawn from the same mixture."""
+    dev = index.device
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    centers = torch.randn((n_centers, index.dim), generator=gen, dtype=torch.float32, device=dev)
+    centers /= centers.norm(dim=1, keepdim=True)
+    done = 0
+    while done < n_rows:
+        m = min(sub_rows, n_rows - done)
+        which = torch.randint(0, n_centers, (m,), generator=gen, device=dev)
+        blk = torch.randn((m, index.dim), generator=gen, dtype=torch.float32, device=dev)
+        blk.mul_(sigma / index.dim ** 0.5).add_(centers[which])
+        index.add(blk, normalize=True)
+        done += m
+    return centers
+
+
+def make_clustered_queries(nq: int, centers: torch.Tensor, sigma: float = 1.0, seed: int = QUERY_SEED) -> torch.Tensor:
+    dev = centers.device
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    which = torch.randint(0, centers.shape[0], (nq,), generator=gen, device=dev)
+    q = torch.randn((nq, centers.shape[1]), generator=gen, dtype=torch.float32, device=dev)
+    return q * (sigma / centers.shape[1] ** 0.5) + centers[which]
