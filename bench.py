@@ -167,6 +167,7 @@ def main():
     config = {"workload": f"configs[1]: single-query exact top-{args.k} over {args.rows}x{args.dim} bf16",
               "rows": args.rows, "dim": args.dim, "k": args.k,
               "sharding": f"row-sharded x{world}" if world > 1 else "single GPU",
+              "arithmetic": "bf16 corpus rows, fp32 query, fp32 products and accumulation",
               "l2": "corpus shard >> 126 MB L2, distinct query per step (no flush needed)"}
 
     if args.impl == "reference":
@@ -294,6 +295,14 @@ def main():
                 "peak": peaks["hbm_gbs"], "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, copy read+write)",
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "frac_of_nominal_8TBs": achieved / 8000.0,
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": shard_bytes, "traffic": None}
+    # DRAM traffic per launch from the committed ncu --set full capture of this kernel on this shape
+    tp = os.path.join(ROOT, "profiles", "scan_topk_traffic_r1.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            tr = json.load(f)
+        if tr["rows"] == hi - lo and tr["dim"] == args.dim:
+            roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            roofline["traffic_source"] = tr["source"]
 
     if rank == 0:
         cpu = None
@@ -311,7 +320,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16 corpus, fp32 query/accumulate", "data": "synthetic",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": config, "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": args.dim * 4,
                     "d2h_bytes_per_step": args.k * 12, "p50_latency_ms": statistics.median(lat) * 1e3,

@@ -5,6 +5,7 @@ configs and tuning sweeps.  Each sub-command prints one JSON line per measuremen
   python bench_extra.py batched   [--rows 10000000 --nq 4096 --k 100]     configs[2]: K3 tcgen05 GEMM + top-k
   python bench_extra.py sweep-scan [--rows 10000000]                      K2 tunables sweep
   python bench_extra.py small-batch [--rows 10000000]                     nq = 1..256 latency curve
+  torchrun --nproc-per-node 8 bench_extra.py sharded [--rows 100000000 --nlist 16384]  configs[3]+[4] at full size
   python bench_extra.py ivf [--rows 40000000 --nlist 16384 --nprobe 32 --rescore 100 --data clustered]
                                                                           configs[4] shape: IVF-Flat fp8 + rescore
 """
@@ -214,9 +215,114 @@ def cmd_ivf(a):
     print(json.dumps(out))
 
 
+def cmd_ivf_q1(a):
+    """Minimal single-query IVF run for the ncu launch list: build, then `iters` single queries."""
+    dev = torch.device("cuda", 0)
+    index = ts.TheoremIndex(a.dim, a.rows, dtype="bf16", device=dev)
+    centers = synthetic.fill_index_clustered(index, a.rows, a.centers or a.nlist, a.sigma, seed=0)
+    q_all = synthetic.make_clustered_queries(64, centers, a.sigma)
+    index.ivf_train(a.nlist, n_sample=a.train_sample, iters=2, seed=0)
+    index.ivf_build(a.list_dtype)
+    torch.cuda.synchronize()
+    for i in range(a.iters):
+        index.ivf_search(q_all[i:i + 1], a.k, nprobe=a.nprobe, rescore_k=a.rescore)
+    torch.cuda.synchronize()
+    print(json.dumps({"bench": "ivf-q1", "launches": ts.kernel_launches()}))
+
+
+def cmd_sharded(a):
+    """configs[3] + configs[4] at their named size under torchrun: rows row-sharded over WORLD_SIZE GPUs.
+    Exact Q=1 / Q=batch, then IVF-Flat (one shared coarse quantiser) with recall vs the sharded exact path."""
+    import time
+    import torch.distributed as dist
+    from theoremsearch_b200.sharded import ShardedIndex, shard_bounds
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lo, hi = shard_bounds(a.rows, world)[rank]
+    index = ts.TheoremIndex(a.dim, hi - lo, dtype="bf16", device=dev)
+    t0 = time.time()
+    if a.data == "clustered":
+        centers = synthetic.fill_index_clustered(index, hi - lo, a.centers or a.nlist, a.sigma, seed=0, first_row=lo)
+        q_all = synthetic.make_clustered_queries(max(a.nq, a.nq_recall), centers, a.sigma)
+    else:
+        synthetic.fill_index(index, lo, hi - lo, seed=0)
+        q_all = synthetic.make_queries(max(a.nq, a.nq_recall), a.dim, dev)
+    torch.cuda.synchronize()
+    fill_s = time.time() - t0
+    sh = ShardedIndex(index, a.rows)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_max(fn, warmup, iters):
+        for _ in range(warmup):
+            fn()
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        sync()
+        t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    pk = peaks()
+    out = {"bench": "sharded", "rows": a.rows, "dim": a.dim, "n_gpus": world, "rows_per_gpu": hi - lo, "data": a.data,
+           "fill_s": fill_s}
+    q1 = [q_all[i:i + 1].contiguous() for i in range(64)]
+    it = iter(itertools.cycle(range(64)))
+    ms1 = timed_max(lambda: sh.search(q1[next(it)], a.k), 10, 100)
+    out["exact_q1_ms"] = ms1
+    out["exact_q1_qps"] = 1e3 / ms1
+    out["exact_q1_aggregate_gbs"] = a.rows * a.dim * 2 / (ms1 * 1e-3) / 1e9
+    out["exact_q1_frac_of_measured_hbm_per_gpu"] = out["exact_q1_aggregate_gbs"] / world / pk["hbm_gbs"]
+    ms1_local = timed_max(lambda: index.search_keys(q1[next(it)], a.k), 5, 50)
+    out["exact_q1_local_scan_ms"] = ms1_local
+    qb = q_all[:a.nq].contiguous()
+    msb = timed_max(lambda: sh.search(qb, a.kb), 1, 2)
+    out["exact_batch"] = {"nq": a.nq, "k": a.kb, "ms": msb, "qps": a.nq / (msb * 1e-3),
+                          "aggregate_tflops": 2.0 * a.nq * a.rows * a.dim / (msb * 1e-3) / 1e12}
+    if a.nlist > 0:
+        sync()
+        t0 = time.time()
+        sh.ivf_train_build(a.nlist, n_sample=a.train_sample, iters=a.train_iters, seed=0, list_dtype=a.list_dtype)
+        sync()
+        out["ivf_train_build_s"] = time.time() - t0
+        qr = q_all[:a.nq_recall].contiguous()
+        _, exact_ids = sh.search(qr, a.k)
+        _, ivf_ids = sh.ivf_search(qr, a.k, nprobe=a.nprobe, rescore_k=a.rescore)
+        ivf = {"nlist": a.nlist, "nprobe": a.nprobe, "rescore_k": a.rescore, "list_dtype": a.list_dtype,
+               "recall_at_k": recall_at_k(ivf_ids, exact_ids), "recall_queries": a.nq_recall}
+        for np_ in a.recall_sweep:
+            _, ids2 = sh.ivf_search(qr, a.k, nprobe=np_, rescore_k=a.rescore)
+            ivf[f"recall_nprobe_{np_}"] = recall_at_k(ids2, exact_ids)
+        sizes = index.ivf_list_sizes().to(torch.float64)
+        ivf["local_list_rows_min_mean_max"] = [sizes.min().item(), sizes.mean().item(), sizes.max().item()]
+        ms = timed_max(lambda: sh.ivf_search(q1[next(it)], a.k, nprobe=a.nprobe, rescore_k=a.rescore), 10, 100)
+        ivf["q1_ms"] = ms
+        ivf["q1_qps"] = 1e3 / ms
+        msb = timed_max(lambda: sh.ivf_search(qb, a.k, nprobe=a.nprobe, rescore_k=a.rescore), 1, 3)
+        ivf["batch"] = {"nq": a.nq, "ms": msb, "qps": a.nq / (msb * 1e-3)}
+        out["ivf"] = ivf
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("cmd", choices=["batched", "sweep-scan", "small-batch", "ivf"])
+    ap.add_argument("cmd", choices=["batched", "sweep-scan", "small-batch", "ivf", "sharded", "ivf-q1"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--dim", type=int, default=1024)
     ap.add_argument("--nq", type=int, default=4096)
@@ -225,6 +331,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--tunable", nargs=2, action="append", metavar=("NAME", "VALUE"))
     ap.add_argument("--fine", action="store_true")
+    ap.add_argument("--kb", type=int, default=100, help="k of the batched exact search in `sharded`")
     ap.add_argument("--nlist", type=int, default=16384)
     ap.add_argument("--nprobe", type=int, default=32)
     ap.add_argument("--rescore", type=int, default=100)
@@ -239,7 +346,7 @@ def main():
     a = ap.parse_args()
     if a.k is None:
         a.k = 100 if a.cmd == "batched" else 10
-    {"batched": cmd_batched, "sweep-scan": cmd_sweep_scan, "small-batch": cmd_small_batch, "ivf": cmd_ivf}[a.cmd](a)
+    {"batched": cmd_batched, "sweep-scan": cmd_sweep_scan, "small-batch": cmd_small_batch, "ivf": cmd_ivf, "sharded": cmd_sharded, "ivf-q1": cmd_ivf_q1}[a.cmd](a)
 
 
 if __name__ == "__main__":

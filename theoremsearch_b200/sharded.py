@@ -61,3 +61,35 @@ class ShardedIndex:
             dist.all_gather_into_tensor(flat, keys.contiguous().view(-1), group=self.group)
             gathered = flat.view((self.world,) + tuple(keys.shape))               # [G, nq, k], shard-major
         return self._merge(gathered, k, shard_base=self.shard_base(keys.device), id_map=self.id_map)
+
+    # -------------------------------------------------------------------------------- IVF-Flat
+    def ivf_train_build(self, nlist: int, n_sample: int = 0, iters: int = 10, seed: int = 0,
+                        list_dtype: str = "fp8", src: int = 0) -> None:
+        """One coarse quantiser for all shards: rank ``src`` trains on (a strided sample of) its own
+        rows, the centroids are broadcast, every rank files its rows under them (every GPU
+        holds all centroids and its slice of each list)."""
+        dev = self.local.device
+        if self.rank == src:
+            self.local.ivf_train(nlist, n_sample=n_sample, iters=iters, seed=seed)
+            cent = self.local.ivf_centroids()
+        else:
+            cent = torch.empty((nlist, self.local.dim), dtype=torch.float32, device=dev)
+        if self.world > 1:
+            dist.broadcast(cent, src=src, group=self.group)
+        if self.rank != src:
+            self.local.ivf_set_centroids(cent)
+        self.local.ivf_build(list_dtype)
+
+    def ivf_search(self, queries: torch.Tensor, k: int, nprobe: int = 32, rescore_k: int = 100,
+                   normalize: bool = True):
+        """ANN over the sharded corpus: every rank probes the same ``nprobe`` lists (same centroids) in
+        its own slice, re-scores its candidates exactly, and the packed keys are gathered and merged
+        exactly like the exact path."""
+        keys = self.local.ivf_search_keys(queries, k, nprobe=nprobe, rescore_k=rescore_k, normalize=normalize)
+        if self.world == 1:
+            gathered = keys.unsqueeze(0)
+        else:
+            flat = torch.empty(self.world * keys.numel(), dtype=keys.dtype, device=keys.device)
+            dist.all_gather_into_tensor(flat, keys.contiguous().view(-1), group=self.group)
+            gathered = flat.view((self.world,) + tuple(keys.shape))
+        return self._merge(gathered, k, shard_base=self.shard_base(keys.device), id_map=self.id_map)

@@ -40,23 +40,39 @@ def make_queries(nq: int, dim: int, device, seed: int = QUERY_SEED) -> torch.Ten
     return torch.randn((nq, dim), generator=gen, dtype=torch.float32, device=device)
 
 
+def clustered_centers(n_centers: int, dim: int, device, seed: int = 0) -> torch.Tensor:
+    gen = torch.Generator(device=device).manual_seed(seed)
+    centers = torch.randn((n_centers, dim), generator=gen, dtype=torch.float32, device=device)
+    return centers / centers.norm(dim=1, keepdim=True)
+
+
 def fill_index_clustered(index: TheoremIndex, n_rows: int, n_centers: int, sigma: float = 1.0, seed: int = 0,
-                         sub_rows: int = 1 << 18) -> torch.Tensor:
+                         sub_rows: int = 1 << 18, first_row: int = 0) -> torch.Tensor:
     """Clustered synthetic corpus (i.i.d. Gaussian rows have no list structure, so IVF recall
-    on them is a pessimistic bound): row = centre[c] + sigma * N(0, I/dim), c uniform.  Returns the unit
-    centres [n_centers, dim] so queries can be drawn from the same mixture."""
+    on them is a pessimistic bound): row = centre[c] + sigma * N(0, I/dim), c uniform.  Appends global rows
+    [first_row, first_row + n_rows); like ``fill_index`` the content of a row depends only on its global
+    position (1 Mi-row chunks, chunk c seeded with seed + 1 + c).  Returns the unit centres
+    [n_centers, dim] so queries can be drawn from the same mixture."""
     dev = index.device
-    gen = torch.Generator(device=dev).manual_seed(seed)
-    centers = torch.randn((n_centers, index.dim), generator=gen, dtype=torch.float32, device=dev)
-    centers /= centers.norm(dim=1, keepdim=True)
-    done = 0
-    while done < n_rows:
-        m = min(sub_rows, n_rows - done)
-        which = torch.randint(0, n_centers, (m,), generator=gen, device=dev)
-        blk = torch.randn((m, index.dim), generator=gen, dtype=torch.float32, device=dev)
-        blk.mul_(sigma / index.dim ** 0.5).add_(centers[which])
-        index.add(blk, normalize=True)
-        done += m
+    centers = clustered_centers(n_centers, index.dim, dev, seed)
+    gen = torch.Generator(device=dev)
+    pos, end = first_row, first_row + n_rows
+    while pos < end:
+        c, off = divmod(pos, CHUNK_ROWS)
+        take = min(end - pos, CHUNK_ROWS - off)
+        gen.manual_seed(seed + 1 + c)
+        done = 0
+        while done < off + take:
+            m = min(sub_rows, off + take - done)
+            which = torch.randint(0, n_centers, (m,), generator=gen, device=dev)
+            blk = torch.randn((m, index.dim), generator=gen, dtype=torch.float32, device=dev)
+            lo = max(off - done, 0)
+            if lo < m:
+                blk = blk[lo:]
+                blk.mul_(sigma / index.dim ** 0.5).add_(centers[which[lo:]])
+                index.add(blk, normalize=True)
+            done += m
+        pos += take
     return centers
 
 
