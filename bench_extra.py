@@ -230,6 +230,48 @@ def cmd_ivf_q1(a):
     print(json.dumps({"bench": "ivf-q1", "launches": ts.kernel_launches()}))
 
 
+def cmd_ivf_q1_sweep(a):
+    """Single-query IVF latency (graph-replayed) over the K4b tunables, plus the phase timeline of one query."""
+    import ctypes as C
+    import numpy as np
+    from theoremsearch_b200 import _lib
+    dev = torch.device("cuda", 0)
+    index = ts.TheoremIndex(a.dim, a.rows, dtype="bf16", device=dev)
+    centers = synthetic.fill_index_clustered(index, a.rows, a.centers or a.nlist, a.sigma, seed=0)
+    q_all = synthetic.make_clustered_queries(64, centers, a.sigma)
+    index.ivf_train(a.nlist, n_sample=a.train_sample, iters=3, seed=0)
+    index.ivf_build(a.list_dtype)
+    torch.cuda.synchronize()
+    qs = q_all[:1].clone()
+    fn = lambda: index.ivf_search(qs, a.k, nprobe=a.nprobe, rescore_k=a.rescore)
+    for warps, rows, parts in [(0, 0, 0), (8, 8, 0), (16, 4, 0), (8, 4, 0), (12, 4, 0), (16, 4, 74), (16, 4, 296), (8, 8, 74)]:
+        ts.set_tunable("ivf.warps", warps)
+        ts.set_tunable("ivf.tile_rows", rows)
+        ts.set_tunable("ivf.parts", parts)
+        index._ws = {}
+        ms = timed_graph(fn, 10, 200)
+        print(json.dumps({"bench": "ivf-q1-sweep", "rows": a.rows, "nlist": a.nlist, "warps": warps, "tile_rows": rows,
+                          "parts": parts, "q1_ms_graph": ms}))
+    for name in ("ivf.warps", "ivf.tile_rows", "ivf.parts"):
+        ts.set_tunable(name, 0)
+    index._ws = {}
+    ts.set_tunable("ivf.timeline", 1)
+    for _ in range(3):
+        fn()
+    buf = np.zeros((148, 8), dtype=np.uint64)
+    _lib.check(_lib.lib.ts_debug_ivf_timeline(buf.ctypes.data, 148))
+    ts.set_tunable("ivf.timeline", 0)
+    t = buf.astype(np.int64)
+    t0 = t[:, 0].min()
+    rel = (t - t0) / 1e3
+    last = int(np.argmax(t[:, 7]))
+    print(json.dumps({"bench": "ivf-q1-timeline", "unit": "us since first CTA start",
+                      "phases": ["start", "table", "prologue", "scan_done", "flushed", "cta_merged", "final_begin", "final_end"],
+                      "median_cta": [float(np.median(rel[:, i])) for i in range(6)],
+                      "max_cta": [float(rel[:, i].max()) for i in range(6)],
+                      "last_cta": [float(x) for x in rel[last]]}))
+
+
 def cmd_sharded(a):
     """configs[3] + configs[4] at their named size under torchrun: rows row-sharded over WORLD_SIZE GPUs.
     Exact Q=1 / Q=batch, then IVF-Flat (one shared coarse quantiser) with recall vs the sharded exact path."""
@@ -322,7 +364,7 @@ def cmd_sharded(a):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("cmd", choices=["batched", "sweep-scan", "small-batch", "ivf", "sharded", "ivf-q1"])
+    ap.add_argument("cmd", choices=["batched", "sweep-scan", "small-batch", "ivf", "sharded", "ivf-q1", "ivf-q1-sweep"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--dim", type=int, default=1024)
     ap.add_argument("--nq", type=int, default=4096)
@@ -346,7 +388,7 @@ def main():
     a = ap.parse_args()
     if a.k is None:
         a.k = 100 if a.cmd == "batched" else 10
-    {"batched": cmd_batched, "sweep-scan": cmd_sweep_scan, "small-batch": cmd_small_batch, "ivf": cmd_ivf, "sharded": cmd_sharded, "ivf-q1": cmd_ivf_q1}[a.cmd](a)
+    {"batched": cmd_batched, "sweep-scan": cmd_sweep_scan, "small-batch": cmd_small_batch, "ivf": cmd_ivf, "sharded": cmd_sharded, "ivf-q1": cmd_ivf_q1, "ivf-q1-sweep": cmd_ivf_q1_sweep}[a.cmd](a)
 
 
 if __name__ == "__main__":

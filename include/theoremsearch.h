@@ -57,6 +57,7 @@ enum ts_dtype {
 
 #define TS_MAX_K 1024   /* largest k any search entry point accepts            */
 #define TS_MAX_DIM 2048 /* largest embedding dimension (reference uses 768/1024) */
+#define TS_IVF_MAX_CANDIDATES 256 /* largest k / rescore_k of the IVF entry points */
 
 typedef struct ts_index ts_index; /* the corpus: quantised rows (+ ids, + IVF lists) on one GPU */
 typedef struct ts_ctx ts_ctx;     /* per-caller search context: workspace, pinned staging, stream */
@@ -227,6 +228,10 @@ TS_API int ts_ivf_get_list_data(const ts_index* index, int64_t first, int64_t n,
  * TS_ERR_BAD_ARG for unknown names. Used by the bench sweeps only. */
 TS_API int ts_set_tunable(const char* name, int value);
 TS_API int ts_get_tunable(const char* name, int* value);
+
+/* With tunable "ivf.timeline" = 1 the list-scan CTAs of query 0 record %globaltimer (ns) at 8 phase
+ * boundaries; this copies [n_ctas][8] stamps to HOST memory. Synchronises the device. */
+TS_API int ts_debug_ivf_timeline(uint64_t* out_host, int n_ctas);
 
 /* How many queries of the most recent batched (K3) search failed the exactness certificate or
  * overflowed their candidate buffer and were therefore re-scanned by the exact K2 path.

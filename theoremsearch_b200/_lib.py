@@ -85,6 +85,7 @@ SIGNATURES = {
     "ts_set_tunable": (_i, [C.c_char_p, _i]),
     "ts_get_tunable": (_i, [C.c_char_p, C.POINTER(_i)]),
     "ts_debug_last_batched_fixups": (_i, []),
+    "ts_debug_ivf_timeline": (_i, [_p, _i]),
 }
 
 

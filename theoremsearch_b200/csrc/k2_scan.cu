@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
             const uint64_t x = __shfl_sync(0xFFFFFFFFu, key, src);
             if (x > thr) {
                 list.insert(x, lane);
-                thr = list.at(k - 1);
+                thr = list.kth(k);
             }
         }
         if (++s == stages) {
@@ -221,21 +221,24 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
             const int pos = j * 32 + lane;
             if (pos < k) out[pos] = list.key[j];
         }
-        if (p.tickets != nullptr) __threadfence();   // publish this CTA's list before taking a ticket
     }
     __syncthreads();  // the list area aliases the TMA slots of the next work item
     if (p.tickets != nullptr) {
-        // ---- fused final merge: the last CTA of this work item to arrive folds all gridDim.x lists
+        // ---- fused final merge: the last CTA of this work item to arrive folds all gridDim.x lists.
+        // One gpu-scope fence on each side of the ticket, by thread 0 only: the barriers order the other
+        // threads' stores before it / loads after it (fences are cumulative).
         __shared__ int s_is_last;
         if (threadIdx.x == 0) {
             __threadfence();
             const uint32_t t = atomicAdd(p.tickets + wi, 1u);
             s_is_last = (t == gridDim.x - 1);
-            if (s_is_last) p.tickets[wi] = 0u;   // self-cleaning: the next launch finds zeros
+            if (s_is_last) {
+                p.tickets[wi] = 0u;   // self-cleaning: the next launch finds zeros
+                __threadfence();
+            }
         }
         __syncthreads();
         if (s_is_last) {
-            __threadfence();
             MergeParams mp = p.fin;
             mp.keys = p.part_keys;
             mp.nlists = gridDim.x;
@@ -284,7 +287,15 @@ static int launch_r(const ts_index* ix, const ScanParams& p0, int nq, int nparts
     auto kern = scan_topk_kernel<ELEM, NCHUNK, KPL, R>;
     TS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
     if (ev0) TS_CHECK_CUDA(cudaEventRecord(ev0, s));
-    kern<<<dim3(nparts, p.qcount ? std::min(nq, 8) : nq), c.warps * 32, c.smem, s>>>(p);
+    // Small tables (e.g. the IVF centroid table): fewer CTAs, so that every warp still gets a few tiles and
+    // the fused final merge folds fewer lists. Only when the merge is fused (it reads gridDim.x lists);
+    // the unfused callers size their merge for nparts lists.
+    int grid = nparts;
+    if (p.tickets != nullptr) {
+        const int64_t tiles = (p.n_rows + R - 1) / R;
+        grid = (int)std::min<int64_t>(nparts, std::max<int64_t>(1, (tiles + c.warps * 4 - 1) / (c.warps * 4)));
+    }
+    kern<<<dim3(grid, p.qcount ? std::min(nq, 8) : nq), c.warps * 32, c.smem, s>>>(p);
     TS_LAUNCH_CHECK();
     if (ev1) TS_CHECK_CUDA(cudaEventRecord(ev1, s));
     return TS_OK;

@@ -438,6 +438,60 @@ __global__ void list_sizes_kernel(const int64_t* __restrict__ offsets, int nlist
 }
 
 // ---------------------------------------------------------------------------------- K4b list scan
+// Descending bitonic sort of P keys (power of two, >= 64) in shared memory by every thread of the CTA.
+// A warp owns 64-key windows: all compare-exchange levels with stride <= 32 run in registers (two keys per
+// lane, shuffles), so only strides >= 64 cost a shared-memory pass and a barrier — 15 barriers instead of 55
+// for 1024 keys.
+__device__ __forceinline__ void cta_bitonic_sort_desc(uint64_t* buf, int P) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    auto reg_block = [&](int size_first, int size_last) {
+        for (int wb = warp * 64; wb < P; wb += nw * 64) {
+            uint64_t a0 = buf[wb + lane], a1 = buf[wb + 32 + lane];
+            for (int size = size_first; size <= size_last; size <<= 1) {
+                const bool desc0 = ((wb + lane) & size) == 0;
+                const bool desc1 = ((wb + 32 + lane) & size) == 0;
+                for (int st = (size >> 1) > 32 ? 32 : (size >> 1); st >= 1; st >>= 1) {
+                    if (st == 32) {
+                        if ((a0 < a1) == desc0) {
+                            const uint64_t t = a0;
+                            a0 = a1;
+                            a1 = t;
+                        }
+                    } else {
+                        const bool lower = (lane & st) != 0;
+                        const uint64_t o0 = __shfl_xor_sync(0xFFFFFFFFu, a0, st);
+                        const uint64_t o1 = __shfl_xor_sync(0xFFFFFFFFu, a1, st);
+                        const bool t0 = (desc0 != lower) ? (o0 > a0) : (o0 < a0);
+                        const bool t1 = (desc1 != lower) ? (o1 > a1) : (o1 < a1);
+                        a0 = t0 ? o0 : a0;
+                        a1 = t1 ? o1 : a1;
+                    }
+                }
+            }
+            buf[wb + lane] = a0;
+            buf[wb + 32 + lane] = a1;
+        }
+        __syncthreads();
+    };
+    reg_block(2, 64 < P ? 64 : P);
+    for (int size = 128; size <= P; size <<= 1) {
+        for (int st = size >> 1; st >= 64; st >>= 1) {
+            for (int i = threadIdx.x; i < P / 2; i += blockDim.x) {
+                const int lo = 2 * i - (i & (st - 1));
+                const int hi = lo + st;
+                const bool desc = (lo & size) == 0;
+                const uint64_t a = buf[lo], b = buf[hi];
+                if ((a < b) == desc) {
+                    buf[lo] = b;
+                    buf[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+        reg_block(size, size);
+    }
+}
+
 struct ListScanParams {
     const uint8_t* list_data;     // [n, row_bytes] rows in list order
     uint32_t row_bytes;           // multiple of 16
@@ -452,7 +506,20 @@ struct ListScanParams {
     uint32_t* tickets;            // [nq] zero on entry, left zero
     uint64_t* out_keys;           // [nq][k] merged candidates, key row = list POSITION
     int stages;
+    unsigned long long* timeline; // diagnostics: [gridDim.x][8] globaltimer stamps of query 0, or nullptr
 };
+
+__device__ unsigned long long g_ivf_timeline[148 * 8];
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define IVF_STAMP(i)                                                                         \
+    do {                                                                                     \
+        if (p.timeline != nullptr && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 148) \
+            p.timeline[blockIdx.x * 8 + (i)] = globaltimer_ns();                             \
+    } while (0)
 
 template <int ELEM, int NCHUNK, int KPL, int R>
 __global__ void __launch_bounds__(512, 1) list_scan_kernel(const ListScanParams p) {
@@ -476,6 +543,7 @@ __global__ void __launch_bounds__(512, 1) list_scan_kernel(const ListScanParams 
     int* s_len = reinterpret_cast<int*>(s_start + nprobe);
     int* s_tpref = s_len + nprobe;   // [nprobe + 1]
 
+    IVF_STAMP(0);
     if (lane == 0) {
         for (int s = 0; s < stages; ++s) mbar_init(&my_bars[s], 1);
         fence_mbar_init();
@@ -509,6 +577,7 @@ __global__ void __launch_bounds__(512, 1) list_scan_kernel(const ListScanParams 
         if (lane == 0) s_tpref[nprobe] = carry;
     }
     __syncthreads();
+    IVF_STAMP(1);
 
     const int64_t T = s_tpref[nprobe];
     const int64_t g = (int64_t)blockIdx.x * W + warp;
@@ -555,22 +624,44 @@ __global__ void __launch_bounds__(512, 1) list_scan_kernel(const ListScanParams 
         }
     }
 
-    float q[NCHUNK * CN];
+    // query slice of this lane: fp32 for bf16 lists, packed half2 for e4m3 lists (see dot16_e4m3_h2)
+    constexpr int QF = (ELEM == 1) ? 1 : NCHUNK * CN;
+    constexpr int QH = (ELEM == 1) ? NCHUNK * CN / 2 : 1;
+    float q[QF];
+    __half2 qh[QH];
     {
         const float* qv = p.queries + (size_t)qi * p.dim_pad;
 #pragma unroll
         for (int j = 0; j < NCHUNK; ++j) {
             const int e0 = (j * 32 + lane) * CN;
+            // dim_pad is a multiple of 8 and rows of the prepared query array are 32-byte aligned: float4 loads
+            if constexpr (ELEM == 1) {
 #pragma unroll
-            for (int i = 0; i < CN; ++i) q[j * CN + i] = (e0 + i < p.dim_pad) ? __ldg(qv + e0 + i) : 0.f;
+                for (int i = 0; i < CN; i += 4) {
+                    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (e0 + i < p.dim_pad) f = __ldg(reinterpret_cast<const float4*>(qv + e0 + i));
+                    qh[(j * CN + i) / 2] = __floats2half2_rn(f.x, f.y);
+                    qh[(j * CN + i) / 2 + 1] = __floats2half2_rn(f.z, f.w);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < CN; i += 4) {
+                    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (e0 + i < p.dim_pad) f = __ldg(reinterpret_cast<const float4*>(qv + e0 + i));
+                    q[j * CN + i] = f.x;
+                    q[j * CN + i + 1] = f.y;
+                    q[j * CN + i + 2] = f.z;
+                    q[j * CN + i + 3] = f.w;
+                }
+            }
         }
     }
 
-    WarpTopK<KPL> list;
-    list.clear();
-    uint64_t thr = 0ull;
+    WarpSelect<KPL> sel;
+    sel.init();
     int s = 0;
     uint32_t parity = 0;
+    IVF_STAMP(2);
     for (int t = t0; t < t1; ++t) {
         const int left = s_len[jc] - tc * R;
         const int64_t pos = s_start[jc] + (int64_t)tc * R + my_row;
@@ -590,7 +681,8 @@ __global__ void __launch_bounds__(512, 1) list_scan_kernel(const ListScanParams 
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const uint4 v = *reinterpret_cast<const uint4*>(slot + (size_t)r * p.row_bytes + off);
-                    acc[r] = Chunk<ELEM>::dot(v, &q[j * CN], acc[r]);
+                    if constexpr (ELEM == 1) acc[r] = dot16_e4m3_h2(v, &qh[j * CN / 2], acc[r]);
+                    else acc[r] = Chunk<ELEM>::dot(v, &q[j * CN], acc[r]);
                 }
             }
         }
@@ -602,56 +694,131 @@ __global__ void __launch_bounds__(512, 1) list_scan_kernel(const ListScanParams 
         advance(jc, tc);
 
         transpose_reduce<R>(acc, lane);
-        const uint64_t key = mine ? pack_key(acc[0] * scale, (uint32_t)pos) : 0ull;
-        unsigned m = __ballot_sync(0xFFFFFFFFu, key > thr);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const uint64_t x = __shfl_sync(0xFFFFFFFFu, key, src);
-            if (x > thr) {
-                list.insert(x, lane);
-                thr = list.at(k - 1);
-            }
-        }
+        sel.offer(mine ? pack_key(acc[0] * scale, (uint32_t)pos) : 0ull, k, lane);
         if (++s == stages) {
             s = 0;
             parity ^= 1u;
         }
     }
+    IVF_STAMP(3);
 
+    // ---- CTA selection. Warps do NOT sort their own candidates: every warp appends its (sorted) best list
+    // and its unsorted pending keys to one dense smem array, and the whole CTA sorts that array once with a
+    // shared-memory bitonic network (all threads on one sort instead of every warp sorting a padded list and
+    // one warp folding them serially: 2-3 us instead of 40+ when a warp has seen only tens of rows).
+    __syncthreads();                                          // every slot has been consumed
+    uint64_t* cbuf = reinterpret_cast<uint64_t*>(smem);       // aliases the drained TMA slots
+    __shared__ int s_n, s_is_last;
+    if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
-    uint64_t* lists = reinterpret_cast<uint64_t*>(smem);  // [W][KPL*32], aliases the drained slots
+    {
+        const uint32_t lt_mask = (1u << lane) - 1u;
+        int nb = 0;                                           // non-empty entries of the sorted list (a prefix)
 #pragma unroll
-    for (int j = 0; j < KPL; ++j) lists[(size_t)warp * (KPL * 32) + j * 32 + lane] = list.key[j];
-    __syncthreads();
-    if (warp == 0) {
-        for (int w = 1; w < W; ++w) merge_sorted_into<KPL>(list, lists + (size_t)w * (KPL * 32), k, k, lane);
-        uint64_t* out = p.part_keys + ((size_t)qi * gridDim.x + blockIdx.x) * k;
+        for (int j = 0; j < KPL; ++j) nb += __popc(__ballot_sync(0xFFFFFFFFu, sel.best.key[j] != 0ull));
+        const int n_w = nb + sel.count;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_n, n_w);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+#pragma unroll
+        for (int j = 0; j < KPL; ++j)
+            if (j * 32 + lane < nb) cbuf[base + j * 32 + lane] = sel.best.key[j];
+        int off = base + nb;
 #pragma unroll
         for (int j = 0; j < KPL; ++j) {
-            const int pos = j * 32 + lane;
-            if (pos < k) out[pos] = list.key[j];
+            const unsigned msk = __ballot_sync(0xFFFFFFFFu, sel.pend[j] != 0ull);
+            if (sel.pend[j] != 0ull) cbuf[off + __popc(msk & lt_mask)] = sel.pend[j];
+            off += __popc(msk);
         }
-        __threadfence();
     }
     __syncthreads();
-    __shared__ int s_is_last;
+    IVF_STAMP(4);
+    {
+        const int n = s_n;
+        int P = 64;
+        while (P < n) P <<= 1;
+        for (int i = n + threadIdx.x; i < P; i += blockDim.x) cbuf[i] = 0ull;
+        __syncthreads();
+        cta_bitonic_sort_desc(cbuf, P);
+        uint64_t* out = p.part_keys + ((size_t)qi * gridDim.x + blockIdx.x) * k;
+        for (int i = threadIdx.x; i < k; i += blockDim.x) out[i] = (i < P) ? cbuf[i] : 0ull;
+    }
+    // publish: the barrier orders every thread's stores before thread 0's gpu-scope fence (fences are
+    // cumulative), so ONE fence suffices — 512 threads fencing at once cost several microseconds
+    __syncthreads();
+    IVF_STAMP(5);
     if (threadIdx.x == 0) {
         __threadfence();
         const uint32_t t = atomicAdd(p.tickets + qi, 1u);
         s_is_last = (t == gridDim.x - 1);
-        if (s_is_last) p.tickets[qi] = 0u;
+        if (s_is_last) {
+            p.tickets[qi] = 0u;
+            __threadfence();   // acquire side: the other CTAs' lists are read (from L2) after this
+        }
     }
     __syncthreads();
-    if (s_is_last) {
-        __threadfence();
+    if (!s_is_last) return;
+
+    // ---- final merge by the last CTA of the query: gridDim.x sorted lists of k keys. Prune first: the k-th
+    // largest key among the first m = ceil(k / lists) entries of every list is a lower bound L on the k-th
+    // largest overall (at least k keys are >= L), so only keys >= L can be in the result — typically a few
+    // hundred of the lists*k keys. They are compacted into smem and sorted by the whole CTA.
+    IVF_STAMP(6);
+    const int nl = gridDim.x;
+    const uint64_t* mine = p.part_keys + (size_t)qi * nl * k;
+    constexpr int CAP = 4096;                                 // keys; fits the smallest smem carve-out (32 KB)
+    const int m = (k + nl - 1) / nl;
+    __shared__ int s_cnt;
+    __shared__ uint64_t s_low;
+    {
+        int P = 64;
+        while (P < nl * m) P <<= 1;                           // <= k + lists - 1 < 512 keys
+        for (int i = threadIdx.x; i < P; i += blockDim.x)
+            cbuf[i] = (i < nl * m) ? __ldcg(mine + (size_t)(i / m) * k + (i % m)) : 0ull;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        cta_bitonic_sort_desc(cbuf, P);
+        if (threadIdx.x == 0) s_low = cbuf[k - 1];            // 0 when fewer than k candidates exist at all
+        __syncthreads();
+    }
+    const uint64_t low = s_low;
+    uint64_t* sel_buf = cbuf;                                 // the head sort is finished with cbuf (barrier above)
+    for (int i0 = threadIdx.x; i0 < nl * k; i0 += 32 * blockDim.x) {   // up to 32 L2 loads in flight per thread
+        uint64_t v[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+            const int i = i0 + u * blockDim.x;
+            v[u] = (i < nl * k) ? __ldcg(mine + i) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+            if (v[u] != 0ull && v[u] >= low) {
+                const int pos = atomicAdd(&s_cnt, 1);
+                if (pos < CAP) sel_buf[pos] = v[u];
+            }
+        }
+    }
+    __syncthreads();
+    const int cnt = s_cnt;
+    uint64_t* dst = p.out_keys + (size_t)qi * k;
+    if (cnt <= CAP) {
+        int P = 64;
+        while (P < cnt) P <<= 1;
+        for (int i = cnt + threadIdx.x; i < P; i += blockDim.x) sel_buf[i] = 0ull;
+        __syncthreads();
+        cta_bitonic_sort_desc(sel_buf, P);
+        for (int i = threadIdx.x; i < k; i += blockDim.x) dst[i] = (i < P) ? sel_buf[i] : 0ull;
+    } else {
+        // more survivors than the buffer holds (lists with long runs of near-equal keys): the register
+        // merge is slower but needs no bound
+        __syncthreads();
         MergeParams mp;
         mp.keys = p.part_keys;
-        mp.nlists = gridDim.x;
+        mp.nlists = nl;
         mp.nq = gridDim.y;
         mp.k = k;
         mp.stride_list = k;
-        mp.stride_query = (int64_t)gridDim.x * k;
+        mp.stride_query = (int64_t)nl * k;
         mp.list_base = nullptr;
         mp.id_map = nullptr;
         mp.out_keys = p.out_keys;
@@ -660,8 +827,9 @@ __global__ void __launch_bounds__(512, 1) list_scan_kernel(const ListScanParams 
         mp.out_stride = k;
         mp.qlist = nullptr;
         mp.qcount = nullptr;
-        merge_lists<KPL>(mp, qi, qi, lists, W);
+        merge_lists<KPL>(mp, qi, qi, cbuf, W);
     }
+    IVF_STAMP(7);
 }
 
 struct ListScanConfig {
@@ -674,14 +842,20 @@ static int launch_list_scan_r(const ts_index* ix, ListScanParams p, int nq, int 
     const Tunables& t = tunables();
     const size_t tile_bytes = (size_t)R * p.row_bytes;
     int stages = t.scan_stages < 2 ? 2 : t.scan_stages;
-    int warps = t.scan_warps < 1 ? 1 : (t.scan_warps > 16 ? 16 : t.scan_warps);
+    // latency mode (a query is spread over several CTAs): 16 warps per SM halve the rows — and so the serial
+    // instruction stream — per warp; throughput mode (one CTA per query, many queries): 8 warps stream at HBM rate
+    int warps = t.ivf_warps > 0 ? t.ivf_warps : (parts > 1 ? 16 : 8);
+    warps = warps > 16 ? 16 : warps;
     const size_t table = (size_t)p.nprobe * 16 + 16;   // s_start, s_len, s_tpref
     const size_t budget = (size_t)(220 * 1024) - 1024 - table;
     while (warps > 1 && (size_t)warps * stages * tile_bytes + 8 * warps * stages > budget) --warps;
     size_t smem = (size_t)warps * stages * tile_bytes + 8 * (size_t)warps * stages + table;
-    const size_t list_bytes = (size_t)warps * KPL * 32 * 8;
-    if (smem < list_bytes) smem = list_bytes;
+    // the epilogue reuses the slot area: every warp's sorted list + pending keys, and the 4096-key final buffer
+    const size_t select_bytes = std::max<size_t>((size_t)warps * 2 * KPL * 32 * 8, 4096 * 8);
+    if (smem < select_bytes) smem = select_bytes;
     p.stages = stages;
+    p.timeline = nullptr;
+    if (t.ivf_timeline) TS_CHECK_CUDA(cudaGetSymbolAddress((void**)&p.timeline, g_ivf_timeline));
     auto kern = list_scan_kernel<ELEM, NCHUNK, KPL, R>;
     TS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(parts, nq), warps * 32, smem, s>>>(p);
@@ -693,10 +867,18 @@ static int launch_list_scan_r(const ts_index* ix, ListScanParams p, int nq, int 
 template <int ELEM, int NCHUNK>
 static int launch_list_scan_k(const ts_index* ix, const ListScanParams& p, int nq, int parts, cudaStream_t s) {
     constexpr int R = (ELEM == 1) ? (NCHUNK == 1 ? 16 : (NCHUNK == 2 ? 8 : 4)) : RowsPerTile<NCHUNK>::value;
+    if constexpr (ELEM == 1 && NCHUNK == 2) {   // the flagship shape (e4m3, 512 < D <= 1024): 4-row tiles too
+        int rows = tunables().ivf_tile_rows;
+        if (rows == 0) rows = parts > 1 ? 4 : 8;
+        if (rows == 4 && p.k <= 128)
+            return p.k <= 32 ? launch_list_scan_r<ELEM, NCHUNK, 1, 4>(ix, p, nq, parts, s)
+                             : launch_list_scan_r<ELEM, NCHUNK, 4, 4>(ix, p, nq, parts, s);
+    }
     if (p.k <= 32) return launch_list_scan_r<ELEM, NCHUNK, 1, R>(ix, p, nq, parts, s);
     if (p.k <= 128) return launch_list_scan_r<ELEM, NCHUNK, 4, R>(ix, p, nq, parts, s);
     if (p.k <= 256) return launch_list_scan_r<ELEM, NCHUNK, 8, R>(ix, p, nq, parts, s);
-    return launch_list_scan_r<ELEM, NCHUNK, 32, R>(ix, p, nq, parts, s);
+    set_error("ivf list scan: max(k, rescore_k) = %d exceeds %d", p.k, TS_IVF_MAX_CANDIDATES);
+    return TS_ERR_UNSUPPORTED;
 }
 
 static int launch_list_scan(const ts_index* ix, const ListScanParams& p, int nq, int parts, cudaStream_t s) {
@@ -723,27 +905,36 @@ static int launch_list_scan(const ts_index* ix, const ListScanParams& p, int nq,
 // One CTA per query: candidates (list positions) -> corpus rows -> exact fp32-query scores in K2's
 // summation order -> bitonic sort -> top-k.
 template <int ELEM>
-__global__ void __launch_bounds__(256) ivf_rescore_kernel(const uint64_t* __restrict__ cand, int kc, int k,
-                                                          const uint32_t* __restrict__ list_rows,
-                                                          const float* __restrict__ q32,
-                                                          const uint8_t* __restrict__ corpus, uint32_t row_bytes,
-                                                          int dim_pad, const int64_t* __restrict__ id_map,
-                                                          uint64_t* __restrict__ out_keys, float* __restrict__ out_scores,
-                                                          int64_t* __restrict__ out_ids) {
+__global__ void __launch_bounds__(1024) ivf_rescore_kernel(const uint64_t* __restrict__ cand, int kc, int k,
+                                                           const uint32_t* __restrict__ list_rows,
+                                                           const float* __restrict__ q32,
+                                                           const uint8_t* __restrict__ corpus, uint32_t row_bytes,
+                                                           int dim_pad, const int64_t* __restrict__ id_map,
+                                                           uint64_t* __restrict__ out_keys, float* __restrict__ out_scores,
+                                                           int64_t* __restrict__ out_ids) {
     constexpr int CN = Chunk<ELEM>::N;
     extern __shared__ uint64_t rs_buf[];
     const int q = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int P = 1;
+    const int nwarps = blockDim.x >> 5;
+    int P = 64;
     while (P < kc) P <<= 1;
     const float* qv = q32 + (size_t)q * dim_pad;
-    for (int j = warp; j < P; j += 8) {
-        uint64_t key = (j < kc) ? cand[(size_t)q * kc + j] : 0ull;
-        if (key != 0ull) {
-            const uint32_t row = list_rows[key_row(key)];
+    // warp w owns candidates w, w + nwarps, ...; lane i looks up the i-th of them (key -> list position ->
+    // corpus row), so all of a warp's dependent lookups are in flight together, then rows are scored one
+    // at a time by the whole warp.
+    {
+        const int jm = warp + lane * nwarps;
+        const uint64_t mykey = (jm < kc) ? cand[(size_t)q * kc + jm] : 0ull;
+        const uint32_t myrow = mykey ? list_rows[key_row(mykey)] : 0u;
+        const unsigned live = __ballot_sync(0xFFFFFFFFu, mykey != 0ull);
+        uint64_t outkey = 0ull;
+        for (int c = 0; c < 32 && warp + c * nwarps < P; ++c) {
+            if (!((live >> c) & 1u)) continue;
+            const uint32_t row = __shfl_sync(0xFFFFFFFFu, myrow, c);
             const uint8_t* r = corpus + (size_t)row * row_bytes;
             float acc = 0.f;
-            for (uint32_t off = (uint32_t)lane * 16u; off < row_bytes; off += 512u) {
+            for (uint32_t off = (uint32_t)lane * 16u; off < row_bytes; off += 512u) {   // K2's chunk order
                 const uint4 v = __ldg(reinterpret_cast<const uint4*>(r + off));
                 float ql[CN];
 #pragma unroll
@@ -751,27 +942,13 @@ __global__ void __launch_bounds__(256) ivf_rescore_kernel(const uint64_t* __rest
                 acc = Chunk<ELEM>::dot(v, ql, acc);
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
-            key = pack_key(acc, row);
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);   // == K2's reduce tree
+            if (lane == c) outkey = pack_key(acc, row);
         }
-        if (lane == 0) rs_buf[j] = key;
+        if (jm < P) rs_buf[jm] = outkey;
     }
     __syncthreads();
-    for (int size = 2; size <= P; size <<= 1) {
-        for (int st = size >> 1; st > 0; st >>= 1) {
-            for (int i = threadIdx.x; i < P / 2; i += blockDim.x) {
-                const int lo = 2 * i - (i & (st - 1));
-                const int hi = lo + st;
-                const bool desc = (lo & size) == 0;
-                const uint64_t a = rs_buf[lo], b = rs_buf[hi];
-                if ((a < b) == desc) {
-                    rs_buf[lo] = b;
-                    rs_buf[hi] = a;
-                }
-            }
-            __syncthreads();
-        }
-    }
+    cta_bitonic_sort_desc(rs_buf, P);
     for (int i = threadIdx.x; i < k; i += blockDim.x) {
         const uint64_t key = (i < P) ? rs_buf[i] : 0ull;
         const size_t o = (size_t)q * k + i;
@@ -1019,6 +1196,13 @@ int ts_ivf_build(ts_index* ix, int list_dtype, void* stream) {
 
 int ts_ivf_nlist(const ts_index* ix) { return ix ? ix->nlist : -1; }
 
+int ts_debug_ivf_timeline(uint64_t* out_host, int n_ctas) {
+    TS_REQUIRE(out_host != nullptr && n_ctas >= 1 && n_ctas <= 148, TS_ERR_BAD_ARG, "debug_ivf_timeline: bad argument");
+    TS_CHECK_CUDA(cudaDeviceSynchronize());
+    TS_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_ivf_timeline, (size_t)n_ctas * 8 * sizeof(uint64_t)));
+    return TS_OK;
+}
+
 int ts_ivf_list_sizes(const ts_index* ix, int64_t* out, void* stream) {
     TS_REQUIRE(ix != nullptr && out != nullptr, TS_ERR_BAD_ARG, "ivf_list_sizes: NULL argument");
     TS_REQUIRE(ix->ivf_built, TS_ERR_STATE, "ivf_list_sizes: lists are not built (call ts_ivf_build)");
@@ -1084,6 +1268,7 @@ static ts_index centroid_view(const ts_index* ix) {
 
 static int ivf_parts(const ts_index* ix, int nq) {
     const int sms = sm_count(ix->device);
+    if (tunables().ivf_parts > 0) return std::min(sms, tunables().ivf_parts);
     return std::max(1, std::min(sms, (2 * sms + nq - 1) / std::max(nq, 1)));
 }
 
@@ -1123,9 +1308,11 @@ static int ivf_search_impl(ts_index* ix, const void* queries, int q_dtype, int n
     TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "ivf_search: index is NULL");
     TS_REQUIRE(ix->ivf_built, TS_ERR_STATE, "ivf_search: lists are not built (call ts_ivf_train + ts_ivf_build)");
     TS_REQUIRE(nq >= 0, TS_ERR_BAD_ARG, "ivf_search: nq=%d", nq);
-    TS_REQUIRE(k >= 1 && k <= TS_MAX_K, TS_ERR_BAD_ARG, "ivf_search: k=%d out of range [1, %d]", k, TS_MAX_K);
+    TS_REQUIRE(k >= 1 && k <= TS_IVF_MAX_CANDIDATES, TS_ERR_BAD_ARG, "ivf_search: k=%d out of range [1, %d]", k,
+               TS_IVF_MAX_CANDIDATES);
     TS_REQUIRE(nprobe >= 1, TS_ERR_BAD_ARG, "ivf_search: nprobe=%d", nprobe);
-    TS_REQUIRE(rescore_k <= TS_MAX_K, TS_ERR_BAD_ARG, "ivf_search: rescore_k=%d exceeds %d", rescore_k, TS_MAX_K);
+    TS_REQUIRE(rescore_k <= TS_IVF_MAX_CANDIDATES, TS_ERR_BAD_ARG, "ivf_search: rescore_k=%d exceeds %d", rescore_k,
+               TS_IVF_MAX_CANDIDATES);
     TS_REQUIRE(q_dtype == TS_F32 || q_dtype == TS_BF16 || q_dtype == TS_F16, TS_ERR_BAD_ARG, "ivf_search: query dtype %d",
                q_dtype);
     if (nq == 0) return TS_OK;
@@ -1138,13 +1325,19 @@ static int ivf_search_impl(ts_index* ix, const void* queries, int q_dtype, int n
     TS_REQUIRE(workspace_bytes >= w.bytes, TS_ERR_CAPACITY, "ivf_search: workspace %zu < %zu bytes", workspace_bytes,
                w.bytes);
     // 1. coarse: exact top-nprobe over the centroid table (K2 for a few queries, K3 for a batch)
+    // (queries are normalised once, by K1's kernel; the coarse scan then takes them as given, which skips
+    // its per-warp fp64 norm — tens of microseconds of a single-query search on this fp64-poor part)
     ts_index view = centroid_view(ix);
-    int rc = search_impl(&view, queries, q_dtype, nq, nprobe, normalize, nullptr, w.probes, nullptr, nullptr, w.coarse,
+    int rc = launch_prepare_queries(queries, q_dtype, nq, ix->dim, ix->dim_pad, normalize, w.q32, s);
+    if (rc) return rc;
+    if (ix->dim == ix->dim_pad)
+        rc = search_impl(&view, w.q32, TS_F32, nq, nprobe, 0, nullptr, w.probes, nullptr, nullptr, w.coarse,
+                         w.coarse_bytes, s, nullptr, nullptr);
+    else   // padded rows: the prepared copy has another stride than the scan's raw-query reader expects
+        rc = search_impl(&view, queries, q_dtype, nq, nprobe, normalize, nullptr, w.probes, nullptr, nullptr, w.coarse,
                          w.coarse_bytes, s, nullptr, nullptr);
     if (rc) return rc;
     // 2. scan the probed lists, keep kc candidates per query
-    rc = launch_prepare_queries(queries, q_dtype, nq, ix->dim, ix->dim_pad, normalize, w.q32, s);
-    if (rc) return rc;
     TS_CHECK_CUDA(cudaMemsetAsync(w.tickets, 0, (size_t)nq * sizeof(uint32_t), s));
     ListScanParams p;
     p.list_data = (const uint8_t*)ix->list_data;
@@ -1163,9 +1356,12 @@ static int ivf_search_impl(ts_index* ix, const void* queries, int q_dtype, int n
     rc = launch_list_scan(ix, p, nq, ivf_parts(ix, nq), s);
     if (rc) return rc;
     // 3. exact re-score of the survivors against the stored corpus rows
-    int P = 1;
+    int P = 64;
     while (P < kc) P <<= 1;
-    ivf_rescore_kernel<2><<<nq, 256, (size_t)P * 8, s>>>(w.cand, kc, k, ix->list_rows, w.q32, (const uint8_t*)ix->data,
+    // a lone query spreads its candidates over 32 warps (latency), a batch keeps CTAs small (throughput)
+    // (P <= 1024 candidates, <= 32 per warp: at least P/32 warps)
+    const int rs_threads = nq < 64 ? 1024 : std::max(256, P);
+    ivf_rescore_kernel<2><<<nq, rs_threads, (size_t)P * 8, s>>>(w.cand, kc, k, ix->list_rows, w.q32, (const uint8_t*)ix->data,
                                                          (uint32_t)ix->row_bytes(), ix->dim_pad,
                                                          ix->has_ids ? ix->ids : nullptr, out_keys, out_scores, out_ids);
     TS_LAUNCH_CHECK();

@@ -441,6 +441,10 @@ static int* tunable_slot(const char* name) {
     if (!strcmp(name, "batch.growth")) return &t.batch_growth;
     if (!strcmp(name, "batch.cta_pair")) return &t.batch_cta_pair;
     if (!strcmp(name, "batch.pair_min_nq")) return &t.batch_pair_min_nq;
+    if (!strcmp(name, "ivf.warps")) return &t.ivf_warps;
+    if (!strcmp(name, "ivf.tile_rows")) return &t.ivf_tile_rows;
+    if (!strcmp(name, "ivf.parts")) return &t.ivf_parts;
+    if (!strcmp(name, "ivf.timeline")) return &t.ivf_timeline;
     return nullptr;
 }
 int ts_debug_last_batched_fixups(void) { return debug_last_batched_fixups(); }

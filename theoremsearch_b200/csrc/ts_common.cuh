@@ -69,6 +69,10 @@ struct Tunables {
                                 // (4096 x 10M x 1024, 40 iterations, power-capped ~1.36 GHz): pairs 74.9 ms vs
                                 // single CTAs 71.8 ms, so single CTAs are the default; the pair kernel stays tested.
     int batch_pair_min_nq = 512;  // batches at least this large use CTA pairs
+    int ivf_warps = 0;          // K4b warps per CTA; 0 = auto (latency mode 16, throughput mode 8)
+    int ivf_tile_rows = 0;      // K4b rows per TMA tile (4 or 8, e4m3 D<=1024 lists only); 0 = auto
+    int ivf_parts = 0;          // K4b CTAs per query; 0 = auto (2*SMs/nq clamped to [1, SMs])
+    int ivf_timeline = 0;       // 1 = K4b CTAs record globaltimer stamps per phase (ts_debug_ivf_timeline)
 };
 Tunables& tunables();
 
@@ -113,6 +117,8 @@ __host__ __device__ __forceinline__ float key_score(uint64_t key) {
 // ---------------------------------------------------------------------------- warp top-k list
 // A descending list of KPL*32 keys held across one warp: position p = j*32 + lane lives in
 // slot j of lane `lane`. Slot values are unique keys or 0 (empty, sorts last).
+__host__ __device__ constexpr int ilog2_c(int v) { return v <= 1 ? 0 : 1 + ilog2_c(v >> 1); }
+
 template <int KPL>
 struct WarpTopK {
     uint64_t key[KPL];
@@ -122,13 +128,14 @@ struct WarpTopK {
         for (int j = 0; j < KPL; ++j) key[j] = 0ull;
     }
 
-    // The key at list position `pos` (warp-uniform pos), broadcast to every lane.
-    __device__ __forceinline__ uint64_t at(int pos) const {
-        uint64_t v = 0ull;
-#pragma unroll
-        for (int j = 0; j < KPL; ++j)
-            if (j == (pos >> 5)) v = key[j];
-        return __shfl_sync(0xFFFFFFFFu, v, pos & 31);
+    // A key that nothing in the top k can be below, broadcast to every lane: the k-th key for
+    // single-register lists, the LAST (32*KPL-th) key otherwise. The weaker bound keeps the register
+    // index static — `key[(k-1) >> 5]` with a run-time k makes nvcc index the array dynamically, which
+    // moves the whole list to local memory — and only admits a few more candidates (K ln(n/K) instead of
+    // k ln(n/k) over n rows).
+    __device__ __forceinline__ uint64_t kth(int k) const {
+        if constexpr (KPL == 1) return __shfl_sync(0xFFFFFFFFu, key[0], k - 1);
+        else return __shfl_sync(0xFFFFFFFFu, key[KPL - 1], 31);
     }
 
     // Insert x (warp-uniform, x != any present key). Entries below x shift down one
@@ -145,20 +152,57 @@ struct WarpTopK {
             carry = last;
         }
     }
+
+    // Merge another descending list held in the same register layout (b[j] = B[j*32 + lane], 0-padded)
+    // and keep the best 32*KPL of the union, sorted descending. Bitonic top-K merge: position p takes
+    // max(A[p], B[K-1-p]) — a bitonic sequence holding the K largest — then log2(K) compare-exchange
+    // stages (register-to-register for strides >= 32 positions, shuffles below). ~100 instructions for
+    // K = 128 where element-wise insertion costs ~60 cycles per entering key.
+    __device__ __forceinline__ void merge_desc(const uint64_t (&b)[KPL], int lane) {
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+            const uint64_t rb = __shfl_sync(0xFFFFFFFFu, b[KPL - 1 - j], 31 - lane);
+            key[j] = key[j] > rb ? key[j] : rb;
+        }
+        // (loops run over log2 of the stride with unit steps so that nvcc fully unrolls them and every
+        // register index is a compile-time constant — a shift-stepped loop is left rolled and drags the
+        // whole list into local memory)
+#pragma unroll
+        for (int ls = ilog2_c(KPL) - 1; ls >= 0; --ls) {
+            const int s = 1 << ls;
+#pragma unroll
+            for (int j = 0; j < KPL; ++j) {
+                if ((j & s) == 0) {
+                    const uint64_t x = key[j], y = key[j | s];
+                    key[j] = x > y ? x : y;
+                    key[j | s] = x > y ? y : x;
+                }
+            }
+        }
+#pragma unroll
+        for (int ls = 4; ls >= 0; --ls) {
+            const int s = 1 << ls;
+            const bool lower = (lane & s) != 0;   // the half of each pair that keeps the smaller key
+#pragma unroll
+            for (int j = 0; j < KPL; ++j) {
+                const uint64_t o = __shfl_xor_sync(0xFFFFFFFFu, key[j], s);
+                const bool take = lower ? (o < key[j]) : (o > key[j]);
+                key[j] = take ? o : key[j];
+            }
+        }
+    }
 };
 
-// Insert the (descending-sorted) list src[0..n) into `list`, stopping at the first element
-// that no longer beats the list's current k-th entry. All lanes call with the same args.
+// Fold the descending-sorted list src[0..n) (n <= 32*KPL, unique keys, 0 = empty) into `list`.
+// All lanes call with the same args. Skipped outright when src[0] cannot enter the top k.
 template <int KPL>
 __device__ __forceinline__ void merge_sorted_into(WarpTopK<KPL>& list, const uint64_t* src, int n,
                                                   int k, int lane) {
-    uint64_t thr = list.at(k - 1);
-    for (int i = 0; i < n; ++i) {
-        uint64_t x = src[i];
-        if (x <= thr) break;  // sorted: nothing after it can enter either (0 = empty too)
-        list.insert(x, lane);
-        thr = list.at(k - 1);
-    }
+    if (n <= 0 || src[0] <= list.kth(k)) return;   // sorted: nothing after src[0] can enter either
+    uint64_t b[KPL];
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) b[j] = (j * 32 + lane < n) ? src[j * 32 + lane] : 0ull;
+    list.merge_desc(b, lane);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
