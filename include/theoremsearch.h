@@ -115,6 +115,18 @@ TS_API int ts_index_get_rows(const ts_index* index, int64_t first, int64_t n, fl
 TS_API const void* ts_index_data(const ts_index* index);
 TS_API size_t ts_index_row_bytes(const ts_index* index);
 
+/* ---- raw access: the stored (normalised, quantised, row-padded) bytes, for saving an index and
+ * loading it back without re-quantising.  Replaces the reference's on-disk corpus container
+ * `torch.save(corpus_embeddings, 'corpus_embeddings.pt')` / `torch.load` (app_create_embeddings.py:85-89,
+ * app_showcase_model.py:52) for the quantised form. HOST buffers; both calls synchronise. */
+TS_API int ts_index_has_ids(const ts_index* index);
+/* rows_out: n * ts_index_row_bytes() bytes, ids_out: int64[n]; either may be NULL. */
+TS_API int ts_index_read_raw_host(const ts_index* index, int64_t first, int64_t n, void* rows_out,
+                                  int64_t* ids_out);
+/* Append n rows that are ALREADY in the index's storage format (as ts_index_read_raw_host returned
+ * them); ids: int64[n] or NULL. */
+TS_API int ts_index_append_raw_host(ts_index* index, const void* rows, int64_t n, const int64_t* ids);
+
 /* ---- exact search --------------------------------------------------------------------
  * Replaces `util.cos_sim(q, corpus)[0]` + `np.argsort(-scores)[:k]` (test_app.py:75-77),
  * `torch.topk(scores, k=min(200, N), sorted=True)` (app_showcase_model.py:92-96),
@@ -211,6 +223,8 @@ TS_API int ts_ivf_search_keys(ts_index* index, const void* queries, int q_dtype,
                               uint64_t* out_keys, void* workspace, size_t workspace_bytes,
                               void* stream);
 TS_API int ts_ivf_nlist(const ts_index* index);
+/* Storage dtype of the built lists (TS_BF16 / TS_FP8_E4M3), -1 if the lists are not built. */
+TS_API int ts_ivf_list_dtype(const ts_index* index);
 /* Copy list sizes (int64[nlist]) to a device buffer — for balance diagnostics. */
 TS_API int ts_ivf_list_sizes(const ts_index* index, int64_t* out, void* stream);
 /* Copy the list layout to device buffers: offsets int64[nlist+1] (list l occupies positions

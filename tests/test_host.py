@@ -2,11 +2,13 @@
 post-filter) against goldens produced by the reference's own functions. The scorer is the test-only
 OracleIndex (no GPU here); tests/test_gpu_store.py runs the same goldens through the CUDA index."""
 import datetime
+import os
 
 import numpy as np
 import pytest
 
 import theoremsearch_b200 as ts
+from oracle import oracle
 from theoremsearch_b200 import store as st
 from tests.helpers import BASE_FILTERS, OracleIndex, TableModel, golden_store_rows, load_golden, unpack_allow_mask
 
@@ -125,3 +127,62 @@ def test_infer_type_and_pool_size():
     assert st.infer_type("Lemma 3.1") == "lemma" and st.infer_type(None) == "theorem"
     assert st.infer_type("Remark") == "theorem" and st.infer_type("Main Theorem (Corollary)") == "theorem"
     assert st.pool_size(1) == 50 and st.pool_size(5) == 50 and st.pool_size(20) == 200
+
+
+# --------------------------------------------------------------------------------------- f4: metrics
+def test_product_metrics_match_reference_run():
+    """theoremsearch_b200.metrics (top-k in) against the numbers the reference's own functions produced
+    (tests/golden/make_golden.py ran compare_embeddings.py's six metrics on the full sim matrix)."""
+    from theoremsearch_b200 import metrics
+    g = load_golden("compare_embeddings_metrics")
+    qrels = {int(q): {int(d): v for d, v in rd.items()} for q, rd in g["qrels"].items()}
+    ranked = np.array(g["ranked_top10"], dtype=np.int64)
+    for k_str, want in g["metrics"].items():
+        k = int(k_str)
+        got = {"precision": metrics.precision_at_k(ranked, qrels, k), "hit": metrics.hit_at_k(ranked, qrels, k),
+               "mrr": metrics.mrr_at_k(ranked, qrels, k), "ndcg": metrics.ndcg_at_k(ranked, qrels, k),
+               "err": metrics.err_at_k(ranked, qrels, k), "q_measure": metrics.q_measure_at_k(ranked, qrels, k)}
+        for name in want:
+            assert got[name] == pytest.approx(want[name], abs=1e-12), (k, name)
+        # identical to the oracle's restatement, and padding (-1) is ignored
+        assert got["ndcg"] == pytest.approx(oracle.ndcg_at_k(ranked, qrels, k), abs=1e-15)
+        padded = np.concatenate([ranked[:, :k], np.full((ranked.shape[0], 3), -1)], axis=1)
+        assert metrics.mrr_at_k(padded, qrels, None) == pytest.approx(want["mrr"], abs=1e-12)
+    rep = metrics.evaluate_rankings(ranked, qrels, 3)
+    assert set(rep) == {"P@1", "H@3", "MRR@3", "nDCG@3", "ERR@3", "Q-measure@3"}
+    assert rep["MRR@3"] == pytest.approx(g["metrics"]["3"]["mrr"], abs=1e-12)
+    q = metrics._generate_qrels([("a", "p1"), ("b", "p2")], [("s", "p1"), ("t", "p2"), ("u", "p1")])
+    assert q == {0: {0: 0.5, 1: 0, 2: 0.5}, 1: {0: 0, 1: 0.5, 2: 0}}
+
+
+# --------------------------------------------------------------------------------------- f2: formats
+def test_pgvector_text_and_latest_slogan():
+    from theoremsearch_b200 import formats
+    v = formats.parse_pgvector_text("[0.5,-1,2e-3]")
+    assert v.dtype == np.float32 and np.allclose(v, [0.5, -1.0, 2e-3])
+    assert np.array_equal(formats.parse_pgvector_text(b"[1,2]"), np.array([1, 2], np.float32))
+    assert np.array_equal(formats.parse_pgvector_text([1.5, 2.5]), np.array([1.5, 2.5], np.float32))
+    with pytest.raises(ValueError):
+        formats.parse_pgvector_text("1,2,3")
+    # DISTINCT ON (theorem_id) ORDER BY theorem_id, slogan_id DESC  (streamlit_app.py:254-259)
+    theorem = [7, 3, 7, 3, 9, 7]
+    slogan = [10, 11, 12, 13, 14, 5]
+    keep, t, s = formats.latest_slogan_per_theorem(theorem, slogan)
+    assert t.tolist() == [3, 7, 9] and s.tolist() == [13, 12, 14] and keep.tolist() == [3, 2, 4]
+
+
+def test_embedding_library_files_roundtrip(tmp_path):
+    """The pair of files app_create_embeddings.py:85-93 writes and app_showcase_model.py:41-58 reads."""
+    import pickle
+    import torch
+    from theoremsearch_b200 import formats
+    emb = torch.from_numpy(oracle.synthetic_rows(0, 12, 16, seed=4))
+    meta = [{"paper_title": f"P{i}", "type": "theorem", "content": f"c{i}"} for i in range(12)]
+    formats.save_embedding_library(str(tmp_path), emb, meta)
+    assert sorted(os.listdir(tmp_path)) == ["corpus_embeddings.pt", "theorems_data.pkl"]
+    assert torch.equal(torch.load(tmp_path / "corpus_embeddings.pt"), emb)            # what the reference loads
+    with open(tmp_path / "theorems_data.pkl", "rb") as f:
+        assert pickle.load(f) == meta
+    e2, m2 = formats.load_embedding_library(str(tmp_path), as_index=False)
+    assert torch.equal(e2, emb) and m2 == meta
+    assert formats.load_embedding_library(str(tmp_path / "missing")) == (None, None)

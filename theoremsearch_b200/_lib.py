@@ -60,6 +60,10 @@ SIGNATURES = {
     "ts_index_get_rows": (_i, [_p, _i64, _i64, _p, _p]),
     "ts_index_data": (_p, [_p]),
     "ts_index_row_bytes": (_sz, [_p]),
+    "ts_index_has_ids": (_i, [_p]),
+    "ts_index_read_raw_host": (_i, [_p, _i64, _i64, _p, _p]),
+    "ts_index_append_raw_host": (_i, [_p, _p, _i64, _p]),
+    "ts_ivf_list_dtype": (_i, [_p]),
     "ts_workspace_bytes": (_sz, [_p, _i, _i]),
     "ts_search": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "ts_search_keys": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),

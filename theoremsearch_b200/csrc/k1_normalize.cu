@@ -13,6 +13,8 @@
 // HBM-bound: reads 4*D, writes 2*D (bf16) bytes per row. One warp per row, grid-stride.
 #include "ts_common.cuh"
 
+#include <algorithm>
+
 namespace ts {
 
 template <typename T>
@@ -132,6 +134,38 @@ int launch_normalize_cast(const void* src, int src_dtype, int64_t n, int dim, in
 int launch_prepare_queries(const void* q, int q_dtype, int nq, int dim, int dim_pad, int normalize,
                            float* out_f32, cudaStream_t s) {
     return launch_normalize_cast(q, q_dtype, nq, dim, dim_pad, normalize, out_f32, TS_F32, s);
+}
+
+// max over rows of ||row||^2 (as stored), atomically folded into *out — the bound K3's certificate uses.
+template <typename T>
+__global__ void __launch_bounds__(256) max_norm2_kernel(const T* __restrict__ rows, int64_t n, int dim_pad,
+                                                        float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    for (int64_t r = w0; r < n; r += (int64_t)gridDim.x * 8) {
+        float s = 0.f;
+        for (int i = lane; i < dim_pad; i += 32) {
+            const float v = load_as_float<T>(rows + r * (int64_t)dim_pad + i);
+            s = fmaf(v, v, s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(s));
+    }
+}
+
+int launch_max_norm2(const void* rows, int dtype, int64_t n, int dim_pad, float* out, cudaStream_t s) {
+    if (n == 0) return TS_OK;
+    const int blocks = (int)std::min<int64_t>((n + 7) / 8, 148 * 16);
+    if (dtype == TS_BF16)
+        max_norm2_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)rows, n, dim_pad, out);
+    else if (dtype == TS_F32)
+        max_norm2_kernel<float><<<blocks, 256, 0, s>>>((const float*)rows, n, dim_pad, out);
+    else {
+        set_error("max_norm2: unsupported dtype %d", dtype);
+        return TS_ERR_UNSUPPORTED;
+    }
+    TS_LAUNCH_CHECK();
+    return TS_OK;
 }
 
 int launch_dequant_rows(const void* src, int src_dtype, int64_t n, int dim, int dim_pad, float* dst,

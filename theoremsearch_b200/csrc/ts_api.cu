@@ -302,6 +302,64 @@ int ts_index_get_rows(const ts_index* ix, int64_t first, int64_t n, float* out, 
                                ix->dim_pad, out, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------------------------ raw access (save / load)
+int ts_index_has_ids(const ts_index* ix) { return ix ? (ix->has_ids ? 1 : 0) : -1; }
+
+int ts_index_read_raw_host(const ts_index* ix, int64_t first, int64_t n, void* rows_out, int64_t* ids_out) {
+    TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "index_read_raw_host: index is NULL");
+    TS_REQUIRE(first >= 0 && n >= 0 && first + n <= ix->size, TS_ERR_BAD_ARG,
+               "index_read_raw_host: [%lld, %lld) outside [0, %lld)", (long long)first, (long long)(first + n),
+               (long long)ix->size);
+    if (n == 0) return TS_OK;
+    DeviceGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "index_read_raw_host: cannot select CUDA device %d", ix->device);
+    if (rows_out)
+        TS_CHECK_CUDA(cudaMemcpy(rows_out, (const char*)ix->data + (size_t)first * ix->row_bytes(),
+                                 (size_t)n * ix->row_bytes(), cudaMemcpyDeviceToHost));
+    if (ids_out) {
+        TS_REQUIRE(ix->has_ids, TS_ERR_STATE, "index_read_raw_host: the index has no id table (ids are row positions)");
+        TS_CHECK_CUDA(cudaMemcpy(ids_out, ix->ids + first, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    }
+    return TS_OK;
+}
+
+int ts_index_append_raw_host(ts_index* ix, const void* rows, int64_t n, const int64_t* ids) {
+    TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "index_append_raw_host: index is NULL");
+    TS_REQUIRE(n >= 0, TS_ERR_BAD_ARG, "index_append_raw_host: n=%lld", (long long)n);
+    if (n == 0) return TS_OK;
+    TS_REQUIRE(rows != nullptr, TS_ERR_BAD_ARG, "index_append_raw_host: rows is NULL");
+    TS_REQUIRE(ix->size + n <= ix->capacity, TS_ERR_CAPACITY, "index_append_raw_host: %lld + %lld rows exceed capacity %lld",
+               (long long)ix->size, (long long)n, (long long)ix->capacity);
+    DeviceGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "index_append_raw_host: cannot select CUDA device %d", ix->device);
+    if (ids != nullptr && !ix->has_ids) {
+        TS_CHECK_CUDA(cudaMalloc(&ix->ids, (size_t)std::max<int64_t>(ix->capacity, 1) * sizeof(int64_t)));
+        if (ix->size > 0) {
+            iota_ids_kernel<<<256, 256>>>(ix->ids, 0, ix->size);
+            TS_LAUNCH_CHECK();
+        }
+        ix->has_ids = true;
+    }
+    char* dst = (char*)ix->data + (size_t)ix->size * ix->row_bytes();
+    TS_CHECK_CUDA(cudaMemcpy(dst, rows, (size_t)n * ix->row_bytes(), cudaMemcpyHostToDevice));
+    if (ix->has_ids) {
+        if (ids != nullptr) {
+            TS_CHECK_CUDA(cudaMemcpy(ix->ids + ix->size, ids, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice));
+        } else {
+            iota_ids_kernel<<<256, 256>>>(ix->ids + ix->size, ix->size, n);
+            TS_LAUNCH_CHECK();
+        }
+    }
+    int rc = launch_max_norm2(dst, ix->dtype, n, ix->dim_pad, ix->max_norm2, nullptr);
+    if (rc) return rc;
+    TS_CHECK_CUDA(cudaDeviceSynchronize());
+    ix->size += n;
+    ix->ivf_built = false;
+    return TS_OK;
+}
+
+int ts_ivf_list_dtype(const ts_index* ix) { return (ix && ix->ivf_built) ? ix->list_dtype : -1; }
+
 // ------------------------------------------------------------------------------------ search
 size_t ts_workspace_bytes(const ts_index* ix, int nq, int k) {
     if (!ix || nq < 0 || k < 1) return 0;

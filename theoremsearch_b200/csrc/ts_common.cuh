@@ -338,6 +338,7 @@ int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k, i
 int launch_normalize_cast(const void* src, int src_dtype, int64_t n, int dim, int dim_pad,
                           int normalize, void* dst, int dst_dtype, cudaStream_t s,
                           float* max_norm2 = nullptr);
+int launch_max_norm2(const void* rows, int dtype, int64_t n, int dim_pad, float* out, cudaStream_t s);
 int launch_dequant_rows(const void* src, int src_dtype, int64_t n, int dim, int dim_pad, float* dst,
                         cudaStream_t s);
 int launch_prepare_queries(const void* q, int q_dtype, int nq, int dim, int dim_pad, int normalize,
