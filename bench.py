@@ -7,8 +7,10 @@ Metric: queries/sec (exact top-10) of the single-query scan over a 10M x 1024 bf
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 * N = 1: the whole corpus on one B200.  N > 1 (under torchrun): the SAME corpus row-sharded
-  over N GPUs (strong scaling); per query every rank scans its shard, one NCCL all-gather of the
-  k packed keys, K5 merge on every rank.
+  over N GPUs (strong scaling); per query every rank scans its shard and the scan kernel's last CTA
+  exchanges the k packed keys with the peers over NVLink (stores into CUDA-IPC mapped peer memory,
+  sequence flags) and merges the N lists — one kernel per query per GPU, no collective call
+  (`--exchange nccl` selects the all-gather + K5 merge form instead).
 * `value`   : device-timed (CUDA events, max over ranks), queries already resident in HBM.
 * `e2e`     : wall-clock through the public host-buffer API (`TheoremIndex.search_host` ->
               `ts_search_host`): per step a 4 KB pinned H2D query copy and a k*(4+8) B D2H result.
@@ -158,6 +160,8 @@ def main():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--cpu-sample-rows", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N>1: in-kernel NVLink peer exchange (default) or NCCL all-gather + merge kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -214,6 +218,11 @@ def main():
     synthetic.fill_index(index, lo, hi - lo, seed=0)
     torch.cuda.synchronize()
     sharded = ShardedIndex(index, args.rows) if world > 1 else None
+    if sharded is not None and args.exchange == "fused":
+        sharded.enable_peer_exchange(max_nq=1, max_k=max(args.k, 32))
+    if sharded is not None:
+        config["exchange"] = ("in-kernel NVLink peer stores + flags (ts_search_sharded)" if args.exchange == "fused"
+                              else "NCCL all-gather of k packed keys + merge kernel")
 
     total = args.warmup + args.steps
     queries = synthetic.make_queries(total, args.dim, dev)           # replicated: same seed on every rank
@@ -329,6 +338,9 @@ def main():
             "top1_id_last_query": int(out[1][0, 0].item()),
         }
         print(json.dumps(line))
+    if sharded is not None:
+        assert not sharded.peer_exchange_error(), "a peer missed the in-kernel exchange time-out"
+        sharded.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

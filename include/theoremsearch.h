@@ -160,6 +160,35 @@ TS_API int ts_merge_topk(const uint64_t* keys, int nshards, int nq, int k,
                          const int64_t* shard_base, const int64_t* id_map, float* out_scores,
                          int64_t* out_ids, void* stream);
 
+/* ---- sharded exact search with the exchange fused into the scan kernel ----------------------
+ * The reference has no sharding; BASELINE.json specifies it: GPU g holds rows
+ * [g*N/G, (g+1)*N/G), every GPU scans its shard, the k (score,row) candidates per GPU are exchanged
+ * and merged.  ts_search_keys + an NCCL all-gather + ts_merge_topk is the portable form; below the
+ * exchange happens INSIDE the scan kernel: the last CTA of each query stores this shard's k packed
+ * keys (rebased to global rows) straight into every peer's receive area over NVLink (CUDA-IPC
+ * mapped peer memory), raises a sequence flag, spins (bounded) on the peers' flags and merges the G
+ * lists — one kernel per query per GPU, no collective launch, no second kernel. */
+typedef struct ts_xchg ts_xchg;
+/* One per rank (one process per GPU). max_nq / max_k bound the searches that will use it. */
+TS_API int ts_xchg_create(ts_xchg** out, int device, int world, int rank, int max_nq, int max_k);
+TS_API void ts_xchg_destroy(ts_xchg* xchg);
+/* Size of / this rank's IPC handle of its receive area (HOST buffer of ts_xchg_handle_bytes()). */
+TS_API int ts_xchg_handle_bytes(void);
+TS_API int ts_xchg_handle(const ts_xchg* xchg, void* out_handle);
+/* all_handles: HOST buffer of world handles in rank order (gathered by the caller with any host-side
+ * collective). Maps every peer's area. world == 1 needs no handles (NULL). */
+TS_API int ts_xchg_connect(ts_xchg* xchg, const void* all_handles);
+/* 1 if a peer failed to arrive within the kernel's 4 s bound since creation, 0 otherwise. Synchronous. */
+TS_API int ts_xchg_error(const ts_xchg* xchg);
+/* Exact top-k over the GLOBAL corpus: every rank calls it with the same queries, nq, k in the same
+ * order. shard_base = global row of this shard's row 0; id_map = optional device table global row ->
+ * caller id. Outputs on every rank. Only the single-query scan path (nq below the batched threshold);
+ * larger batches return TS_ERR_UNSUPPORTED (use ts_search_keys + all-gather + ts_merge_topk). */
+TS_API int ts_search_sharded(ts_index* index, ts_xchg* xchg, const void* queries, int q_dtype, int nq,
+                             int k, int normalize_queries, const uint32_t* allow_mask,
+                             int64_t shard_base, const int64_t* id_map, float* out_scores,
+                             int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Packed candidate key: high 32 bits = order-preserving image of the fp32 score, low 32 bits
  * = 0xFFFFFFFF - row, so unsigned `max` == "higher score, then lower row". 0 = empty slot. */
 TS_API uint64_t ts_pack_key(float score, uint32_t row);

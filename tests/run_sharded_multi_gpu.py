@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Multi-GPU check of the sharded exact path, run under torchrun on N GPUs of one box:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29533 tests/run_sharded_multi_gpu.py
+
+Every rank holds a row shard; the fused in-kernel exchange (ts_search_sharded), the NCCL all-gather +
+K5 path and an unsharded index on rank 0 must return identical scores and ids.  Not collected by
+pytest (needs N GPUs); prints one JSON line and exits non-zero on a mismatch."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.distributed as dist
+
+import theoremsearch_b200 as ts
+from theoremsearch_b200 import synthetic
+from theoremsearch_b200.sharded import ShardedIndex, shard_bounds
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    n, d = 2_000_003, 1024
+    lo, hi = shard_bounds(n, world)[rank]
+    index = ts.TheoremIndex(d, hi - lo, device=dev)
+    synthetic.fill_index(index, lo, hi - lo, seed=0)
+    sh = ShardedIndex(index, n)
+    q = synthetic.make_queries(40, d, dev)
+    ok = True
+    ref = []
+    for i in range(40):
+        ref.append(sh.search(q[i:i + 1], 10))                 # NCCL all-gather + K5
+    sh.enable_peer_exchange(max_nq=3, max_k=128)
+    for i in range(40):
+        s, ids = sh.search(q[i:i + 1], 10)                    # fused exchange
+        ok &= torch.equal(s, ref[i][0]) and torch.equal(ids, ref[i][1])
+    s3, i3 = sh.search(q[:3], 100)
+    sh._xchg_saved, sh._xchg = sh._xchg, None
+    s3r, i3r = sh.search(q[:3], 100)
+    sh._xchg = sh._xchg_saved
+    ok &= torch.equal(s3, s3r) and torch.equal(i3, i3r)
+    ok &= not sh.peer_exchange_error()
+    if rank == 0:                                             # unsharded truth
+        full = ts.TheoremIndex(d, n, device=dev)
+        synthetic.fill_index(full, 0, n, seed=0)
+        for i in range(0, 40, 7):
+            s, ids = full.search(q[i:i + 1], 10)
+            ok &= torch.equal(s, ref[i][0]) and torch.equal(ids, ref[i][1])
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    # timing: fused vs gather path
+    def timed(fn, iters=200):
+        for _ in range(20):
+            fn()
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    ms_fused = timed(lambda: sh.search(q[:1], 10))
+    sh._xchg = None
+    ms_gather = timed(lambda: sh.search(q[:1], 10))
+    sh._xchg = sh._xchg_saved
+    ms_local = timed(lambda: index.search_keys(q[:1], 10))
+    if rank == 0:
+        print(json.dumps({"check": "sharded_multi_gpu", "world": world, "rows": n, "ok": bool(flag.item()),
+                          "ms_fused_exchange": ms_fused, "ms_allgather_merge": ms_gather, "ms_local_scan_only": ms_local}))
+    sh.close()
+    dist.destroy_process_group()
+    return 0 if flag.item() else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

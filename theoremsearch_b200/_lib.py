@@ -68,6 +68,13 @@ SIGNATURES = {
     "ts_search": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "ts_search_keys": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
     "ts_merge_topk": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "ts_xchg_create": (_i, [C.POINTER(_p), _i, _i, _i, _i, _i]),
+    "ts_xchg_destroy": (None, [_p]),
+    "ts_xchg_handle_bytes": (_i, []),
+    "ts_xchg_handle": (_i, [_p, _p]),
+    "ts_xchg_connect": (_i, [_p, _p]),
+    "ts_xchg_error": (_i, [_p]),
+    "ts_search_sharded": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _sz, _p]),
     "ts_pack_key": (_u64, [C.c_float, C.c_uint32]),
     "ts_unpack_key": (None, [_u64, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "ts_ctx_create": (_i, [C.POINTER(_p), _p, _i, _i]),

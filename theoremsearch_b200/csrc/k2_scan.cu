@@ -52,7 +52,25 @@ struct ScanParams {
     // grid's per-CTA lists and writes the final result (fin.keys / nlists / strides are filled in-kernel)
     uint32_t* tickets;        // [work items], zero on entry, left zero on exit
     MergeParams fin;
+    // fused cross-GPU exchange (sharded search): the last CTA stores this shard's k keys into every peer's
+    // receive area over NVLink, waits for the peers' keys and merges the world lists — no NCCL call, no
+    // second kernel
+    XchgDev xchg;
 };
+
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns2() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ float load_query_elem(const void* base, int dtype, size_t idx) {
     if (dtype == TS_F32) return __ldg(reinterpret_cast<const float*>(base) + idx);
@@ -245,7 +263,53 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
             mp.k = k;
             mp.stride_list = k;
             mp.stride_query = (int64_t)gridDim.x * k;
-            merge_lists<KPL>(mp, wi, qi, lists, W);
+            if (p.xchg.world == 0) {
+                merge_lists<KPL>(mp, wi, qi, lists, W);
+            } else {
+                // ---- fused exchange. 1) this shard's top-k (local rows) into its own slot of the own area
+                const XchgDev& x = p.xchg;
+                const uint32_t par = x.seq & 1u;
+                const size_t slot_sz = (size_t)x.max_k;
+                const size_t my_slot = (((size_t)par * x.world + x.rank) * x.max_nq + qi) * slot_sz;
+                mp.out_keys = x.my_slots + my_slot - (size_t)qi * slot_sz;   // merge_lists adds qi * out_stride
+                mp.out_stride = (int64_t)slot_sz;
+                mp.out_scores = nullptr;
+                mp.out_ids = nullptr;
+                merge_lists<KPL>(mp, wi, qi, lists, W);
+                // 2) rebased to global rows and stored into every peer's area (NVLink stores), then the flags
+                __threadfence();
+                __syncthreads();
+                for (int i = threadIdx.x; i < k; i += blockDim.x) {
+                    const uint64_t key = rebase_key(__ldcg(x.my_slots + my_slot + i), x.base);
+                    for (int g = 0; g < x.world; ++g) x.peer_slots[g][my_slot + i] = key;
+                }
+                __threadfence_system();
+                __syncthreads();
+                const size_t flag_idx = ((size_t)par * x.world + x.rank) * x.max_nq + qi;
+                if ((int)threadIdx.x < x.world) st_release_sys_u32(x.peer_flags[threadIdx.x] + flag_idx, x.seq);
+                // 3) wait for every rank's keys (bounded: a dead peer must not hang the GPU)
+                if ((int)threadIdx.x < x.world) {
+                    const uint32_t* f = x.my_flags + ((size_t)par * x.world + threadIdx.x) * x.max_nq + qi;
+                    const unsigned long long t0 = globaltimer_ns2();
+                    while (ld_acquire_sys_u32(f) != x.seq) {
+                        if (globaltimer_ns2() - t0 > 4000000000ull) {   // 4 s
+                            *x.error = 1;
+                            break;
+                        }
+                    }
+                }
+                __threadfence_system();
+                __syncthreads();
+                // 4) merge the world lists (already global rows) and emit the final result
+                MergeParams fp = p.fin;
+                fp.keys = x.my_slots + (size_t)par * x.world * x.max_nq * slot_sz;
+                fp.nlists = x.world;
+                fp.k = k;
+                fp.stride_list = (int64_t)x.max_nq * slot_sz;
+                fp.stride_query = (int64_t)slot_sz;
+                fp.list_base = nullptr;
+                merge_lists<KPL>(fp, qi, qi, lists, W);
+            }
         }
     }
     }  // work items
@@ -358,6 +422,7 @@ int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64
     p.dim = ix->dim;
     p.tickets = nullptr;
     memset(&p.fin, 0, sizeof(p.fin));
+    memset(&p.xchg, 0, sizeof(p.xchg));
     if (fused != nullptr) {
         p.q_raw = fused->q_raw;
         p.q_dtype = fused->q_dtype;
@@ -369,6 +434,7 @@ int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64
         p.fin.out_scores = fused->out_scores;
         p.fin.out_ids = fused->out_ids;
         p.fin.out_stride = k;
+        p.xchg = fused->xchg;
     }
     if (data_dtype == TS_BF16) {
         p.row_bytes = (uint32_t)ix->dim_pad * 2;

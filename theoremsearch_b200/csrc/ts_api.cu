@@ -102,6 +102,7 @@ int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k,
     f.out_keys = out_keys;
     f.out_scores = out_scores;
     f.out_ids = out_ids;
+    memset(&f.xchg, 0, sizeof(f.xchg));
     return launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, w.part_keys, w.nparts,
                             s, ev0, ev1, nullptr, nullptr, &f);
 }
@@ -483,6 +484,147 @@ int ts_search_host(ts_ctx* c, const float* queries, int nq, int k, int normalize
     memcpy(out_ids, c->h_ids, n * sizeof(int64_t));
     if (c->timing) TS_CHECK_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
     return TS_OK;
+}
+
+// ------------------------------------------------------------------------------------ peer exchange
+static size_t xchg_slot_count(const ts_xchg* x) { return (size_t)2 * x->world * x->max_nq * x->max_k; }
+static size_t xchg_flag_count(const ts_xchg* x) { return (size_t)2 * x->world * x->max_nq; }
+
+int ts_xchg_create(ts_xchg** out, int device, int world, int rank, int max_nq, int max_k) {
+    TS_REQUIRE(out != nullptr, TS_ERR_BAD_ARG, "xchg_create: out is NULL");
+    *out = nullptr;
+    TS_REQUIRE(world >= 1 && world <= 16 && rank >= 0 && rank < world, TS_ERR_BAD_ARG, "xchg_create: world=%d rank=%d",
+               world, rank);
+    TS_REQUIRE(max_nq >= 1 && max_k >= 1 && max_k <= TS_MAX_K, TS_ERR_BAD_ARG, "xchg_create: max_nq=%d max_k=%d", max_nq,
+               max_k);
+    DeviceGuard g(device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "xchg_create: cannot select CUDA device %d", device);
+    ts_xchg* x = new ts_xchg();
+    x->device = device;
+    x->world = world;
+    x->rank = rank;
+    x->max_nq = max_nq;
+    x->max_k = max_k;
+    x->bytes = xchg_slot_count(x) * sizeof(uint64_t) + xchg_flag_count(x) * sizeof(uint32_t);
+    cudaError_t e = cudaMalloc(&x->base, x->bytes);
+    if (e == cudaSuccess) e = cudaMemset(x->base, 0, x->bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&x->d_peer_slots, 16 * sizeof(void*));
+    if (e == cudaSuccess) e = cudaMalloc(&x->d_peer_flags, 16 * sizeof(void*));
+    if (e == cudaSuccess) e = cudaMalloc(&x->d_error, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(x->d_error, 0, sizeof(int));
+    if (e != cudaSuccess) {
+        set_error("xchg_create: allocation failed: %s", cudaGetErrorString(e));
+        ts_xchg_destroy(x);
+        cudaGetLastError();
+        return TS_ERR_OOM;
+    }
+    x->slots = (uint64_t*)x->base;
+    x->flags = (uint32_t*)((char*)x->base + xchg_slot_count(x) * sizeof(uint64_t));
+    x->peer_base[rank] = x->base;
+    *out = x;
+    return TS_OK;
+}
+
+void ts_xchg_destroy(ts_xchg* x) {
+    if (!x) return;
+    DeviceGuard g(x->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < x->world; ++r)
+        if (r != x->rank && x->peer_base[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
+    cudaFree(x->base);
+    cudaFree(x->d_peer_slots);
+    cudaFree(x->d_peer_flags);
+    cudaFree(x->d_error);
+    delete x;
+}
+
+int ts_xchg_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int ts_xchg_handle(const ts_xchg* x, void* out_handle) {
+    TS_REQUIRE(x != nullptr && out_handle != nullptr, TS_ERR_BAD_ARG, "xchg_handle: NULL argument");
+    DeviceGuard g(x->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "xchg_handle: cannot select CUDA device %d", x->device);
+    cudaIpcMemHandle_t h;
+    TS_CHECK_CUDA(cudaIpcGetMemHandle(&h, x->base));
+    memcpy(out_handle, &h, sizeof(h));
+    return TS_OK;
+}
+
+int ts_xchg_connect(ts_xchg* x, const void* all_handles) {
+    TS_REQUIRE(x != nullptr && (all_handles != nullptr || x->world == 1), TS_ERR_BAD_ARG, "xchg_connect: NULL argument");
+    DeviceGuard g(x->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "xchg_connect: cannot select CUDA device %d", x->device);
+    for (int r = 0; r < x->world; ++r) {
+        if (r == x->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)all_handles + (size_t)r * sizeof(h), sizeof(h));
+        TS_CHECK_CUDA(cudaIpcOpenMemHandle(&x->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    uint64_t* hs[16] = {nullptr};
+    uint32_t* hf[16] = {nullptr};
+    for (int r = 0; r < x->world; ++r) {
+        hs[r] = (uint64_t*)x->peer_base[r];
+        hf[r] = (uint32_t*)((char*)x->peer_base[r] + xchg_slot_count(x) * sizeof(uint64_t));
+    }
+    TS_CHECK_CUDA(cudaMemcpy(x->d_peer_slots, hs, sizeof(hs), cudaMemcpyHostToDevice));
+    TS_CHECK_CUDA(cudaMemcpy(x->d_peer_flags, hf, sizeof(hf), cudaMemcpyHostToDevice));
+    x->connected = true;
+    return TS_OK;
+}
+
+int ts_xchg_error(const ts_xchg* x) {
+    if (!x) return -1;
+    DeviceGuard g(x->device);
+    int v = -1;
+    if (cudaMemcpy(&v, x->d_error, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return v;
+}
+
+int ts_search_sharded(ts_index* ix, ts_xchg* x, const void* queries, int q_dtype, int nq, int k, int normalize_queries,
+                      const uint32_t* allow_mask, int64_t shard_base, const int64_t* id_map, float* out_scores,
+                      int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream) {
+    TS_REQUIRE(ix != nullptr && x != nullptr, TS_ERR_BAD_ARG, "search_sharded: NULL handle");
+    TS_REQUIRE(x->connected, TS_ERR_STATE, "search_sharded: ts_xchg_connect has not been called");
+    TS_REQUIRE(x->device == ix->device, TS_ERR_BAD_ARG, "search_sharded: index on device %d, exchange on %d", ix->device,
+               x->device);
+    TS_REQUIRE(nq >= 1 && nq <= x->max_nq, TS_ERR_CAPACITY, "search_sharded: nq=%d outside [1, %d]", nq, x->max_nq);
+    TS_REQUIRE(k >= 1 && k <= x->max_k, TS_ERR_CAPACITY, "search_sharded: k=%d outside [1, %d]", k, x->max_k);
+    TS_REQUIRE(!use_batched(ix, nq), TS_ERR_UNSUPPORTED,
+               "search_sharded: nq=%d goes to the batched path, whose results are exchanged with an all-gather", nq);
+    TS_REQUIRE(q_dtype == TS_F32 || q_dtype == TS_BF16 || q_dtype == TS_F16, TS_ERR_BAD_ARG, "search_sharded: query dtype %d",
+               q_dtype);
+    TS_REQUIRE(queries && out_scores && out_ids && workspace, TS_ERR_BAD_ARG, "search_sharded: NULL buffer");
+    TS_REQUIRE(shard_base >= 0 && shard_base + ix->size < (int64_t)0xFFFFFFFFll, TS_ERR_UNSUPPORTED,
+               "search_sharded: global rows must fit 32 bits");
+    DeviceGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "search_sharded: cannot select CUDA device %d", ix->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    SearchWs w = carve_ws(ix, nq, k, workspace);
+    TS_REQUIRE(workspace_bytes >= w.bytes, TS_ERR_CAPACITY, "search_sharded: workspace %zu < %zu bytes", workspace_bytes,
+               w.bytes);
+    TS_CHECK_CUDA(cudaMemsetAsync(w.tickets, 0, (size_t)nq * sizeof(uint32_t), s));
+    ScanFused f;
+    f.q_raw = queries;
+    f.q_dtype = q_dtype;
+    f.q_normalize = normalize_queries;
+    f.tickets = w.tickets;
+    f.id_map = id_map;
+    f.out_keys = nullptr;
+    f.out_scores = out_scores;
+    f.out_ids = out_ids;
+    f.xchg.peer_slots = x->d_peer_slots;
+    f.xchg.peer_flags = x->d_peer_flags;
+    f.xchg.my_slots = x->slots;
+    f.xchg.my_flags = x->flags;
+    f.xchg.error = x->d_error;
+    f.xchg.world = x->world;
+    f.xchg.rank = x->rank;
+    f.xchg.max_nq = x->max_nq;
+    f.xchg.max_k = x->max_k;
+    f.xchg.seq = ++x->seq;
+    f.xchg.base = shard_base;
+    return launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, w.part_keys, w.nparts, s,
+                            nullptr, nullptr, nullptr, nullptr, &f);
 }
 
 // ------------------------------------------------------------------------------------ tunables

@@ -312,6 +312,23 @@ struct ts_index {
     size_t row_bytes() const { return (size_t)dim_pad * elem_bytes(); }
 };
 
+// Peer exchange of the sharded exact search: every rank owns a receive area other ranks store into over
+// NVLink (CUDA IPC mappings). Layout of one area: slots[2 parities][world][max_nq][max_k] packed keys and
+// flags[2][world][max_nq] sequence numbers.
+struct ts_xchg {
+    int device = 0, world = 1, rank = 0, max_nq = 0, max_k = 0;
+    uint64_t* slots = nullptr;        // this rank's receive area (cudaMalloc, exported by IPC handle)
+    uint32_t* flags = nullptr;        // same allocation, after the slots
+    void* base = nullptr;             // the allocation
+    size_t bytes = 0;
+    void* peer_base[16] = {nullptr};  // mapped base of every rank's area (own entry = base)
+    uint64_t** d_peer_slots = nullptr;   // device array [world]
+    uint32_t** d_peer_flags = nullptr;   // device array [world]
+    int* d_error = nullptr;           // device flag: 1 = a peer did not arrive within the time-out
+    uint32_t seq = 0;                 // searches issued so far (identical on every rank)
+    bool connected = false;
+};
+
 struct ts_ctx {
     ts_index* index = nullptr;
     int max_nq = 0, max_k = 0;
@@ -346,6 +363,17 @@ int launch_prepare_queries(const void* q, int q_dtype, int nq, int dim, int dim_
 // K2: per-CTA candidate lists part_keys[nq][nparts][k]
 int scan_nparts(const ts_index* ix);
 // Optional fused stages of K2: in-kernel query normalisation and in-kernel final merge.
+// device view of a ts_xchg for one search (world == 0: no exchange)
+struct XchgDev {
+    uint64_t* const* peer_slots;   // [world] every rank's slot area (mapped)
+    uint32_t* const* peer_flags;   // [world] every rank's flag area (mapped)
+    uint64_t* my_slots;
+    uint32_t* my_flags;
+    int* error;
+    int world, rank, max_nq, max_k;
+    uint32_t seq;
+    int64_t base;                  // global row of this shard's row 0
+};
 struct ScanFused {
     const void* q_raw;      // caller's queries [nq, dim] (nullptr: read prepared fp32 queries instead)
     int q_dtype, q_normalize;
@@ -354,6 +382,7 @@ struct ScanFused {
     uint64_t* out_keys;     // any of the three may be nullptr
     float* out_scores;
     int64_t* out_ids;
+    XchgDev xchg;           // world > 0: exchange the shard results with the peers inside the kernel
 };
 int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64_t n_rows,
                      const float* queries_f32, int nq, int k, const uint32_t* allow_mask,

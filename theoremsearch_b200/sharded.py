@@ -12,7 +12,13 @@ from typing import Callable, Optional
 import torch
 import torch.distributed as dist
 
-from .index import TheoremIndex, merge_topk
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+from .index import _TORCH_TO_TS, TheoremIndex, _stream_ptr, merge_topk
 
 
 def shard_bounds(n_rows: int, world_size: int) -> list[tuple[int, int]]:
@@ -44,15 +50,77 @@ class ShardedIndex:
         self._merge = merge or merge_topk
         self.id_map = id_map
         self._base = None
+        self._xchg = None
+        self._xchg_limits = (0, 0)
 
     def shard_base(self, device) -> torch.Tensor:
         if self._base is None or self._base.device != torch.device(device):
             self._base = torch.tensor([lo for lo, _ in self.bounds], dtype=torch.int64, device=device)
         return self._base
 
+    # -------------------------------------------------------------------------------- fused peer exchange
+    def enable_peer_exchange(self, max_nq: int = 3, max_k: int = 256) -> "ShardedIndex":
+        """Set up the in-kernel exchange (``ts_search_sharded``): every rank allocates a receive area,
+        the CUDA-IPC handles are all-gathered once (host-side plumbing), peers are mapped.  Afterwards
+        small-batch searches need no collective call at all: the scan kernel's last CTA stores its k keys
+        into the peers' memory over NVLink, waits for theirs and merges."""
+        if self._xchg is not None:
+            return self
+        dev = self.local.device
+        h = C.c_void_p()
+        check(lib.ts_xchg_create(C.byref(h), dev.index, self.world, self.rank, int(max_nq), int(max_k)))
+        hb = int(lib.ts_xchg_handle_bytes())
+        mine = np.zeros(hb, dtype=np.uint8)
+        check(lib.ts_xchg_handle(h, mine.ctypes.data))
+        if self.world > 1:
+            t = torch.from_numpy(mine).to(dev)
+            allh = torch.empty(self.world * hb, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, t, group=self.group)
+            host = np.ascontiguousarray(allh.cpu().numpy())
+            check(lib.ts_xchg_connect(h, host.ctypes.data))
+            dist.barrier(group=self.group)          # every rank has mapped every area before anyone stores
+        else:
+            check(lib.ts_xchg_connect(h, None))
+        self._xchg = h
+        self._xchg_limits = (int(max_nq), int(max_k))
+        return self
+
+    def close(self) -> None:
+        if self._xchg is not None:
+            if self.world > 1 and dist.is_initialized():
+                torch.cuda.synchronize()
+                dist.barrier(group=self.group)      # nobody unmaps while a peer may still store
+            lib.ts_xchg_destroy(self._xchg)
+            self._xchg = None
+
+    def _fused_ok(self, nq: int, k: int) -> bool:
+        return (self._xchg is not None and nq <= self._xchg_limits[0] and k <= self._xchg_limits[1]
+                and nq < _lib.get_tunable("batch.min_nq"))
+
+    def _search_fused(self, queries, k: int, normalize: bool, allow_mask):
+        ix = self.local
+        q = ix._prep_queries(queries)
+        nq = q.shape[0]
+        scores = torch.empty((nq, k), dtype=torch.float32, device=ix.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=ix.device)
+        ws = ix._workspace(nq, k)
+        check(lib.ts_search_sharded(ix.handle, self._xchg, q.data_ptr(), _TORCH_TO_TS[q.dtype], nq, int(k),
+                                    int(normalize), ix._mask_ptr(allow_mask), int(self.lo),
+                                    self.id_map.data_ptr() if self.id_map is not None else None,
+                                    scores.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    _stream_ptr(ix.device)))
+        q.record_stream(torch.cuda.current_stream(ix.device))
+        return scores, ids
+
+    def peer_exchange_error(self) -> bool:
+        return self._xchg is not None and int(lib.ts_xchg_error(self._xchg)) != 0
+
     def search(self, queries: torch.Tensor, k: int, normalize: bool = True,
                allow_mask: Optional[torch.Tensor] = None):
         """Replicated queries [nq, D] -> global (scores [nq, k], ids [nq, k]) on every rank."""
+        nq = 1 if queries.dim() == 1 else queries.shape[0]
+        if self._fused_ok(nq, k):
+            return self._search_fused(queries, k, normalize, allow_mask)
         keys = self._local_search(queries, k, normalize, allow_mask)          # [nq, k] packed keys
         if self.world == 1:
             gathered = keys.unsqueeze(0)
