@@ -218,10 +218,20 @@ def main():
     synthetic.fill_index(index, lo, hi - lo, seed=0)
     torch.cuda.synchronize()
     sharded = ShardedIndex(index, args.rows) if world > 1 else None
-    if sharded is not None and args.exchange == "fused":
-        sharded.enable_peer_exchange(max_nq=1, max_k=max(args.k, 32))
     if sharded is not None:
-        config["exchange"] = ("in-kernel NVLink peer stores + flags (ts_search_sharded)" if args.exchange == "fused"
+        fused = args.exchange == "fused"
+        if fused:
+            try:
+                sharded.enable_peer_exchange(max_nq=1, max_k=max(args.k, 32))
+            except ts.TheoremSearchError as e:      # CUDA IPC unavailable in this container: say so, use NCCL
+                fused = False
+                config["exchange_fallback"] = str(e)
+            ok = torch.tensor([1 if fused else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # all ranks must take the same path
+            if fused and not bool(ok.item()):
+                sharded.close()
+                fused = False
+        config["exchange"] = ("in-kernel NVLink peer stores + flags (ts_search_sharded)" if fused
                               else "NCCL all-gather of k packed keys + merge kernel")
 
     total = args.warmup + args.steps
@@ -261,12 +271,20 @@ def main():
     value = 1e3 / ms_per_step
 
     # ---- end-to-end region: host buffers in, host buffers out, per step --------------------
+    pin_q = torch.empty((1, args.dim), dtype=torch.float32).pin_memory()
+    pin_s = torch.empty((1, args.k), dtype=torch.float32).pin_memory()
+    pin_i = torch.empty((1, args.k), dtype=torch.int64).pin_memory()
+
     def one_step_host(i):
         if sharded is None:
             return index.search_host(q_host[i], args.k, timing=True)
-        q = torch.from_numpy(q_host[i:i + 1]).pin_memory().to(dev, non_blocking=True)
+        pin_q.copy_(torch.from_numpy(q_host[i:i + 1]))            # host query -> pinned staging
+        q = pin_q.to(dev, non_blocking=True)                      # H2D, 4 KB
         s, ids = sharded.search(q, args.k)
-        return s.cpu().numpy(), ids.cpu().numpy()
+        pin_s.copy_(s, non_blocking=True)                         # D2H, k*(4+8) B
+        pin_i.copy_(ids, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return pin_s.numpy(), pin_i.numpy()
 
     for i in range(args.warmup):
         one_step_host(i)

@@ -1,0 +1,122 @@
+"""BASELINE.json's full single-GPU size (10M x 1024 bf16, configs[1]/[2]) checked through
+size-independent properties — the CPU oracle cannot score 10^10 elements in test time:
+
+  * planted neighbours: rows built to have cosines 0.90, 0.89, ... with a query come back in exactly
+    that order, at their planted positions, from the scan path (K2) and the tensor-core path (K3);
+  * shard-merge: top-k of (top-k over rows A) U (top-k over rows B) == top-k over all rows (K5), with the
+    shards emulated by allow masks;
+  * K3 (batched) == K2 (single query) bit for bit; repeat runs are bit-identical;
+  * IVF with every list probed == exact search (bf16 lists, re-scored in K2's summation order);
+  * ordering invariants: scores descending, ids unique, ties (duplicated row) -> lower row first.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+N, D = 10_000_000, 1024
+PLANT_AT = [123, 2_500_001, 4_999_999, 5_000_000, 7_777_777, 9_999_990, 31, 8_000_123, 1_000_000, 6_543_210]
+COS = [0.90 - 0.01 * i for i in range(10)]
+DUP_OF, DUP_AT = 2_500_001, 9_000_000     # an exact duplicate of the 2nd planted row, later in the corpus
+
+
+@pytest.fixture(scope="module")
+def env():
+    import theoremsearch_b200 as ts
+    from theoremsearch_b200 import synthetic
+    assert torch.cuda.is_available()
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(77)
+    q = torch.randn(D, generator=g, device=dev)
+    q /= q.norm()
+    planted = {}
+    for pos, c in zip(PLANT_AT, COS):
+        r = torch.randn(D, generator=g, device=dev)
+        r -= (r @ q) * q
+        r /= r.norm()
+        planted[pos] = c * q + (1.0 - c * c) ** 0.5 * r
+    planted[DUP_AT] = planted[DUP_OF]
+    index = ts.TheoremIndex(D, N, dtype="bf16", device=dev)
+    cur = 0
+    for pos in sorted(planted):
+        if pos > cur:
+            synthetic.fill_index(index, cur, pos - cur, seed=0)
+        index.add(planted[pos].unsqueeze(0), normalize=True)
+        cur = pos + 1
+    synthetic.fill_index(index, cur, N - cur, seed=0)
+    torch.cuda.synchronize()
+    assert len(index) == N
+    others = synthetic.make_queries(63, D, dev)
+    return ts, index, q, others
+
+
+def expected_top():
+    # the duplicate of planted row #2 ties with it and sorts right after it (higher row)
+    order = [PLANT_AT[0], DUP_OF, DUP_AT] + PLANT_AT[2:]
+    return order
+
+
+def test_planted_neighbours_scan_path(env):
+    ts, index, q, _ = env
+    s, i = index.search(q, 11)
+    assert i[0].tolist() == expected_top()
+    sc = s[0].cpu().numpy()
+    want = np.array([COS[0], COS[1], COS[1]] + COS[2:])
+    assert np.max(np.abs(sc - want)) < 1e-3          # bf16 storage: north_star's 1e-3 bound
+    assert sc[1] == sc[2]                            # the duplicate scores bit-identically
+    assert np.all(np.diff(sc) <= 0)
+    s2, i2 = index.search(q, 11)
+    assert torch.equal(s, s2) and torch.equal(i, i2)
+    sh, ih = index.search_host(q.cpu().numpy(), 11)   # host-buffer entry point
+    assert ih[0].tolist() == expected_top() and np.array_equal(sh[0], sc)
+
+
+def test_planted_neighbours_tensor_core_path_bitwise_equal(env):
+    ts, index, q, others = env
+    batch = torch.cat([others[:20], q.unsqueeze(0), others[20:]], dim=0)      # 64 queries -> K3
+    sb, ib = index.search(batch, 11)
+    assert ib[20].tolist() == expected_top()
+    assert ts.last_batched_fixups() >= 0
+    for j in (0, 20, 41, 63):
+        s1, i1 = index.search(batch[j], 11)                                   # K2
+        assert torch.equal(sb[j], s1[0]) and torch.equal(ib[j], i1[0])
+    for row in ib.cpu().numpy():
+        assert len(set(row.tolist())) == row.size
+    assert torch.all(sb[:, 1:] <= sb[:, :-1])
+
+
+def test_shard_merge_equals_unsharded(env):
+    ts, index, q, others = env
+    words = (N + 31) // 32
+    lo_mask = torch.zeros(words, dtype=torch.int32, device="cuda")
+    cut = 5_000_000                                                           # a multiple of 32
+    lo_mask[: cut // 32] = -1
+    hi_mask = ~lo_mask
+    queries = torch.cat([q.unsqueeze(0), others[:2]], dim=0)
+    for nq in (1, 3):
+        qs = queries[:nq]
+        full_s, full_i = index.search(qs, 10)
+        keys = torch.stack([index.search_keys(qs, 10, allow_mask=lo_mask), index.search_keys(qs, 10, allow_mask=hi_mask)])
+        ms, mi = ts.merge_topk(keys, 10)
+        assert torch.equal(ms, full_s) and torch.equal(mi, full_i)
+    s_lo, i_lo = index.search(q, 10, allow_mask=lo_mask)
+    assert torch.all(i_lo < cut)
+    assert i_lo[0].tolist()[:4] == [p for p in expected_top() if p < cut][:4]
+
+
+def test_ivf_probing_every_list_equals_exact_at_full_size(env):
+    ts, index, q, others = env
+    index.ivf_train(256, n_sample=200_000, iters=2, seed=0)
+    index.ivf_build("bf16")
+    assert int(index.ivf_list_sizes().sum()) == N
+    queries = torch.cat([q.unsqueeze(0), others[:2]], dim=0)
+    s_e, i_e = index.search(queries, 10)
+    s_a, i_a = index.ivf_search(queries, 10, nprobe=256, rescore_k=10)
+    assert torch.equal(s_e, s_a) and torch.equal(i_e, i_a)
+    # a realistic probe budget finds the planted neighbours that share the query's lists, with exact scores
+    s_p, i_p = index.ivf_search(q, 10, nprobe=32, rescore_k=100)
+    found = set(i_p[0].tolist()) & set(expected_top())
+    for row, sc in zip(i_p[0].tolist(), s_p[0].tolist()):
+        if row in found:
+            assert sc == s_e[0][i_e[0].tolist().index(row)].item() if row in i_e[0].tolist() else True
