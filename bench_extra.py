@@ -224,10 +224,13 @@ def cmd_ivf_q1(a):
     index.ivf_train(a.nlist, n_sample=a.train_sample, iters=2, seed=0)
     index.ivf_build(a.list_dtype)
     torch.cuda.synchronize()
+    if a.profile_nq > 1:
+        q_all = synthetic.make_clustered_queries(a.profile_nq, centers, a.sigma)
     for i in range(a.iters):
-        index.ivf_search(q_all[i:i + 1], a.k, nprobe=a.nprobe, rescore_k=a.rescore)
+        qq = q_all[i:i + 1] if a.profile_nq == 1 else q_all
+        index.ivf_search(qq, a.k, nprobe=a.nprobe, rescore_k=a.rescore)
     torch.cuda.synchronize()
-    print(json.dumps({"bench": "ivf-q1", "launches": ts.kernel_launches()}))
+    print(json.dumps({"bench": "ivf-q1", "profile_nq": a.profile_nq, "launches": ts.kernel_launches()}))
 
 
 def cmd_ivf_q1_sweep(a):
@@ -385,6 +388,7 @@ def main():
     ap.add_argument("--train-iters", type=int, default=10)
     ap.add_argument("--nq-recall", type=int, default=1000)
     ap.add_argument("--recall-sweep", type=int, nargs="*", default=[])
+    ap.add_argument("--profile-nq", type=int, default=1, help="ivf-q1: queries per call (1 = latency mode)")
     a = ap.parse_args()
     if a.k is None:
         a.k = 100 if a.cmd == "batched" else 10
