@@ -275,6 +275,29 @@ def cmd_ivf_q1_sweep(a):
                       "last_cta": [float(x) for x in rel[last]]}))
 
 
+def cmd_fp8_scan(a):
+    """BASELINE north_star: single-query scan over an fp8-e4m3 corpus, re-scored in fp32 — half the bytes."""
+    dev = torch.device("cuda", 0)
+    pk = peaks()
+    index = build(a.rows, a.dim, dev)
+    index.build_fp8_shadow()
+    q_all = synthetic.make_queries(max(256, a.nq_recall), a.dim, dev)
+    qr = q_all[:a.nq_recall]
+    _, exact_ids = index.search(qr, a.k)
+    out = {"bench": "fp8-scan", "rows": a.rows, "dim": a.dim, "k": a.k, "data": "gaussian (hardest case: no structure)"}
+    for rk in (32, 64, 128, 256):
+        ids = torch.cat([index.search_fp8(qr[i:i + 64], a.k, rescore_k=rk)[1] for i in range(0, a.nq_recall, 64)])
+        out[f"recall_at_{a.k}_rescore_{rk}"] = recall_at_k(ids, exact_ids)
+    qs = q_all[:1].clone()
+    ms = timed_graph(lambda: index.search_fp8(qs, a.k, rescore_k=a.rescore), 10, 100)
+    ms_exact = timed_graph(lambda: index.search(qs, a.k), 10, 100)
+    nbytes = a.rows * (a.dim + 4)
+    out.update({"rescore_k": a.rescore, "fp8_q1_ms": ms, "fp8_q1_qps": 1e3 / ms, "fp8_scan_gbs": nbytes / (ms * 1e-3) / 1e9,
+                "fp8_frac_of_measured_hbm": nbytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "bf16_exact_q1_ms": ms_exact,
+                "speedup_vs_bf16_exact": ms_exact / ms})
+    print(json.dumps(out))
+
+
 def cmd_sharded(a):
     """configs[3] + configs[4] at their named size under torchrun: rows row-sharded over WORLD_SIZE GPUs.
     Exact Q=1 / Q=batch, then IVF-Flat (one shared coarse quantiser) with recall vs the sharded exact path."""
@@ -367,7 +390,7 @@ def cmd_sharded(a):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("cmd", choices=["batched", "sweep-scan", "small-batch", "ivf", "sharded", "ivf-q1", "ivf-q1-sweep"])
+    ap.add_argument("cmd", choices=["batched", "sweep-scan", "small-batch", "ivf", "sharded", "ivf-q1", "ivf-q1-sweep", "fp8-scan"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--dim", type=int, default=1024)
     ap.add_argument("--nq", type=int, default=4096)
@@ -392,7 +415,7 @@ def main():
     a = ap.parse_args()
     if a.k is None:
         a.k = 100 if a.cmd == "batched" else 10
-    {"batched": cmd_batched, "sweep-scan": cmd_sweep_scan, "small-batch": cmd_small_batch, "ivf": cmd_ivf, "sharded": cmd_sharded, "ivf-q1": cmd_ivf_q1, "ivf-q1-sweep": cmd_ivf_q1_sweep}[a.cmd](a)
+    {"batched": cmd_batched, "sweep-scan": cmd_sweep_scan, "small-batch": cmd_small_batch, "ivf": cmd_ivf, "sharded": cmd_sharded, "ivf-q1": cmd_ivf_q1, "ivf-q1-sweep": cmd_ivf_q1_sweep, "fp8-scan": cmd_fp8_scan}[a.cmd](a)
 
 
 if __name__ == "__main__":

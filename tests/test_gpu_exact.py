@@ -294,3 +294,37 @@ def test_errors_are_loud(ts):
         index.search(torch.zeros(64), 5000)  # k too large
     with pytest.raises(ts.TheoremSearchError):
         index.search(torch.zeros(65), 5)     # wrong dim
+
+
+# ------------------------------------------------------------------------------------------- property tests
+def test_random_shapes_equal_oracle_hypothesis(ts):
+    """on random small shapes the CUDA path equals the oracle; the merge of shard results
+    equals the unsharded result."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as hst
+
+    @settings(max_examples=30, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(n=hst.integers(1, 2500), d=hst.integers(1, 260), k=hst.integers(1, 40), nq=hst.integers(1, 6),
+           dtype=hst.sampled_from(["bf16", "f32"]), seed=hst.integers(0, 10_000), dup=hst.booleans())
+    def run(n, d, k, nq, dtype, seed, dup):
+        x = oracle.synthetic_rows(0, n, d, seed=seed)
+        if dup and n > 3:
+            x[n - 1] = x[1]                      # tie -> lower row
+        index = ts.build_index(x, dtype=dtype)
+        q = oracle.synthetic_queries(nq, d, seed=seed + 1)
+        s, i = index.search(torch.from_numpy(q), k)
+        check_against_oracle(ts, index, oracle.normalize_f64(q), k, s, i)
+        # shard-merge: two masks that partition the rows
+        cut = (n // 2 // 32) * 32
+        if cut > 0:
+            allow = np.zeros(n, dtype=bool)
+            allow[:cut] = True
+            m_lo = ts.pack_allow_mask(allow, index.device)
+            m_hi = ts.pack_allow_mask(~allow, index.device)
+            keys = torch.stack([index.search_keys(torch.from_numpy(q), k, allow_mask=m_lo),
+                                index.search_keys(torch.from_numpy(q), k, allow_mask=m_hi)])
+            ms, mi = ts.merge_topk(keys, k)
+            assert torch.equal(ms, s) and torch.equal(mi, i)
+        index.close()
+
+    run()

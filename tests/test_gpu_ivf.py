@@ -233,3 +233,22 @@ def test_shared_centroids_and_state_errors(ts):
     c.add(x[:10])
     with pytest.raises(ts.TheoremSearchError):
         c.ivf_search(torch.zeros(1, 256), 5)
+
+
+def test_fp8_exhaustive_scan_mode(ts):
+    """north_star's 'optionally fp8-e4m3, rescored in fp32' scan: one list with every row in row order."""
+    x = clustered_rows(20000, 1024, 50, 1.0, seed=77)
+    index = ts.build_index(x)
+    index.build_fp8_shadow()
+    off, rows = layout(index)
+    assert off.tolist() == [0, 20000] and np.array_equal(rows, np.arange(20000))
+    q = torch.from_numpy(oracle.normalize_f64(clustered_rows(8, 1024, 50, 1.0, seed=77)))
+    s_e, i_e = index.search(q, 10, normalize=False)
+    s_f, i_f = index.search_fp8(q, 10, rescore_k=200, normalize=False)
+    assert oracle.recall_at_k(i_f.cpu().numpy(), i_e.cpu().numpy()) >= 0.95
+    se, ie, sf, i_f = s_e.cpu().numpy(), i_e.cpu().numpy(), s_f.cpu().numpy(), i_f.cpu().numpy()
+    for qi in range(8):          # every returned row carries its exact score
+        exact = dict(zip(ie[qi].tolist(), se[qi].tolist()))
+        for r, sc in zip(i_f[qi].tolist(), sf[qi].tolist()):
+            if r in exact:
+                assert sc == exact[r]

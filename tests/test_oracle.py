@@ -149,3 +149,30 @@ def test_ivf_oracle_full_probe_equals_exact():
     assert np.array_equal(i, i2[0])
     s3, i3 = oracle.ivf_search(q, rows, cent, assign, 10, nprobe=2)
     assert 0.0 < oracle.recall_at_k(i3, i2[0]) <= 1.0
+
+
+def test_merge_of_shards_equals_unsharded_hypothesis():
+    """Top-k of a union == top-k of the per-shard top-k's, for any contiguous sharding."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as hst
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(n=hst.integers(1, 400), d=hst.integers(1, 24), k=hst.integers(1, 30), world=hst.integers(1, 5),
+           seed=hst.integers(0, 1000))
+    def run(n, d, k, world, seed):
+        rows = oracle.bf16_round(oracle.normalize_f64(oracle.synthetic_rows(0, n, d, seed=seed)))
+        if n > 2:
+            rows[n - 1] = rows[0]
+        q = oracle.normalize_f64(oracle.synthetic_queries(2, d, seed=seed + 7))
+        want_s, want_i = oracle.exact_search(q, rows, k)
+        ss, rr, base = [], [], []
+        for lo, hi in oracle.shard_bounds(n, world):
+            s, i = oracle.exact_search(q, rows[lo:hi], k)
+            ss.append(s)
+            rr.append(i)
+            base.append(lo)
+        s, r = oracle.merge_shards(ss, rr, base, k)
+        assert np.array_equal(r, want_i)
+        assert np.allclose(s[r >= 0], want_s[want_i >= 0])
+
+    run()

@@ -625,15 +625,16 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
                              pair ? bn / 2 : bn);
     if (rc) return rc;
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};   // function attributes are per device
+    const int dslot = ix->device & 63;
+    if (!attr_set[dslot]) {
         TS_CHECK_CUDA(cudaFuncSetAttribute(batched_gemm_topk_kernel<false>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         TS_CHECK_CUDA(cudaFuncSetAttribute(batched_gemm_topk_kernel<true>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         TS_CHECK_CUDA(cudaFuncSetAttribute(compact_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            64 * 1024));
-        attr_set = true;
+        attr_set[dslot] = true;
     }
     int P = 1;
     while (P < k + cap) P <<= 1;

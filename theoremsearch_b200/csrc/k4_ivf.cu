@@ -231,11 +231,11 @@ static int launch_assign(int device, const void* rows, int64_t n_rows, size_t ro
     p.best = best;
     rc = make_tmap_bf16_rows(&tmap_b, cent, (uint64_t)nlist, (uint64_t)dim_pad, (uint64_t)dim_pad * 2, (uint32_t)p.bn);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};   // function attributes are per device
+    if (!attr_set[device & 63]) {
         TS_CHECK_CUDA(cudaFuncSetAttribute(assign_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)SMEM_BYTES));
-        attr_set = true;
+        attr_set[device & 63] = true;
     }
     const int grid = std::min(p.num_m_blocks, sm_count(device));
     assign_argmax_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(tmap_a, tmap_b, p);
@@ -832,6 +832,15 @@ __global__ void __launch_bounds__(512, 1) list_scan_kernel(const ListScanParams 
     IVF_STAMP(7);
 }
 
+// A query spread over several CTAs whose warps would each see only a few hundred rows is latency-bound
+// (short per-warp instruction streams matter more than bytes in flight); long scans — many rows per warp,
+// e.g. the one-list fp8 shadow of the whole corpus — stream best with K2's configuration.
+static bool latency_mode(const ts_index* ix, int nprobe, int parts) {
+    if (parts <= 1) return false;
+    const double rows = (double)nprobe * (double)ix->size / (double)std::max(ix->nlist, 1);
+    return rows / ((double)parts * 16.0) < 512.0;
+}
+
 struct ListScanConfig {
     int warps, stages;
     size_t smem;
@@ -844,7 +853,7 @@ static int launch_list_scan_r(const ts_index* ix, ListScanParams p, int nq, int 
     int stages = t.scan_stages < 2 ? 2 : t.scan_stages;
     // latency mode (a query is spread over several CTAs): 16 warps per SM halve the rows — and so the serial
     // instruction stream — per warp; throughput mode (one CTA per query, many queries): 8 warps stream at HBM rate
-    int warps = t.ivf_warps > 0 ? t.ivf_warps : (parts > 1 ? 16 : 8);
+    int warps = t.ivf_warps > 0 ? t.ivf_warps : (latency_mode(ix, p.nprobe, parts) ? 16 : 8);
     warps = warps > 16 ? 16 : warps;
     const size_t table = (size_t)p.nprobe * 16 + 16;   // s_start, s_len, s_tpref
     const size_t budget = (size_t)(220 * 1024) - 1024 - table;
@@ -869,7 +878,7 @@ static int launch_list_scan_k(const ts_index* ix, const ListScanParams& p, int n
     constexpr int R = (ELEM == 1) ? (NCHUNK == 1 ? 16 : (NCHUNK == 2 ? 8 : 4)) : RowsPerTile<NCHUNK>::value;
     if constexpr (ELEM == 1 && NCHUNK == 2) {   // the flagship shape (e4m3, 512 < D <= 1024): 4-row tiles too
         int rows = tunables().ivf_tile_rows;
-        if (rows == 0) rows = parts > 1 ? 4 : 8;
+        if (rows == 0) rows = latency_mode(ix, p.nprobe, parts) ? 4 : 8;
         if (rows == 4 && p.k <= 128)
             return p.k <= 32 ? launch_list_scan_r<ELEM, NCHUNK, 1, 4>(ix, p, nq, parts, s)
                              : launch_list_scan_r<ELEM, NCHUNK, 4, 4>(ix, p, nq, parts, s);
@@ -1003,18 +1012,6 @@ static int ivf_finish_centroids(ts_index* ix, cudaStream_t s) {
     return TS_OK;
 }
 
-struct DevGuard {
-    int prev = -1;
-    bool ok = true;
-    explicit DevGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
-        else if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
-    }
-    ~DevGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
 // temp device buffers of the train/build calls (build-time only; searches never allocate)
 struct TempBufs {
     std::vector<void*> ptrs;
@@ -1070,7 +1067,7 @@ int ts_ivf_train(ts_index* ix, const float* sample, int64_t n_sample, int nlist,
     TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "ivf_train: index is NULL");
     TS_REQUIRE(nlist >= 1 && nlist <= (1 << 20), TS_ERR_BAD_ARG, "ivf_train: nlist=%d out of range [1, 2^20]", nlist);
     TS_REQUIRE(iters >= 0 && iters <= 1000, TS_ERR_BAD_ARG, "ivf_train: iters=%d", iters);
-    DevGuard g(ix->device);
+    DeviceGuard g(ix->device);
     TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_train: cannot select CUDA device %d", ix->device);
     cudaStream_t s = (cudaStream_t)stream;
     TempBufs tmp;
@@ -1127,7 +1124,7 @@ int ts_ivf_train(ts_index* ix, const float* sample, int64_t n_sample, int nlist,
 int ts_ivf_set_centroids(ts_index* ix, const float* centroids, int nlist, void* stream) {
     TS_REQUIRE(ix != nullptr && centroids != nullptr, TS_ERR_BAD_ARG, "ivf_set_centroids: NULL argument");
     TS_REQUIRE(nlist >= 1 && nlist <= (1 << 20), TS_ERR_BAD_ARG, "ivf_set_centroids: nlist=%d", nlist);
-    DevGuard g(ix->device);
+    DeviceGuard g(ix->device);
     TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_set_centroids: cannot select CUDA device %d", ix->device);
     cudaStream_t s = (cudaStream_t)stream;
     int rc = ivf_alloc_centroids(ix, nlist);
@@ -1142,7 +1139,7 @@ int ts_ivf_set_centroids(ts_index* ix, const float* centroids, int nlist, void* 
 int ts_ivf_get_centroids(const ts_index* ix, float* out, void* stream) {
     TS_REQUIRE(ix != nullptr && out != nullptr, TS_ERR_BAD_ARG, "ivf_get_centroids: NULL argument");
     TS_REQUIRE(ix->nlist > 0, TS_ERR_STATE, "ivf_get_centroids: no centroids (call ts_ivf_train first)");
-    DevGuard g(ix->device);
+    DeviceGuard g(ix->device);
     TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_get_centroids: cannot select CUDA device %d", ix->device);
     return launch_dequant_rows(ix->centroids, TS_F32, ix->nlist, ix->dim, ix->dim_pad, out, (cudaStream_t)stream);
 }
@@ -1154,7 +1151,7 @@ int ts_ivf_build(ts_index* ix, int list_dtype, void* stream) {
     TS_REQUIRE(list_dtype == TS_BF16 || list_dtype == TS_FP8_E4M3, TS_ERR_BAD_ARG,
                "ivf_build: list dtype must be TS_BF16 or TS_FP8_E4M3 (got %d)", list_dtype);
     TS_REQUIRE(ix->dtype == TS_BF16, TS_ERR_UNSUPPORTED, "ivf_build: the corpus must be stored as bf16");
-    DevGuard g(ix->device);
+    DeviceGuard g(ix->device);
     TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_build: cannot select CUDA device %d", ix->device);
     cudaStream_t s = (cudaStream_t)stream;
     ivf_free_lists(ix);
@@ -1206,7 +1203,7 @@ int ts_debug_ivf_timeline(uint64_t* out_host, int n_ctas) {
 int ts_ivf_list_sizes(const ts_index* ix, int64_t* out, void* stream) {
     TS_REQUIRE(ix != nullptr && out != nullptr, TS_ERR_BAD_ARG, "ivf_list_sizes: NULL argument");
     TS_REQUIRE(ix->ivf_built, TS_ERR_STATE, "ivf_list_sizes: lists are not built (call ts_ivf_build)");
-    DevGuard g(ix->device);
+    DeviceGuard g(ix->device);
     TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_list_sizes: cannot select CUDA device %d", ix->device);
     list_sizes_kernel<<<(ix->nlist + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ix->list_offsets, ix->nlist, out);
     TS_LAUNCH_CHECK();
@@ -1216,7 +1213,7 @@ int ts_ivf_list_sizes(const ts_index* ix, int64_t* out, void* stream) {
 int ts_ivf_get_lists(const ts_index* ix, int64_t* offsets_out, int64_t* rows_out, void* stream) {
     TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "ivf_get_lists: index is NULL");
     TS_REQUIRE(ix->ivf_built, TS_ERR_STATE, "ivf_get_lists: lists are not built (call ts_ivf_build)");
-    DevGuard g(ix->device);
+    DeviceGuard g(ix->device);
     TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_get_lists: cannot select CUDA device %d", ix->device);
     cudaStream_t s = (cudaStream_t)stream;
     if (offsets_out)
@@ -1236,7 +1233,7 @@ int ts_ivf_get_list_data(const ts_index* ix, int64_t first, int64_t n, float* ou
                (long long)first, (long long)(first + n), (long long)ix->size);
     if (n == 0) return TS_OK;
     TS_REQUIRE(out != nullptr, TS_ERR_BAD_ARG, "ivf_get_list_data: out is NULL");
-    DevGuard g(ix->device);
+    DeviceGuard g(ix->device);
     TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_get_list_data: cannot select CUDA device %d", ix->device);
     const int64_t total = n * (int64_t)ix->dim;
     const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
@@ -1319,7 +1316,7 @@ static int ivf_search_impl(ts_index* ix, const void* queries, int q_dtype, int n
     TS_REQUIRE(queries != nullptr && workspace != nullptr, TS_ERR_BAD_ARG, "ivf_search: NULL buffer");
     nprobe = std::min(std::min(nprobe, ix->nlist), TS_MAX_K);
     const int kc = std::max(k, rescore_k);
-    DevGuard g(ix->device);
+    DeviceGuard g(ix->device);
     TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_search: cannot select CUDA device %d", ix->device);
     IvfWs w = carve_ivf(ix, nq, kc, nprobe, workspace);
     TS_REQUIRE(workspace_bytes >= w.bytes, TS_ERR_CAPACITY, "ivf_search: workspace %zu < %zu bytes", workspace_bytes,

@@ -27,21 +27,6 @@ Tunables& tunables() {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = true;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) {
-            ok = false;
-            return;
-        }
-        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
 // Workspace layout for exact search: [prepared queries fp32 | per-CTA candidate keys]
 struct SearchWs {
     float* q_f32;

@@ -55,6 +55,22 @@ inline int sm_count(int device) {
     return n;
 }
 
+// selects a CUDA device for the lifetime of the object, restores the previous one
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            ok = false;
+            return;
+        }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 // ---------------------------------------------------------------------------- tunables
 struct Tunables {
     int scan_ctas_per_sm = 1;   // persistent CTAs per SM for K2

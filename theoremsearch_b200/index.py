@@ -291,6 +291,19 @@ class TheoremIndex:
         check(lib.ts_ivf_get_list_data(self._h, first, n, out.data_ptr(), _stream_ptr(self.device)))
         return out
 
+    # -------------------------------------------------------------------------------- fp8 exhaustive scan
+    def build_fp8_shadow(self) -> "TheoremIndex":
+        """An e4m3 copy of the whole corpus (one inverted list holding every row, in row order) for
+        BASELINE.json's "optionally fp8-e4m3, rescored in fp32" single-query scan: half the bytes per query."""
+        self.ivf_train(1, n_sample=1, iters=0)
+        return self.ivf_build("fp8")
+
+    def search_fp8(self, queries, k: int, rescore_k: int = 128, normalize: bool = True):
+        """Exhaustive scan of the e4m3 shadow (K4b), exact re-score of the ``rescore_k`` best against the bf16
+        rows (K4c).  Scores are exact for the returned rows; the id set is the exact top-k unless a true
+        neighbour falls outside the e4m3 top-``rescore_k`` (reported as recall by ``bench_extra.py fp8-scan``)."""
+        return self.ivf_search(queries, k, nprobe=1, rescore_k=rescore_k, normalize=normalize)
+
     def _ivf_workspace(self, nq: int, k: int, nprobe: int, rescore_k: int) -> torch.Tensor:
         need = int(lib.ts_ivf_workspace_bytes(self._h, nq, k, nprobe, rescore_k))
         key = ("ivf", nq, k, nprobe, rescore_k)
