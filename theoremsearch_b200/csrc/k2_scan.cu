@@ -1,396 +1,13 @@
-// K2 — single-query exact scan with the top-k fused into the scan (HBM-bandwidth bound).
-//
-// Replaces, per query, the reference's
-//     cosine_scores = util.cos_sim(query_embedding, embeddings_db)[0]      (test_app.py:76)
-//     top = np.argsort(-cosine_scores.cpu())[:5]                           (test_app.py:77)
-//     torch.topk(cosine_scores, k=min(200, N), sorted=True)                (app_showcase_model.py:96)
-//     ORDER BY e.embedding <#> q ASC LIMIT k                               (streamlit_app.py:281-282)
-// which re-normalise the corpus, materialise all N scores and fully sort them.
-//
-// Design (B200):
-//   * persistent grid, ctas_per_sm CTAs per SM, W warps each; every warp runs its OWN
-//     TMA pipeline: `stages` shared-memory slots, one mbarrier per slot; lane 0 issues
-//     cp.async.bulk (1-D TMA, whole rows are contiguous so no tensor map is needed) for the
-//     warp's next tile as soon as the warp has finished reading a slot. No block-wide
-//     barrier inside the scan loop.
-//   * a tile is R whole rows (~8 KB). Lanes read the slot with conflict-free 128-bit LDS
-//     (lane l takes bytes [16l, 16l+16) of each 512-byte chunk of a row), convert bf16->fp32
-//     with one shift/mask per element and FMA against the query held in registers as fp32.
-//   * the R per-row partial sums are reduced with a transposing butterfly (R-1 + log2(32/R)
-//     shuffles per tile instead of 5R).
-//   * top-k: each warp keeps a sorted list of 64-bit keys (score,row) in registers
-//     (WarpTopK); a candidate is inserted only if it beats the warp's current k-th key, which
-//     after warm-up is rare, so the steady state costs one compare + one ballot per tile.
-//     Scores never go to HBM: each CTA writes only its k best keys; K5 merges the CTA lists.
-//
-// Algorithmic bytes: N * row_bytes per query (+ D*4 query + nparts*k*8 candidates).
-#include <algorithm>
-
-#include "merge_device.cuh"
-#include "scan_device.cuh"
+// K2 host side: grid sizing and dispatch to the kernel instantiations, which are compiled in four
+// translation units (k2_scan_{bf16,f32}_{small,large}.cu) so that the build parallelises.
+#include "k2_scan_impl.cuh"
 
 namespace ts {
 
-struct ScanParams {
-    const uint8_t* data;      // [n_rows, row_bytes]
-    int64_t n_rows;
-    uint32_t row_bytes;       // dim_pad * elem size, multiple of 16
-    int dim_pad;
-    const float* queries;     // [nq, dim_pad] fp32, already normalised / zero padded
-    int k;
-    const uint32_t* mask;     // allow bitmask or nullptr
-    uint64_t* part_keys;      // [work item, nparts, k]
-    int stages;
-    int nq;                   // work items when qcount == nullptr (work item w scans query w)
-    const int* qlist;         // fix-up mode: work item w scans query qlist[w] ...
-    const int* qcount;        // ... for w < *qcount (device-side count; 0 = every CTA exits at once)
-    // fused query preparation: when q_raw != nullptr the kernel normalises the caller's query itself
-    // (bit-identical to K1's arithmetic) instead of reading a prepared fp32 copy from `queries`
-    const void* q_raw;        // [nq, dim] of q_dtype
-    int q_dtype, q_normalize, dim;
-    // fused final merge: when tickets != nullptr the last CTA of a work item to finish merges the
-    // grid's per-CTA lists and writes the final result (fin.keys / nlists / strides are filled in-kernel)
-    uint32_t* tickets;        // [work items], zero on entry, left zero on exit
-    MergeParams fin;
-    // fused cross-GPU exchange (sharded search): the last CTA stores this shard's k keys into every peer's
-    // receive area over NVLink, waits for the peers' keys and merges the world lists — no NCCL call, no
-    // second kernel
-    XchgDev xchg;
-};
-
-__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns2() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
-__device__ __forceinline__ float load_query_elem(const void* base, int dtype, size_t idx) {
-    if (dtype == TS_F32) return __ldg(reinterpret_cast<const float*>(base) + idx);
-    if (dtype == TS_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
-    return __half2float(reinterpret_cast<const __half*>(base)[idx]);
-}
-
-template <int ELEM, int NCHUNK, int KPL, int R>
-__global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
-    constexpr int CN = Chunk<ELEM>::N;       // elements per 16-byte chunk
-    constexpr int GROUP = 32 / R;            // lanes that end up holding the same row's score
-    extern __shared__ __align__(128) uint8_t smem[];
-
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int W = blockDim.x >> 5;
-    const int stages = p.stages;
-    const uint32_t tile_bytes = R * p.row_bytes;
-
-    uint8_t* my_slots = smem + (size_t)warp * stages * tile_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)W * stages * tile_bytes);
-    uint64_t* my_bars = bars + warp * stages;
-
-    if (lane == 0) {
-        for (int s = 0; s < stages; ++s) mbar_init(&my_bars[s], 1);
-        fence_mbar_init();
-    }
-    __syncwarp();
-
-    const int64_t num_tiles = (p.n_rows + R - 1) / R;
-    const int64_t gw = (int64_t)blockIdx.x * W + warp;
-    const int64_t tw = (int64_t)gridDim.x * W;
-    const uint64_t policy = l2_policy_evict_first();
-    const int k = p.k;
-    const int my_row = row_of_lane<R>(lane);
-    const bool leader = (lane & (GROUP - 1)) == 0;
-
-    auto issue = [&](int64_t tile, int s) {
-        const int64_t row0 = tile * R;
-        const int64_t rows = (p.n_rows - row0 < R) ? (p.n_rows - row0) : R;
-        const uint32_t bytes = (uint32_t)rows * p.row_bytes;
-        mbar_expect_tx(&my_bars[s], bytes);
-        tma_load_1d_hint(my_slots + (size_t)s * tile_bytes, p.data + (size_t)row0 * p.row_bytes, bytes,
-                         &my_bars[s], policy);
-    };
-
-    // ring position persists across work items (mbarrier phases cannot be rewound)
-    int s = 0;
-    uint32_t parity = 0;
-    const int nwork = p.qcount ? *p.qcount : p.nq;
-    for (int wi = blockIdx.y; wi < nwork; wi += gridDim.y) {
-    const int qi = p.qlist ? p.qlist[wi] : wi;
-
-    if (lane == 0) {   // get the corpus stream going before anything else
-        int ss = s;
-        for (int i = 0; i < stages; ++i) {
-            const int64_t t = gw + (int64_t)i * tw;
-            if (t < num_tiles) issue(t, ss);
-            if (++ss == stages) ss = 0;
-        }
-    }
-
-    // query slice of this lane, fp32 in registers
-    float q[NCHUNK * CN];
-    if (p.q_raw == nullptr) {
-        const float* qv = p.queries + (size_t)qi * p.dim_pad;
-#pragma unroll
-        for (int j = 0; j < NCHUNK; ++j) {
-            const int e0 = (j * 32 + lane) * CN;
-#pragma unroll
-            for (int i = 0; i < CN; ++i) q[j * CN + i] = (e0 + i < p.dim_pad) ? __ldg(qv + e0 + i) : 0.f;
-        }
-    } else {
-        // K1's arithmetic, replicated per warp (4 KB from L2): ||x|| accumulated in fp64 with lane i
-        // taking elements i, i+32, ... then the butterfly; fp32 division by max((float)sqrt, 1e-12).
-        const size_t qoff = (size_t)qi * p.dim;
-        float den = 1.0f;
-        if (p.q_normalize) {
-            double ss = 0.0;
-            for (int i = lane; i < p.dim; i += 32) {
-                const double v = (double)load_query_elem(p.q_raw, p.q_dtype, qoff + i);
-                ss = fma(v, v, ss);
-            }
-            ss = warp_sum(ss);
-            den = fmaxf((float)sqrt(ss), 1e-12f);
-        }
-#pragma unroll
-        for (int j = 0; j < NCHUNK; ++j) {
-            const int e0 = (j * 32 + lane) * CN;
-#pragma unroll
-            for (int i = 0; i < CN; ++i) {
-                float v = (e0 + i < p.dim) ? load_query_elem(p.q_raw, p.q_dtype, qoff + e0 + i) : 0.f;
-                if (p.q_normalize) v = __fdiv_rn(v, den);
-                q[j * CN + i] = v;
-            }
-        }
-    }
-
-    WarpTopK<KPL> list;
-    list.clear();
-    uint64_t thr = 0ull;  // current k-th key of this warp's list (0 while it has < k entries)
-
-    for (int64_t tile = gw; tile < num_tiles; tile += tw) {
-        const int64_t row0 = tile * R;
-        const int64_t row = row0 + my_row;
-        const bool in_range = row < p.n_rows;
-
-        // fetch the allow bit early so its latency hides behind the barrier wait + FMAs
-        bool allowed = in_range && leader;
-        if (p.mask != nullptr && allowed) allowed = (__ldg(p.mask + (row >> 5)) >> (row & 31)) & 1u;
-
-        mbar_wait(&my_bars[s], parity);
-
-        const uint8_t* slot = my_slots + (size_t)s * tile_bytes;
-        float acc[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = 0.f;
-#pragma unroll
-        for (int j = 0; j < NCHUNK; ++j) {
-            const uint32_t off = (uint32_t)(j * 32 + lane) * 16u;
-            if (off < p.row_bytes) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    // rows past the end of a short last tile hold stale smem; masked below
-                    const uint4 v = *reinterpret_cast<const uint4*>(slot + (size_t)r * p.row_bytes + off);
-                    acc[r] = Chunk<ELEM>::dot(v, &q[j * CN], acc[r]);
-                }
-            }
-        }
-        __syncwarp();  // every lane is done reading the slot
-        if (lane == 0) {
-            const int64_t nt = tile + (int64_t)stages * tw;
-            if (nt < num_tiles) issue(nt, s);
-        }
-
-        transpose_reduce<R>(acc, lane);
-        const uint64_t key = allowed ? pack_key(acc[0], (uint32_t)row) : 0ull;
-        unsigned m = __ballot_sync(0xFFFFFFFFu, key > thr);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const uint64_t x = __shfl_sync(0xFFFFFFFFu, key, src);
-            if (x > thr) {
-                list.insert(x, lane);
-                thr = list.kth(k);
-            }
-        }
-        if (++s == stages) {
-            s = 0;
-            parity ^= 1u;
-        }
-    }
-
-    // ---- CTA merge: warps park their lists in smem (the pipeline has drained: every issued
-    // copy was waited on), warp 0 folds them into its own and writes the CTA's k best.
-    __syncthreads();
-    uint64_t* lists = reinterpret_cast<uint64_t*>(smem);  // [W][KPL*32]
-#pragma unroll
-    for (int j = 0; j < KPL; ++j) lists[(size_t)warp * (KPL * 32) + j * 32 + lane] = list.key[j];
-    __syncthreads();
-    if (warp == 0) {
-        for (int w = 1; w < W; ++w) merge_sorted_into<KPL>(list, lists + (size_t)w * (KPL * 32), k, k, lane);
-        uint64_t* out = p.part_keys + ((size_t)wi * gridDim.x + blockIdx.x) * k;
-#pragma unroll
-        for (int j = 0; j < KPL; ++j) {
-            const int pos = j * 32 + lane;
-            if (pos < k) out[pos] = list.key[j];
-        }
-    }
-    __syncthreads();  // the list area aliases the TMA slots of the next work item
-    if (p.tickets != nullptr) {
-        // ---- fused final merge: the last CTA of this work item to arrive folds all gridDim.x lists.
-        // One gpu-scope fence on each side of the ticket, by thread 0 only: the barriers order the other
-        // threads' stores before it / loads after it (fences are cumulative).
-        __shared__ int s_is_last;
-        if (threadIdx.x == 0) {
-            __threadfence();
-            const uint32_t t = atomicAdd(p.tickets + wi, 1u);
-            s_is_last = (t == gridDim.x - 1);
-            if (s_is_last) {
-                p.tickets[wi] = 0u;   // self-cleaning: the next launch finds zeros
-                __threadfence();
-            }
-        }
-        __syncthreads();
-        if (s_is_last) {
-            MergeParams mp = p.fin;
-            mp.keys = p.part_keys;
-            mp.nlists = gridDim.x;
-            mp.k = k;
-            mp.stride_list = k;
-            mp.stride_query = (int64_t)gridDim.x * k;
-            if (p.xchg.world == 0) {
-                merge_lists<KPL>(mp, wi, qi, lists, W);
-            } else {
-                // ---- fused exchange. 1) this shard's top-k (local rows) into its own slot of the own area
-                const XchgDev& x = p.xchg;
-                const uint32_t par = x.seq & 1u;
-                const size_t slot_sz = (size_t)x.max_k;
-                const size_t my_slot = (((size_t)par * x.world + x.rank) * x.max_nq + qi) * slot_sz;
-                mp.out_keys = x.my_slots + my_slot - (size_t)qi * slot_sz;   // merge_lists adds qi * out_stride
-                mp.out_stride = (int64_t)slot_sz;
-                mp.out_scores = nullptr;
-                mp.out_ids = nullptr;
-                merge_lists<KPL>(mp, wi, qi, lists, W);
-                // 2) rebased to global rows and stored into every peer's area (NVLink stores), then the flags
-                __threadfence();
-                __syncthreads();
-                for (int i = threadIdx.x; i < k; i += blockDim.x) {
-                    const uint64_t key = rebase_key(__ldcg(x.my_slots + my_slot + i), x.base);
-                    for (int g = 0; g < x.world; ++g) x.peer_slots[g][my_slot + i] = key;
-                }
-                __threadfence_system();
-                __syncthreads();
-                const size_t flag_idx = ((size_t)par * x.world + x.rank) * x.max_nq + qi;
-                if ((int)threadIdx.x < x.world) st_release_sys_u32(x.peer_flags[threadIdx.x] + flag_idx, x.seq);
-                // 3) wait for every rank's keys (bounded: a dead peer must not hang the GPU)
-                if ((int)threadIdx.x < x.world) {
-                    const uint32_t* f = x.my_flags + ((size_t)par * x.world + threadIdx.x) * x.max_nq + qi;
-                    const unsigned long long t0 = globaltimer_ns2();
-                    while (ld_acquire_sys_u32(f) != x.seq) {
-                        if (globaltimer_ns2() - t0 > 4000000000ull) {   // 4 s
-                            *x.error = 1;
-                            break;
-                        }
-                    }
-                }
-                __threadfence_system();
-                __syncthreads();
-                // 4) merge the world lists (already global rows) and emit the final result
-                MergeParams fp = p.fin;
-                fp.keys = x.my_slots + (size_t)par * x.world * x.max_nq * slot_sz;
-                fp.nlists = x.world;
-                fp.k = k;
-                fp.stride_list = (int64_t)x.max_nq * slot_sz;
-                fp.stride_query = (int64_t)slot_sz;
-                fp.list_base = nullptr;
-                merge_lists<KPL>(fp, qi, qi, lists, W);
-            }
-        }
-    }
-    }  // work items
-}
-
-// ------------------------------------------------------------------------------------ host side
-struct ScanConfig {
-    int grid, warps, stages;
-    size_t smem;
-};
-
-template <int ELEM, int NCHUNK, int R>
-static ScanConfig scan_config(const ts_index* ix, int kpl) {
-    const Tunables& t = tunables();
-    const size_t tile_bytes = (size_t)R * ix->dim_pad * ELEM;
-    int stages = t.scan_stages < 2 ? 2 : t.scan_stages;
-    int ctas = t.scan_ctas_per_sm < 1 ? 1 : t.scan_ctas_per_sm;
-    int warps = t.scan_warps < 1 ? 1 : (t.scan_warps > 16 ? 16 : t.scan_warps);
-    const size_t budget = (size_t)(220 * 1024) / ctas - 1024;
-    while (warps > 1 && (size_t)warps * stages * tile_bytes + 8 * warps * stages > budget) --warps;
-    while (stages > 2 && (size_t)warps * stages * tile_bytes + 8 * warps * stages > budget) --stages;
-    size_t smem = (size_t)warps * stages * tile_bytes + 8 * (size_t)warps * stages;
-    const size_t list_bytes = (size_t)warps * kpl * 32 * 8;
-    if (smem < list_bytes) smem = list_bytes;
-    ScanConfig c;
-    c.grid = sm_count(ix->device) * ctas;
-    c.warps = warps;
-    c.stages = stages;
-    c.smem = smem;
-    return c;
-}
-
-template <int ELEM, int NCHUNK, int KPL, int R>
-static int launch_r(const ts_index* ix, const ScanParams& p0, int nq, int nparts, cudaStream_t s,
-                    cudaEvent_t ev0, cudaEvent_t ev1) {
-    ScanConfig c = scan_config<ELEM, NCHUNK, R>(ix, KPL);
-    ScanParams p = p0;
-    p.stages = c.stages;
-    auto kern = scan_topk_kernel<ELEM, NCHUNK, KPL, R>;
-    TS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-    if (ev0) TS_CHECK_CUDA(cudaEventRecord(ev0, s));
-    // Small tables (e.g. the IVF centroid table): fewer CTAs, so that every warp still gets a few tiles and
-    // the fused final merge folds fewer lists. Only when the merge is fused (it reads gridDim.x lists);
-    // the unfused callers size their merge for nparts lists.
-    int grid = nparts;
-    if (p.tickets != nullptr) {
-        const int64_t tiles = (p.n_rows + R - 1) / R;
-        grid = (int)std::min<int64_t>(nparts, std::max<int64_t>(1, (tiles + c.warps * 4 - 1) / (c.warps * 4)));
-    }
-    kern<<<dim3(grid, p.qcount ? std::min(nq, 8) : nq), c.warps * 32, c.smem, s>>>(p);
-    TS_LAUNCH_CHECK();
-    if (ev1) TS_CHECK_CUDA(cudaEventRecord(ev1, s));
-    return TS_OK;
-}
-
-// rows per TMA tile: the default aims at ~8 KB; "scan.tile_rows" (2/4/8/16) overrides it for the
-// common k <= 32 kernels (the large-k instances keep the default to bound compile time).
-template <int ELEM, int NCHUNK, int KPL>
-static int launch_one(const ts_index* ix, const ScanParams& p, int nq, int nparts, cudaStream_t s,
-                      cudaEvent_t ev0, cudaEvent_t ev1) {
-    constexpr int RD = RowsPerTile<NCHUNK>::value;
-    if constexpr (KPL == 1) {
-        switch (tunables().scan_tile_rows) {
-            case 2: return launch_r<ELEM, NCHUNK, KPL, 2>(ix, p, nq, nparts, s, ev0, ev1);
-            case 4: return launch_r<ELEM, NCHUNK, KPL, 4>(ix, p, nq, nparts, s, ev0, ev1);
-            case 8: return launch_r<ELEM, NCHUNK, KPL, 8>(ix, p, nq, nparts, s, ev0, ev1);
-            case 16: return launch_r<ELEM, NCHUNK, KPL, 16>(ix, p, nq, nparts, s, ev0, ev1);
-            default: break;
-        }
-    }
-    return launch_r<ELEM, NCHUNK, KPL, RD>(ix, p, nq, nparts, s, ev0, ev1);
-}
-
-template <int ELEM, int NCHUNK>
-static int launch_k(const ts_index* ix, const ScanParams& p, int nq, int nparts, cudaStream_t s,
-                    cudaEvent_t ev0, cudaEvent_t ev1) {
-    if (p.k <= 32) return launch_one<ELEM, NCHUNK, 1>(ix, p, nq, nparts, s, ev0, ev1);
-    if (p.k <= 128) return launch_one<ELEM, NCHUNK, 4>(ix, p, nq, nparts, s, ev0, ev1);
-    if (p.k <= 256) return launch_one<ELEM, NCHUNK, 8>(ix, p, nq, nparts, s, ev0, ev1);
-    return launch_one<ELEM, NCHUNK, 32>(ix, p, nq, nparts, s, ev0, ev1);
-}
+int launch_scan_bf16_small(const ts_index*, const ScanParams&, int nchunk, int nq, int nparts, cudaStream_t, cudaEvent_t, cudaEvent_t);
+int launch_scan_bf16_large(const ts_index*, const ScanParams&, int nchunk, int nq, int nparts, cudaStream_t, cudaEvent_t, cudaEvent_t);
+int launch_scan_f32_small(const ts_index*, const ScanParams&, int nchunk, int nq, int nparts, cudaStream_t, cudaEvent_t, cudaEvent_t);
+int launch_scan_f32_large(const ts_index*, const ScanParams&, int nchunk, int nq, int nparts, cudaStream_t, cudaEvent_t, cudaEvent_t);
 
 int scan_nparts(const ts_index* ix) {
     int ctas = tunables().scan_ctas_per_sm < 1 ? 1 : tunables().scan_ctas_per_sm;
@@ -439,22 +56,13 @@ int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64
     if (data_dtype == TS_BF16) {
         p.row_bytes = (uint32_t)ix->dim_pad * 2;
         const int nchunk = (ix->dim_pad + 255) / 256;
-        switch (nchunk) {
-            case 1: return launch_k<2, 1>(ix, p, nq, nparts, s, ev0, ev1);
-            case 2: return launch_k<2, 2>(ix, p, nq, nparts, s, ev0, ev1);
-            case 3: return launch_k<2, 3>(ix, p, nq, nparts, s, ev0, ev1);
-            case 4: return launch_k<2, 4>(ix, p, nq, nparts, s, ev0, ev1);
-            default:
-                if (nchunk <= 8) return launch_k<2, 8>(ix, p, nq, nparts, s, ev0, ev1);
-        }
+        if (nchunk <= 3) return launch_scan_bf16_small(ix, p, nchunk, nq, nparts, s, ev0, ev1);
+        if (nchunk <= 8) return launch_scan_bf16_large(ix, p, nchunk, nq, nparts, s, ev0, ev1);
     } else if (data_dtype == TS_F32) {
         p.row_bytes = (uint32_t)ix->dim_pad * 4;
         const int nchunk = (ix->dim_pad + 127) / 128;
-        if (nchunk <= 2) return launch_k<4, 2>(ix, p, nq, nparts, s, ev0, ev1);
-        if (nchunk <= 4) return launch_k<4, 4>(ix, p, nq, nparts, s, ev0, ev1);
-        if (nchunk <= 6) return launch_k<4, 6>(ix, p, nq, nparts, s, ev0, ev1);
-        if (nchunk <= 8) return launch_k<4, 8>(ix, p, nq, nparts, s, ev0, ev1);
-        if (nchunk <= 16) return launch_k<4, 16>(ix, p, nq, nparts, s, ev0, ev1);
+        if (nchunk <= 6) return launch_scan_f32_small(ix, p, nchunk, nq, nparts, s, ev0, ev1);
+        if (nchunk <= 16) return launch_scan_f32_large(ix, p, nchunk, nq, nparts, s, ev0, ev1);
     }
     set_error("scan: no kernel for dtype %d dim %d", data_dtype, ix->dim);
     return TS_ERR_UNSUPPORTED;

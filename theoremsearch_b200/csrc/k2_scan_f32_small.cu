@@ -1,0 +1,15 @@
+// K2 kernel instantiations: fp32 rows up to 768 elements
+#include "k2_scan_impl.cuh"
+
+namespace ts {
+
+int launch_scan_f32_small(const ts_index* ix, const ScanParams& p, int nchunk, int nq, int nparts, cudaStream_t s,
+        cudaEvent_t ev0, cudaEvent_t ev1) {
+    if (nchunk <= 2) return launch_k<4, 2>(ix, p, nq, nparts, s, ev0, ev1);
+    if (nchunk <= 4) return launch_k<4, 4>(ix, p, nq, nparts, s, ev0, ev1);
+    if (nchunk <= 6) return launch_k<4, 6>(ix, p, nq, nparts, s, ev0, ev1);
+    set_error("scan: no kernel for %d chunks per row", nchunk);
+    return TS_ERR_UNSUPPORTED;
+}
+
+}  // namespace ts

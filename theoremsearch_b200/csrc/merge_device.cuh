@@ -36,27 +36,50 @@ __device__ __forceinline__ void merge_lists(const MergeParams& p, int qi, int qo
     const int k = p.k;
     WarpTopK<KPL> list;
     list.clear();
-    // Every list is fetched whole into registers in the WarpTopK layout (coalesced 256-byte loads; the
-    // next list is requested before the current one is merged) and folded in with the bitonic merge.
     auto list_ptr = [&](int l) { return p.keys + (int64_t)l * p.stride_list + (int64_t)qi * p.stride_query; };
-    auto fetch = [&](int l, uint64_t (&b)[KPL]) {
-        const uint64_t* src = list_ptr(l);
+    if constexpr (KPL <= 8) {
+        // Every list is fetched whole into registers in the WarpTopK layout (coalesced 256-byte loads; the
+        // next list is requested before the current one is merged) and folded in with the bitonic merge.
+        auto fetch = [&](int l, uint64_t (&b)[KPL]) {
+            const uint64_t* src = list_ptr(l);
 #pragma unroll
-        for (int j = 0; j < KPL; ++j) b[j] = (j * 32 + lane < k) ? __ldcg(src + j * 32 + lane) : 0ull;
-    };
-    uint64_t nxt[KPL];
-    if (warp < p.nlists) fetch(warp, nxt);
-    for (int l = warp; l < p.nlists; l += nwarps) {
-        uint64_t cur[KPL];
+            for (int j = 0; j < KPL; ++j) b[j] = (j * 32 + lane < k) ? __ldcg(src + j * 32 + lane) : 0ull;
+        };
+        uint64_t nxt[KPL];
+        if (warp < p.nlists) fetch(warp, nxt);
+        for (int l = warp; l < p.nlists; l += nwarps) {
+            uint64_t cur[KPL];
 #pragma unroll
-        for (int j = 0; j < KPL; ++j) cur[j] = nxt[j];
-        if (KPL <= 8 && l + nwarps < p.nlists) fetch(l + nwarps, nxt);
-        const int64_t base = p.list_base ? p.list_base[l] : 0;
+            for (int j = 0; j < KPL; ++j) cur[j] = nxt[j];
+            if (l + nwarps < p.nlists) fetch(l + nwarps, nxt);
+            const int64_t base = p.list_base ? p.list_base[l] : 0;
 #pragma unroll
-        for (int j = 0; j < KPL; ++j) cur[j] = rebase_key(cur[j], base);
-        const uint64_t head = __shfl_sync(0xFFFFFFFFu, cur[0], 0);
-        if (head > list.kth(k)) list.merge_desc(cur, lane);
-        if (KPL > 8 && l + nwarps < p.nlists) fetch(l + nwarps, nxt);
+            for (int j = 0; j < KPL; ++j) cur[j] = rebase_key(cur[j], base);
+            const uint64_t head = __shfl_sync(0xFFFFFFFFu, cur[0], 0);
+            if (head > list.kth(k)) list.merge_desc(cur, lane);
+        }
+    } else {
+        // k > 256: lists are read 32 keys at a time and inserted element-wise, stopping at the first key of a
+        // list that cannot enter (see merge_sorted_into)
+        for (int l = warp; l < p.nlists; l += nwarps) {
+            const uint64_t* src = list_ptr(l);
+            const int64_t base = p.list_base ? p.list_base[l] : 0;
+            uint64_t thr = list.kth(k);
+            bool done = false;
+            for (int i0 = 0; i0 < k && !done; i0 += 32) {
+                const uint64_t cur = (i0 + lane < k) ? __ldcg(src + i0 + lane) : 0ull;
+                const int n = (k - i0 < 32) ? (k - i0) : 32;
+                for (int i = 0; i < n; ++i) {
+                    const uint64_t x = rebase_key(__shfl_sync(0xFFFFFFFFu, cur, i), base);
+                    if (x <= thr) {
+                        done = true;
+                        break;
+                    }
+                    list.insert(x, lane);
+                    thr = list.kth(k);
+                }
+            }
+        }
     }
 #pragma unroll
     for (int j = 0; j < KPL; ++j) lists[(size_t)warp * (KPL * 32) + j * 32 + lane] = list.key[j];

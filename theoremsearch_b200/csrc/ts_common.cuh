@@ -215,10 +215,22 @@ template <int KPL>
 __device__ __forceinline__ void merge_sorted_into(WarpTopK<KPL>& list, const uint64_t* src, int n,
                                                   int k, int lane) {
     if (n <= 0 || src[0] <= list.kth(k)) return;   // sorted: nothing after src[0] can enter either
-    uint64_t b[KPL];
+    if constexpr (KPL <= 8) {
+        uint64_t b[KPL];
 #pragma unroll
-    for (int j = 0; j < KPL; ++j) b[j] = (j * 32 + lane < n) ? src[j * 32 + lane] : 0ull;
-    list.merge_desc(b, lane);
+        for (int j = 0; j < KPL; ++j) b[j] = (j * 32 + lane < n) ? src[j * 32 + lane] : 0ull;
+        list.merge_desc(b, lane);
+    } else {
+        // k > 256 (rare): element-wise insertion — the 1024-key bitonic network unrolls to tens of thousands
+        // of instructions per call site and dominated the build time
+        uint64_t thr = list.kth(k);
+        for (int i = 0; i < n; ++i) {
+            const uint64_t x = src[i];
+            if (x <= thr) break;
+            list.insert(x, lane);
+            thr = list.kth(k);
+        }
+    }
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
