@@ -240,17 +240,19 @@ TS_API size_t ts_ivf_workspace_bytes(const ts_index* index, int nq, int k, int n
  * those lists keeping max(k, rescore_k) candidates by list-precision score (K4b), exact
  * re-score of the candidates against the stored bf16 rows with the fp32 query (K4c; returned
  * scores are bit-identical to ts_search's for the same rows), top-k out.  Same output
- * conventions as ts_search. nprobe is clamped to min(nlist, TS_MAX_K). */
+ * conventions as ts_search. nprobe is clamped to min(nlist, TS_MAX_K). allow_mask: optional device
+ * bitmask over corpus rows, applied INSIDE the list scan (pgvector filters after its ivfflat scan
+ * and can return fewer than k rows; here the k best ELIGIBLE rows of the probed lists come back). */
 TS_API int ts_ivf_search(ts_index* index, const void* queries, int q_dtype, int nq, int k,
-                         int nprobe, int rescore_k, int normalize_queries, float* out_scores,
-                         int64_t* out_ids, void* workspace, size_t workspace_bytes,
-                         void* stream);
+                         int nprobe, int rescore_k, int normalize_queries,
+                         const uint32_t* allow_mask, float* out_scores, int64_t* out_ids,
+                         void* workspace, size_t workspace_bytes, void* stream);
 /* Same, returning packed keys out_keys[nq, k] (score, local row): the all-gather payload of
  * the sharded IVF path, merged by ts_merge_topk. */
 TS_API int ts_ivf_search_keys(ts_index* index, const void* queries, int q_dtype, int nq, int k,
                               int nprobe, int rescore_k, int normalize_queries,
-                              uint64_t* out_keys, void* workspace, size_t workspace_bytes,
-                              void* stream);
+                              const uint32_t* allow_mask, uint64_t* out_keys, void* workspace,
+                              size_t workspace_bytes, void* stream);
 TS_API int ts_ivf_nlist(const ts_index* index);
 /* Storage dtype of the built lists (TS_BF16 / TS_FP8_E4M3), -1 if the lists are not built. */
 TS_API int ts_ivf_list_dtype(const ts_index* index);

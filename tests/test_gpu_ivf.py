@@ -252,3 +252,44 @@ def test_fp8_exhaustive_scan_mode(ts):
         for r, sc in zip(i_f[qi].tolist(), sf[qi].tolist()):
             if r in exact:
                 assert sc == exact[r]
+
+
+@pytest.mark.parametrize("list_dtype", ["bf16", "fp8"])
+def test_filtered_ivf_search(ts, list_dtype):
+    """The SQL WHERE of streamlit_app.py:175-243 applied inside the list scan: exact top-k among the ELIGIBLE
+    rows of the probed lists."""
+    n, d, nlist, nprobe, k = 12000, 512, 48, 6, 10
+    x = clustered_rows(n, d, 60, 0.9, seed=91)
+    index = built(ts, x, nlist, list_dtype)
+    rng = np.random.default_rng(5)
+    allow = rng.random(n) < 0.3
+    mask = ts.pack_allow_mask(allow, index.device)
+    q = oracle.normalize_f64(clustered_rows(10, d, 60, 0.9, seed=91))
+    s, i = index.ivf_search(torch.from_numpy(q), k, nprobe=nprobe, rescore_k=200, normalize=False, allow_mask=mask)
+    s, i = s.cpu().numpy(), i.cpu().numpy()
+    stored = index.get_rows().cpu().numpy()
+    cent = oracle.bf16_round(index.ivf_centroids().cpu().numpy())
+    off, rows = layout(index)
+    assign = assignment_from_lists(off, rows, n)
+    hits = tot = 0
+    for qi in range(q.shape[0]):
+        cs = cent.astype(np.float64) @ q[qi].astype(np.float64)
+        order = np.sort(cs)[::-1]
+        if order[nprobe - 1] - order[nprobe] < 1e-6:
+            continue
+        probe = oracle.rank_desc(cs, nprobe)
+        member = np.isin(assign, probe) & allow
+        ref_s, ref_i = oracle.exact_search(q[qi], stored, k, allow=member)
+        got = i[qi][i[qi] >= 0]
+        assert np.all(allow[got]) and np.all(np.isin(assign[got], probe))
+        alls = stored.astype(np.float64) @ q[qi].astype(np.float64)
+        assert np.max(np.abs(s[qi][i[qi] >= 0] - alls[got]), initial=0.0) <= SCORE_TOL
+        if list_dtype == "bf16":
+            assert np.array_equal(i[qi], ref_i[0]) or np.all(np.abs(alls[got] - alls[ref_i[0][ref_i[0] >= 0]]) <= TIE_EPS)
+        hits += len(set(got.tolist()) & set(ref_i[0][ref_i[0] >= 0].tolist()))
+        tot += int((ref_i[0] >= 0).sum())
+    assert tot > 0 and hits / tot >= 0.99
+    # an empty filter returns padding only
+    none = ts.pack_allow_mask(np.zeros(n, dtype=bool), index.device)
+    s0, i0 = index.ivf_search(torch.from_numpy(q[:2]), k, nprobe=nprobe, rescore_k=50, normalize=False, allow_mask=none)
+    assert torch.all(i0 == -1) and torch.all(torch.isneginf(s0))

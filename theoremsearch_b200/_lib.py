@@ -85,8 +85,8 @@ SIGNATURES = {
     "ts_ivf_train": (_i, [_p, _p, _i64, _i, _i, _u64, _p]),
     "ts_ivf_build": (_i, [_p, _i, _p]),
     "ts_ivf_workspace_bytes": (_sz, [_p, _i, _i, _i, _i]),
-    "ts_ivf_search": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
-    "ts_ivf_search_keys": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "ts_ivf_search": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "ts_ivf_search_keys": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
     "ts_ivf_set_centroids": (_i, [_p, _p, _i, _p]),
     "ts_ivf_get_centroids": (_i, [_p, _p, _p]),
     "ts_ivf_get_lists": (_i, [_p, _p, _p, _p]),

@@ -501,6 +501,8 @@ struct ListScanParams {
     const uint64_t* probes;       // [nq, nprobe] packed (score, list) keys from the coarse step; 0 = none
     int nprobe;
     const float* queries;         // [nq, dim_pad] fp32 normalised
+    const uint32_t* mask;         // allow bitmask over CORPUS rows (SQL WHERE before ORDER BY/LIMIT) or nullptr
+    const uint32_t* list_rows;    // [n] corpus row of every list position (only read when mask != nullptr)
     int k;                        // candidates kept per query (rescore_k)
     uint64_t* part_keys;          // [nq][gridDim.x][k]
     uint32_t* tickets;            // [nq] zero on entry, left zero
@@ -665,7 +667,11 @@ __global__ void __launch_bounds__(512, 1) list_scan_kernel(const ListScanParams 
     for (int t = t0; t < t1; ++t) {
         const int left = s_len[jc] - tc * R;
         const int64_t pos = s_start[jc] + (int64_t)tc * R + my_row;
-        const bool mine = leader && my_row < left;
+        bool mine = leader && my_row < left;
+        if (p.mask != nullptr && mine) {   // filtered search: position -> corpus row -> allow bit
+            const uint32_t row = __ldg(p.list_rows + pos);
+            mine = (__ldg(p.mask + (row >> 5)) >> (row & 31)) & 1u;
+        }
         float scale = 1.0f;
         if (ELEM == 1 && mine) scale = __ldg(p.scales + pos);
 
@@ -1300,7 +1306,7 @@ static IvfWs carve_ivf(const ts_index* ix, int nq, int kc, int nprobe, void* bas
 }
 
 static int ivf_search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k, int nprobe, int rescore_k,
-                           int normalize, uint64_t* out_keys, float* out_scores, int64_t* out_ids, void* workspace,
+                           int normalize, const uint32_t* allow_mask, uint64_t* out_keys, float* out_scores, int64_t* out_ids, void* workspace,
                            size_t workspace_bytes, cudaStream_t s) {
     TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "ivf_search: index is NULL");
     TS_REQUIRE(ix->ivf_built, TS_ERR_STATE, "ivf_search: lists are not built (call ts_ivf_train + ts_ivf_build)");
@@ -1345,6 +1351,8 @@ static int ivf_search_impl(ts_index* ix, const void* queries, int q_dtype, int n
     p.probes = w.probes;
     p.nprobe = nprobe;
     p.queries = w.q32;
+    p.mask = allow_mask;
+    p.list_rows = ix->list_rows;
     p.k = kc;
     p.part_keys = w.part_keys;
     p.tickets = w.tickets;
@@ -1376,18 +1384,19 @@ size_t ts_ivf_workspace_bytes(const ts_index* ix, int nq, int k, int nprobe, int
 }
 
 int ts_ivf_search(ts_index* ix, const void* queries, int q_dtype, int nq, int k, int nprobe, int rescore_k,
-                  int normalize_queries, float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
-                  void* stream) {
+                  int normalize_queries, const uint32_t* allow_mask, float* out_scores, int64_t* out_ids,
+                  void* workspace, size_t workspace_bytes, void* stream) {
     TS_REQUIRE(nq == 0 || (out_scores != nullptr && out_ids != nullptr), TS_ERR_BAD_ARG,
                "ivf_search: output pointers are NULL");
-    return ivf_search_impl(ix, queries, q_dtype, nq, k, nprobe, rescore_k, normalize_queries, nullptr, out_scores,
+    return ivf_search_impl(ix, queries, q_dtype, nq, k, nprobe, rescore_k, normalize_queries, allow_mask, nullptr, out_scores,
                            out_ids, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int ts_ivf_search_keys(ts_index* ix, const void* queries, int q_dtype, int nq, int k, int nprobe, int rescore_k,
-                       int normalize_queries, uint64_t* out_keys, void* workspace, size_t workspace_bytes, void* stream) {
+                       int normalize_queries, const uint32_t* allow_mask, uint64_t* out_keys, void* workspace,
+                       size_t workspace_bytes, void* stream) {
     TS_REQUIRE(nq == 0 || out_keys != nullptr, TS_ERR_BAD_ARG, "ivf_search_keys: out_keys is NULL");
-    return ivf_search_impl(ix, queries, q_dtype, nq, k, nprobe, rescore_k, normalize_queries, out_keys, nullptr, nullptr,
+    return ivf_search_impl(ix, queries, q_dtype, nq, k, nprobe, rescore_k, normalize_queries, allow_mask, out_keys, nullptr, nullptr,
                            workspace, workspace_bytes, (cudaStream_t)stream);
 }
 

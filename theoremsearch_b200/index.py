@@ -298,11 +298,12 @@ class TheoremIndex:
         self.ivf_train(1, n_sample=1, iters=0)
         return self.ivf_build("fp8")
 
-    def search_fp8(self, queries, k: int, rescore_k: int = 128, normalize: bool = True):
+    def search_fp8(self, queries, k: int, rescore_k: int = 128, normalize: bool = True,
+                   allow_mask: Optional[torch.Tensor] = None):
         """Exhaustive scan of the e4m3 shadow (K4b), exact re-score of the ``rescore_k`` best against the bf16
         rows (K4c).  Scores are exact for the returned rows; the id set is the exact top-k unless a true
         neighbour falls outside the e4m3 top-``rescore_k`` (reported as recall by ``bench_extra.py fp8-scan``)."""
-        return self.ivf_search(queries, k, nprobe=1, rescore_k=rescore_k, normalize=normalize)
+        return self.ivf_search(queries, k, nprobe=1, rescore_k=rescore_k, normalize=normalize, allow_mask=allow_mask)
 
     def _ivf_workspace(self, nq: int, k: int, nprobe: int, rescore_k: int) -> torch.Tensor:
         need = int(lib.ts_ivf_workspace_bytes(self._h, nq, k, nprobe, rescore_k))
@@ -313,7 +314,8 @@ class TheoremIndex:
             self._ws = {key: ws}
         return ws
 
-    def ivf_search(self, queries, k: int, nprobe: int = 32, rescore_k: int = 100, normalize: bool = True):
+    def ivf_search(self, queries, k: int, nprobe: int = 32, rescore_k: int = 100, normalize: bool = True,
+                   allow_mask: Optional[torch.Tensor] = None):
         """ANN top-k: probe the ``nprobe`` nearest lists, keep ``rescore_k`` candidates by list-precision
         score, re-score them exactly.  Returns (scores [nq, k], ids [nq, k]) like :meth:`search`."""
         q = self._prep_queries(queries)
@@ -322,19 +324,20 @@ class TheoremIndex:
         ids = torch.empty((nq, k), dtype=torch.int64, device=self.device)
         ws = self._ivf_workspace(nq, k, nprobe, rescore_k)
         check(lib.ts_ivf_search(self._h, q.data_ptr(), _TORCH_TO_TS[q.dtype], nq, int(k), int(nprobe), int(rescore_k),
-                                int(normalize), scores.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(),
-                                _stream_ptr(self.device)))
+                                int(normalize), self._mask_ptr(allow_mask), scores.data_ptr(), ids.data_ptr(),
+                                ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
         q.record_stream(torch.cuda.current_stream(self.device))
         return scores, ids
 
-    def ivf_search_keys(self, queries, k: int, nprobe: int = 32, rescore_k: int = 100, normalize: bool = True):
+    def ivf_search_keys(self, queries, k: int, nprobe: int = 32, rescore_k: int = 100, normalize: bool = True,
+                        allow_mask: Optional[torch.Tensor] = None):
         q = self._prep_queries(queries)
         nq = q.shape[0]
         keys = torch.empty((nq, k), dtype=torch.int64, device=self.device)
         ws = self._ivf_workspace(nq, k, nprobe, rescore_k)
         check(lib.ts_ivf_search_keys(self._h, q.data_ptr(), _TORCH_TO_TS[q.dtype], nq, int(k), int(nprobe),
-                                     int(rescore_k), int(normalize), keys.data_ptr(), ws.data_ptr(), ws.numel(),
-                                     _stream_ptr(self.device)))
+                                     int(rescore_k), int(normalize), self._mask_ptr(allow_mask), keys.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
         q.record_stream(torch.cuda.current_stream(self.device))
         return keys
 
