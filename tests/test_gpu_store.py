@@ -94,3 +94,27 @@ def test_where_mask_through_kernel(ts):
     assert [r["theorem_id"] for r in got] == [1000 + int(i) for i in order]
     assert np.allclose([r["similarity"] for r in got], sim, atol=1e-5)
     assert all(r["source"] == "Stacks Project" for r in got)
+
+
+def test_streamlit_rows_golden_through_ivf_store(ts):
+    """The app-level search over the IVF path (all lists probed => same rows as the exact scan), filters and
+    citation re-rank included: what switching the production table to an ivfflat index would serve."""
+    from theoremsearch_b200 import store as st
+    g = load_golden("streamlit_rows")
+    emb = np.array(g["embeddings"], np.float32)
+    index = ts.build_index(emb, dtype="bf16", normalize=False)
+    nlist = max(2, min(8, emb.shape[0] // 4))
+    index.ivf_train(nlist, iters=3, seed=0)
+    index.ivf_build("bf16")
+    exact = st.TheoremStore(golden_store_rows(g), index)
+    ann = st.TheoremStore(golden_store_rows(g), index, ann={"nprobe": nlist, "rescore_k": 64})
+    model = TableModel({k: np.array(v, np.float32) for k, v in g["queries"].items()})
+    for res in g["results"]:
+        filters = dict(BASE_FILTERS, top_k=res["top_k"], citation_weight=res["citation_weight"])
+        a, b = ann.search(res["query"], model, filters), exact.search(res["query"], model, filters)
+        assert a == b
+        assert [r["theorem_id"] for r in a] == [r["theorem_id"] for r in res["results"]]
+    # a filter that removes most rows still fills top_k from the eligible ones
+    filters = dict(BASE_FILTERS, top_k=3, citation_weight=0.0, sources=["arXiv"])
+    q = next(iter(g["queries"]))
+    assert ann.search(q, model, filters) == exact.search(q, model, filters)

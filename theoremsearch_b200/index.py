@@ -329,6 +329,16 @@ class TheoremIndex:
         q.record_stream(torch.cuda.current_stream(self.device))
         return scores, ids
 
+    def ivf_search_host(self, queries: np.ndarray, k: int, nprobe: int = 32, rescore_k: int = 100,
+                        normalize: bool = True, allow_mask: Optional[torch.Tensor] = None):
+        """Host buffers in / out like :meth:`search_host`, over the IVF path."""
+        q = np.ascontiguousarray(np.asarray(queries, dtype=np.float32))
+        if q.ndim == 1:
+            q = q[None, :]
+        s, i = self.ivf_search(torch.from_numpy(q).to(self.device, non_blocking=True), k, nprobe=nprobe,
+                               rescore_k=rescore_k, normalize=normalize, allow_mask=allow_mask)
+        return s.cpu().numpy(), i.cpu().numpy()
+
     def ivf_search_keys(self, queries, k: int, nprobe: int = 32, rescore_k: int = 100, normalize: bool = True,
                         allow_mask: Optional[torch.Tensor] = None):
         q = self._prep_queries(queries)

@@ -149,11 +149,12 @@ class ShardedIndex:
         self.local.ivf_build(list_dtype)
 
     def ivf_search(self, queries: torch.Tensor, k: int, nprobe: int = 32, rescore_k: int = 100,
-                   normalize: bool = True):
+                   normalize: bool = True, allow_mask: Optional[torch.Tensor] = None):
         """ANN over the sharded corpus: every rank probes the same ``nprobe`` lists (same centroids) in
         its own slice, re-scores its candidates exactly, and the packed keys are gathered and merged
         exactly like the exact path."""
-        keys = self.local.ivf_search_keys(queries, k, nprobe=nprobe, rescore_k=rescore_k, normalize=normalize)
+        keys = self.local.ivf_search_keys(queries, k, nprobe=nprobe, rescore_k=rescore_k, normalize=normalize,
+                                          allow_mask=allow_mask)
         if self.world == 1:
             gathered = keys.unsqueeze(0)
         else:

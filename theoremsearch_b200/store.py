@@ -59,9 +59,13 @@ class TheoremStore:
     ``rows[i]`` is a tuple in ``COLUMNS`` order and describes index row ``i``.  ``index`` needs
     ``search_host(queries, k, normalize, allow_mask)`` and ``device`` (a ``TheoremIndex``)."""
 
-    def __init__(self, rows: Sequence[Sequence[Any]], index):
+    def __init__(self, rows: Sequence[Sequence[Any]], index, ann: Optional[dict] = None):
+        """``ann``: None = exact scan (what the reference's index-less table does, rds_schema.sql); or
+        ``{"nprobe": 32, "rescore_k": 100}`` = the IVF-Flat path (pgvector ``ivfflat`` with
+        ``SET ivfflat.probes``) on an index whose lists are built — filters still apply inside the scan."""
         self.rows = [tuple(r) for r in rows]
         self.index = index
+        self.ann = dict(ann) if ann else None
         n = len(self.rows)
         col = {c: [r[j] for r in self.rows] for j, c in enumerate(COLUMNS)}
         link_l = [(l or "").lower() for l in col["link"]]
@@ -162,6 +166,13 @@ class TheoremStore:
         }
 
     # ---------------------------------------------------------------------------- search
+    def _topk(self, query_vec, k: int, mask):
+        if self.ann is None:
+            return self.index.search_host(query_vec, k, normalize=False, allow_mask=mask)
+        return self.index.ivf_search_host(query_vec, k, nprobe=int(self.ann.get("nprobe", 32)),
+                                          rescore_k=max(k, int(self.ann.get("rescore_k", 100))),
+                                          normalize=False, allow_mask=mask)
+
     def search(self, query, model, filters: dict) -> list[dict]:
         """``search_and_display(query, model, filters)`` up to (not including) rendering."""
         if not filters["sources"]:                                             # :166-168
@@ -177,7 +188,7 @@ class TheoremStore:
             return []
         if citation_weight == 0.0:                                             # :252-314
             k = min(top_k, n_ok)
-            scores, rows = self.index.search_host(query_vec, k, normalize=False, allow_mask=mask)
+            scores, rows = self._topk(query_vec, k, mask)
             out = []
             for s, r in zip(scores[0], rows[0]):
                 if r < 0:
@@ -186,7 +197,7 @@ class TheoremStore:
                 out.append(self.result_row(int(r), sim, sim))
             return out
         pool = min(pool_size(top_k), n_ok)                                     # :317
-        scores, rows = self.index.search_host(query_vec, pool, normalize=False, allow_mask=mask)
+        scores, rows = self._topk(query_vec, pool, mask)
         cand = [(1.0 + float(s), int(r)) for s, r in zip(scores[0], rows[0]) if r >= 0]
         weighted = []
         for sim, r in cand:                                                    # :351-360
