@@ -275,6 +275,32 @@ def cmd_ivf_q1_sweep(a):
                       "last_cta": [float(x) for x in rel[last]]}))
 
 
+def cmd_k1(a):
+    """K1 (normalise + quantise) throughput: fp32 rows in HBM -> bf16 index rows. Bytes = 4*D read + 2*D written."""
+    dev = torch.device("cuda", 0)
+    pk = peaks()
+    blk = 1 << 20
+    x = torch.randn((blk, a.dim), dtype=torch.float32, device=dev)
+    reps = 8
+    index = ts.TheoremIndex(a.dim, blk * (reps + 2), dtype="bf16", device=dev)
+    from theoremsearch_b200._lib import lib, check
+    from theoremsearch_b200.index import _stream_ptr
+    def add():
+        check(lib.ts_index_add(index.handle, x.data_ptr(), 0, blk, 1, None, _stream_ptr(dev)))
+    add(); add()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        add()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    gbs = blk * a.dim * 6 / (ms * 1e-3) / 1e9
+    print(json.dumps({"bench": "k1", "rows_per_launch": blk, "dim": a.dim, "ms_per_launch": ms, "gbs": gbs,
+                      "frac_of_measured_hbm": gbs / pk["hbm_gbs"], "rows_per_s": blk / (ms * 1e-3)}))
+
+
 def cmd_fp8_scan(a):
     """BASELINE north_star: single-query scan over an fp8-e4m3 corpus, re-scored in fp32 — half the bytes."""
     dev = torch.device("cuda", 0)
@@ -390,7 +416,7 @@ def cmd_sharded(a):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("cmd", choices=["batched", "sweep-scan", "small-batch", "ivf", "sharded", "ivf-q1", "ivf-q1-sweep", "fp8-scan"])
+    ap.add_argument("cmd", choices=["batched", "sweep-scan", "small-batch", "ivf", "sharded", "ivf-q1", "ivf-q1-sweep", "fp8-scan", "k1"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--dim", type=int, default=1024)
     ap.add_argument("--nq", type=int, default=4096)
@@ -415,7 +441,7 @@ def main():
     a = ap.parse_args()
     if a.k is None:
         a.k = 100 if a.cmd == "batched" else 10
-    {"batched": cmd_batched, "sweep-scan": cmd_sweep_scan, "small-batch": cmd_small_batch, "ivf": cmd_ivf, "sharded": cmd_sharded, "ivf-q1": cmd_ivf_q1, "ivf-q1-sweep": cmd_ivf_q1_sweep, "fp8-scan": cmd_fp8_scan}[a.cmd](a)
+    {"batched": cmd_batched, "sweep-scan": cmd_sweep_scan, "small-batch": cmd_small_batch, "ivf": cmd_ivf, "sharded": cmd_sharded, "ivf-q1": cmd_ivf_q1, "ivf-q1-sweep": cmd_ivf_q1_sweep, "fp8-scan": cmd_fp8_scan, "k1": cmd_k1}[a.cmd](a)
 
 
 if __name__ == "__main__":

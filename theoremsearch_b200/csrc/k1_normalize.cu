@@ -37,13 +37,16 @@ __device__ __forceinline__ void store_from_float<__nv_bfloat16>(__nv_bfloat16* p
     *p = __float2bfloat16_rn(v);
 }
 
-// Each lane owns element pairs (2*lane, 2*lane+1) + 64*i so bf16 stores are 4-byte, 128 B/warp.
-__device__ __forceinline__ float stored_value(float v, float*) { return v; }
-__device__ __forceinline__ float stored_value(float v, __nv_bfloat16*) {
-    return __bfloat162float(__float2bfloat16_rn(v));
-}
-
-template <typename SRC, typename DST>
+// One warp per row, the row held in registers: lane l owns elements l, l+32, ... (NJ of them).
+//   * one coalesced pass over the source (all NJ loads of a lane are independent and in flight together);
+//   * ||x||^2 accumulated in fp64 in exactly the order K2's in-kernel query normalisation uses;
+//   * the IEEE fp32 division x / nrm is evaluated as (float)((double)x * (1.0 / (double)nrm)): 3 instructions
+//     instead of ~10, and bit-identical — the fp64 product is within 2^-52 of the exact quotient, and the
+//     quotient of two 24-bit floats is never closer than 2^-49 (relative) to an fp32 rounding boundary;
+//     results in the fp32-subnormal range (where that bound does not apply) take the division instruction;
+//   * bf16 stores are 4-byte: lane pairs swap one value per two elements (even lanes store element pair
+//     (l, l+1) of step j, odd lanes that of step j+1).
+template <typename SRC, typename DST, int NJ>
 __global__ void __launch_bounds__(256) normalize_cast_kernel(const SRC* __restrict__ src, int64_t n,
                                                              int dim, int dim_pad, int normalize,
                                                              DST* __restrict__ dst,
@@ -54,28 +57,50 @@ __global__ void __launch_bounds__(256) normalize_cast_kernel(const SRC* __restri
     for (int64_t row = warp0; row < n; row += nwarps) {
         const SRC* x = src + row * (int64_t)dim;
         DST* y = dst + row * (int64_t)dim_pad;
-        float inv_den = 1.0f;
+        float v[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int i = lane + 32 * j;
+            v[j] = (i < dim) ? load_as_float<SRC>(x + i) : 0.0f;
+        }
         if (normalize) {
             double ss = 0.0;
-            for (int i = lane; i < dim; i += 32) {
-                double v = (double)load_as_float<SRC>(x + i);
-                ss = fma(v, v, ss);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const double d = (double)v[j];
+                ss = fma(d, d, ss);          // elements past dim are zeros: they leave ss unchanged
             }
             ss = warp_sum(ss);
-            inv_den = fmaxf((float)sqrt(ss), 1e-12f);
+            const float nrm = fmaxf((float)sqrt(ss), 1e-12f);
+            const double rd = 1.0 / (double)nrm;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                float q = (float)((double)v[j] * rd);
+                if (fabsf(q) < 1.17549435e-38f) q = __fdiv_rn(v[j], nrm);
+                v[j] = q;
+            }
         }
         float qs = 0.f;  // squared norm of the row AS STORED (bounds |<dq, row>| in K3's certificate)
-        for (int i = 2 * lane; i < dim_pad; i += 64) {
-            float a = (i < dim) ? load_as_float<SRC>(x + i) : 0.0f;
-            float b = (i + 1 < dim) ? load_as_float<SRC>(x + i + 1) : 0.0f;
-            if (normalize) {
-                a = __fdiv_rn(a, inv_den);
-                b = __fdiv_rn(b, inv_den);
+        if constexpr (sizeof(DST) == 4) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int i = lane + 32 * j;
+                if (i < dim_pad) store_from_float<DST>(y + i, v[j]);
+                qs = fmaf(v[j], v[j], qs);
             }
-            store_from_float<DST>(y + i, a);
-            if (i + 1 < dim_pad) store_from_float<DST>(y + i + 1, b);
-            const float sa = stored_value(a, (DST*)nullptr), sb = stored_value(b, (DST*)nullptr);
-            qs = fmaf(sa, sa, fmaf(sb, sb, qs));
+        } else {
+            const bool odd = (lane & 1) != 0;
+#pragma unroll
+            for (int j = 0; j < NJ; j += 2) {
+                const float recv = __shfl_xor_sync(0xFFFFFFFFu, odd ? v[j] : v[j + 1], 1);
+                const float a0 = odd ? recv : v[j];
+                const float a1 = odd ? v[j + 1] : recv;
+                const int i = odd ? (lane - 1 + 32 * (j + 1)) : (lane + 32 * j);
+                const __nv_bfloat162 b = __floats2bfloat162_rn(a0, a1);
+                if (i < dim_pad) *reinterpret_cast<__nv_bfloat162*>(y + i) = b;
+                const float2 sb = __bfloat1622float2(b);
+                qs = fmaf(sb.x, sb.x, fmaf(sb.y, sb.y, qs));
+            }
         }
         if (max_norm2 != nullptr) {
             qs = warp_sum(qs);
@@ -98,24 +123,34 @@ __global__ void __launch_bounds__(256) dequant_rows_kernel(const SRC* __restrict
     }
 }
 
-template <typename SRC>
-static int launch_nc(const void* src, int64_t n, int dim, int dim_pad, int normalize, void* dst,
-                     int dst_dtype, cudaStream_t s, float* max_norm2) {
-    if (n == 0) return TS_OK;
+template <typename SRC, int NJ>
+static int launch_nc_nj(const void* src, int64_t n, int dim, int dim_pad, int normalize, void* dst,
+                        int dst_dtype, cudaStream_t s, float* max_norm2) {
     int64_t blocks64 = (n + 7) / 8;
     int blocks = (int)(blocks64 > 148 * 32 ? 148 * 32 : blocks64);
     if (dst_dtype == TS_BF16) {
-        normalize_cast_kernel<SRC, __nv_bfloat16><<<blocks, 256, 0, s>>>(
+        normalize_cast_kernel<SRC, __nv_bfloat16, NJ><<<blocks, 256, 0, s>>>(
             (const SRC*)src, n, dim, dim_pad, normalize, (__nv_bfloat16*)dst, max_norm2);
     } else if (dst_dtype == TS_F32) {
-        normalize_cast_kernel<SRC, float><<<blocks, 256, 0, s>>>((const SRC*)src, n, dim, dim_pad,
-                                                                 normalize, (float*)dst, max_norm2);
+        normalize_cast_kernel<SRC, float, NJ><<<blocks, 256, 0, s>>>((const SRC*)src, n, dim, dim_pad,
+                                                                     normalize, (float*)dst, max_norm2);
     } else {
         set_error("normalize_cast: unsupported destination dtype %d", dst_dtype);
         return TS_ERR_UNSUPPORTED;
     }
     TS_LAUNCH_CHECK();
     return TS_OK;
+}
+
+template <typename SRC>
+static int launch_nc(const void* src, int64_t n, int dim, int dim_pad, int normalize, void* dst,
+                     int dst_dtype, cudaStream_t s, float* max_norm2) {
+    if (n == 0) return TS_OK;
+    if (dim_pad <= 256) return launch_nc_nj<SRC, 8>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
+    if (dim_pad <= 512) return launch_nc_nj<SRC, 16>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
+    if (dim_pad <= 768) return launch_nc_nj<SRC, 24>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
+    if (dim_pad <= 1024) return launch_nc_nj<SRC, 32>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
+    return launch_nc_nj<SRC, 64>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
 }
 
 int launch_normalize_cast(const void* src, int src_dtype, int64_t n, int dim, int dim_pad,
