@@ -261,18 +261,20 @@ def cmd_ivf_q1_sweep(a):
     ts.set_tunable("ivf.timeline", 1)
     for _ in range(3):
         fn()
-    buf = np.zeros((148, 8), dtype=np.uint64)
+    buf = np.zeros((148, 12), dtype=np.uint64)
     _lib.check(_lib.lib.ts_debug_ivf_timeline(buf.ctypes.data, 148))
     ts.set_tunable("ivf.timeline", 0)
     t = buf.astype(np.int64)
     t0 = t[:, 0].min()
     rel = (t - t0) / 1e3
     last = int(np.argmax(t[:, 7]))
+    t[t == 0] = t0
     print(json.dumps({"bench": "ivf-q1-timeline", "unit": "us since first CTA start",
-                      "phases": ["start", "table", "prologue", "scan_done", "flushed", "cta_merged", "final_begin", "final_end"],
+                      "phases": ["start", "table", "prologue", "scan_done", "gathered", "cta_sorted", "final_begin", "final_end",
+                                 "heads_sorted", "survivors_compacted", "survivors_sorted"],
                       "median_cta": [float(np.median(rel[:, i])) for i in range(6)],
                       "max_cta": [float(rel[:, i].max()) for i in range(6)],
-                      "last_cta": [float(x) for x in rel[last]]}))
+                      "last_cta": [float(x) for x in rel[last][:11]]}))
 
 
 def cmd_k1(a):

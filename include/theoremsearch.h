@@ -275,7 +275,7 @@ TS_API int ts_set_tunable(const char* name, int value);
 TS_API int ts_get_tunable(const char* name, int* value);
 
 /* With tunable "ivf.timeline" = 1 the list-scan CTAs of query 0 record %globaltimer (ns) at 8 phase
- * boundaries; this copies [n_ctas][8] stamps to HOST memory. Synchronises the device. */
+ * boundaries; this copies [n_ctas][12] stamps to HOST memory. Synchronises the device. */
 TS_API int ts_debug_ivf_timeline(uint64_t* out_host, int n_ctas);
 
 /* How many queries of the most recent batched (K3) search failed the exactness certificate or

@@ -511,7 +511,7 @@ struct ListScanParams {
     unsigned long long* timeline; // diagnostics: [gridDim.x][8] globaltimer stamps of query 0, or nullptr
 };
 
-__device__ unsigned long long g_ivf_timeline[148 * 8];
+__device__ unsigned long long g_ivf_timeline[148 * 12];
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -520,7 +520,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 #define IVF_STAMP(i)                                                                         \
     do {                                                                                     \
         if (p.timeline != nullptr && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 148) \
-            p.timeline[blockIdx.x * 8 + (i)] = globaltimer_ns();                             \
+            p.timeline[blockIdx.x * 12 + (i)] = globaltimer_ns();                            \
     } while (0)
 
 template <int ELEM, int NCHUNK, int KPL, int R>
@@ -787,6 +787,7 @@ __global__ void __launch_bounds__(512, 1) list_scan_kernel(const ListScanParams 
         if (threadIdx.x == 0) s_low = cbuf[k - 1];            // 0 when fewer than k candidates exist at all
         __syncthreads();
     }
+    IVF_STAMP(8);
     const uint64_t low = s_low;
     uint64_t* sel_buf = cbuf;                                 // the head sort is finished with cbuf (barrier above)
     for (int i0 = threadIdx.x; i0 < nl * k; i0 += 32 * blockDim.x) {   // up to 32 L2 loads in flight per thread
@@ -805,6 +806,7 @@ __global__ void __launch_bounds__(512, 1) list_scan_kernel(const ListScanParams 
         }
     }
     __syncthreads();
+    IVF_STAMP(9);
     const int cnt = s_cnt;
     uint64_t* dst = p.out_keys + (size_t)qi * k;
     if (cnt <= CAP) {
@@ -813,6 +815,7 @@ __global__ void __launch_bounds__(512, 1) list_scan_kernel(const ListScanParams 
         for (int i = cnt + threadIdx.x; i < P; i += blockDim.x) sel_buf[i] = 0ull;
         __syncthreads();
         cta_bitonic_sort_desc(sel_buf, P);
+        IVF_STAMP(10);
         for (int i = threadIdx.x; i < k; i += blockDim.x) dst[i] = (i < P) ? sel_buf[i] : 0ull;
     } else {
         // more survivors than the buffer holds (lists with long runs of near-equal keys): the register
@@ -1202,7 +1205,7 @@ int ts_ivf_nlist(const ts_index* ix) { return ix ? ix->nlist : -1; }
 int ts_debug_ivf_timeline(uint64_t* out_host, int n_ctas) {
     TS_REQUIRE(out_host != nullptr && n_ctas >= 1 && n_ctas <= 148, TS_ERR_BAD_ARG, "debug_ivf_timeline: bad argument");
     TS_CHECK_CUDA(cudaDeviceSynchronize());
-    TS_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_ivf_timeline, (size_t)n_ctas * 8 * sizeof(uint64_t)));
+    TS_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_ivf_timeline, (size_t)n_ctas * 12 * sizeof(uint64_t)));
     return TS_OK;
 }
 

@@ -37,7 +37,26 @@ __device__ __forceinline__ void merge_lists(const MergeParams& p, int qi, int qo
     WarpTopK<KPL> list;
     list.clear();
     auto list_ptr = [&](int l) { return p.keys + (int64_t)l * p.stride_list + (int64_t)qi * p.stride_query; };
-    if constexpr (KPL <= 8) {
+    if constexpr (KPL == 1) {
+        // k <= 32: a list is one key per lane. Fetch this warp's lists eight at a time (eight independent L2
+        // loads in flight instead of a dependent chain of ~1 us round trips), then fold them in.
+        for (int l0 = warp; l0 < p.nlists; l0 += 8 * nwarps) {
+            uint64_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int l = l0 + u * nwarps;
+                v[u] = (l < p.nlists && lane < k) ? __ldcg(list_ptr(l) + lane) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int l = l0 + u * nwarps;
+                if (l >= p.nlists) break;
+                uint64_t cur[1] = {rebase_key(v[u], p.list_base ? p.list_base[l] : 0)};
+                const uint64_t head = __shfl_sync(0xFFFFFFFFu, cur[0], 0);
+                if (head > list.kth(k)) list.merge_desc(cur, lane);
+            }
+        }
+    } else if constexpr (KPL <= 8) {
         // Every list is fetched whole into registers in the WarpTopK layout (coalesced 256-byte loads; the
         // next list is requested before the current one is merged) and folded in with the bitonic merge.
         auto fetch = [&](int l, uint64_t (&b)[KPL]) {
