@@ -47,11 +47,14 @@ def test_fused_exchange_rebases_rows_and_maps_ids(ts):
     sh = ShardedIndex(index, 2000)
     sh.lo, sh.hi = 5000, 7000                 # pretend this rank holds global rows [5000, 7000)
     sh.enable_peer_exchange(max_nq=2, max_k=32)
-    q = torch.from_numpy(oracle.synthetic_queries(2, 256))
-    s0, i0 = index.search(q, 10)
-    s1, i1 = sh.search(q, 10)
-    assert torch.equal(s0, s1) and torch.equal(i1, i0 + 5000)
-    sh.id_map = (torch.arange(7000, dtype=torch.int64, device="cuda") * 2 + 1)
-    s2, i2 = sh.search(q, 10)
-    assert torch.equal(i2, (i0 + 5000) * 2 + 1)
+    qs = torch.from_numpy(oracle.synthetic_queries(2, 256))
+    for j in range(2):                        # single queries: the fused in-kernel exchange path
+        q = qs[j:j + 1]
+        s0, i0 = index.search(q, 10)
+        s1, i1 = sh.search(q, 10)
+        assert torch.equal(s0, s1) and torch.equal(i1, i0 + 5000)
+        sh.id_map = (torch.arange(7000, dtype=torch.int64, device="cuda") * 2 + 1)
+        s2, i2 = sh.search(q, 10)
+        assert torch.equal(i2, (i0 + 5000) * 2 + 1)
+        sh.id_map = None
     sh.close()
