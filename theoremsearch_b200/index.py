@@ -58,7 +58,7 @@ class TheoremIndex:
         h = C.c_void_p()
         check(lib.ts_index_create(C.byref(h), self.device.index, self.dim, _NAME_TO_TS[dtype], int(capacity)))
         self._h = h
-        self._ws: dict[tuple[int, int], torch.Tensor] = {}
+        self._ws: dict[tuple, torch.Tensor] = {}
         self._ctx: dict[tuple[int, int], C.c_void_p] = {}
 
     # -------------------------------------------------------------------------------- lifecycle
@@ -150,7 +150,9 @@ class TheoremIndex:
         ws = self._ws.get(key)
         if ws is None or ws.numel() < need:
             ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-            self._ws = {key: ws}  # keep one workspace; shapes rarely alternate
+            if len(self._ws) >= 4:          # a few shapes may alternate (single queries + one batch size)
+                self._ws.pop(next(iter(self._ws)))
+            self._ws[key] = ws
         return ws
 
     def _prep_queries(self, queries) -> torch.Tensor:
@@ -311,7 +313,9 @@ class TheoremIndex:
         ws = self._ws.get(key)
         if ws is None or ws.numel() < need:
             ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
-            self._ws = {key: ws}
+            if len(self._ws) >= 4:
+                self._ws.pop(next(iter(self._ws)))
+            self._ws[key] = ws
         return ws
 
     def ivf_search(self, queries, k: int, nprobe: int = 32, rescore_k: int = 100, normalize: bool = True,
