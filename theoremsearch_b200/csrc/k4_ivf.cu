@@ -765,26 +765,49 @@ __global__ void __launch_bounds__(512, 1) list_scan_kernel(const ListScanParams 
     __syncthreads();
     if (!s_is_last) return;
 
-    // ---- final merge by the last CTA of the query: gridDim.x sorted lists of k keys. Prune first: the k-th
-    // largest key among the first m = ceil(k / lists) entries of every list is a lower bound L on the k-th
-    // largest overall (at least k keys are >= L), so only keys >= L can be in the result — typically a few
-    // hundred of the lists*k keys. They are compacted into smem and sorted by the whole CTA.
+    // ---- final merge by the last CTA of the query: gridDim.x sorted lists of k keys. Prune first with a lower
+    // bound L on the k-th largest key overall: for any j, the j-th largest of the lists' entries at position
+    // ceil(k/j)-1 is such a bound (j lists hold at least ceil(k/j) keys >= it). j = k is "the k-th largest
+    // head" (good when the best keys are spread over the lists), j = 1 is "the largest k-th entry" (good when
+    // they sit in a few lists, e.g. the CTAs that scanned the query's own cluster); powers of four in between.
+    // Only keys >= L can be in the result — typically a few hundred of the lists*k keys.
     IVF_STAMP(6);
     const int nl = gridDim.x;
     const uint64_t* mine = p.part_keys + (size_t)qi * nl * k;
     constexpr int CAP = 4096;                                 // keys; fits the smallest smem carve-out (32 KB)
-    const int m = (k + nl - 1) / nl;
-    __shared__ int s_cnt;
-    __shared__ uint64_t s_low;
+    constexpr int MAXJ = 12;
+    __shared__ int s_cnt, s_nj;
+    __shared__ int s_j[MAXJ], s_pos[MAXJ];
+    __shared__ unsigned long long s_low;
+    if (threadIdx.x == 0) {
+        int nj = 0;
+        for (int j = 1; j < nl && j < k && nj < MAXJ - 1; j <<= 2) {   // 1, 4, 16, 64: each choice costs lists^2 compares
+            s_j[nj] = j;
+            s_pos[nj++] = (k + j - 1) / j - 1;
+        }
+        const int jl = k < nl ? k : nl;                       // the widest choice: k heads, or every list
+        s_j[nj] = jl;
+        s_pos[nj++] = (k + jl - 1) / jl - 1;
+        s_nj = nj;
+        s_cnt = 0;
+        s_low = 0ull;                                         // stays 0 when no bound applies: every key survives
+    }
+    __syncthreads();
     {
-        int P = 64;
-        while (P < nl * m) P <<= 1;                           // <= k + lists - 1 < 512 keys
-        for (int i = threadIdx.x; i < P; i += blockDim.x)
-            cbuf[i] = (i < nl * m) ? __ldcg(mine + (size_t)(i / m) * k + (i % m)) : 0ull;
-        if (threadIdx.x == 0) s_cnt = 0;
+        const int nj = s_nj;
+        uint64_t* hv = cbuf;                                  // [nj][nl]
+        for (int i = threadIdx.x; i < nj * nl; i += blockDim.x)
+            hv[i] = __ldcg(mine + (size_t)(i % nl) * k + s_pos[i / nl]);
         __syncthreads();
-        cta_bitonic_sort_desc(cbuf, P);
-        if (threadIdx.x == 0) s_low = cbuf[k - 1];            // 0 when fewer than k candidates exist at all
+        for (int i = threadIdx.x; i < nj * nl; i += blockDim.x) {
+            const uint64_t key = hv[i];
+            if (key == 0ull) continue;
+            const uint64_t* row = hv + (size_t)(i / nl) * nl;
+            int rank = 0;
+#pragma unroll 4
+            for (int l = 0; l < nl; ++l) rank += (row[l] > key) ? 1 : 0;
+            if (rank == s_j[i / nl] - 1) atomicMax(&s_low, (unsigned long long)key);
+        }
         __syncthreads();
     }
     IVF_STAMP(8);
@@ -809,13 +832,24 @@ __global__ void __launch_bounds__(512, 1) list_scan_kernel(const ListScanParams 
     IVF_STAMP(9);
     const int cnt = s_cnt;
     uint64_t* dst = p.out_keys + (size_t)qi * k;
-    if (cnt <= CAP) {
+    if (cnt <= 384) {
+        // few survivors (the usual case): rank by counting; the rank is the output position
+        for (int i = threadIdx.x; i < k; i += blockDim.x) dst[i] = 0ull;
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const uint64_t key = sel_buf[i];
+            int rank = 0;
+#pragma unroll 8
+            for (int j = 0; j < cnt; ++j) rank += (sel_buf[j] > key) ? 1 : 0;
+            if (rank < k) dst[rank] = key;
+        }
+        IVF_STAMP(10);
+    } else if (cnt <= CAP) {
         int P = 64;
         while (P < cnt) P <<= 1;
         for (int i = cnt + threadIdx.x; i < P; i += blockDim.x) sel_buf[i] = 0ull;
         __syncthreads();
         cta_bitonic_sort_desc(sel_buf, P);
-        IVF_STAMP(10);
         for (int i = threadIdx.x; i < k; i += blockDim.x) dst[i] = (i < P) ? sel_buf[i] : 0ull;
     } else {
         // more survivors than the buffer holds (lists with long runs of near-equal keys): the register
@@ -939,46 +973,77 @@ __global__ void __launch_bounds__(1024) ivf_rescore_kernel(const uint64_t* __res
     while (P < kc) P <<= 1;
     const float* qv = q32 + (size_t)q * dim_pad;
     // warp w owns candidates w, w + nwarps, ...; lane i looks up the i-th of them (key -> list position ->
-    // corpus row), so all of a warp's dependent lookups are in flight together, then rows are scored one
-    // at a time by the whole warp.
+    // corpus row), so all of a warp's dependent lookups are in flight together; rows are then scored four at
+    // a time (their loads are independent and overlap), each by the whole warp in K2's summation order.
     {
         const int jm = warp + lane * nwarps;
         const uint64_t mykey = (jm < kc) ? cand[(size_t)q * kc + jm] : 0ull;
         const uint32_t myrow = mykey ? list_rows[key_row(mykey)] : 0u;
         const unsigned live = __ballot_sync(0xFFFFFFFFu, mykey != 0ull);
         uint64_t outkey = 0ull;
-        for (int c = 0; c < 32 && warp + c * nwarps < P; ++c) {
-            if (!((live >> c) & 1u)) continue;
-            const uint32_t row = __shfl_sync(0xFFFFFFFFu, myrow, c);
-            const uint8_t* r = corpus + (size_t)row * row_bytes;
-            float acc = 0.f;
+        for (int c0 = 0; c0 < 32 && warp + c0 * nwarps < P; c0 += 4) {
+            if (((live >> c0) & 0xFu) == 0u) continue;
+            uint32_t row[4];
+            const uint8_t* r[4];
+            float acc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                row[u] = __shfl_sync(0xFFFFFFFFu, myrow, (c0 + u) & 31);   // dead slots read row 0: harmless
+                r[u] = corpus + (size_t)row[u] * row_bytes;
+                acc[u] = 0.f;
+            }
+#pragma unroll 2
             for (uint32_t off = (uint32_t)lane * 16u; off < row_bytes; off += 512u) {   // K2's chunk order
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(r + off));
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(r[u] + off));
                 float ql[CN];
 #pragma unroll
-                for (int i = 0; i < CN; ++i) ql[i] = __ldg(qv + off / ELEM + i);
-                acc = Chunk<ELEM>::dot(v, ql, acc);
+                for (int i = 0; i < CN; i += 4) {
+                    const float4 f = __ldg(reinterpret_cast<const float4*>(qv + off / ELEM + i));
+                    ql[i] = f.x;
+                    ql[i + 1] = f.y;
+                    ql[i + 2] = f.z;
+                    ql[i + 3] = f.w;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc[u] = Chunk<ELEM>::dot(v[u], ql, acc[u]);
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);   // == K2's reduce tree
-            if (lane == c) outkey = pack_key(acc, row);
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xFFFFFFFFu, acc[u], o);   // == K2's reduce tree
+                if (lane == c0 + u && ((live >> (c0 + u)) & 1u)) outkey = pack_key(acc[u], row[u]);
+            }
         }
         if (jm < P) rs_buf[jm] = outkey;
     }
     __syncthreads();
-    cta_bitonic_sort_desc(rs_buf, P);
-    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    // rank by counting: P <= 256 keys, one per thread, unique (distinct rows) or 0 — a key's rank is the number
+    // of larger keys; 128 x 128 compares cost a fraction of a 28-level bitonic network's barriers
+    {
+        const int i = threadIdx.x;
         const uint64_t key = (i < P) ? rs_buf[i] : 0ull;
-        const size_t o = (size_t)q * k + i;
-        if (out_keys) out_keys[o] = key;
-        if (out_scores) out_scores[o] = key ? key_score(key) : -INFINITY;
-        if (out_ids) {
-            int64_t id = -1;
-            if (key) {
-                const uint32_t row = key_row(key);
-                id = id_map ? id_map[row] : (int64_t)row;
+        const int nnz = __syncthreads_count(key != 0ull);
+        if (key != 0ull) {
+            int rank = 0;
+#pragma unroll 8
+            for (int j = 0; j < P; ++j) rank += (rs_buf[j] > key) ? 1 : 0;
+            if (rank < k) {
+                const size_t o = (size_t)q * k + rank;
+                if (out_keys) out_keys[o] = key;
+                if (out_scores) out_scores[o] = key_score(key);
+                if (out_ids) {
+                    const uint32_t row = key_row(key);
+                    out_ids[o] = id_map ? id_map[row] : (int64_t)row;
+                }
             }
-            out_ids[o] = id;
+        }
+        for (int r = nnz + i; r < k; r += blockDim.x) {   // fewer eligible rows than k: padding
+            const size_t o = (size_t)q * k + r;
+            if (out_keys) out_keys[o] = 0ull;
+            if (out_scores) out_scores[o] = -INFINITY;
+            if (out_ids) out_ids[o] = -1;
         }
     }
 }
