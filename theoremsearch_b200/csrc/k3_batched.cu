@@ -26,6 +26,7 @@
 // and K3c re-scans it exactly with the K2 path, so the result is exact in all cases.
 //
 // Algorithmic FLOPs: 2 * Q * N * D per batch.
+#include "merge_device.cuh"
 #include "umma_device.cuh"
 
 namespace ts {
@@ -364,25 +365,11 @@ __global__ void __launch_bounds__(256) compact_candidates_kernel(uint64_t* cand,
     if (cnt == 0) {  // nothing appended in this chunk: list and threshold stand
         return;
     }
-    int P = 1;
+    int P = 64;
     while (P < n) P <<= 1;
     for (int i = threadIdx.x; i < P; i += blockDim.x) sort_buf[i] = (i < n) ? mine[i] : 0ull;
     __syncthreads();
-    for (int size = 2; size <= P; size <<= 1) {
-        for (int stride_ = size >> 1; stride_ > 0; stride_ >>= 1) {
-            for (int i = threadIdx.x; i < P / 2; i += blockDim.x) {
-                const int lo = 2 * i - (i & (stride_ - 1));   // index with bit `stride_` clear
-                const int hi = lo + stride_;
-                const bool desc = (lo & size) == 0;           // descending blocks first -> overall descending
-                const uint64_t a = sort_buf[lo], b = sort_buf[hi];
-                if ((a < b) == desc) {
-                    sort_buf[lo] = b;
-                    sort_buf[hi] = a;
-                }
-            }
-            __syncthreads();
-        }
-    }
+    cta_bitonic_sort_desc(sort_buf, P);   // register-blocked: strides <= 32 in shuffles, barriers only above
     for (int i = threadIdx.x; i < k; i += blockDim.x) mine[i] = sort_buf[i];
     if (threadIdx.x == 0) {
         const uint64_t kth = sort_buf[k - 1];
@@ -447,7 +434,7 @@ __global__ void __launch_bounds__(256) rescore_certify_kernel(uint64_t* cand, si
     const int q = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t* mine = cand + (size_t)q * cand_stride;
-    int P = 1;
+    int P = 64;
     while (P < kp) P <<= 1;
     const uint64_t worst_kept = mine[kp - 1];   // 0 when fewer than kp rows were eligible at all
     const float* qv = q32 + (size_t)q * dim_pad;
@@ -477,21 +464,7 @@ __global__ void __launch_bounds__(256) rescore_certify_kernel(uint64_t* cand, si
         if (lane == 0) rs_buf[j] = key;
     }
     __syncthreads();
-    for (int size = 2; size <= P; size <<= 1) {
-        for (int st = size >> 1; st > 0; st >>= 1) {
-            for (int i = threadIdx.x; i < P / 2; i += blockDim.x) {
-                const int lo = 2 * i - (i & (st - 1));
-                const int hi = lo + st;
-                const bool desc = (lo & size) == 0;
-                const uint64_t a = rs_buf[lo], b = rs_buf[hi];
-                if ((a < b) == desc) {
-                    rs_buf[lo] = b;
-                    rs_buf[hi] = a;
-                }
-            }
-            __syncthreads();
-        }
-    }
+    cta_bitonic_sort_desc(rs_buf, P);
     for (int i = threadIdx.x; i < k; i += blockDim.x) mine[i] = rs_buf[i];
     if (threadIdx.x == 0) {
         bool ok = overflow[q] == 0;
@@ -636,7 +609,7 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
                                            64 * 1024));
         attr_set[dslot] = true;
     }
-    int P = 1;
+    int P = 64;
     while (P < k + cap) P <<= 1;
     const size_t sort_smem = (size_t)P * 8;
     TS_REQUIRE(sort_smem <= 64 * 1024, TS_ERR_UNSUPPORTED, "batched: kp + cap = %d too large for the compaction sort", k + cap);
@@ -697,7 +670,7 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
     if (ev1) TS_CHECK_CUDA(cudaEventRecord(ev1, s));
     // cand[q][0..kp): best kp by bf16-query score. Re-score with the fp32 query, keep k_out, certify.
     const size_t cstride = (size_t)k + cap;
-    int PR = 1;
+    int PR = 64;
     while (PR < k) PR <<= 1;
     rescore_certify_kernel<<<nq, 256, (size_t)PR * 8, s>>>(cand, cstride, k, k_out, q32, (const uint8_t*)ix->data,
                                                            (uint32_t)ix->row_bytes(), ix->dim_pad, qerr, ix->max_norm2,
