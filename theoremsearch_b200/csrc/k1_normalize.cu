@@ -37,77 +37,112 @@ __device__ __forceinline__ void store_from_float<__nv_bfloat16>(__nv_bfloat16* p
     *p = __float2bfloat16_rn(v);
 }
 
-// One warp per row, the row held in registers: lane l owns elements l, l+32, ... (NJ of them).
-//   * one coalesced pass over the source (all NJ loads of a lane are independent and in flight together);
-//   * ||x||^2 accumulated in fp64 in exactly the order K2's in-kernel query normalisation uses;
+// One warp per row, the row held in registers: lane l owns the element PAIRS (2l, 2l+1) + 64j, j < NP.
+//   * one coalesced pass over the source (8-byte loads, all of a lane's loads independent and in flight);
+//   * ||x||^2 accumulated in fp64, lane-local in ascending element order, then the xor butterfly — exactly the
+//     order K2's in-kernel query normalisation uses, so both produce the same bits;
 //   * the IEEE fp32 division x / nrm is evaluated as (float)((double)x * (1.0 / (double)nrm)): 3 instructions
 //     instead of ~10, and bit-identical — the fp64 product is within 2^-52 of the exact quotient, and the
-//     quotient of two 24-bit floats is never closer than 2^-49 (relative) to an fp32 rounding boundary;
-//     results in the fp32-subnormal range (where that bound does not apply) take the division instruction;
-//   * bf16 stores are 4-byte: lane pairs swap one value per two elements (even lanes store element pair
-//     (l, l+1) of step j, odd lanes that of step j+1).
-template <typename SRC, typename DST, int NJ>
-__global__ void __launch_bounds__(256) normalize_cast_kernel(const SRC* __restrict__ src, int64_t n,
+//     quotient of two 24-bit floats is never closer than 2^-49 (relative) to an fp32 rounding boundary. The
+//     bound does not hold for results in the fp32-subnormal range: a lane whose smallest |result| is below
+//     FLT_MIN (exact zeros included) redoes its elements with the division instruction;
+//   * stores are one bf16x2 (or float2) per pair, no shuffles;
+//   * max ||stored row||^2 for K3's certificate is an upper bound: sum q^2 in fp32, times (1 + 2^-8)^2 for the
+//     bf16 rounding and a little slack for the fp32 summation.
+// a pair that lies inside the row, as one vector load (row and pair aligned) / two scalar loads
+template <typename SRC>
+__device__ __forceinline__ float2 ld_pair_vec(const SRC* p);
+template <>
+__device__ __forceinline__ float2 ld_pair_vec<float>(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+template <>
+__device__ __forceinline__ float2 ld_pair_vec<__nv_bfloat16>(const __nv_bfloat16* p) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+template <>
+__device__ __forceinline__ float2 ld_pair_vec<__half>(const __half* p) {
+    return __half22float2(*reinterpret_cast<const __half2*>(p));
+}
+// Branch-free inside the unrolled loop (predicated loads), so all of a lane's loads issue back to back.
+template <typename SRC, int NP>
+__device__ __forceinline__ void load_row_pairs(const SRC* x, int lane, int dim, bool vec_ok, float2 (&v)[NP]) {
+    if (vec_ok) {   // warp-uniform: even dim => every pair is aligned and entirely inside or outside the row
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            const int i = 2 * lane + 64 * j;
+            v[j] = make_float2(0.f, 0.f);
+            if (i < dim) v[j] = ld_pair_vec<SRC>(x + i);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            const int i = 2 * lane + 64 * j;
+            v[j].x = (i < dim) ? load_as_float<SRC>(x + i) : 0.f;
+            v[j].y = (i + 1 < dim) ? load_as_float<SRC>(x + i + 1) : 0.f;
+        }
+    }
+}
+
+template <typename SRC, typename DST, int NP>
+__global__ void __launch_bounds__(256, NP <= 16 ? 2 : 1) normalize_cast_kernel(const SRC* __restrict__ src, int64_t n,
                                                              int dim, int dim_pad, int normalize,
                                                              DST* __restrict__ dst,
                                                              float* __restrict__ max_norm2) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const bool vec_ok = (dim & 1) == 0;   // even rows keep every pair aligned to its vector load
+    float warp_max = 0.f;                 // running max over this warp's rows: ONE atomic per warp at the end
     for (int64_t row = warp0; row < n; row += nwarps) {
         const SRC* x = src + row * (int64_t)dim;
         DST* y = dst + row * (int64_t)dim_pad;
-        float v[NJ];
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const int i = lane + 32 * j;
-            v[j] = (i < dim) ? load_as_float<SRC>(x + i) : 0.0f;
-        }
+        float2 v[NP];
+        load_row_pairs<SRC, NP>(x, lane, dim, vec_ok, v);
         if (normalize) {
             double ss = 0.0;
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const double d = (double)v[j];
-                ss = fma(d, d, ss);          // elements past dim are zeros: they leave ss unchanged
+            for (int j = 0; j < NP; ++j) {   // elements past dim are zeros: they leave ss unchanged
+                const double a = (double)v[j].x, b = (double)v[j].y;
+                ss = fma(a, a, ss);
+                ss = fma(b, b, ss);
             }
             ss = warp_sum(ss);
             const float nrm = fmaxf((float)sqrt(ss), 1e-12f);
             const double rd = 1.0 / (double)nrm;
+            float amin = 3.0e38f;
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                float q = (float)((double)v[j] * rd);
-                if (fabsf(q) < 1.17549435e-38f) q = __fdiv_rn(v[j], nrm);
-                v[j] = q;
+            for (int j = 0; j < NP; ++j) {
+                v[j].x = (float)((double)v[j].x * rd);
+                v[j].y = (float)((double)v[j].y * rd);
+                amin = fminf(amin, fminf(fabsf(v[j].x), fabsf(v[j].y)));
+            }
+            if (amin < 1.17549435e-38f) {   // subnormal (or zero) results in this lane: reload, divide exactly
+                load_row_pairs<SRC, NP>(x, lane, dim, vec_ok, v);
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    v[j].x = __fdiv_rn(v[j].x, nrm);
+                    v[j].y = __fdiv_rn(v[j].y, nrm);
+                }
             }
         }
-        float qs = 0.f;  // squared norm of the row AS STORED (bounds |<dq, row>| in K3's certificate)
-        if constexpr (sizeof(DST) == 4) {
+        float qs = 0.f;
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const int i = lane + 32 * j;
-                if (i < dim_pad) store_from_float<DST>(y + i, v[j]);
-                qs = fmaf(v[j], v[j], qs);
-            }
-        } else {
-            const bool odd = (lane & 1) != 0;
-#pragma unroll
-            for (int j = 0; j < NJ; j += 2) {
-                const float recv = __shfl_xor_sync(0xFFFFFFFFu, odd ? v[j] : v[j + 1], 1);
-                const float a0 = odd ? recv : v[j];
-                const float a1 = odd ? v[j + 1] : recv;
-                const int i = odd ? (lane - 1 + 32 * (j + 1)) : (lane + 32 * j);
-                const __nv_bfloat162 b = __floats2bfloat162_rn(a0, a1);
-                if (i < dim_pad) *reinterpret_cast<__nv_bfloat162*>(y + i) = b;
-                const float2 sb = __bfloat1622float2(b);
-                qs = fmaf(sb.x, sb.x, fmaf(sb.y, sb.y, qs));
+        for (int j = 0; j < NP; ++j) {
+            const int i = 2 * lane + 64 * j;
+            qs = fmaf(v[j].x, v[j].x, fmaf(v[j].y, v[j].y, qs));
+            if (i < dim_pad) {   // dim_pad is a multiple of 8 and i is even: the pair is inside the row
+                if constexpr (sizeof(DST) == 4) *reinterpret_cast<float2*>(y + i) = v[j];
+                else *reinterpret_cast<__nv_bfloat162*>(y + i) = __floats2bfloat162_rn(v[j].x, v[j].y);
             }
         }
         if (max_norm2 != nullptr) {
-            qs = warp_sum(qs);
+            qs = warp_sum(qs) * (sizeof(DST) == 4 ? 1.0001f : 1.0081f);
             // non-negative floats order like their bit patterns; NaN/Inf rows poison the bound on purpose
-            if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(max_norm2), __float_as_uint(qs));
+            warp_max = __uint_as_float(max(__float_as_uint(warp_max), __float_as_uint(qs)));
         }
     }
+    // (a per-row atomic on one address serialises in L2: 10^6 of them cost more than streaming the rows)
+    if (max_norm2 != nullptr && lane == 0 && __float_as_uint(warp_max) != 0u)
+        atomicMax(reinterpret_cast<unsigned int*>(max_norm2), __float_as_uint(warp_max));
 }
 
 template <typename SRC>
@@ -123,16 +158,16 @@ __global__ void __launch_bounds__(256) dequant_rows_kernel(const SRC* __restrict
     }
 }
 
-template <typename SRC, int NJ>
+template <typename SRC, int NP>
 static int launch_nc_nj(const void* src, int64_t n, int dim, int dim_pad, int normalize, void* dst,
                         int dst_dtype, cudaStream_t s, float* max_norm2) {
     int64_t blocks64 = (n + 7) / 8;
     int blocks = (int)(blocks64 > 148 * 32 ? 148 * 32 : blocks64);
     if (dst_dtype == TS_BF16) {
-        normalize_cast_kernel<SRC, __nv_bfloat16, NJ><<<blocks, 256, 0, s>>>(
+        normalize_cast_kernel<SRC, __nv_bfloat16, NP><<<blocks, 256, 0, s>>>(
             (const SRC*)src, n, dim, dim_pad, normalize, (__nv_bfloat16*)dst, max_norm2);
     } else if (dst_dtype == TS_F32) {
-        normalize_cast_kernel<SRC, float, NJ><<<blocks, 256, 0, s>>>((const SRC*)src, n, dim, dim_pad,
+        normalize_cast_kernel<SRC, float, NP><<<blocks, 256, 0, s>>>((const SRC*)src, n, dim, dim_pad,
                                                                      normalize, (float*)dst, max_norm2);
     } else {
         set_error("normalize_cast: unsupported destination dtype %d", dst_dtype);
@@ -146,11 +181,11 @@ template <typename SRC>
 static int launch_nc(const void* src, int64_t n, int dim, int dim_pad, int normalize, void* dst,
                      int dst_dtype, cudaStream_t s, float* max_norm2) {
     if (n == 0) return TS_OK;
-    if (dim_pad <= 256) return launch_nc_nj<SRC, 8>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
-    if (dim_pad <= 512) return launch_nc_nj<SRC, 16>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
-    if (dim_pad <= 768) return launch_nc_nj<SRC, 24>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
-    if (dim_pad <= 1024) return launch_nc_nj<SRC, 32>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
-    return launch_nc_nj<SRC, 64>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
+    if (dim_pad <= 256) return launch_nc_nj<SRC, 4>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
+    if (dim_pad <= 512) return launch_nc_nj<SRC, 8>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
+    if (dim_pad <= 768) return launch_nc_nj<SRC, 12>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
+    if (dim_pad <= 1024) return launch_nc_nj<SRC, 16>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
+    return launch_nc_nj<SRC, 32>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
 }
 
 int launch_normalize_cast(const void* src, int src_dtype, int64_t n, int dim, int dim_pad,

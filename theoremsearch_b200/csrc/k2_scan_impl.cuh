@@ -146,15 +146,20 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
             for (int i = 0; i < CN; ++i) q[j * CN + i] = (e0 + i < p.dim_pad) ? __ldg(qv + e0 + i) : 0.f;
         }
     } else {
-        // K1's arithmetic, replicated per warp (4 KB from L2): ||x|| accumulated in fp64 with lane i
-        // taking elements i, i+32, ... then the butterfly; fp32 division by max((float)sqrt, 1e-12).
+        // K1's arithmetic, replicated per warp (4 KB from L2): ||x|| accumulated in fp64 with lane l
+        // taking the pairs (2l, 2l+1) + 64j in ascending order, then the butterfly; fp32 division by
+        // max((float)sqrt, 1e-12).
         const size_t qoff = (size_t)qi * p.dim;
         float den = 1.0f;
         if (p.q_normalize) {
             double ss = 0.0;
-            for (int i = lane; i < p.dim; i += 32) {
-                const double v = (double)load_query_elem(p.q_raw, p.q_dtype, qoff + i);
-                ss = fma(v, v, ss);
+            for (int i = 2 * lane; i < p.dim; i += 64) {   // K1's order: lane l owns pairs (2l, 2l+1) + 64j
+                const double a = (double)load_query_elem(p.q_raw, p.q_dtype, qoff + i);
+                ss = fma(a, a, ss);
+                if (i + 1 < p.dim) {
+                    const double b = (double)load_query_elem(p.q_raw, p.q_dtype, qoff + i + 1);
+                    ss = fma(b, b, ss);
+                }
             }
             ss = warp_sum(ss);
             den = fmaxf((float)sqrt(ss), 1e-12f);
