@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(256) max_norm2_kernel(const T* __restrict__ ro
                                                         float* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    float warp_max = 0.f;   // one atomic per warp, not per row (same-address atomics serialise in L2)
     for (int64_t r = w0; r < n; r += (int64_t)gridDim.x * 8) {
         float s = 0.f;
         for (int i = lane; i < dim_pad; i += 32) {
@@ -219,8 +220,10 @@ __global__ void __launch_bounds__(256) max_norm2_kernel(const T* __restrict__ ro
             s = fmaf(v, v, s);
         }
         s = warp_sum(s);
-        if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(s));
+        warp_max = __uint_as_float(max(__float_as_uint(warp_max), __float_as_uint(s)));
     }
+    if (lane == 0 && __float_as_uint(warp_max) != 0u)
+        atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(warp_max));
 }
 
 int launch_max_norm2(const void* rows, int dtype, int64_t n, int dim_pad, float* out, cudaStream_t s) {
