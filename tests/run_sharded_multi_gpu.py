@@ -53,6 +53,20 @@ def main():
         for i in range(0, 40, 7):
             s, ids = full.search(q[i:i + 1], 10)
             ok &= torch.equal(s, ref[i][0]) and torch.equal(ids, ref[i][1])
+    # sharded IVF: one coarse quantiser (rank 0 trains, centroids broadcast); probing every list must equal the
+    # sharded exact search bit for bit, a realistic probe budget must return exact scores for what it returns
+    sh.ivf_train_build(64, n_sample=100_000, iters=3, seed=0, list_dtype="bf16")
+    s_e, i_e = sh.search(q[:8], 10)
+    sh._xchg_saved, sh._xchg = sh._xchg, None
+    s_a, i_a = sh.ivf_search(q[:8], 10, nprobe=64, rescore_k=10)
+    ok &= torch.equal(s_e, s_a) and torch.equal(i_e, i_a)
+    sh.ivf_train_build(64, n_sample=100_000, iters=3, seed=0, list_dtype="fp8")
+    s_p, i_p = sh.ivf_search(q[:8], 10, nprobe=16, rescore_k=100)
+    for a in range(8):
+        exact = dict(zip(i_e[a].tolist(), s_e[a].tolist()))
+        for r, sc in zip(i_p[a].tolist(), s_p[a].tolist()):
+            ok &= (r not in exact) or (sc == exact[r])
+    sh._xchg = sh._xchg_saved
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     # timing: fused vs gather path
