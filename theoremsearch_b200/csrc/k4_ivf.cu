@@ -453,6 +453,7 @@ struct ListScanParams {
     uint64_t* part_keys;          // [nq][gridDim.x][k]
     uint32_t* tickets;            // [nq] zero on entry, left zero
     uint64_t* out_keys;           // [nq][k] merged candidates, key row = list POSITION
+    const uint32_t* run_flag;     // non-null: run only if *run_flag != 0 (fallback of the list-major path K4d)
     int stages;
     unsigned long long* timeline; // diagnostics: [gridDim.x][8] globaltimer stamps of query 0, or nullptr
 };
@@ -474,6 +475,7 @@ __global__ void __launch_bounds__(512, 1) list_scan_kernel(const ListScanParams 
     constexpr int CN = Chunk<ELEM>::N;
     constexpr int GROUP = 32 / R;
     extern __shared__ __align__(128) uint8_t smem[];
+    if (p.run_flag != nullptr && *p.run_flag == 0u) return;   // the list-major path did the work
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -1289,7 +1291,13 @@ static int ivf_parts(const ts_index* ix, int nq) {
     return std::max(1, std::min(sms, (2 * sms + nq - 1) / std::max(nq, 1)));
 }
 
+static bool ivf_use_grouped(const ts_index* ix, int nq, int kc) {
+    const int m = tunables().ivf_group_min_nq;
+    return m > 0 && nq >= m && ivf_grouped_supported(ix, kc);
+}
+
 struct IvfWs {
+    void* grouped;
     float* q32;
     uint64_t* probes;
     void* coarse;
@@ -1315,6 +1323,7 @@ static IvfWs carve_ivf(const ts_index* ix, int nq, int kc, int nprobe, void* bas
     w.part_keys = (uint64_t*)take((size_t)nq * ivf_parts(ix, nq) * kc * 8);
     w.tickets = (uint32_t*)take((size_t)nq * 4);
     w.cand = (uint64_t*)take((size_t)nq * kc * 8);
+    w.grouped = ivf_use_grouped(ix, nq, kc) ? take(ivf_grouped_workspace_bytes(ix, nq, nprobe)) : nullptr;
     w.bytes = off;
     return w;
 }
@@ -1371,7 +1380,14 @@ static int ivf_search_impl(ts_index* ix, const void* queries, int q_dtype, int n
     p.part_keys = w.part_keys;
     p.tickets = w.tickets;
     p.out_keys = w.cand;
+    p.run_flag = nullptr;
     p.stages = 0;
+    if (w.grouped != nullptr) {
+        // large batch: list-major scan (each probed list read once per 4 queries); K4b below runs only if the
+        // score buffer turned out too small for this batch (decided on the device)
+        rc = launch_ivf_grouped(ix, w.probes, w.q32, nq, nprobe, kc, allow_mask, w.grouped, w.cand, &p.run_flag, s);
+        if (rc) return rc;
+    }
     rc = launch_list_scan(ix, p, nq, ivf_parts(ix, nq), s);
     if (rc) return rc;
     // 3. exact re-score of the survivors against the stored corpus rows

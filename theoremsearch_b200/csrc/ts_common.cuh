@@ -89,6 +89,7 @@ struct Tunables {
     int ivf_tile_rows = 0;      // K4b rows per TMA tile (4 or 8, e4m3 D<=1024 lists only); 0 = auto
     int ivf_parts = 0;          // K4b CTAs per query; 0 = auto (2*SMs/nq clamped to [1, SMs])
     int ivf_timeline = 0;       // 1 = K4b CTAs record globaltimer stamps per phase (ts_debug_ivf_timeline)
+    int ivf_group_min_nq = 64;  // batches at least this large take the list-major scan (K4d); 0 = never
 };
 Tunables& tunables();
 
@@ -383,6 +384,12 @@ int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k, i
 int launch_normalize_cast(const void* src, int src_dtype, int64_t n, int dim, int dim_pad,
                           int normalize, void* dst, int dst_dtype, cudaStream_t s,
                           float* max_norm2 = nullptr);
+// K4d: list-major batched IVF scan (k4_ivf_grouped.cu)
+bool ivf_grouped_supported(const ts_index* ix, int kc);
+size_t ivf_grouped_workspace_bytes(const ts_index* ix, int nq, int nprobe);
+int launch_ivf_grouped(const ts_index* ix, const uint64_t* probes, const float* q32, int nq, int nprobe, int kc,
+                       const uint32_t* allow_mask, void* workspace, uint64_t* cand, const uint32_t** flag_out,
+                       cudaStream_t s);
 int launch_max_norm2(const void* rows, int dtype, int64_t n, int dim_pad, float* out, cudaStream_t s);
 int launch_dequant_rows(const void* src, int src_dtype, int64_t n, int dim, int dim_pad, float* dst,
                         cudaStream_t s);
