@@ -293,3 +293,50 @@ def test_filtered_ivf_search(ts, list_dtype):
     none = ts.pack_allow_mask(np.zeros(n, dtype=bool), index.device)
     s0, i0 = index.ivf_search(torch.from_numpy(q[:2]), k, nprobe=nprobe, rescore_k=50, normalize=False, allow_mask=none)
     assert torch.all(i0 == -1) and torch.all(torch.isneginf(s0))
+
+
+def test_list_major_batch_path_and_its_fallback(ts):
+    """K4d (batches >= 64 queries over e4m3 lists) against the per-query scan K4b: same top-k after the exact
+    re-score.  Then a corpus so skewed that the batch's score buffer cannot hold it: the device-side flag must
+    route the batch to K4b and the result must not change."""
+    x = clustered_rows(30000, 1024, 80, 0.9, seed=123)
+    index = built(ts, x, 96, "fp8")
+    q = torch.from_numpy(oracle.normalize_f64(clustered_rows(200, 1024, 80, 0.9, seed=123)))
+    s_g, i_g = index.ivf_search(q, 10, nprobe=12, rescore_k=100)          # list-major
+    old = ts.get_tunable("ivf.group_min_nq")
+    try:
+        ts.set_tunable("ivf.group_min_nq", 0)
+        index._ws = {}
+        s_c, i_c = index.ivf_search(q, 10, nprobe=12, rescore_k=100)      # per-query scan
+    finally:
+        ts.set_tunable("ivf.group_min_nq", old)
+        index._ws = {}
+    assert oracle.recall_at_k(i_g.cpu().numpy(), i_c.cpu().numpy()) >= 0.995
+    same = (i_g == i_c).all(dim=1)
+    assert torch.equal(s_g[same], s_c[same])                                # exact (re-scored) scores either way
+    # skewed: almost every row in one list, every query probes it -> nq * len >> 2 * nq * nprobe * avg_len
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal(1024).astype(np.float32)
+    big = base[None, :] + 0.05 * rng.standard_normal((24000, 1024)).astype(np.float32)
+    rest = clustered_rows(1000, 1024, 60, 0.5, seed=9)
+    xs = np.concatenate([rest, big])
+    skew = built(ts, xs, 64, "fp8", iters=3)
+    sizes = skew.ivf_list_sizes().cpu().numpy()
+    assert sizes.max() > 20000
+    qs = torch.from_numpy(oracle.normalize_f64(big[:128] + 0.01 * rng.standard_normal((128, 1024)).astype(np.float32)))
+    s1, i1 = skew.ivf_search(qs, 10, nprobe=2, rescore_k=128)             # flag trips -> K4b does the work
+    for j in (0, 17, 127):
+        s0, i0 = skew.ivf_search(qs[j], 10, nprobe=2, rescore_k=128)      # single query: K4b directly
+        assert torch.equal(i1[j], i0[0]) and torch.equal(s1[j], s0[0])
+
+
+@pytest.mark.parametrize("d", [768, 100, 264])
+def test_list_major_batch_path_other_dims(ts, d):
+    x = clustered_rows(9000, d, 40, 0.9, seed=d)
+    index = built(ts, x, 32, "fp8")
+    q = torch.from_numpy(oracle.normalize_f64(clustered_rows(80, d, 40, 0.9, seed=d)))
+    s_g, i_g = index.ivf_search(q, 10, nprobe=32, rescore_k=200)          # K4d, every list probed
+    s_e, i_e = index.search(q, 10)                                         # exact
+    assert oracle.recall_at_k(i_g.cpu().numpy(), i_e.cpu().numpy()) >= 0.99
+    same = (i_g == i_e).all(dim=1)
+    assert same.sum() >= 70 and torch.equal(s_g[same], s_e[same])
