@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(1024) ivf_invert_scan_kernel(const uint32_t* _
                                                                uint32_t* __restrict__ item_start,
                                                                unsigned long long* __restrict__ base,
                                                                uint32_t* __restrict__ totals,
-                                                               unsigned long long score_cap) {
+                                                               unsigned long long score_cap, int qb) {
     __shared__ unsigned long long w_a[32], w_b[32], w_c[32];
     __shared__ unsigned long long carry[3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(1024) ivf_invert_scan_kernel(const uint32_t* _
         if (l < nlist) {
             const unsigned long long n = cnt[l];
             a = n;
-            b = (n + g4::QB - 1) / g4::QB;
+            b = (n + qb - 1) / qb;
             c = n * (unsigned long long)(((list_offsets[l + 1] - list_offsets[l]) + 3) & ~3ll);   // runs padded to 16 B
         }
         unsigned long long ia = a, ib = b, ic = c;   // inclusive warp scans
@@ -146,10 +146,10 @@ __global__ void ivf_invert_fill_kernel(const uint64_t* __restrict__ probes, int 
 
 // item_list[item] = the list a work item belongs to (so a CTA needs one load, not a binary search)
 __global__ void ivf_item_table_kernel(const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ item_start, int nlist,
-                                      uint32_t* __restrict__ item_list) {
+                                      uint32_t* __restrict__ item_list, int qb) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlist) return;
-    const uint32_t n = (cnt[l] + g4::QB - 1) / g4::QB;
+    const uint32_t n = (cnt[l] + qb - 1) / qb;
     for (uint32_t g = 0; g < n; ++g) item_list[item_start[l] + g] = (uint32_t)l;
 }
 
@@ -312,6 +312,179 @@ __global__ void __launch_bounds__(384, 1) ivf_grouped_scan_kernel(const GroupedP
     }
 }
 
+// ---------------------------------------------------------------------------------- G4 on the tensor cores
+// Same work item, 8 queries per group, scored with legacy mma.sync m16n8k16 (f16 x f16 -> f32): the CUDA-core
+// variant above is bound by the FP16 FMA pipe (16 HFMA2 per row-query per lane); here 16 rows x 8 queries x 16
+// dims cost one HMMA + 4 F2FP + 3 LDS, i.e. ~4 instructions per row-query per lane, accumulation is fp32 and the
+// queries stay fp16 (no query quantisation) — the scan goes back to being HBM-bound, at 1/8 of K4b's volume.
+//   * A (rows): a 16-row tile is copied row by row (one 1-D TMA copy each, one mbarrier per tile) into smem with
+//     a row stride of row_bytes + 16, so the fragment loads — lane (g, t) reads the 4 e4m3 bytes at k0 + 4t of
+//     rows g and g + 8 — hit 32 distinct banks. The 4 bytes become a0/a2 (row g) and a1/a3 (row g + 8): the
+//     fragment's logical k pairs (2t, 2t+1) and (2t+8, 2t+9) are mapped onto the PHYSICAL bytes 4t..4t+3, a
+//     permutation of k inside each 16-block that B uses too, so the dot products are unchanged.
+//   * B (queries): fp16 in smem [8][D + 8]; lane (g, t) reads query g's 4 halves at k0 + 4t as one 8-byte load.
+//   * C: c0/c1 = (row g, queries 2t, 2t+1), c2/c3 = (row g + 8, same) -> x row scale -> the dense score buffer.
+namespace g4m {
+constexpr int QB = 8;
+constexpr int R = 16;
+constexpr int WARPS = 6;    // 6 warps x 2 stages x 16 padded rows = 195 KB of the 227 KB
+constexpr int STAGES = 2;
+}  // namespace g4m
+
+__device__ __forceinline__ void mma_m16n8k16_f16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// four e4m3 bytes of one 32-bit word -> two packed f16x2 registers (bytes 0,1 and bytes 2,3): two F2FP, no repacking
+__device__ __forceinline__ void e4m3x4_to_f16x2x2(uint32_t w, uint32_t& lo, uint32_t& hi) {
+    asm("{\n\t.reg .b16 l, h;\n\t"
+        "mov.b32 {l, h}, %2;\n\t"
+        "cvt.rn.f16x2.e4m3x2 %0, l;\n\t"
+        "cvt.rn.f16x2.e4m3x2 %1, h;\n\t}"
+        : "=r"(lo), "=r"(hi)
+        : "r"(w));
+}
+
+__global__ void __launch_bounds__(g4m::WARPS * 32, 1) ivf_grouped_mma_kernel(const GroupedParams p) {
+    using namespace g4m;
+    extern __shared__ __align__(128) uint8_t smem[];
+    if (p.totals[1] != 0u) return;
+    const uint32_t item = blockIdx.x;
+    if (item >= p.totals[0]) return;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t row_stride = p.row_bytes + 16u;              // padded: fragment loads are bank-conflict free
+    const uint32_t tile_bytes = R * row_stride;
+    const uint32_t q_stride = (uint32_t)p.row_bytes + 16u;      // halves per query row in smem: word stride = 8 mod 32,
+                                                                // so a half-warp's 8-byte B loads cover all 32 banks once
+    uint8_t* my_slots = smem + (size_t)warp * STAGES * tile_bytes;
+    uint64_t* my_bars = reinterpret_cast<uint64_t*>(smem + (size_t)WARPS * STAGES * tile_bytes) + warp * STAGES;
+    __half* qs = reinterpret_cast<__half*>(smem + (size_t)WARPS * STAGES * tile_bytes + 8 * WARPS * STAGES);
+    if (lane == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&my_bars[s], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+
+    const int l = (int)p.item_list[item];
+    const int grp = (int)(item - p.item_start[l]);
+    const int c = (int)p.cnt[l];
+    const int nqg = (c - grp * QB < QB) ? (c - grp * QB) : QB;
+    const uint32_t s0 = p.slot_start[l] + (uint32_t)grp * QB;
+    const int64_t start = p.list_offsets[l];
+    const int len = (int)(p.list_offsets[l + 1] - start);
+    const int T = (len + R - 1) / R;
+    const int t0 = (int)((int64_t)T * warp / WARPS), t1 = (int)((int64_t)T * (warp + 1) / WARPS);
+    const uint64_t policy = l2_policy_evict_first();
+    auto issue = [&](int tile, int s) {   // whole warp: lane 0 arms the barrier, lanes 0..rows-1 copy one row each
+        const int left = len - tile * R;
+        const int rows = left < R ? left : R;
+        if (lane == 0) mbar_expect_tx(&my_bars[s], (uint32_t)rows * p.row_bytes);
+        __syncwarp();
+        if (lane < rows)
+            tma_load_1d_hint(my_slots + (size_t)s * tile_bytes + (size_t)lane * row_stride,
+                             p.list_data + (size_t)(start + (int64_t)tile * R + lane) * p.row_bytes, p.row_bytes,
+                             &my_bars[s], policy);
+    };
+    for (int s = 0; s < STAGES && t0 + s < t1; ++s) issue(t0 + s, s);
+
+    // the group's queries as fp16 in smem (zeros for missing queries and past dim_pad)
+    unsigned long long obase0 = 0ull, obase1 = 0ull;   // score runs of the two queries this lane's accumulators belong to
+    for (int i = threadIdx.x; i < QB * (int)p.row_bytes / 4; i += blockDim.x) {   // 4 dims per thread per step
+        const int qq = (4 * i) / (int)p.row_bytes, d = (4 * i) % (int)p.row_bytes;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (qq < nqg && d < p.dim_pad) {   // dim_pad is a multiple of 8: the four dims are inside or outside together
+            const uint32_t e = p.inv[s0 + qq];
+            v = __ldg(reinterpret_cast<const float4*>(p.queries + (size_t)(e / (uint32_t)p.nprobe) * p.dim_pad + d));
+        }
+        __half2* dst = reinterpret_cast<__half2*>(qs + (size_t)qq * q_stride + d);
+        dst[0] = __floats2half2_rn(v.x, v.y);
+        dst[1] = __floats2half2_rn(v.z, v.w);
+    }
+    if (2 * t < nqg) obase0 = p.pair_off[p.inv[s0 + 2 * t]];
+    if (2 * t + 1 < nqg) obase1 = p.pair_off[p.inv[s0 + 2 * t + 1]];
+    __syncthreads();
+
+    const int ksteps = (int)p.row_bytes / 16;
+    const __half* qrow = qs + (size_t)g * q_stride + 4 * t;
+    int s = 0;
+    uint32_t parity = 0;
+    for (int tile = t0; tile < t1; ++tile) {
+        const int left = len - tile * R;
+        const int r_lo = tile * R + g, r_hi = r_lo + 8;        // rows in the list this lane's accumulators cover
+        const bool ok_lo = g < left, ok_hi = g + 8 < left;
+        float sc_lo = 0.f, sc_hi = 0.f;
+        bool al_lo = true, al_hi = true;
+        if (t == 0) {   // one lane per row fetches the row's scale / allow bit, shared below by shuffle
+            if (ok_lo) sc_lo = __ldg(p.scales + start + r_lo);
+            if (ok_hi) sc_hi = __ldg(p.scales + start + r_hi);
+            if (p.mask != nullptr) {
+                if (ok_lo) {
+                    const uint32_t row = __ldg(p.list_rows + start + r_lo);
+                    al_lo = (__ldg(p.mask + (row >> 5)) >> (row & 31)) & 1u;
+                }
+                if (ok_hi) {
+                    const uint32_t row = __ldg(p.list_rows + start + r_hi);
+                    al_hi = (__ldg(p.mask + (row >> 5)) >> (row & 31)) & 1u;
+                }
+            }
+        }
+        mbar_wait(&my_bars[s], parity);
+        const uint8_t* slot = my_slots + (size_t)s * tile_bytes;
+        const uint8_t* a_lo = slot + (size_t)g * row_stride + 4 * t;
+        const uint8_t* a_hi = a_lo + 8 * (size_t)row_stride;
+        // four independent accumulator chains (k-steps 4i, 4i+1, 4i+2, 4i+3): an HMMA depends on its accumulator,
+        // a single chain would serialise the 64 k-steps on the instruction's latency
+        float acc4[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc4[u][i] = 0.f;
+        auto kstep = [&](int ks, float (&c)[4]) {
+            const uint32_t w_lo = *reinterpret_cast<const uint32_t*>(a_lo + ks * 16);
+            const uint32_t w_hi = *reinterpret_cast<const uint32_t*>(a_hi + ks * 16);
+            const uint2 bq = *reinterpret_cast<const uint2*>(qrow + ks * 16);
+            uint32_t a[4];   // a0/a2: row g, bytes (0,1)/(2,3); a1/a3: row g + 8
+            e4m3x4_to_f16x2x2(w_lo, a[0], a[2]);
+            e4m3x4_to_f16x2x2(w_hi, a[1], a[3]);
+            const uint32_t b[2] = {bq.x, bq.y};
+            mma_m16n8k16_f16(c, a, b);
+        };
+        const int ks_full = ksteps & ~3;
+        for (int ks0 = 0; ks0 < ks_full; ks0 += 4) {   // branch-free body: the 12 fragment loads issue back to back
+#pragma unroll
+            for (int u = 0; u < 4; ++u) kstep(ks0 + u, acc4[u]);
+        }
+        for (int ks = ks_full; ks < ksteps; ++ks) kstep(ks, acc4[0]);
+        float acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = (acc4[0][i] + acc4[1][i]) + (acc4[2][i] + acc4[3][i]);
+        __syncwarp();
+        if (tile + STAGES < t1) issue(tile + STAGES, s);
+
+        sc_lo = __shfl_sync(0xFFFFFFFFu, sc_lo, lane & ~3);
+        sc_hi = __shfl_sync(0xFFFFFFFFu, sc_hi, lane & ~3);
+        al_lo = __shfl_sync(0xFFFFFFFFu, (int)al_lo, lane & ~3) != 0;
+        al_hi = __shfl_sync(0xFFFFFFFFu, (int)al_hi, lane & ~3) != 0;
+        if (2 * t < nqg) {
+            if (ok_lo) p.scores[obase0 + (unsigned long long)r_lo] = al_lo ? acc[0] * sc_lo : -INFINITY;
+            if (ok_hi) p.scores[obase0 + (unsigned long long)r_hi] = al_hi ? acc[2] * sc_hi : -INFINITY;
+        }
+        if (2 * t + 1 < nqg) {
+            if (ok_lo) p.scores[obase1 + (unsigned long long)r_lo] = al_lo ? acc[1] * sc_lo : -INFINITY;
+            if (ok_hi) p.scores[obase1 + (unsigned long long)r_hi] = al_hi ? acc[3] * sc_hi : -INFINITY;
+        }
+        if (++s == STAGES) {
+            s = 0;
+            parity ^= 1u;
+        }
+    }
+}
+
 // Per query: best k keys over the score runs of its probed lists. The whole CTA walks the runs 1024 rows at a
 // time (one 16-byte load per thread, the next step's load issued before the current one is consumed); keys that
 // beat the running threshold are appended to one shared buffer (warp-aggregated slot allocation); when the buffer
@@ -402,7 +575,7 @@ size_t ivf_grouped_workspace_bytes(const ts_index* ix, int nq, int nprobe) {
     size_t b = 0;
     b += g_al(nl * 4) * 2;                 // cnt, cursor
     b += g_al((nl + 1) * 4) * 2;           // slot_start, item_start
-    b += g_al((np / g4::QB + std::min(nl, np) + 1) * 4);   // item_list
+    b += g_al((np / g4::QB + std::min(nl, np) + 1) * 4);   // item_list (sized for the smaller group width)
     b += g_al((nl + 1) * 8);               // base
     b += 256;                              // totals
     b += g_al(np * 4) * 3;                 // inv, pair_len, pair_pos0
@@ -448,13 +621,15 @@ int launch_ivf_grouped(const ts_index* ix, const uint64_t* probes, const float* 
     const int pb = (int)std::min<size_t>((np + 255) / 256, 148 * 8);
     ivf_invert_count_kernel<<<pb, 256, 0, s>>>(probes, (int)np, cnt);
     TS_LAUNCH_CHECK();
+    const bool use_mma = tunables().ivf_group_mma != 0;
+    const int qb = use_mma ? g4m::QB : g4::QB;
     ivf_invert_scan_kernel<<<1, 1024, 0, s>>>(cnt, ix->list_offsets, ix->nlist, slot_start, item_start, base, totals,
-                                              (unsigned long long)cap);
+                                              (unsigned long long)cap, qb);
     TS_LAUNCH_CHECK();
     ivf_invert_fill_kernel<<<pb, 256, 0, s>>>(probes, (int)np, slot_start, base, ix->list_offsets, cursor, inv, pair_off,
                                               pair_len, pair_pos0);
     TS_LAUNCH_CHECK();
-    ivf_item_table_kernel<<<(ix->nlist + 255) / 256, 256, 0, s>>>(cnt, item_start, ix->nlist, item_list);
+    ivf_item_table_kernel<<<(ix->nlist + 255) / 256, 256, 0, s>>>(cnt, item_start, ix->nlist, item_list, qb);
     TS_LAUNCH_CHECK();
 
     GroupedParams p;
@@ -477,16 +652,23 @@ int launch_ivf_grouped(const ts_index* ix, const uint64_t* probes, const float* 
     p.totals = totals;
     p.scores = scores;
     p.stages = 2;
-    const int warps = 12;   // 152 registers x 384 threads fill the register file: 3 warps per scheduler
-    const size_t tile_bytes = (size_t)g4::R * p.row_bytes;
-    const size_t smem = (size_t)warps * p.stages * tile_bytes + 8 * (size_t)warps * p.stages;
-    TS_REQUIRE(max_items < ((size_t)1 << 31), TS_ERR_UNSUPPORTED, "ivf grouped scan: too many work items");
-    if (p.row_bytes <= 512) {
-        TS_CHECK_CUDA(cudaFuncSetAttribute(ivf_grouped_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ivf_grouped_scan_kernel<1><<<(unsigned)max_items, warps * 32, smem, s>>>(p);
+    if (use_mma) {
+        const size_t tile_bytes = (size_t)g4m::R * (p.row_bytes + 16);
+        const size_t smem = (size_t)g4m::WARPS * g4m::STAGES * tile_bytes + 8 * g4m::WARPS * g4m::STAGES +
+                            (size_t)g4m::QB * (p.row_bytes + 16) * sizeof(__half);
+        TS_CHECK_CUDA(cudaFuncSetAttribute(ivf_grouped_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ivf_grouped_mma_kernel<<<(unsigned)max_items, g4m::WARPS * 32, smem, s>>>(p);
     } else {
-        TS_CHECK_CUDA(cudaFuncSetAttribute(ivf_grouped_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ivf_grouped_scan_kernel<2><<<(unsigned)max_items, warps * 32, smem, s>>>(p);
+        const int warps = 12;   // 152 registers x 384 threads fill the register file: 3 warps per scheduler
+        const size_t tile_bytes = (size_t)g4::R * p.row_bytes;
+        const size_t smem = (size_t)warps * p.stages * tile_bytes + 8 * (size_t)warps * p.stages;
+        if (p.row_bytes <= 512) {
+            TS_CHECK_CUDA(cudaFuncSetAttribute(ivf_grouped_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ivf_grouped_scan_kernel<1><<<(unsigned)max_items, warps * 32, smem, s>>>(p);
+        } else {
+            TS_CHECK_CUDA(cudaFuncSetAttribute(ivf_grouped_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ivf_grouped_scan_kernel<2><<<(unsigned)max_items, warps * 32, smem, s>>>(p);
+        }
     }
     TS_LAUNCH_CHECK();
 

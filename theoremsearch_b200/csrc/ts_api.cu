@@ -631,6 +631,7 @@ static int* tunable_slot(const char* name) {
     if (!strcmp(name, "ivf.parts")) return &t.ivf_parts;
     if (!strcmp(name, "ivf.timeline")) return &t.ivf_timeline;
     if (!strcmp(name, "ivf.group_min_nq")) return &t.ivf_group_min_nq;
+    if (!strcmp(name, "ivf.group_mma")) return &t.ivf_group_mma;
     return nullptr;
 }
 int ts_debug_last_batched_fixups(void) { return debug_last_batched_fixups(); }
