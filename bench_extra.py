@@ -149,6 +149,8 @@ def recall_at_k(got: torch.Tensor, exact: torch.Tensor) -> float:
 def cmd_ivf(a):
     import time
     dev = torch.device("cuda", 0)
+    for name, val in (a.tunable or []):
+        ts.set_tunable(name, int(val))
     pk = peaks()
     index = ts.TheoremIndex(a.dim, a.rows, dtype="bf16", device=dev)
     if a.data == "clustered":
@@ -212,6 +214,7 @@ def cmd_ivf(a):
     out["batch_qps"] = a.nq / (ms_b * 1e-3)
     out["batch_list_scan_gbs"] = a.nq * scan_bytes / (ms_b * 1e-3) / 1e9
     out["batch_frac_of_measured_hbm"] = out["batch_list_scan_gbs"] / pk["hbm_gbs"]
+    out["tunables"] = a.tunable
     print(json.dumps(out))
 
 

@@ -325,10 +325,11 @@ __global__ void __launch_bounds__(384, 1) ivf_grouped_scan_kernel(const GroupedP
 //   * B (queries): fp16 in smem [8][D + 8]; lane (g, t) reads query g's 4 halves at k0 + 4t as one 8-byte load.
 //   * C: c0/c1 = (row g, queries 2t, 2t+1), c2/c3 = (row g + 8, same) -> x row scale -> the dense score buffer.
 namespace g4m {
-constexpr int QB = 8;
 constexpr int R = 16;
-constexpr int WARPS = 6;    // 6 warps x 2 stages x 16 padded rows = 195 KB of the 227 KB
 constexpr int STAGES = 2;
+// NT = n-tiles of 8 queries per group. 2 stages x 16 padded rows per warp (33 KB) + the queries (16.5 KB per
+// n-tile) must fit 227 KB: 6 warps with 8 queries, 5 with 16.
+constexpr int warps_for(int nt) { return nt == 1 ? 6 : 5; }
 }  // namespace g4m
 
 __device__ __forceinline__ void mma_m16n8k16_f16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
@@ -347,8 +348,11 @@ __device__ __forceinline__ void e4m3x4_to_f16x2x2(uint32_t w, uint32_t& lo, uint
         : "r"(w));
 }
 
-__global__ void __launch_bounds__(g4m::WARPS * 32, 1) ivf_grouped_mma_kernel(const GroupedParams p) {
+template <int NT>
+__global__ void __launch_bounds__(g4m::warps_for(NT) * 32, 1) ivf_grouped_mma_kernel(const GroupedParams p) {
     using namespace g4m;
+    constexpr int QB = 8 * NT;
+    constexpr int WARPS = warps_for(NT);
     extern __shared__ __align__(128) uint8_t smem[];
     if (p.totals[1] != 0u) return;
     const uint32_t item = blockIdx.x;
@@ -393,7 +397,7 @@ __global__ void __launch_bounds__(g4m::WARPS * 32, 1) ivf_grouped_mma_kernel(con
     for (int s = 0; s < STAGES && t0 + s < t1; ++s) issue(t0 + s, s);
 
     // the group's queries as fp16 in smem (zeros for missing queries and past dim_pad)
-    unsigned long long obase0 = 0ull, obase1 = 0ull;   // score runs of the two queries this lane's accumulators belong to
+    unsigned long long obase[NT][2];   // score runs of the queries this lane's accumulators belong to
     for (int i = threadIdx.x; i < QB * (int)p.row_bytes / 4; i += blockDim.x) {   // 4 dims per thread per step
         const int qq = (4 * i) / (int)p.row_bytes, d = (4 * i) % (int)p.row_bytes;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -405,8 +409,13 @@ __global__ void __launch_bounds__(g4m::WARPS * 32, 1) ivf_grouped_mma_kernel(con
         dst[0] = __floats2half2_rn(v.x, v.y);
         dst[1] = __floats2half2_rn(v.z, v.w);
     }
-    if (2 * t < nqg) obase0 = p.pair_off[p.inv[s0 + 2 * t]];
-    if (2 * t + 1 < nqg) obase1 = p.pair_off[p.inv[s0 + 2 * t + 1]];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int qq = nt * 8 + 2 * t + h;
+            obase[nt][h] = qq < nqg ? p.pair_off[p.inv[s0 + qq]] : 0ull;
+        }
     __syncthreads();
 
     const int ksteps = (int)p.row_bytes / 16;
@@ -439,30 +448,37 @@ __global__ void __launch_bounds__(g4m::WARPS * 32, 1) ivf_grouped_mma_kernel(con
         const uint8_t* a_hi = a_lo + 8 * (size_t)row_stride;
         // four independent accumulator chains (k-steps 4i, 4i+1, 4i+2, 4i+3): an HMMA depends on its accumulator,
         // a single chain would serialise the 64 k-steps on the instruction's latency
-        float acc4[4][4];
+        float acc4[4][NT][4];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc4[u][i] = 0.f;
-        auto kstep = [&](int ks, float (&c)[4]) {
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc4[u][nt][i] = 0.f;
+        auto kstep = [&](int ks, float (&c)[NT][4]) {
             const uint32_t w_lo = *reinterpret_cast<const uint32_t*>(a_lo + ks * 16);
             const uint32_t w_hi = *reinterpret_cast<const uint32_t*>(a_hi + ks * 16);
-            const uint2 bq = *reinterpret_cast<const uint2*>(qrow + ks * 16);
-            uint32_t a[4];   // a0/a2: row g, bytes (0,1)/(2,3); a1/a3: row g + 8
+            uint32_t a[4];   // a0/a2: row g, bytes (0,1)/(2,3); a1/a3: row g + 8 — converted once for all n-tiles
             e4m3x4_to_f16x2x2(w_lo, a[0], a[2]);
             e4m3x4_to_f16x2x2(w_hi, a[1], a[3]);
-            const uint32_t b[2] = {bq.x, bq.y};
-            mma_m16n8k16_f16(c, a, b);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const uint2 bq = *reinterpret_cast<const uint2*>(qrow + (size_t)nt * 8 * q_stride + ks * 16);
+                const uint32_t b[2] = {bq.x, bq.y};
+                mma_m16n8k16_f16(c[nt], a, b);
+            }
         };
         const int ks_full = ksteps & ~3;
-        for (int ks0 = 0; ks0 < ks_full; ks0 += 4) {   // branch-free body: the 12 fragment loads issue back to back
+        for (int ks0 = 0; ks0 < ks_full; ks0 += 4) {   // branch-free body: the fragment loads issue back to back
 #pragma unroll
             for (int u = 0; u < 4; ++u) kstep(ks0 + u, acc4[u]);
         }
         for (int ks = ks_full; ks < ksteps; ++ks) kstep(ks, acc4[0]);
-        float acc[4];
+        float acc[NT][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] = (acc4[0][i] + acc4[1][i]) + (acc4[2][i] + acc4[3][i]);
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[nt][i] = (acc4[0][nt][i] + acc4[1][nt][i]) + (acc4[2][nt][i] + acc4[3][nt][i]);
         __syncwarp();
         if (tile + STAGES < t1) issue(tile + STAGES, s);
 
@@ -470,14 +486,15 @@ __global__ void __launch_bounds__(g4m::WARPS * 32, 1) ivf_grouped_mma_kernel(con
         sc_hi = __shfl_sync(0xFFFFFFFFu, sc_hi, lane & ~3);
         al_lo = __shfl_sync(0xFFFFFFFFu, (int)al_lo, lane & ~3) != 0;
         al_hi = __shfl_sync(0xFFFFFFFFu, (int)al_hi, lane & ~3) != 0;
-        if (2 * t < nqg) {
-            if (ok_lo) p.scores[obase0 + (unsigned long long)r_lo] = al_lo ? acc[0] * sc_lo : -INFINITY;
-            if (ok_hi) p.scores[obase0 + (unsigned long long)r_hi] = al_hi ? acc[2] * sc_hi : -INFINITY;
-        }
-        if (2 * t + 1 < nqg) {
-            if (ok_lo) p.scores[obase1 + (unsigned long long)r_lo] = al_lo ? acc[1] * sc_lo : -INFINITY;
-            if (ok_hi) p.scores[obase1 + (unsigned long long)r_hi] = al_hi ? acc[3] * sc_hi : -INFINITY;
-        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (nt * 8 + 2 * t + h < nqg) {
+                    if (ok_lo) p.scores[obase[nt][h] + (unsigned long long)r_lo] = al_lo ? acc[nt][h] * sc_lo : -INFINITY;
+                    if (ok_hi) p.scores[obase[nt][h] + (unsigned long long)r_hi] = al_hi ? acc[nt][2 + h] * sc_hi : -INFINITY;
+                }
+            }
         if (++s == STAGES) {
             s = 0;
             parity ^= 1u;
@@ -622,7 +639,7 @@ int launch_ivf_grouped(const ts_index* ix, const uint64_t* probes, const float* 
     ivf_invert_count_kernel<<<pb, 256, 0, s>>>(probes, (int)np, cnt);
     TS_LAUNCH_CHECK();
     const bool use_mma = tunables().ivf_group_mma != 0;
-    const int qb = use_mma ? g4m::QB : g4::QB;
+    const int qb = use_mma ? (tunables().ivf_group_mma >= 2 ? 16 : 8) : g4::QB;
     ivf_invert_scan_kernel<<<1, 1024, 0, s>>>(cnt, ix->list_offsets, ix->nlist, slot_start, item_start, base, totals,
                                               (unsigned long long)cap, qb);
     TS_LAUNCH_CHECK();
@@ -653,11 +670,18 @@ int launch_ivf_grouped(const ts_index* ix, const uint64_t* probes, const float* 
     p.scores = scores;
     p.stages = 2;
     if (use_mma) {
+        const int nt = qb / 8;
+        const int warps = g4m::warps_for(nt);
         const size_t tile_bytes = (size_t)g4m::R * (p.row_bytes + 16);
-        const size_t smem = (size_t)g4m::WARPS * g4m::STAGES * tile_bytes + 8 * g4m::WARPS * g4m::STAGES +
-                            (size_t)g4m::QB * (p.row_bytes + 16) * sizeof(__half);
-        TS_CHECK_CUDA(cudaFuncSetAttribute(ivf_grouped_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ivf_grouped_mma_kernel<<<(unsigned)max_items, g4m::WARPS * 32, smem, s>>>(p);
+        const size_t smem = (size_t)warps * g4m::STAGES * tile_bytes + 8 * warps * g4m::STAGES +
+                            (size_t)qb * (p.row_bytes + 16) * sizeof(__half);
+        if (nt == 1) {
+            TS_CHECK_CUDA(cudaFuncSetAttribute(ivf_grouped_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ivf_grouped_mma_kernel<1><<<(unsigned)max_items, warps * 32, smem, s>>>(p);
+        } else {
+            TS_CHECK_CUDA(cudaFuncSetAttribute(ivf_grouped_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ivf_grouped_mma_kernel<2><<<(unsigned)max_items, warps * 32, smem, s>>>(p);
+        }
     } else {
         const int warps = 12;   // 152 registers x 384 threads fill the register file: 3 warps per scheduler
         const size_t tile_bytes = (size_t)g4::R * p.row_bytes;
