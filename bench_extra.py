@@ -3,11 +3,15 @@
 configs and tuning sweeps.  Each sub-command prints one JSON line per measurement.
 
   python bench_extra.py batched   [--rows 10000000 --nq 4096 --k 100]     configs[2]: K3 tcgen05 GEMM + top-k
+  python bench_extra.py small-batch [--rows 10000000]                     nq = 1..4096 latency curve
   python bench_extra.py sweep-scan [--rows 10000000]                      K2 tunables sweep
-  python bench_extra.py small-batch [--rows 10000000]                     nq = 1..256 latency curve
-  torchrun --nproc-per-node 8 bench_extra.py sharded [--rows 100000000 --nlist 16384]  configs[3]+[4] at full size
-  python bench_extra.py ivf [--rows 40000000 --nlist 16384 --nprobe 32 --rescore 100 --data clustered]
-                                                                          configs[4] shape: IVF-Flat fp8 + rescore
+  python bench_extra.py k1                                                K1 normalise+quantise throughput
+  python bench_extra.py fp8-scan  [--rows 10000000]                       exhaustive e4m3 scan + exact re-score
+  python bench_extra.py ivf [--rows 40000000 --nlist 16384 --nprobe 32 --rescore 100 --data clustered|gaussian]
+                                                                          configs[4] shape on one GPU: IVF-Flat fp8 + rescore
+  python bench_extra.py ivf-q1 / ivf-q1-sweep                             minimal runs for ncu / K4b tunables + phase timeline
+  torchrun --nproc-per-node 8 bench_extra.py sharded [--rows 100000000 --nlist 16384]
+                                                                          configs[3]+[4] at full size (exact + IVF, sharded)
 """
 from __future__ import annotations
 
