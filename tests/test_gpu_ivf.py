@@ -24,7 +24,10 @@ ASSIGN_EPS = 2e-5
 def ts():
     import theoremsearch_b200 as ts
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
-    return ts
+    # the list-major batch path (K4d) normally wants >= 4 x SMs lists; the small test indexes must reach it too
+    ts.set_tunable("ivf.group_min_lists", 1)
+    yield ts
+    ts.set_tunable("ivf.group_min_lists", 0)
 
 
 def clustered_rows(n, d, ncenters, sigma, seed):
@@ -340,3 +343,22 @@ def test_list_major_batch_path_other_dims(ts, d):
     assert oracle.recall_at_k(i_g.cpu().numpy(), i_e.cpu().numpy()) >= 0.99
     same = (i_g == i_e).all(dim=1)
     assert same.sum() >= 70 and torch.equal(s_g[same], s_e[same])
+
+
+def test_few_lists_keep_the_per_query_scan(ts):
+    """One-list index (the fp8 shadow): a batch must not be handed to the list-major kernel (one CTA per query
+    group would scan the whole corpus); with the default policy it stays on K4b and matches single queries."""
+    ts.set_tunable("ivf.group_min_lists", 0)
+    try:
+        x = clustered_rows(20000, 512, 30, 1.0, seed=4)
+        index = ts.build_index(x)
+        index.build_fp8_shadow()
+        q = torch.from_numpy(oracle.normalize_f64(clustered_rows(32, 512, 30, 1.0, seed=4)))
+        before = ts.kernel_launches()
+        s_b, i_b = index.search_fp8(q, 10, rescore_k=64)
+        launches = ts.kernel_launches() - before
+        s_1, i_1 = index.search_fp8(q[5], 10, rescore_k=64)
+        assert torch.equal(i_b[5], i_1[0]) and torch.equal(s_b[5], s_1[0])
+        assert launches <= 30      # coarse (K3 chunks) + K4b + re-score: none of K4d's table/scan/select kernels
+    finally:
+        ts.set_tunable("ivf.group_min_lists", 1)

@@ -1291,9 +1291,14 @@ static int ivf_parts(const ts_index* ix, int nq) {
     return std::max(1, std::min(sms, (2 * sms + nq - 1) / std::max(nq, 1)));
 }
 
-static bool ivf_use_grouped(const ts_index* ix, int nq, int kc) {
+// K4d hands whole lists to CTAs: it needs many lists (one list = one CTA per query group, so an index with a
+// handful of huge lists — e.g. the one-list fp8 shadow — would run on a handful of SMs) and a batch.
+static bool ivf_use_grouped(const ts_index* ix, int nq, int kc, int nprobe) {
     const int m = tunables().ivf_group_min_nq;
-    return m > 0 && nq >= m && ivf_grouped_supported(ix, kc);
+    if (m <= 0 || nq < m || !ivf_grouped_supported(ix, kc)) return false;
+    const int64_t pairs = (int64_t)nq * std::min(nprobe, ix->nlist);
+    const int min_lists = tunables().ivf_group_min_lists > 0 ? tunables().ivf_group_min_lists : 4 * sm_count(ix->device);
+    return ix->nlist >= min_lists && pairs >= min_lists;
 }
 
 struct IvfWs {
@@ -1323,7 +1328,7 @@ static IvfWs carve_ivf(const ts_index* ix, int nq, int kc, int nprobe, void* bas
     w.part_keys = (uint64_t*)take((size_t)nq * ivf_parts(ix, nq) * kc * 8);
     w.tickets = (uint32_t*)take((size_t)nq * 4);
     w.cand = (uint64_t*)take((size_t)nq * kc * 8);
-    w.grouped = ivf_use_grouped(ix, nq, kc) ? take(ivf_grouped_workspace_bytes(ix, nq, nprobe)) : nullptr;
+    w.grouped = ivf_use_grouped(ix, nq, kc, nprobe) ? take(ivf_grouped_workspace_bytes(ix, nq, nprobe)) : nullptr;
     w.bytes = off;
     return w;
 }

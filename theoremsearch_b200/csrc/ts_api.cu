@@ -632,6 +632,7 @@ static int* tunable_slot(const char* name) {
     if (!strcmp(name, "ivf.timeline")) return &t.ivf_timeline;
     if (!strcmp(name, "ivf.group_min_nq")) return &t.ivf_group_min_nq;
     if (!strcmp(name, "ivf.group_mma")) return &t.ivf_group_mma;
+    if (!strcmp(name, "ivf.group_min_lists")) return &t.ivf_group_min_lists;
     return nullptr;
 }
 int ts_debug_last_batched_fixups(void) { return debug_last_batched_fixups(); }

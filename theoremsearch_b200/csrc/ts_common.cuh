@@ -90,6 +90,7 @@ struct Tunables {
     int ivf_parts = 0;          // K4b CTAs per query; 0 = auto (2*SMs/nq clamped to [1, SMs])
     int ivf_timeline = 0;       // 1 = K4b CTAs record globaltimer stamps per phase (ts_debug_ivf_timeline)
     int ivf_group_min_nq = 16;  // batches at least this large take the list-major scan (K4d); 0 = never (sweep: profiles/sweep_ivf_batch_r1.txt)
+    int ivf_group_min_lists = 0;  // K4d needs at least this many lists (and query-list pairs); 0 = 4 x SM count
     int ivf_group_mma = 1;      // K4d scoring: 1 / 2 = mma.sync f16 tensor-core variant with 8 / 16 queries per group,
                                 // 0 = packed HFMA2 on the CUDA cores (4 queries per group)
 };
