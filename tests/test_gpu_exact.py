@@ -328,3 +328,36 @@ def test_random_shapes_equal_oracle_hypothesis(ts):
         index.close()
 
     run()
+
+
+def test_concurrent_host_threads_share_one_index(ts):
+    """SURVEY §8b threading contract: searches on one index from several host threads (Streamlit: one script
+    thread per session over a cached resource, streamlit_app.py:52-59) are safe — each thread gets its own
+    ctx (stream, pinned staging, workspace) and its own device workspace."""
+    import threading
+    x = oracle.synthetic_rows(0, 60000, 512, seed=31)
+    index = ts.build_index(x)
+    qs = oracle.synthetic_queries(64, 512, seed=32)
+    want_s, want_i = index.search_host(qs, 10)
+    errors = []
+
+    def worker(t):
+        try:
+            for rep in range(30):
+                j = (t * 7 + rep) % 64
+                s, i = index.search_host(qs[j], 10)                  # host path: per-thread ctx
+                assert np.array_equal(i[0], want_i[j]) and np.array_equal(s[0], want_s[j])
+                with torch.cuda.stream(streams[t]):                   # device path: per-thread, per-stream workspace
+                    sd, idd = index.search(torch.from_numpy(qs[j]), 10)
+                    streams[t].synchronize()
+                assert np.array_equal(idd.cpu().numpy()[0], want_i[j])
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    streams = [torch.cuda.Stream() for _ in range(6)]
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors[:3]

@@ -8,6 +8,7 @@ Host-side mirror of the reference's corpus containers: the ``embeddings_db`` ten
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import Optional, Sequence
 
 import numpy as np
@@ -59,7 +60,8 @@ class TheoremIndex:
         check(lib.ts_index_create(C.byref(h), self.device.index, self.dim, _NAME_TO_TS[dtype], int(capacity)))
         self._h = h
         self._ws: dict[tuple, torch.Tensor] = {}
-        self._ctx: dict[tuple[int, int], C.c_void_p] = {}
+        self._ctx: dict[tuple, C.c_void_p] = {}
+        self._lock = threading.Lock()
 
     # -------------------------------------------------------------------------------- lifecycle
     def close(self) -> None:
@@ -146,13 +148,16 @@ class TheoremIndex:
     # -------------------------------------------------------------------------------- searching
     def _workspace(self, nq: int, k: int) -> torch.Tensor:
         need = int(lib.ts_workspace_bytes(self._h, nq, k))
-        key = (nq, k)
+        # one workspace per (host thread, stream): concurrent searches on one index must not share scratch
+        # (Streamlit runs one script thread per session over a cached index, streamlit_app.py:52-59)
+        key = (threading.get_ident(), _stream_ptr(self.device), nq, k)
         ws = self._ws.get(key)
         if ws is None or ws.numel() < need:
             ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-            if len(self._ws) >= 4:          # a few shapes may alternate (single queries + one batch size)
-                self._ws.pop(next(iter(self._ws)))
-            self._ws[key] = ws
+            with self._lock:
+                if len(self._ws) >= 16:     # a few shapes per thread may alternate (single queries + one batch size)
+                    self._ws.pop(next(iter(self._ws)))
+                self._ws[key] = ws
         return ws
 
     def _prep_queries(self, queries) -> torch.Tensor:
@@ -205,12 +210,17 @@ class TheoremIndex:
         return allow_mask.data_ptr()
 
     def _get_ctx(self, nq: int, k: int) -> C.c_void_p:
-        for (mq, mk), ctx in self._ctx.items():
-            if nq <= mq and k <= mk:
-                return ctx
+        """A ts_ctx (stream + pinned staging + workspace) of this host thread: one ctx per thread makes
+        concurrent ``search_host`` calls on one index safe (include/theoremsearch.h, ts_ctx_create)."""
+        tid = threading.get_ident()
+        with self._lock:
+            for (t, mq, mk), ctx in self._ctx.items():
+                if t == tid and nq <= mq and k <= mk:
+                    return ctx
         ctx = C.c_void_p()
         check(lib.ts_ctx_create(C.byref(ctx), self._h, max(nq, 1), max(k, 1)))
-        self._ctx[(max(nq, 1), max(k, 1))] = ctx
+        with self._lock:
+            self._ctx[(tid, max(nq, 1), max(k, 1))] = ctx
         return ctx
 
     def search_host(self, queries: np.ndarray, k: int, normalize: bool = True,
@@ -309,13 +319,14 @@ class TheoremIndex:
 
     def _ivf_workspace(self, nq: int, k: int, nprobe: int, rescore_k: int) -> torch.Tensor:
         need = int(lib.ts_ivf_workspace_bytes(self._h, nq, k, nprobe, rescore_k))
-        key = ("ivf", nq, k, nprobe, rescore_k)
+        key = ("ivf", threading.get_ident(), _stream_ptr(self.device), nq, k, nprobe, rescore_k)
         ws = self._ws.get(key)
         if ws is None or ws.numel() < need:
             ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
-            if len(self._ws) >= 4:
-                self._ws.pop(next(iter(self._ws)))
-            self._ws[key] = ws
+            with self._lock:
+                if len(self._ws) >= 16:
+                    self._ws.pop(next(iter(self._ws)))
+                self._ws[key] = ws
         return ws
 
     def ivf_search(self, queries, k: int, nprobe: int = 32, rescore_k: int = 100, normalize: bool = True,
