@@ -196,7 +196,7 @@ def main():
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
         return 0
 
     # ------------------------------------------------------------------------- our arm
@@ -355,12 +355,21 @@ def main():
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "top1_id_last_query": int(out[1][0, 0].item()),
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    # The JSON line is out and flushed; tear down in order (peer mappings, index, process group). A crash in
+    # library teardown at interpreter exit must not cost the measurement, so multi-rank runs leave through
+    # os._exit once every rank is past the barrier.
     if sharded is not None:
         assert not sharded.peer_exchange_error(), "a peer missed the in-kernel exchange time-out"
         sharded.close()
+    index.close()
     if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

@@ -219,7 +219,7 @@ def cmd_ivf(a):
     out["batch_list_scan_gbs"] = a.nq * scan_bytes / (ms_b * 1e-3) / 1e9
     out["batch_frac_of_measured_hbm"] = out["batch_list_scan_gbs"] / pk["hbm_gbs"]
     out["tunables"] = a.tunable
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
 
 
 def cmd_ivf_q1(a):
@@ -330,7 +330,7 @@ def cmd_fp8_scan(a):
     out.update({"rescore_k": a.rescore, "fp8_q1_ms": ms, "fp8_q1_qps": 1e3 / ms, "fp8_scan_gbs": nbytes / (ms * 1e-3) / 1e9,
                 "fp8_frac_of_measured_hbm": nbytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "bf16_exact_q1_ms": ms_exact,
                 "speedup_vs_bf16_exact": ms_exact / ms})
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
 
 
 def cmd_sharded(a):
@@ -418,9 +418,14 @@ def cmd_sharded(a):
         ivf["batch"] = {"nq": a.nq, "ms": msb, "qps": a.nq / (msb * 1e-3)}
         out["ivf"] = ivf
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    index.close()
     if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():

@@ -90,7 +90,7 @@ def main():
     ms_local = timed(lambda: index.search_keys(q[:1], 10))
     if rank == 0:
         print(json.dumps({"check": "sharded_multi_gpu", "world": world, "rows": n, "ok": bool(flag.item()),
-                          "ms_fused_exchange": ms_fused, "ms_allgather_merge": ms_gather, "ms_local_scan_only": ms_local}))
+                          "ms_fused_exchange": ms_fused, "ms_allgather_merge": ms_gather, "ms_local_scan_only": ms_local}), flush=True)
     sh.close()
     dist.destroy_process_group()
     return 0 if flag.item() else 1
