@@ -362,3 +362,20 @@ def test_few_lists_keep_the_per_query_scan(ts):
         assert launches <= 30      # coarse (K3 chunks) + K4b + re-score: none of K4d's table/scan/select kernels
     finally:
         ts.set_tunable("ivf.group_min_lists", 1)
+
+
+def test_filtered_search_through_the_list_major_path(ts):
+    """The allow mask inside K4d (scores of disallowed rows become -inf and never reach the selection)."""
+    n, d = 20000, 1024
+    x = clustered_rows(n, d, 60, 0.9, seed=55)
+    index = built(ts, x, 64, "fp8")
+    rng = np.random.default_rng(8)
+    allow = rng.random(n) < 0.25
+    mask = ts.pack_allow_mask(allow, index.device)
+    q = torch.from_numpy(oracle.normalize_f64(clustered_rows(96, d, 60, 0.9, seed=55)))
+    s_g, i_g = index.ivf_search(q, 10, nprobe=8, rescore_k=128, allow_mask=mask)           # K4d (96 queries)
+    got = i_g.cpu().numpy()
+    assert np.all(allow[got[got >= 0]])
+    for j in (0, 31, 95):
+        s_1, i_1 = index.ivf_search(q[j], 10, nprobe=8, rescore_k=128, allow_mask=mask)   # K4b
+        assert torch.equal(i_g[j], i_1[0]) and torch.equal(s_g[j], s_1[0])
