@@ -221,16 +221,11 @@ def main():
     if sharded is not None:
         fused = args.exchange == "fused"
         if fused:
-            try:
+            try:   # raises on EVERY rank if any rank cannot map its peers (the ranks agree inside)
                 sharded.enable_peer_exchange(max_nq=1, max_k=max(args.k, 32))
             except ts.TheoremSearchError as e:      # CUDA IPC unavailable in this container: say so, use NCCL
                 fused = False
                 config["exchange_fallback"] = str(e)
-            ok = torch.tensor([1 if fused else 0], device=dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # all ranks must take the same path
-            if fused and not bool(ok.item()):
-                sharded.close()
-                fused = False
         config["exchange"] = ("in-kernel NVLink peer stores + flags (ts_search_sharded)" if fused
                               else "NCCL all-gather of k packed keys + merge kernel")
 

@@ -67,20 +67,43 @@ class ShardedIndex:
         if self._xchg is not None:
             return self
         dev = self.local.device
-        h = C.c_void_p()
-        check(lib.ts_xchg_create(C.byref(h), dev.index, self.world, self.rank, int(max_nq), int(max_k)))
+        # Every rank runs the SAME sequence of collectives whatever fails locally (a rank that raised early
+        # while its peers wait in a collective would deadlock the job); the outcome is agreed on at the end.
         hb = int(lib.ts_xchg_handle_bytes())
         mine = np.zeros(hb, dtype=np.uint8)
-        check(lib.ts_xchg_handle(h, mine.ctypes.data))
+        h = C.c_void_p()
+        err = None
+        try:
+            check(lib.ts_xchg_create(C.byref(h), dev.index, self.world, self.rank, int(max_nq), int(max_k)))
+            check(lib.ts_xchg_handle(h, mine.ctypes.data))
+        except _lib.TheoremSearchError as e:
+            err = e
         if self.world > 1:
-            t = torch.from_numpy(mine).to(dev)
             allh = torch.empty(self.world * hb, dtype=torch.uint8, device=dev)
-            dist.all_gather_into_tensor(allh, t, group=self.group)
+            dist.all_gather_into_tensor(allh, torch.from_numpy(mine).to(dev), group=self.group)
             host = np.ascontiguousarray(allh.cpu().numpy())
-            check(lib.ts_xchg_connect(h, host.ctypes.data))
-            dist.barrier(group=self.group)          # every rank has mapped every area before anyone stores
+            if err is None:
+                try:
+                    check(lib.ts_xchg_connect(h, host.ctypes.data))
+                except _lib.TheoremSearchError as e:
+                    err = e
+            ok = torch.tensor([0 if err is not None else 1], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)   # also: every area is mapped before any store
+            if not bool(ok.item()):
+                if h:
+                    lib.ts_xchg_destroy(h)
+                raise err if err is not None else _lib.TheoremSearchError(
+                    -2, "peer exchange unavailable: another rank could not map the peer memory")
         else:
-            check(lib.ts_xchg_connect(h, None))
+            if err is None:
+                try:
+                    check(lib.ts_xchg_connect(h, None))
+                except _lib.TheoremSearchError as e:
+                    err = e
+            if err is not None:
+                if h:
+                    lib.ts_xchg_destroy(h)
+                raise err
         self._xchg = h
         self._xchg_limits = (int(max_nq), int(max_k))
         return self
