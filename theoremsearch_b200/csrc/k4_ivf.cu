@@ -289,10 +289,13 @@ __global__ void __launch_bounds__(256) update_centroids_kernel(const uint8_t* __
                                                                int64_t n_rows, const uint32_t* __restrict__ members,
                                                                const int64_t* __restrict__ offsets, int dim_pad,
                                                                uint64_t seed, float* __restrict__ cent,
-                                                               __nv_bfloat16* __restrict__ cent16) {
+                                                               __nv_bfloat16* __restrict__ cent16,
+                                                               const uint32_t* __restrict__ assign, int nlist,
+                                                               int split_small) {
     constexpr int MAXC = TS_MAX_DIM / 256;   // columns per thread
     __shared__ float red[8];
     __shared__ float s_norm;
+    __shared__ long long s_alt;
     const int c = blockIdx.x;
     const int64_t b = offsets[c], e = offsets[c + 1];
     float sum[MAXC];
@@ -320,11 +323,27 @@ __global__ void __launch_bounds__(256) update_centroids_kernel(const uint8_t* __
     }
     __syncthreads();
     const float nrm = s_norm;
-    const bool reseed = !(nrm > 1e-20f);   // empty list, cancelling members, or NaN
+    // Re-seed: empty / degenerate lists always; with split_small also lists below a quarter of the mean size —
+    // random-row initialisation leaves some true clusters without a centroid and others with several, a local
+    // optimum Lloyd iterations cannot leave. The new centroid is a member of a list at least twice the mean
+    // size (a few hashed tries), i.e. the big merged lists get split; the last iterations run without it.
+    const double mean = (double)n_rows / (double)nlist;
+    const bool reseed = !(nrm > 1e-20f) || (split_small && (double)(e - b) < 0.25 * mean);
+    if (threadIdx.x == 0) {
+        long long pick = -1;
+        if (reseed) {
+            for (int t = 0; t < 16; ++t) {
+                const uint64_t r = splitmix64(seed ^ (0xABCDull << 32) ^ ((uint64_t)t << 48) ^ (uint64_t)c) % (uint64_t)n_rows;
+                const uint32_t l = assign[r];
+                pick = (long long)r;
+                if ((double)(offsets[l + 1] - offsets[l]) > 2.0 * mean) break;
+            }
+        }
+        s_alt = pick;
+    }
+    __syncthreads();
     const __nv_bfloat16* alt = nullptr;
-    if (reseed)
-        alt = reinterpret_cast<const __nv_bfloat16*>(
-            rows + (size_t)(splitmix64(seed ^ (0xABCDull << 32) ^ (uint64_t)c) % (uint64_t)n_rows) * row_stride);
+    if (reseed) alt = reinterpret_cast<const __nv_bfloat16*>(rows + (size_t)s_alt * row_stride);
 #pragma unroll
     for (int i = 0; i < MAXC; ++i) {
         const int col = threadIdx.x + 256 * i;
@@ -1134,7 +1153,7 @@ int ts_ivf_train(ts_index* ix, const float* sample, int64_t n_sample, int nlist,
         if (rc) return rc;
         update_centroids_kernel<<<nlist, 256, 0, s>>>(rows, row_stride, n, members, offsets, ix->dim_pad,
                                                       splitmix64(seed + 1 + (uint64_t)it), ix->centroids,
-                                                      ix->centroids_bf16);
+                                                      ix->centroids_bf16, assign, nlist, it + 2 < iters ? 1 : 0);
         TS_LAUNCH_CHECK();
     }
     rc = ivf_finish_centroids(ix, s);
