@@ -87,3 +87,48 @@ def test_shard_bounds_cover_and_balance():
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
             assert b == oracle.shard_bounds(n, w)
+
+
+def _ivf_worker(rank, world, port, n, d, k, nlist, nprobe, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from theoremsearch_b200.sharded import ShardedIndex, shard_bounds
+    rows = oracle.bf16_round(oracle.normalize_f64(oracle.synthetic_rows(0, n, d, seed=2)))
+    cent = oracle.bf16_round(oracle.normalize_f64(oracle.synthetic_rows(0, nlist, d, seed=3)))   # ONE coarse quantiser
+    q = oracle.normalize_f64(oracle.synthetic_queries(4, d))
+    lo, hi = shard_bounds(n, world)[rank]
+    local_rows = rows[lo:hi]
+    local_assign = oracle.ivf_assign(local_rows, cent)          # every rank files its own slice of every list
+
+    def local_ivf_search(queries, kk, npr, rescore_k, normalize, allow_mask):
+        s = np.full((queries.shape[0], kk), -np.inf)
+        i = np.full((queries.shape[0], kk), -1, dtype=np.int64)
+        for a, qq in enumerate(queries.numpy()):
+            ss, ii = oracle.ivf_search(qq, local_rows, cent, local_assign, kk, npr)
+            s[a, :len(ss)], i[a, :len(ii)] = ss, ii
+        return _keys_from(s.astype(np.float32), i)
+
+    sh = ShardedIndex(None, n, local_search=None, merge=_oracle_merge, local_ivf_search=local_ivf_search)
+    s, i = sh.ivf_search(torch.from_numpy(q), k, nprobe=nprobe, rescore_k=k, normalize=False)
+    np.save(os.path.join(out_dir, f"ivf_ids_{rank}.npy"), i.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_ivf_equals_unsharded(tmp_path, world):
+    """Row-sharded IVF with one shared coarse quantiser: every rank probes the same lists in its own
+    slice; gather + merge must equal the unsharded IVF result."""
+    n, d, k, nlist, nprobe = 1203, 32, 10, 12, 4
+    port = 29700 + world + (os.getpid() % 200)
+    mp.spawn(_ivf_worker, args=(world, port, n, d, k, nlist, nprobe, str(tmp_path)), nprocs=world, join=True)
+    rows = oracle.bf16_round(oracle.normalize_f64(oracle.synthetic_rows(0, n, d, seed=2)))
+    cent = oracle.bf16_round(oracle.normalize_f64(oracle.synthetic_rows(0, nlist, d, seed=3)))
+    q = oracle.normalize_f64(oracle.synthetic_queries(4, d))
+    assign = oracle.ivf_assign(rows, cent)
+    for r in range(world):
+        ids = np.load(tmp_path / f"ivf_ids_{r}.npy")
+        for a in range(4):
+            _, want = oracle.ivf_search(q[a], rows, cent, assign, k, nprobe)
+            assert ids[a].tolist() == want.tolist(), (r, a)

@@ -37,7 +37,7 @@ class ShardedIndex:
 
     def __init__(self, local: Optional[TheoremIndex], n_total: int, group=None,
                  local_search: Optional[Callable] = None, merge: Optional[Callable] = None,
-                 id_map: Optional[torch.Tensor] = None):
+                 id_map: Optional[torch.Tensor] = None, local_ivf_search: Optional[Callable] = None):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -48,6 +48,9 @@ class ShardedIndex:
         self._local_search = local_search or (lambda q, k, normalize, allow_mask:
                                               local.search_keys(q, k, normalize=normalize, allow_mask=allow_mask))
         self._merge = merge or merge_topk
+        self._local_ivf_search = local_ivf_search or (
+            lambda q, k, nprobe, rescore_k, normalize, allow_mask:
+            local.ivf_search_keys(q, k, nprobe=nprobe, rescore_k=rescore_k, normalize=normalize, allow_mask=allow_mask))
         self.id_map = id_map
         self._base = None
         self._xchg = None
@@ -176,8 +179,7 @@ class ShardedIndex:
         """ANN over the sharded corpus: every rank probes the same ``nprobe`` lists (same centroids) in
         its own slice, re-scores its candidates exactly, and the packed keys are gathered and merged
         exactly like the exact path."""
-        keys = self.local.ivf_search_keys(queries, k, nprobe=nprobe, rescore_k=rescore_k, normalize=normalize,
-                                          allow_mask=allow_mask)
+        keys = self._local_ivf_search(queries, k, nprobe, rescore_k, normalize, allow_mask)
         if self.world == 1:
             gathered = keys.unsqueeze(0)
         else:
