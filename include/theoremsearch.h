@@ -253,6 +253,12 @@ TS_API int ts_ivf_search_keys(ts_index* index, const void* queries, int q_dtype,
                               int nprobe, int rescore_k, int normalize_queries,
                               const uint32_t* allow_mask, uint64_t* out_keys, void* workspace,
                               size_t workspace_bytes, void* stream);
+/* The host-buffer form of ts_ivf_search on a ts_ctx (see ts_search_host): queries HOST [nq, dim] fp32,
+ * outputs HOST [nq, k]; H2D, the four IVF stages, D2H and the synchronise happen inside the call. The ctx
+ * grows its IVF workspace the first time a shape needs it. */
+TS_API int ts_ivf_search_host(ts_ctx* ctx, const float* queries, int nq, int k, int nprobe, int rescore_k,
+                              int normalize_queries, const uint32_t* allow_mask, float* out_scores,
+                              int64_t* out_ids);
 TS_API int ts_ivf_nlist(const ts_index* index);
 /* Storage dtype of the built lists (TS_BF16 / TS_FP8_E4M3), -1 if the lists are not built. */
 TS_API int ts_ivf_list_dtype(const ts_index* index);

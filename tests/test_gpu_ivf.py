@@ -379,3 +379,15 @@ def test_filtered_search_through_the_list_major_path(ts):
     for j in (0, 31, 95):
         s_1, i_1 = index.ivf_search(q[j], 10, nprobe=8, rescore_k=128, allow_mask=mask)   # K4b
         assert torch.equal(i_g[j], i_1[0]) and torch.equal(s_g[j], s_1[0])
+
+
+def test_ivf_host_buffer_entry_point(ts):
+    """ts_ivf_search_host: numpy in, numpy out, same result as the device-tensor call."""
+    x = clustered_rows(15000, 1024, 40, 0.9, seed=66)
+    index = built(ts, x, 64, "fp8")
+    q = oracle.normalize_f64(clustered_rows(20, 1024, 40, 0.9, seed=66))
+    s_d, i_d = index.ivf_search(torch.from_numpy(q), 10, nprobe=8, rescore_k=100, normalize=False)
+    s_h, i_h = index.ivf_search_host(q, 10, nprobe=8, rescore_k=100, normalize=False)
+    assert np.array_equal(i_h, i_d.cpu().numpy()) and np.array_equal(s_h, s_d.cpu().numpy())
+    s_1, i_1 = index.ivf_search_host(q[3], 10, nprobe=8, rescore_k=100, normalize=False)
+    assert np.array_equal(i_1[0], i_h[3])

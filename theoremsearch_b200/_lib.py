@@ -91,6 +91,7 @@ SIGNATURES = {
     "ts_ivf_get_centroids": (_i, [_p, _p, _p]),
     "ts_ivf_get_lists": (_i, [_p, _p, _p, _p]),
     "ts_ivf_get_list_data": (_i, [_p, _i64, _i64, _p, _p]),
+    "ts_ivf_search_host": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "ts_ivf_nlist": (_i, [_p]),
     "ts_ivf_list_sizes": (_i, [_p, _p, _p]),
     "ts_set_tunable": (_i, [C.c_char_p, _i]),

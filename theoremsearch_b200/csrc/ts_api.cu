@@ -288,6 +288,41 @@ int ts_index_get_rows(const ts_index* ix, int64_t first, int64_t n, float* out, 
                                ix->dim_pad, out, (cudaStream_t)stream);
 }
 
+int ts_ivf_search_host(ts_ctx* c, const float* queries, int nq, int k, int nprobe, int rescore_k, int normalize_queries,
+                       const uint32_t* allow_mask, float* out_scores, int64_t* out_ids) {
+    TS_REQUIRE(c != nullptr, TS_ERR_BAD_ARG, "ivf_search_host: ctx is NULL");
+    TS_REQUIRE(nq >= 0 && nq <= c->max_nq, TS_ERR_CAPACITY, "ivf_search_host: nq=%d exceeds ctx max_nq=%d", nq, c->max_nq);
+    TS_REQUIRE(k >= 1 && k <= c->max_k, TS_ERR_CAPACITY, "ivf_search_host: k=%d exceeds ctx max_k=%d", k, c->max_k);
+    if (nq == 0) return TS_OK;
+    TS_REQUIRE(queries && out_scores && out_ids, TS_ERR_BAD_ARG, "ivf_search_host: NULL buffer");
+    ts_index* ix = c->index;
+    DeviceGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_search_host: cannot select CUDA device %d", ix->device);
+    const size_t need = ts_ivf_workspace_bytes(ix, nq, k, nprobe, rescore_k);
+    TS_REQUIRE(need > 0, TS_ERR_STATE, "ivf_search_host: the index has no IVF lists (ts_ivf_train + ts_ivf_build)");
+    if (need > c->ivf_workspace_bytes) {   // first call with this shape only
+        TS_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(c->ivf_workspace);
+        c->ivf_workspace = nullptr;
+        c->ivf_workspace_bytes = 0;
+        TS_CHECK_CUDA(cudaMalloc(&c->ivf_workspace, need));
+        c->ivf_workspace_bytes = need;
+    }
+    const size_t qb = (size_t)nq * ix->dim * sizeof(float);
+    memcpy(c->h_queries, queries, qb);
+    TS_CHECK_CUDA(cudaMemcpyAsync(c->d_queries, c->h_queries, qb, cudaMemcpyHostToDevice, c->stream));
+    int rc = ts_ivf_search(ix, c->d_queries, TS_F32, nq, k, nprobe, rescore_k, normalize_queries, allow_mask, c->d_scores,
+                           c->d_ids, c->ivf_workspace, c->ivf_workspace_bytes, c->stream);
+    if (rc) return rc;
+    const size_t n = (size_t)nq * k;
+    TS_CHECK_CUDA(cudaMemcpyAsync(c->h_scores, c->d_scores, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    TS_CHECK_CUDA(cudaMemcpyAsync(c->h_ids, c->d_ids, n * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    TS_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(out_scores, c->h_scores, n * sizeof(float));
+    memcpy(out_ids, c->h_ids, n * sizeof(int64_t));
+    return TS_OK;
+}
+
 // ------------------------------------------------------------------------------------ raw access (save / load)
 int ts_index_has_ids(const ts_index* ix) { return ix ? (ix->has_ids ? 1 : 0) : -1; }
 
@@ -428,6 +463,7 @@ void ts_ctx_destroy(ts_ctx* c) {
     cudaFree(c->d_scores);
     cudaFree(c->d_ids);
     cudaFree(c->workspace);
+    cudaFree(c->ivf_workspace);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);

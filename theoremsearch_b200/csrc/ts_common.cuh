@@ -373,6 +373,8 @@ struct ts_ctx {
     int64_t* d_ids = nullptr;
     void* workspace = nullptr;
     size_t workspace_bytes = 0;
+    void* ivf_workspace = nullptr;      // grown on demand by ts_ivf_search_host (outside the timed path after warm-up)
+    size_t ivf_workspace_bytes = 0;
     bool timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = -1.f;

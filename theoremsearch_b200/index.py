@@ -346,13 +346,19 @@ class TheoremIndex:
 
     def ivf_search_host(self, queries: np.ndarray, k: int, nprobe: int = 32, rescore_k: int = 100,
                         normalize: bool = True, allow_mask: Optional[torch.Tensor] = None):
-        """Host buffers in / out like :meth:`search_host`, over the IVF path."""
+        """Host buffers in / out like :meth:`search_host`, over the IVF path (``ts_ivf_search_host``)."""
         q = np.ascontiguousarray(np.asarray(queries, dtype=np.float32))
         if q.ndim == 1:
             q = q[None, :]
-        s, i = self.ivf_search(torch.from_numpy(q).to(self.device, non_blocking=True), k, nprobe=nprobe,
-                               rescore_k=rescore_k, normalize=normalize, allow_mask=allow_mask)
-        return s.cpu().numpy(), i.cpu().numpy()
+        if q.shape[1] != self.dim:
+            raise _lib.TheoremSearchError(-1, f"queries must be [nq, {self.dim}], got {q.shape}")
+        nq = q.shape[0]
+        ctx = self._get_ctx(nq, k)
+        scores = np.empty((nq, k), dtype=np.float32)
+        ids = np.empty((nq, k), dtype=np.int64)
+        check(lib.ts_ivf_search_host(ctx, q.ctypes.data, nq, int(k), int(nprobe), int(rescore_k), int(normalize),
+                                     self._mask_ptr(allow_mask), scores.ctypes.data, ids.ctypes.data))
+        return scores, ids
 
     def ivf_search_keys(self, queries, k: int, nprobe: int = 32, rescore_k: int = 100, normalize: bool = True,
                         allow_mask: Optional[torch.Tensor] = None):
