@@ -531,6 +531,8 @@ int ts_xchg_create(ts_xchg** out, int device, int world, int rank, int max_nq, i
     if (e == cudaSuccess) e = cudaMemset(x->base, 0, x->bytes);
     if (e == cudaSuccess) e = cudaMalloc(&x->d_peer_slots, 16 * sizeof(void*));
     if (e == cudaSuccess) e = cudaMalloc(&x->d_peer_flags, 16 * sizeof(void*));
+    if (e == cudaSuccess) e = cudaMalloc(&x->d_tickets, (size_t)max_nq * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(x->d_tickets, 0, (size_t)max_nq * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&x->d_error, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(x->d_error, 0, sizeof(int));
     if (e != cudaSuccess) {
@@ -555,6 +557,7 @@ void ts_xchg_destroy(ts_xchg* x) {
     cudaFree(x->base);
     cudaFree(x->d_peer_slots);
     cudaFree(x->d_peer_flags);
+    cudaFree(x->d_tickets);
     cudaFree(x->d_error);
     delete x;
 }
@@ -623,12 +626,12 @@ int ts_search_sharded(ts_index* ix, ts_xchg* x, const void* queries, int q_dtype
     SearchWs w = carve_ws(ix, nq, k, workspace);
     TS_REQUIRE(workspace_bytes >= w.bytes, TS_ERR_CAPACITY, "search_sharded: workspace %zu < %zu bytes", workspace_bytes,
                w.bytes);
-    TS_CHECK_CUDA(cudaMemsetAsync(w.tickets, 0, (size_t)nq * sizeof(uint32_t), s));
+    // the exchange context owns self-cleaning tickets: the whole search is ONE stream operation (the kernel)
     ScanFused f;
     f.q_raw = queries;
     f.q_dtype = q_dtype;
     f.q_normalize = normalize_queries;
-    f.tickets = w.tickets;
+    f.tickets = x->d_tickets;
     f.id_map = id_map;
     f.out_keys = nullptr;
     f.out_scores = out_scores;

@@ -356,6 +356,7 @@ struct ts_xchg {
     void* peer_base[16] = {nullptr};  // mapped base of every rank's area (own entry = base)
     uint64_t** d_peer_slots = nullptr;   // device array [world]
     uint32_t** d_peer_flags = nullptr;   // device array [world]
+    uint32_t* d_tickets = nullptr;    // [max_nq] last-CTA tickets: zero at creation, left zero by every kernel (no per-call memset)
     int* d_error = nullptr;           // device flag: 1 = a peer did not arrive within the time-out
     uint32_t seq = 0;                 // searches issued so far (identical on every rank)
     bool connected = false;
