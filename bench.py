@@ -210,9 +210,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION/INFO; stdout must carry the JSON line only
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout must carry the JSON line only
+        if os.environ.get("NCCL_DEBUG", "WARN").upper() in ("WARN", "VERSION"):   # (the launcher's default) NCCL prints its version banner on STDOUT at these levels
+            os.environ["NCCL_DEBUG"] = "NONE"
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 

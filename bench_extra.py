@@ -345,8 +345,8 @@ def cmd_sharded(a):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's banner off stdout
+        if os.environ.get("NCCL_DEBUG", "WARN").upper() in ("WARN", "VERSION"):   # (the launcher's default) NCCL prints its version banner on STDOUT at these levels
+            os.environ["NCCL_DEBUG"] = "NONE"
         dist.init_process_group("nccl", device_id=dev)
     lo, hi = shard_bounds(a.rows, world)[rank]
     index = ts.TheoremIndex(a.dim, hi - lo, dtype="bf16", device=dev)

@@ -26,8 +26,8 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's banner off stdout
+    if os.environ.get("NCCL_DEBUG", "WARN").upper() in ("WARN", "VERSION"):   # (the launcher's default) NCCL prints its version banner on STDOUT at these levels
+        os.environ["NCCL_DEBUG"] = "NONE"
     dist.init_process_group("nccl", device_id=dev)
     n, d = 2_000_003, 1024
     lo, hi = shard_bounds(n, world)[rank]
