@@ -186,3 +186,23 @@ def test_embedding_library_files_roundtrip(tmp_path):
     e2, m2 = formats.load_embedding_library(str(tmp_path), as_index=False)
     assert torch.equal(e2, emb) and m2 == meta
     assert formats.load_embedding_library(str(tmp_path / "missing")) == (None, None)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) works without a GPU and prints
+    exactly one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2",
+                          "--warmup", "1", "--rows", "200000", "--cpu-sample-rows", "20000"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "queries/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("configs[1]") and d["gpu_launches"] == 0
