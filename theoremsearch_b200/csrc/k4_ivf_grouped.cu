@@ -3,16 +3,21 @@
 // The per-query list scan (K4b) reads a list once for every query that probes it; with a batch of 4096
 // queries x 32 probes over 16384 lists every list is wanted by ~8 queries, so the batch reads the probed part
 // of the corpus 8 times over and is HBM-bound at that inflated volume. Here the (query, list) pairs are
-// inverted into a per-list query table, a CTA takes one (list, group of <= QB queries) work item, streams the
-// list's e4m3 rows through the same per-warp TMA pipeline, converts each row to half2 once and scores it
-// against the QB queries held in registers (packed HFMA2). Scores go to a dense fp32 buffer laid out per
-// (query, probe) pair — 4 bytes written per row-query against 1 KB of row read per QB queries — and a selection
-// kernel picks each query's best k' (buffered warp select + CTA sort), which the exact re-score (K4c) consumes.
+// inverted into a per-list query table and a CTA takes one (list, group of <= QB queries) work item and streams
+// the list's e4m3 rows once. Two scoring variants:
+//   * tensor cores (default): legacy mma.sync m16n8k16, fp16 queries in smem, e4m3 rows converted in registers,
+//     fp32 accumulation, QB = 8 (or 16) — back at the HBM bound of the reduced volume (see the comment above
+//     ivf_grouped_mma_kernel);
+//   * CUDA cores: rows converted to half2 once, QB = 4 queries held in registers, packed HFMA2 — bound by the
+//     FP16 FMA pipe (kept as `ivf.group_mma = 0`).
+// Scores go to a dense fp32 buffer laid out per (query, probe) pair — 4 bytes written per row-query against
+// 1 KB of row read per QB queries — and a selection kernel picks each query's best k' (threshold filter into a
+// shared buffer + cooperative CTA sorts), which the exact re-score (K4c) consumes.
 //
 //   G1 ivf_invert_count_kernel   histogram of probes per list
 //   G2 ivf_invert_scan_kernel    exclusive scans: table slots, work items (ceil(cnt/QB)), score-buffer bases
-//   G3 ivf_invert_fill_kernel    per-list query table + per-pair score offsets
-//   G4 ivf_grouped_scan_kernel   the scan (HBM: probed rows once per QB queries; ALU: 20 instr / row-query / lane)
+//   G3 ivf_invert_fill_kernel    per-list query table + per-pair score offsets; ivf_item_table_kernel: item -> list
+//   G4 ivf_grouped_mma_kernel / ivf_grouped_scan_kernel   the scan
 //   G5 ivf_select_kernel         per-query top-k' over its pairs' score runs
 //
 // If the score buffer the caller's workspace provides is too small for this batch (heavily skewed lists) G2
