@@ -124,9 +124,15 @@ def test_ascending_order_overflows_buffers_and_is_fixed_up(ts):
     order = np.argsort(oracle.bf16_round(rows) @ qn[0])
     rows = rows[order]
     index = ts.build_index(rows, dtype="bf16", normalize=False)
-    s, i = index.search(torch.from_numpy(q_raw), k)
-    assert ts.last_batched_fixups() >= 1
+    ts.set_tunable("batch.dense", 0)     # a corpus this small would take the dense path, which cannot overflow
+    try:
+        s, i = index.search(torch.from_numpy(q_raw), k)
+        assert ts.last_batched_fixups() >= 1
+    finally:
+        ts.set_tunable("batch.dense", 1)
     check_against_oracle(ts, index, prepared(q_raw), k, s, i)
+    s_d, i_d = index.search(torch.from_numpy(q_raw), k)   # the dense path on the same adversarial order
+    assert torch.equal(s_d, s) and torch.equal(i_d, i)
 
 
 @pytest.mark.parametrize("n,d,nq,k", [
@@ -150,3 +156,27 @@ def test_cta_pair_kernel_matches_oracle(ts, n, d, nq, k):
     finally:
         ts.set_tunable("batch.pair_min_nq", old)
         ts.set_tunable("batch.cta_pair", old_pair)
+
+
+def test_dense_small_corpus_path_equals_chunked_path(ts):
+    """Small corpora (nq * N * 4 B <= 1 GiB) take one dense GEMM pass + a select kernel instead of the chunked
+    threshold filter; both feed the same re-score / certificate, so results are bit-identical."""
+    x = oracle.synthetic_rows(0, 30000, 1024, seed=91)
+    x[29999] = x[7]
+    index = ts.build_index(x)
+    q = torch.from_numpy(oracle.synthetic_queries(70, 1024, seed=92))
+    allow = np.random.default_rng(1).random(30000) < 0.5
+    mask = ts.pack_allow_mask(allow, index.device)
+    for k in (10, 100, 300):
+        s_d, i_d = index.search(q, k)
+        s_dm, i_dm = index.search(q, k, allow_mask=mask)
+        ts.set_tunable("batch.dense", 0)
+        try:
+            s_c, i_c = index.search(q, k)
+            s_cm, i_cm = index.search(q, k, allow_mask=mask)
+        finally:
+            ts.set_tunable("batch.dense", 1)
+        assert torch.equal(s_d, s_c) and torch.equal(i_d, i_c)
+        assert torch.equal(s_dm, s_cm) and torch.equal(i_dm, i_cm)
+    s10, i10 = index.search(q, 10)
+    check_against_oracle(ts, index, oracle.normalize_f64(q.numpy()), 10, s10, i10)

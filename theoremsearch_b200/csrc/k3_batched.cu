@@ -55,6 +55,8 @@ struct BatchParams {
     uint32_t* count;              // [nq] candidates appended in this chunk
     uint64_t* cand;               // [nq][k + cap]: [0,k) sorted best so far, [k, k+cap) appended
     const uint32_t* mask;         // allow bitmask or nullptr
+    float* dense;                 // small tables: write EVERY score to dense[query][row] instead of filtering
+    int64_t dense_stride;         // elements between consecutive queries in `dense`
 };
 
 // ---------------------------------------------------------------------------------- K3 kernel
@@ -290,6 +292,19 @@ batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c * 32), v);
                 tmem_ld_wait();
+                if (p.dense != nullptr) {
+                    // small corpus (e.g. an IVF centroid table): no threshold exists yet that would filter anything,
+                    // so the tile goes to a dense score matrix — for a fixed query the warp's 32 rows are 32
+                    // consecutive floats (one coalesced 128-byte store per column) — and a select kernel follows
+                    if (row < p.row_end) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int q = q0 + c * 32 + j;
+                            if (q < p.nq) p.dense[(int64_t)q * p.dense_stride + row] = row_ok ? __uint_as_float(v[j]) : -INFINITY;
+                        }
+                    }
+                    continue;
+                }
                 const float4* th4 = reinterpret_cast<const float4*>(thr_t + c * 32);
                 bool any = false;
 #pragma unroll
@@ -505,6 +520,70 @@ __global__ void __launch_bounds__(1024) build_fix_list_kernel(const int* __restr
     if (threadIdx.x == 0) *count = base;
 }
 
+// ---------------------------------------------------------------------------------- dense select (small corpora)
+// One CTA per query: the best kp keys of its dense score row. The CTA walks the row 1024 scores per step; keys above
+// the running threshold are appended to a shared buffer (warp-aggregated slots) which is compacted with a cooperative
+// sort (keep kp, raise the threshold) when the next step could overflow it. Output: cand[q][0..kp) sorted descending.
+constexpr int DSEL_CAP = 3072;
+__global__ void __launch_bounds__(256) dense_select_kernel(const float* __restrict__ dense, int64_t stride, int64_t n_rows,
+                                                           int kp, uint64_t* __restrict__ cand, size_t cand_stride,
+                                                           uint32_t* __restrict__ overflow) {
+    __shared__ __align__(16) uint64_t buf[4096];
+    __shared__ int s_cnt;
+    __shared__ unsigned long long s_thr;
+    const int q = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const float* row = dense + (int64_t)q * stride;
+    if (threadIdx.x == 0) {
+        s_cnt = 0;
+        s_thr = 0ull;
+        overflow[q] = 0u;
+    }
+    __syncthreads();
+    auto compact = [&]() {
+        const int n = s_cnt;
+        int P = 64;
+        while (P < n) P <<= 1;
+        for (int i = n + threadIdx.x; i < P; i += blockDim.x) buf[i] = 0ull;
+        __syncthreads();
+        cta_bitonic_sort_desc(buf, P);
+        if (threadIdx.x == 0) {
+            s_cnt = n < kp ? n : kp;
+            s_thr = n >= kp ? buf[kp - 1] : 0ull;
+        }
+        __syncthreads();
+    };
+    for (int64_t r0 = 0; r0 < n_rows; r0 += 1024) {
+        const unsigned long long thr = s_thr;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t r = r0 + u * 256 + threadIdx.x;   // coalesced 4-byte loads (the row stride need not be aligned)
+            const float f = (r < n_rows) ? __ldg(row + r) : -INFINITY;
+            const uint64_t key = f > -INFINITY ? pack_key(f, (uint32_t)r) : 0ull;
+            const bool pass = key > thr;
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_cnt, __popc(m));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (pass) buf[base + __popc(m & lt_mask)] = key;
+            }
+        }
+        __syncthreads();
+        if (s_cnt > DSEL_CAP - 1024) compact();
+    }
+    compact();
+    uint64_t* mine = cand + (size_t)q * cand_stride;
+    for (int i = threadIdx.x; i < kp; i += blockDim.x) mine[i] = (i < s_cnt) ? buf[i] : 0ull;
+}
+
+// Small corpora take the dense path when the score matrix fits this budget.
+static bool dense_eligible(const ts_index* ix, int nq) {
+    return ix->size > 0 && (size_t)nq * (size_t)ix->size * 4 <= ((size_t)1 << 30);
+}
+static size_t dense_stride_of(const ts_index* ix) { return ((size_t)ix->size + 31) / 32 * 32; }
+
 // ---------------------------------------------------------------------------------- host side
 // candidates kept per query by the GEMM stage: k plus a margin that makes the exactness
 // certificate succeed (the gap between the k-th and kp-th score must exceed the bf16 query
@@ -543,6 +622,7 @@ size_t batched_workspace_bytes(const ts_index* ix, int nq, int k) {
     b += al((size_t)nq * 4) * 2 + 256;                       // flags, fix list, fix count
     b += al((size_t)nq * ((size_t)kp + batched_cap(kp)) * 8);  // candidates
     b += al((size_t)nq * nparts * k * 8);                    // K2 fix-up partial lists (worst case: every query)
+    if (dense_eligible(ix, nq)) b += al((size_t)nq * dense_stride_of(ix) * 4);   // dense scores of a small corpus
     return b;
 }
 
@@ -580,6 +660,8 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
     int* fix_count = (int*)take(256);
     uint64_t* cand = (uint64_t*)take((size_t)nq * ((size_t)k + cap) * 8);
     uint64_t* fix_parts = (uint64_t*)take((size_t)nq * nparts * k_out * 8);
+    const bool dense = t.batch_dense != 0 && dense_eligible(ix, nq);
+    float* dscores = dense ? (float*)take((size_t)nq * dense_stride_of(ix) * 4) : nullptr;
 
     int rc = launch_prepare_queries(queries, q_dtype, nq, ix->dim, ix->dim_pad, normalize, q32, s);
     if (rc) return rc;
@@ -593,7 +675,7 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
     if (rc) return rc;
     // CTA pairs pay off once the batch is tensor-bound; small batches (HBM-bound) keep single CTAs, which
     // spread the corpus stream over all 148 SMs' TMA queues.
-    const bool pair = t.batch_cta_pair != 0 && nq >= t.batch_pair_min_nq;
+    const bool pair = t.batch_cta_pair != 0 && nq >= t.batch_pair_min_nq && !dense;   // the dense pass uses single CTAs
     rc = make_tmap_bf16_rows(&tmap_b, q16, (uint64_t)nq, (uint64_t)ix->dim_pad, (uint64_t)ix->dim_pad * 2,
                              pair ? bn / 2 : bn);
     if (rc) return rc;
@@ -625,6 +707,8 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
     p.count = count;
     p.cand = cand;
     p.mask = allow_mask;
+    p.dense = nullptr;
+    p.dense_stride = 0;
     const int sms = sm_count(ix->device);
 
     // chunk schedule: first chunk fills the buffers (every row passes thr = -inf), then chunks
@@ -634,6 +718,22 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
     if (first < 2 * BM) first = 2 * BM;
     int64_t pos = 0;
     if (ev0) TS_CHECK_CUDA(cudaEventRecord(ev0, s));
+    if (dense) {
+        // Small corpus: one GEMM pass writes every score, a select kernel keeps the kp best per query. The
+        // chunked threshold filter below has nothing to filter with on its first chunk (threshold -inf: every
+        // score is appended and sorted), which dominates when the whole corpus is a few chunks.
+        p.dense = dscores;
+        p.dense_stride = (int64_t)dense_stride_of(ix);
+        p.row_begin = 0;
+        p.row_end = ix->size;
+        p.num_m_blocks = (int)((ix->size + BM - 1) / BM);
+        const int tiles = p.num_m_blocks * p.num_n_blocks;
+        batched_gemm_topk_kernel<false><<<tiles < sms ? tiles : sms, THREADS, SMEM_BYTES, s>>>(tmap_a, tmap_b, p);
+        TS_LAUNCH_CHECK();
+        dense_select_kernel<<<nq, 256, 0, s>>>(dscores, p.dense_stride, ix->size, k, cand, (size_t)k + cap, overflow);
+        TS_LAUNCH_CHECK();
+        pos = ix->size;
+    }
     while (pos < ix->size) {
         int64_t chunk = (pos == 0) ? first : pos * (int64_t)growth;
         chunk = (chunk + 2 * BM - 1) / (2 * BM) * (2 * BM);
