@@ -6,6 +6,8 @@ configs and tuning sweeps.  Each sub-command prints one JSON line per measuremen
   python bench_extra.py small-batch [--rows 10000000]                     nq = 1..4096 latency curve
   python bench_extra.py sweep-scan [--rows 10000000]                      K2 tunables sweep
   python bench_extra.py k1                                                K1 normalise+quantise throughput
+  python bench_extra.py cfg0                                              configs[0] (73 queries x 100k x 1024 fp32, top-10):
+                                                                          host-buffer calls beside the reference expression on the CPU
   python bench_extra.py fp8-scan  [--rows 10000000]                       exhaustive e4m3 scan + exact re-score
   python bench_extra.py ivf [--rows 40000000 --nlist 16384 --nprobe 32 --rescore 100 --data clustered|gaussian]
                                                                           configs[4] shape on one GPU: IVF-Flat fp8 + rescore
@@ -119,6 +121,67 @@ def cmd_small_batch(a):
         ms = timed(lambda: index.search(q[:nq], a.k), 3, 10 if nq < 1024 else 3)
         print(json.dumps({"bench": "small-batch", "nq": nq, "k": a.k, "ms": ms, "queries_per_s": nq / (ms * 1e-3),
                           "corpus_gbs": a.rows * a.dim * 2 / (ms * 1e-3) / 1e9}))
+
+
+def cmd_cfg0(a):
+    """configs[0] at the reference's own shape. GPU side: host fp32 queries in, host results out through
+    ``ts_search_host`` (copies inside the timed region, wall clock). CPU side (oracle = the checker, used here as
+    the reported baseline only): ``util.cos_sim`` + ``argsort`` per query (test_app.py:76-77), the batched form
+    (compare_embeddings.py:61,105) and the pgvector-shaped form (rows normalised at write time, dot + top-k)."""
+    import time
+
+    import numpy as np
+
+    from oracle import oracle
+    n, d, nq, k = 100_000, a.dim, 73, 10
+    rows = oracle.synthetic_rows(0, n, d, seed=0) * 3.0
+    queries = oracle.synthetic_queries(nq, d) * 0.25
+    out = {"bench": "cfg0", "rows": n, "dim": d, "nq": nq, "k": k, "host_threads": torch.get_num_threads(),
+           "host_cores": os.cpu_count()}
+
+    t0 = time.perf_counter()
+    index32 = ts.build_index(rows, dtype="f32", normalize=True)
+    torch.cuda.synchronize()
+    out["gpu_build_f32_ms_incl_h2d"] = (time.perf_counter() - t0) * 1e3
+    index16 = ts.build_index(rows, dtype="bf16", normalize=True)
+    torch.cuda.synchronize()
+
+    def wall(fn, warmup, iters):
+        for _ in range(warmup):
+            fn()
+        lat = []
+        for _ in range(iters):
+            t = time.perf_counter()
+            fn()
+            lat.append(time.perf_counter() - t)
+        return np.array(lat)
+
+    for name, index in (("f32_rows", index32), ("bf16_rows", index16)):
+        it = itertools.cycle(range(nq))
+        lat = wall(lambda: index.search_host(queries[next(it)], k), 10, 3 * nq)
+        out[f"gpu_{name}_single_p50_ms"] = float(np.median(lat) * 1e3)
+        out[f"gpu_{name}_single_qps"] = float(1.0 / lat.mean())
+        lat = wall(lambda: index.search_host(queries, k), 3, 20)
+        out[f"gpu_{name}_batch73_ms"] = float(np.median(lat) * 1e3)
+        out[f"gpu_{name}_batch73_qps"] = float(nq / np.median(lat))
+
+    rows_t, q_t = torch.from_numpy(rows), torch.from_numpy(queries)
+    lat = wall(lambda i=itertools.cycle(range(nq)): oracle.reference_single_query_verbatim(q_t[next(i)], rows_t, k), 1, 12)
+    out["cpu_reference_single_p50_ms"] = float(np.median(lat) * 1e3)
+    out["cpu_reference_single_qps"] = float(1.0 / lat.mean())
+    lat = wall(lambda: oracle.batched_ranking(q_t, rows_t, k), 0, 2)
+    out["cpu_reference_batch73_ms"] = float(np.median(lat) * 1e3)
+    stored = oracle.normalize(rows_t)
+    qn = oracle.normalize(q_t)
+
+    def pg_shaped(i=itertools.cycle(range(nq))):
+        sc = torch.mv(stored, qn[next(i)])
+        return torch.topk(sc, k)
+    lat = wall(pg_shaped, 2, 40)
+    out["cpu_prenormalised_dot_topk_p50_ms"] = float(np.median(lat) * 1e3)
+    out["speedup_single_query_vs_reference"] = out["cpu_reference_single_p50_ms"] / out["gpu_f32_rows_single_p50_ms"]
+    out["speedup_batch73_vs_reference"] = out["cpu_reference_batch73_ms"] / out["gpu_f32_rows_batch73_ms"]
+    print(json.dumps(out))
 
 
 def timed_graph(fn, warmup, iters):
@@ -432,7 +495,7 @@ def cmd_sharded(a):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("cmd", choices=["batched", "sweep-scan", "small-batch", "ivf", "sharded", "ivf-q1", "ivf-q1-sweep", "fp8-scan", "k1"])
+    ap.add_argument("cmd", choices=["batched", "sweep-scan", "small-batch", "ivf", "sharded", "ivf-q1", "ivf-q1-sweep", "fp8-scan", "k1", "cfg0"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--dim", type=int, default=1024)
     ap.add_argument("--nq", type=int, default=4096)
@@ -457,7 +520,7 @@ def main():
     a = ap.parse_args()
     if a.k is None:
         a.k = 100 if a.cmd == "batched" else 10
-    {"batched": cmd_batched, "sweep-scan": cmd_sweep_scan, "small-batch": cmd_small_batch, "ivf": cmd_ivf, "sharded": cmd_sharded, "ivf-q1": cmd_ivf_q1, "ivf-q1-sweep": cmd_ivf_q1_sweep, "fp8-scan": cmd_fp8_scan, "k1": cmd_k1}[a.cmd](a)
+    {"batched": cmd_batched, "sweep-scan": cmd_sweep_scan, "small-batch": cmd_small_batch, "ivf": cmd_ivf, "sharded": cmd_sharded, "ivf-q1": cmd_ivf_q1, "ivf-q1-sweep": cmd_ivf_q1_sweep, "fp8-scan": cmd_fp8_scan, "k1": cmd_k1, "cfg0": cmd_cfg0}[a.cmd](a)
 
 
 if __name__ == "__main__":
