@@ -361,3 +361,9 @@ def test_concurrent_host_threads_share_one_index(ts):
     for th in threads:
         th.join()
     assert not errors, errors[:3]
+    # contexts of exited threads are reclaimed (Streamlit: a fresh script thread per rerun) and a larger
+    # context replaces this thread's smaller one: the table is bounded by live threads
+    assert len(index._ctx) == 7
+    s20, i20 = index.search_host(qs, 20)
+    assert len(index._ctx) == 1
+    assert np.array_equal(i20[:, :10], want_i)

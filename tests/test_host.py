@@ -80,6 +80,82 @@ def test_where_clause_three_valued_logic():
         [True, False, False, False, False]
 
 
+def _sql_where_row(row, f):
+    """The WHERE clause of streamlit_app.py:175-243 evaluated for ONE row the way Postgres would
+    (a NULL operand makes the predicate not-true) — the slow, obvious form ``build_allow`` must equal."""
+    (_pid, title, authors, link, last_updated, _s, journal_ref, category, _c, citations, _tid, name, _b, _sl) = row
+    arxiv = link is not None and "arxiv.org" in link.lower()
+    not_arxiv = link is not None and "arxiv.org" not in link.lower()
+    ok = True
+    src = f.get("sources") or []
+    if "arXiv" in src or "Stacks Project" in src:
+        ok &= ("arXiv" in src and arxiv) or ("Stacks Project" in src and not_arxiv)
+    if f.get("authors"):
+        ok &= bool(set(authors or ()) & set(f["authors"]))
+    if f.get("tags"):
+        ok &= category is not None and category in f["tags"]
+    if f.get("year_range"):
+        y0, y1 = f["year_range"]
+        ok &= (arxiv and last_updated is not None and y0 <= last_updated.year <= y1) or not_arxiv
+    if f.get("journal_status") == "Journal Article":
+        ok &= arxiv and journal_ref is not None
+    elif f.get("journal_status") == "Preprint Only":
+        ok &= arxiv and journal_ref is None
+    pf = f.get("paper_filter") or {}
+    ids = [str(i).lower() for i in pf.get("ids", ())]
+    titles = [str(t).lower() for t in pf.get("titles", ())]
+    if ids or titles:
+        ok &= (link is not None and any(i in link.lower() for i in ids)) or \
+              (title is not None and any(t in title.lower() for t in titles))
+    if f.get("types"):
+        ok &= name is not None and any(str(t).lower() in name.lower() for t in f["types"])
+    low, high = f["citation_range"]
+    between = citations is not None and low <= citations <= high
+    ok &= between or (f["include_unknown_citations"] and citations is None)
+    return bool(ok)
+
+
+def test_vectorised_where_equals_row_by_row_sql_semantics():
+    rng = np.random.default_rng(5)
+    authors = ["Ann", "Bob", "Cy", "Dee", "Eli", "Fay"]
+    cats = ["math.AP", "math.AG", "math.NT", "cs.LG", None]
+    names = ["Theorem 1.2", "Lemma 3", "Main Proposition", "Corollary A", "Remark", None, "lemma (Zorn)"]
+    links = ["http://arxiv.org/abs/1905.12345v1", "https://stacks.math.columbia.edu/tag/00AB", None,
+             "HTTP://ARXIV.ORG/abs/2001.00001", "http://arxiv.org/abs/2203.04567"]
+    titles = ["Optimal transport and curvature", "Stacks", None, "On the Riemann zeta function", "TRANSPORT maps"]
+    rows = []
+    for i in range(400):
+        pick = lambda xs: xs[int(rng.integers(len(xs)))]
+        au = None if rng.random() < 0.1 else [authors[j] for j in rng.choice(len(authors), int(rng.integers(0, 4)), replace=False)]
+        date = None if rng.random() < 0.15 else datetime.datetime(int(rng.integers(2005, 2026)), 1, 1)
+        cit = None if rng.random() < 0.3 else int(rng.integers(0, 300))
+        rows.append((f"p{i}", pick(titles), au, pick(links), date, "s", pick([None, "J. Math. 1"]), pick(cats),
+                     "c", cit, i, pick(names), "body", "slogan"))
+    s = st.TheoremStore(rows, OracleIndex(np.zeros((len(rows), 4), np.float32)))
+    for trial in range(200):
+        f = dict(BASE_FILTERS)
+        if rng.random() < 0.5:
+            f["sources"] = [x for x in ("arXiv", "Stacks Project") if rng.random() < 0.6] or ["arXiv"]
+        if rng.random() < 0.4:
+            f["authors"] = [authors[j] for j in rng.choice(len(authors), 2, replace=False)] + ["Nobody"]
+        if rng.random() < 0.4:
+            f["tags"] = [c for c in cats[:4] if rng.random() < 0.5] + ["math.ZZ"]
+        if rng.random() < 0.4:
+            y0 = int(rng.integers(2000, 2026))
+            f["year_range"] = (y0, y0 + int(rng.integers(0, 12)))
+        f["journal_status"] = ["All", "Journal Article", "Preprint Only"][int(rng.integers(3))]
+        if rng.random() < 0.3:
+            f["paper_filter"] = {"ids": {"1905.12345", "tag/00"} if rng.random() < 0.5 else set(),
+                                 "titles": {"Transport"} if rng.random() < 0.7 else set()}
+        if rng.random() < 0.4:
+            f["types"] = [t for t in ("Lemma", "corollary", "theorem", "proposition") if rng.random() < 0.5]
+        lo = int(rng.integers(0, 100))
+        f["citation_range"] = (lo, lo + int(rng.integers(0, 250)))
+        f["include_unknown_citations"] = bool(rng.random() < 0.5)
+        want = [_sql_where_row(r, f) for r in rows]
+        assert s.build_allow(f).tolist() == want, f
+
+
 def test_filters_apply_before_limit():
     s = _mini_store()
     model = TableModel({"q": np.array([0.1, 0.9, 0.5, 0.4, 0.3, 0, 0, 0], np.float32)})

@@ -211,16 +211,26 @@ class TheoremIndex:
 
     def _get_ctx(self, nq: int, k: int) -> C.c_void_p:
         """A ts_ctx (stream + pinned staging + workspace) of this host thread: one ctx per thread makes
-        concurrent ``search_host`` calls on one index safe (include/theoremsearch.h, ts_ctx_create)."""
+        concurrent ``search_host`` calls on one index safe (include/theoremsearch.h, ts_ctx_create).
+        Streamlit starts a fresh script thread per rerun over the cached index (streamlit_app.py:52-59),
+        so contexts of threads that have exited are destroyed here, and a larger context replaces the
+        smaller ones of the same thread: the table stays bounded by live threads."""
         tid = threading.get_ident()
+        nq, k = max(int(nq), 1), max(int(k), 1)
         with self._lock:
             for (t, mq, mk), ctx in self._ctx.items():
                 if t == tid and nq <= mq and k <= mk:
                     return ctx
+            alive = {t.ident for t in threading.enumerate()}
+            stale = [key for key in self._ctx
+                     if key[0] not in alive or (key[0] == tid and key[1] <= nq and key[2] <= k)]
+            doomed = [self._ctx.pop(key) for key in stale]
+        for ctx in doomed:          # no live thread can be inside a call on these
+            lib.ts_ctx_destroy(ctx)
         ctx = C.c_void_p()
-        check(lib.ts_ctx_create(C.byref(ctx), self._h, max(nq, 1), max(k, 1)))
+        check(lib.ts_ctx_create(C.byref(ctx), self._h, nq, k))
         with self._lock:
-            self._ctx[(tid, max(nq, 1), max(k, 1))] = ctx
+            self._ctx[(tid, nq, k)] = ctx
         return ctx
 
     def search_host(self, queries: np.ndarray, k: int, normalize: bool = True,

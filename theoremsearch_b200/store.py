@@ -26,6 +26,13 @@ COLUMNS = ("paper_id", "title", "authors", "link", "last_updated", "summary", "j
            "theorem_slogan")
 
 
+def _contains(haystacks: np.ndarray, needle: str) -> np.ndarray:
+    """Row-wise ``needle in haystack`` (SQL ``ILIKE '%needle%'`` on pre-lowered text), vectorised."""
+    if haystacks.size == 0:
+        return np.zeros(0, dtype=bool)
+    return np.char.find(haystacks, needle) >= 0
+
+
 def infer_type(name: Optional[str]) -> str:
     """streamlit_app.py:61-68."""
     if not name:
@@ -68,16 +75,26 @@ class TheoremStore:
         self.ann = dict(ann) if ann else None
         n = len(self.rows)
         col = {c: [r[j] for r in self.rows] for j, c in enumerate(COLUMNS)}
-        link_l = [(l or "").lower() for l in col["link"]]
+        # every filter column is encoded ONCE into numpy form so the per-query WHERE is vectorised
+        # (a Python loop over 10M rows per query would cost more than the scan it gates)
+        link_l = np.array([(l or "").lower() for l in col["link"]], dtype=str)
         self._has_link = np.array([l is not None for l in col["link"]], dtype=bool)
-        self._is_arxiv = np.array(["arxiv.org" in l for l in link_l], dtype=bool)
+        self._is_arxiv = _contains(link_l, "arxiv.org")
         self._link_l = link_l
-        self._title_l = [(t or "").lower() if t is not None else None for t in col["title"]]
-        self._authors = [set(a or ()) for a in col["authors"]]
-        self._category = col["primary_category"]
+        self._has_title = np.array([t is not None for t in col["title"]], dtype=bool)
+        self._title_l = np.array([(t or "").lower() for t in col["title"]], dtype=str)
+        self._author_rows: dict[Any, list[int]] = {}                   # author -> rows (p.authors && %s)
+        for i, a in enumerate(col["authors"]):
+            for name in set(a or ()):
+                self._author_rows.setdefault(name, []).append(i)
+        cats = {}
+        self._category_code = np.array([cats.setdefault(c, len(cats)) for c in col["primary_category"]],
+                                       dtype=np.int64).reshape(n)
+        self._category_of = cats
         self._year = np.array([(d.year if d is not None else -1) for d in col["last_updated"]], dtype=np.int64)
         self._has_journal = np.array([j is not None for j in col["journal_ref"]], dtype=bool)
-        self._name_l = [(nm.lower() if nm is not None else None) for nm in col["theorem_name"]]
+        self._has_name = np.array([nm is not None for nm in col["theorem_name"]], dtype=bool)
+        self._name_l = np.array([(nm or "").lower() for nm in col["theorem_name"]], dtype=str)
         self._cit_known = np.array([c is not None for c in col["citations"]], dtype=bool)
         self._cit = np.array([(c if c is not None else 0) for c in col["citations"]], dtype=np.int64)
         assert n == len(self._cit)
@@ -106,11 +123,13 @@ class TheoremStore:
             if hit:
                 allow &= m
         if filters.get("authors"):                                             # :189-191  p.authors && %s
-            want = set(filters["authors"])
-            allow &= np.array([bool(a & want) for a in self._authors], dtype=bool)
+            m = np.zeros(n, dtype=bool)
+            for name in set(filters["authors"]):
+                m[self._author_rows.get(name, [])] = True
+            allow &= m
         if filters.get("tags"):                                                # :194-196
-            want = set(filters["tags"])
-            allow &= np.array([c in want for c in self._category], dtype=bool)
+            codes = [self._category_of[c] for c in set(filters["tags"]) if c is not None and c in self._category_of]
+            allow &= np.isin(self._category_code, np.array(codes, dtype=np.int64))
         if filters.get("year_range"):                                          # :199-205
             y0, y1 = filters["year_range"]
             allow &= (arxiv & (self._year >= y0) & (self._year <= y1)) | not_arxiv
@@ -124,14 +143,16 @@ class TheoremStore:
         titles = [str(t).lower() for t in pf.get("titles", ())]
         if ids or titles:
             m = np.zeros(n, dtype=bool)
-            if ids:
-                m |= np.array([h and any(i in l for i in ids) for h, l in zip(self._has_link, self._link_l)], dtype=bool)
-            if titles:
-                m |= np.array([t is not None and any(s in t for s in titles) for t in self._title_l], dtype=bool)
+            for i in ids:
+                m |= self._has_link & _contains(self._link_l, i)
+            for t in titles:
+                m |= self._has_title & _contains(self._title_l, t)
             allow &= m
         if filters.get("types"):                                               # :230-233
-            want = [str(t).lower() for t in filters["types"]]
-            allow &= np.array([nm is not None and any(t in nm for t in want) for nm in self._name_l], dtype=bool)
+            m = np.zeros(n, dtype=bool)
+            for t in filters["types"]:
+                m |= _contains(self._name_l, str(t).lower())
+            allow &= m & self._has_name
         low, high = filters["citation_range"]                                  # :236-245
         between = self._cit_known & (self._cit >= low) & (self._cit <= high)
         if filters["include_unknown_citations"]:
