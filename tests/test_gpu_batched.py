@@ -159,7 +159,7 @@ def test_cta_pair_kernel_matches_oracle(ts, n, d, nq, k):
 
 
 def test_dense_small_corpus_path_equals_chunked_path(ts):
-    """Small corpora (nq * N * 4 B <= 1 GiB) take one dense GEMM pass + a select kernel instead of the chunked
+    """Small corpora (N <= 2^18 rows and nq * N * 4 B <= 1 GiB) take one dense GEMM pass + a select kernel instead of the chunked
     threshold filter; both feed the same re-score / certificate, so results are bit-identical."""
     x = oracle.synthetic_rows(0, 30000, 1024, seed=91)
     x[29999] = x[7]

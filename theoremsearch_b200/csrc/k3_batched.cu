@@ -578,9 +578,12 @@ __global__ void __launch_bounds__(256) dense_select_kernel(const float* __restri
     for (int i = threadIdx.x; i < kp; i += blockDim.x) mine[i] = (i < s_cnt) ? buf[i] : 0ull;
 }
 
-// Small corpora take the dense path when the score matrix fits this budget.
+// Small corpora take the dense path: the select kernel walks a query's whole score row with ONE CTA, so the
+// row must be short (2^18 scores = 1 MB, ~10 us) whatever nq is — at 10M rows and a handful of queries the
+// matrix would fit the byte budget but the select would take 20 ms (measured) against 3.3 ms chunked.
+constexpr int64_t DENSE_MAX_ROWS = (int64_t)1 << 18;
 static bool dense_eligible(const ts_index* ix, int nq) {
-    return ix->size > 0 && (size_t)nq * (size_t)ix->size * 4 <= ((size_t)1 << 30);
+    return ix->size > 0 && ix->size <= DENSE_MAX_ROWS && (size_t)nq * (size_t)ix->size * 4 <= ((size_t)1 << 30);
 }
 static size_t dense_stride_of(const ts_index* ix) { return ((size_t)ix->size + 31) / 32 * 32; }
 
