@@ -86,6 +86,33 @@ def test_planted_neighbours_tensor_core_path_bitwise_equal(env):
     assert torch.all(sb[:, 1:] <= sb[:, :-1])
 
 
+def test_small_batches_cost_about_one_corpus_pass(env):
+    """2..16 queries go through K3 with a narrow n-block and must stay near ONE pass over the 20 GB corpus
+    (3.3 ms vs 2.85 ms for one query) — a guard against path-selection regressions (a dense-score path meant
+    for short tables once took these shapes and cost 20 ms). Generous bound: 3x the single-query time."""
+    ts, index, q, others = env
+
+    def ms(fn, iters=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    t1 = ms(lambda: index.search(others[0], 10))
+    for nq in (2, 4, 16):
+        tb = ms(lambda: index.search(others[:nq], 10))
+        assert tb < 3.0 * t1, f"nq={nq}: {tb:.2f} ms vs {t1:.2f} ms for one query"
+    sb, ib = index.search(others[:4], 10)
+    for j in range(4):
+        s1, i1 = index.search(others[j], 10)
+        assert torch.equal(sb[j], s1[0]) and torch.equal(ib[j], i1[0])
+
+
 def test_shard_merge_equals_unsharded(env):
     ts, index, q, others = env
     words = (N + 31) // 32
