@@ -174,6 +174,22 @@ def test_filters_apply_before_limit():
     assert got[0]["similarity"] == pytest.approx(1.0 + qn[2], abs=1e-6)
 
 
+def test_search_accepts_an_embedded_query():
+    """``search(query: str or ndarray, model, filters)`` — a raw embedding gives the rows the
+    text query gives (it is normalised like ``normalize_embeddings=True``), with no model call."""
+    import torch
+    s = _mini_store()
+    raw = np.array([0.1, 0.9, 0.5, 0.4, 0.3, 0, 0, 0], np.float32)
+    model = TableModel({"q": raw})
+    f = dict(BASE_FILTERS, top_k=3, citation_weight=0.0)
+    want = s.search("q", model, f)
+    for emb in (raw * 5.0, torch.from_numpy(raw * 0.01)):
+        got = s.search(emb, None, f)
+        assert [r["theorem_id"] for r in got] == [r["theorem_id"] for r in want]
+        assert [r["similarity"] for r in got] == pytest.approx([r["similarity"] for r in want], abs=1e-6)
+    assert s.search(raw, None, dict(f, citation_weight=0.5))[0]["score"] >= want[0]["similarity"] - 1e-6
+
+
 def test_citation_weight_reranks_pool():
     s = _mini_store()
     model = TableModel({"q": np.array([0.5, 0.5, 0.5, 0.5, 0.49, 0, 0, 0], np.float32)})

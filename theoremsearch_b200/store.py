@@ -199,7 +199,14 @@ class TheoremStore:
         if not filters["sources"]:                                             # :166-168
             return []
         citation_weight = float(filters["citation_weight"])                    # :170
-        query_vec = model.encode(query or "", normalize_embeddings=True, convert_to_numpy=True)  # :173
+        if isinstance(query, np.ndarray) or hasattr(query, "detach"):
+            # an already-embedded query (``query: str or ndarray``): what ``model.encode`` would have
+            # returned, L2-normalised here the way ``normalize_embeddings=True`` does (x / max(||x||, 1e-12))
+            query_vec = np.asarray(query.detach().cpu().numpy() if hasattr(query, "detach") else query,
+                                   dtype=np.float32).reshape(-1)
+            query_vec = query_vec / max(float(np.linalg.norm(query_vec.astype(np.float64))), 1e-12)
+        else:
+            query_vec = model.encode(query or "", normalize_embeddings=True, convert_to_numpy=True)  # :173
         query_vec = np.asarray(query_vec, dtype=np.float32).reshape(-1)
         top_k = int(filters["top_k"])
         allow = self.build_allow(filters)
