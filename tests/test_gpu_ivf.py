@@ -257,6 +257,30 @@ def test_fp8_exhaustive_scan_mode(ts):
                 assert sc == exact[r]
 
 
+def test_build_index_fp8_dtype_scans_e4m3_and_rescores_exactly(ts):
+    """``build_index(..., dtype='bf16' or 'fp8')`` — the fp8 index answers ``cos_sim_topk`` from the
+    e4m3 copy with exact re-scored scores; a k beyond the candidate budget takes the exact bf16 scan."""
+    x = clustered_rows(20000, 1024, 50, 1.0, seed=78)
+    exact = ts.build_index(x)
+    idx8 = ts.build_index(x, dtype="fp8")
+    assert idx8.scan_dtype == "fp8" and idx8.dtype == "bf16" and idx8.nlist == 1 and len(idx8) == 20000
+    q = torch.from_numpy(oracle.normalize_f64(clustered_rows(8, 1024, 50, 1.0, seed=79)))
+    s_e, i_e = ts.cos_sim_topk(q, exact, 10, normalize_queries=False)
+    s_f, i_f = ts.cos_sim_topk(q, idx8, 10, normalize_queries=False)
+    assert oracle.recall_at_k(i_f.cpu().numpy(), i_e.cpu().numpy()) >= 0.95
+    se, ie, sf, jf = s_e.cpu().numpy(), i_e.cpu().numpy(), s_f.cpu().numpy(), i_f.cpu().numpy()
+    for qi in range(8):
+        exact_of = dict(zip(ie[qi].tolist(), se[qi].tolist()))
+        assert all(sc == exact_of[r] for r, sc in zip(jf[qi].tolist(), sf[qi].tolist()) if r in exact_of)
+    s1, i1 = ts.cos_sim_topk(q[0], idx8, 10, normalize_queries=False)
+    assert i1.shape == (10,) and torch.equal(i1, i_f[0]) and torch.equal(s1, s_f[0])
+    s_big, i_big = ts.cos_sim_topk(q, idx8, 200, normalize_queries=False)
+    s_big_e, i_big_e = ts.cos_sim_topk(q, exact, 200, normalize_queries=False)
+    assert torch.equal(i_big, i_big_e) and torch.equal(s_big, s_big_e)
+    with pytest.raises(ts.TheoremSearchError):
+        ts.build_index(x[:0], dtype="fp8")
+
+
 @pytest.mark.parametrize("list_dtype", ["bf16", "fp8"])
 def test_filtered_ivf_search(ts, list_dtype):
     """The SQL WHERE of streamlit_app.py:175-243 applied inside the list scan: exact top-k among the ELIGIBLE

@@ -16,7 +16,11 @@ from typing import Optional
 import numpy as np
 import torch
 
+from ._lib import TheoremSearchError
 from .index import TheoremIndex
+
+_FP8_NAMES = ("fp8", "fp8_e4m3", "e4m3")
+TS_IVF_MAX_CANDIDATES = 256    # include/theoremsearch.h
 
 
 def build_index(embeddings, ids=None, dtype: str = "bf16", normalize: bool = True,
@@ -24,13 +28,24 @@ def build_index(embeddings, ids=None, dtype: str = "bf16", normalize: bool = Tru
     """Corpus [N, D] (torch tensor on any device, or numpy) -> resident index.  ``normalize=True``
     performs once, at build time, the ``F.normalize`` that ``util.cos_sim`` repeats on every
     query (test_app.py:76) — and that the production writer already applies
-    (ec2/generate_embeddings/embeddings.py:27,35)."""
+    (ec2/generate_embeddings/embeddings.py:27,35).  ``dtype``: "bf16" (default), "f32", or "fp8" = bf16 rows
+    plus an e4m3 scan copy: ``cos_sim_topk`` then scans half the bytes and re-scores the best
+    ``max(128, 2k)`` candidates exactly."""
     n, d = int(embeddings.shape[0]), int(embeddings.shape[1])
-    ix = TheoremIndex(d, capacity if capacity is not None else max(n, 1), dtype=dtype, device=device)
+    fp8 = dtype in _FP8_NAMES
+    ix = TheoremIndex(d, capacity if capacity is not None else max(n, 1), dtype="bf16" if fp8 else dtype,
+                      device=device)
     if n:
         if isinstance(embeddings, torch.Tensor) and embeddings.is_cuda and embeddings.device != ix.device:
             embeddings = embeddings.to(ix.device)
         ix.add(embeddings, ids=ids, normalize=normalize)
+    if fp8:
+        # ``dtype='fp8'`` (SURVEY §8b, BASELINE "optionally fp8-e4m3, rescored in fp32"): the scan reads an
+        # e4m3 copy (1 byte / element + a per-row scale); the bf16 rows stay resident for the exact re-score.
+        if n == 0:
+            raise TheoremSearchError(-1, "build_index(dtype='fp8') needs the rows up front (the e4m3 copy is built once)")
+        ix.build_fp8_shadow()
+        ix.scan_dtype = "fp8"
     return ix
 
 
@@ -39,7 +54,11 @@ def cos_sim_topk(queries, corpus_index: TheoremIndex, k: int, normalize_queries:
     """(scores float32 [Q, k], ids int64 [Q, k]) sorted by score desc then id asc.  A 1-D query
     returns 1-D rows so ``idx.item()`` / ``scores[i].item()`` consumers (test_app.py:85-88) work."""
     one_d = (queries.ndim if hasattr(queries, "ndim") else np.asarray(queries).ndim) == 1
-    scores, ids = corpus_index.search(queries, k, normalize=normalize_queries, allow_mask=allow_mask)
+    if getattr(corpus_index, "scan_dtype", None) == "fp8" and 2 * k <= TS_IVF_MAX_CANDIDATES:
+        scores, ids = corpus_index.search_fp8(queries, k, rescore_k=min(TS_IVF_MAX_CANDIDATES, max(128, 2 * k)),
+                                              normalize=normalize_queries, allow_mask=allow_mask)
+    else:
+        scores, ids = corpus_index.search(queries, k, normalize=normalize_queries, allow_mask=allow_mask)
     return (scores[0], ids[0]) if one_d else (scores, ids)
 
 

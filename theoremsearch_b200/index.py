@@ -56,6 +56,7 @@ class TheoremIndex:
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         self.dim = int(dim)
         self.dtype = dtype
+        self.scan_dtype = dtype      # "fp8" once build_index(dtype="fp8") has attached the e4m3 scan copy
         h = C.c_void_p()
         check(lib.ts_index_create(C.byref(h), self.device.index, self.dim, _NAME_TO_TS[dtype], int(capacity)))
         self._h = h
