@@ -6,6 +6,7 @@ configs and tuning sweeps.  Each sub-command prints one JSON line per measuremen
   python bench_extra.py small-batch [--rows 10000000]                     nq = 1..4096 latency curve
   python bench_extra.py sweep-scan [--rows 10000000]                      K2 tunables sweep
   python bench_extra.py k1                                                K1 normalise+quantise throughput
+  python bench_extra.py torch-compare                                     library comparator: torch.topk(corpus @ q) vs K2
   python bench_extra.py cfg0                                              configs[0] (73 queries x 100k x 1024 fp32, top-10):
                                                                           host-buffer calls beside the reference expression on the CPU
   python bench_extra.py fp8-scan  [--rows 10000000]                       exhaustive e4m3 scan + exact re-score
@@ -182,6 +183,38 @@ def cmd_cfg0(a):
     out["speedup_single_query_vs_reference"] = out["cpu_reference_single_p50_ms"] / out["gpu_f32_rows_single_p50_ms"]
     out["speedup_batch73_vs_reference"] = out["cpu_reference_batch73_ms"] / out["gpu_f32_rows_batch73_ms"]
     print(json.dumps(out))
+
+
+def cmd_torch_compare(a):
+    """Optional GPU comparator of SURVEY §8(d): the same single-query top-10 done with library calls on the same
+    box — ``torch.topk(corpus_bf16 @ q_bf16, 10)`` (cuBLAS GEMV writing N scores + a separate top-k kernel) —
+    beside K2 on an index of the same shape. Library arithmetic is bf16 x bf16 (the query is rounded), so it is
+    a speed comparator only, not a parity one."""
+    dev = torch.device("cuda", 0)
+    n, d = a.rows, a.dim
+    x = torch.empty((n, d), dtype=torch.bfloat16, device=dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    for lo in range(0, n, 1 << 20):
+        hi = min(n, lo + (1 << 20))
+        blk = torch.randn((hi - lo, d), generator=g, device=dev)
+        x[lo:hi] = torch.nn.functional.normalize(blk, dim=1).to(torch.bfloat16)
+    q = torch.nn.functional.normalize(torch.randn((64, d), generator=g, device=dev), dim=1)
+    qb = q.to(torch.bfloat16)
+    it = itertools.cycle(range(64))
+    ms_mv = timed(lambda: torch.mv(x, qb[next(it)]), 5, 40)
+    ms_lib = timed(lambda: torch.topk(torch.mv(x, qb[next(it)]), a.k), 5, 40)
+    index = ts.TheoremIndex(d, n, dtype="bf16", device=dev)
+    for lo in range(0, n, 1 << 20):
+        index.add(x[lo:min(n, lo + (1 << 20))], normalize=False)
+    ms_k2 = timed(lambda: index.search(q[next(it)], a.k, normalize=False), 5, 40)
+    s_lib, i_lib = torch.topk(torch.mv(x, qb[0]).float(), a.k)
+    s_k2, i_k2 = index.search(q[0], a.k, normalize=False)
+    nbytes = n * d * 2
+    print(json.dumps({"bench": "torch-compare", "rows": n, "dim": d, "k": a.k,
+                      "torch_mv_ms": ms_mv, "torch_mv_topk_ms": ms_lib, "k2_scan_topk_ms": ms_k2,
+                      "torch_gbs": nbytes / (ms_lib * 1e-3) / 1e9, "k2_gbs": nbytes / (ms_k2 * 1e-3) / 1e9,
+                      "speedup_vs_torch": ms_lib / ms_k2,
+                      "top10_overlap_with_bf16_query_library_result": len(set(i_lib.tolist()) & set(i_k2[0].tolist()))}))
 
 
 def timed_graph(fn, warmup, iters):
@@ -495,7 +528,7 @@ def cmd_sharded(a):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("cmd", choices=["batched", "sweep-scan", "small-batch", "ivf", "sharded", "ivf-q1", "ivf-q1-sweep", "fp8-scan", "k1", "cfg0"])
+    ap.add_argument("cmd", choices=["batched", "sweep-scan", "small-batch", "ivf", "sharded", "ivf-q1", "ivf-q1-sweep", "fp8-scan", "k1", "cfg0", "torch-compare"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--dim", type=int, default=1024)
     ap.add_argument("--nq", type=int, default=4096)
@@ -520,7 +553,7 @@ def main():
     a = ap.parse_args()
     if a.k is None:
         a.k = 100 if a.cmd == "batched" else 10
-    {"batched": cmd_batched, "sweep-scan": cmd_sweep_scan, "small-batch": cmd_small_batch, "ivf": cmd_ivf, "sharded": cmd_sharded, "ivf-q1": cmd_ivf_q1, "ivf-q1-sweep": cmd_ivf_q1_sweep, "fp8-scan": cmd_fp8_scan, "k1": cmd_k1, "cfg0": cmd_cfg0}[a.cmd](a)
+    {"batched": cmd_batched, "sweep-scan": cmd_sweep_scan, "small-batch": cmd_small_batch, "ivf": cmd_ivf, "sharded": cmd_sharded, "ivf-q1": cmd_ivf_q1, "ivf-q1-sweep": cmd_ivf_q1_sweep, "fp8-scan": cmd_fp8_scan, "k1": cmd_k1, "cfg0": cmd_cfg0, "torch-compare": cmd_torch_compare}[a.cmd](a)
 
 
 if __name__ == "__main__":
