@@ -161,15 +161,28 @@ TS_API int ts_merge_topk(const uint64_t* keys, int nshards, int nq, int k,
                          const int64_t* shard_base, const int64_t* id_map, float* out_scores,
                          int64_t* out_ids, void* stream);
 
-/* ---- sharded exact search with the exchange fused into the scan kernel ----------------------
+/* ---- sharded exact search with the cross-GPU exchange done by the GPUs themselves ---------------
  * The reference has no sharding; BASELINE.json specifies it: GPU g holds rows
  * [g*N/G, (g+1)*N/G), every GPU scans its shard, the k (score,row) candidates per GPU are exchanged
  * and merged.  ts_search_keys + an NCCL all-gather + ts_merge_topk is the portable form; below the
- * exchange happens INSIDE the scan kernel: the last CTA of each query stores this shard's k packed
- * keys (rebased to global rows) straight into every peer's receive area over NVLink (CUDA-IPC
- * mapped peer memory), raises a sequence flag, spins (bounded) on the peers' flags and merges the G
- * lists — one kernel per query per GPU, no collective launch, no second kernel. */
+ * exchange is device-initiated: the shard's k packed keys (rebased to global rows) are stored straight
+ * into every peer's receive area over NVLink (CUDA-IPC mapped peer memory), a sequence flag is raised,
+ * the peers' flags are awaited (bounded) and the G lists merged — no collective call.
+ *   default (two kernels chained by programmatic dependent launch): the scan kernel writes its per-CTA
+ *     lists; the exchange kernel — resident early, asleep until the scan completes — merges, exchanges
+ *     and writes the result while the scan of the NEXT search already streams the corpus, so a stream
+ *     of searches runs at the local scan rate and no launch gap or peer wait sits on its critical path;
+ *   TS_SHARDED_ONE_KERNEL: the last CTA of the scan kernel does the exchange itself (one launch per
+ *     search, the peers' arrival is awaited inside the scan kernel). */
 typedef struct ts_xchg ts_xchg;
+enum ts_sharded_flags {
+    /* Promise: queries, allow_mask and the corpus are NOT written by the kernel enqueued immediately before
+     * this call on `stream` (e.g. the queries were uploaded earlier). Lets the scan start streaming the
+     * corpus before that kernel — normally the previous search's exchange kernel — has completed. Without
+     * it the scan waits for the preceding kernel first (always correct, loses the overlap). */
+    TS_SHARDED_INDEPENDENT = 1,
+    TS_SHARDED_ONE_KERNEL = 2
+};
 /* One per rank (one process per GPU). max_nq / max_k bound the searches that will use it. */
 TS_API int ts_xchg_create(ts_xchg** out, int device, int world, int rank, int max_nq, int max_k);
 TS_API void ts_xchg_destroy(ts_xchg* xchg);
@@ -179,16 +192,36 @@ TS_API int ts_xchg_handle(const ts_xchg* xchg, void* out_handle);
 /* all_handles: HOST buffer of world handles in rank order (gathered by the caller with any host-side
  * collective). Maps every peer's area. world == 1 needs no handles (NULL). */
 TS_API int ts_xchg_connect(ts_xchg* xchg, const void* all_handles);
-/* 1 if a peer failed to arrive within the kernel's 4 s bound since creation, 0 otherwise. Synchronous. */
+/* Sticky time-out flag: 1 once a search on this rank waited longer than the time-out for a peer's keys
+ * (that search's result was written as score = -inf, id = -1 in every position, never a partial merge),
+ * 0 otherwise. Lives in host-mapped memory: reading it does NOT synchronise the device, so it is checked
+ * at the start of every ts_search_sharded call (TS_ERR_STATE once set). */
 TS_API int ts_xchg_error(const ts_xchg* xchg);
+/* Time-out of the wait for the peers (default 10 s, or the TS_XCHG_TIMEOUT_MS environment variable). */
+TS_API int ts_xchg_set_timeout_ms(ts_xchg* xchg, int64_t ms);
+/* Recovery after a time-out or after the ranks' call sequences diverged (one rank raised between calls):
+ * synchronises the device, clears this rank's receive area, the sequence counter and the error flag.
+ * Collective by contract: every rank calls it between two host-side barriers (nobody may be searching). */
+TS_API int ts_xchg_reset(ts_xchg* xchg);
+/* Searches issued on this exchange so far (identical on every rank while they are in step). */
+TS_API uint32_t ts_xchg_seq(const ts_xchg* xchg);
 /* Exact top-k over the GLOBAL corpus: every rank calls it with the same queries, nq, k in the same
  * order. shard_base = global row of this shard's row 0; id_map = optional device table global row ->
- * caller id. Outputs on every rank. Only the single-query scan path (nq below the batched threshold);
- * larger batches return TS_ERR_UNSUPPORTED (use ts_search_keys + all-gather + ts_merge_topk). */
+ * caller id. Outputs on every rank. flags: ts_sharded_flags. Only the single-query scan path (nq below
+ * the batched threshold); larger batches return TS_ERR_UNSUPPORTED (use ts_search_keys + all-gather +
+ * ts_merge_topk). */
 TS_API int ts_search_sharded(ts_index* index, ts_xchg* xchg, const void* queries, int q_dtype, int nq,
                              int k, int normalize_queries, const uint32_t* allow_mask,
                              int64_t shard_base, const int64_t* id_map, float* out_scores,
-                             int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream);
+                             int64_t* out_ids, void* workspace, size_t workspace_bytes, int flags,
+                             void* stream);
+/* The host-buffer (end-to-end) form: queries HOST [nq, dim] fp32, outputs HOST [nq, k]. Pinned staging,
+ * H2D copy, scan + exchange, D2H copy and the stream synchronise happen inside the call, on a stream and
+ * buffers owned by the exchange handle (created on first use). Returns TS_ERR_STATE, with the outputs
+ * poisoned, if a peer did not arrive in time. */
+TS_API int ts_search_sharded_host(ts_index* index, ts_xchg* xchg, const float* queries, int nq, int k,
+                                  int normalize_queries, const uint32_t* allow_mask, int64_t shard_base,
+                                  const int64_t* id_map, float* out_scores, int64_t* out_ids);
 
 /* Packed candidate key: high 32 bits = order-preserving image of the fp32 score, low 32 bits
  * = 0xFFFFFFFF - row, so unsigned `max` == "higher score, then lower row". 0 = empty slot. */

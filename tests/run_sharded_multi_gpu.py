@@ -4,8 +4,9 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29533 tests/run_sharded_multi_gpu.py
 
-Every rank holds a row shard; the fused in-kernel exchange (ts_search_sharded), the NCCL all-gather +
-K5 path and an unsharded index on rank 0 must return identical scores and ids.  Not collected by
+Every rank holds a row shard; the device-initiated exchange (ts_search_sharded: two-kernel form, its
+independent-stream mode, one-kernel form, host-buffer entry point), the NCCL all-gather + K5 path and an
+unsharded index on rank 0 must return identical scores and ids.  Not collected by
 pytest (needs N GPUs); prints one JSON line and exits non-zero on a mismatch."""
 import json
 import os
@@ -40,9 +41,15 @@ def main():
     for i in range(40):
         ref.append(sh.search(q[i:i + 1], 10))                 # NCCL all-gather + K5
     sh.enable_peer_exchange(max_nq=3, max_k=128)
-    for i in range(40):
-        s, ids = sh.search(q[i:i + 1], 10)                    # fused exchange
-        ok &= torch.equal(s, ref[i][0]) and torch.equal(ids, ref[i][1])
+    for form in ({}, {"independent": True}, {"one_kernel": True}):
+        outs = [sh.search(q[i:i + 1], 10, **form) for i in range(40)]      # device-initiated exchange, back to back
+        torch.cuda.synchronize()
+        for i, (s, ids) in enumerate(outs):
+            ok &= torch.equal(s, ref[i][0]) and torch.equal(ids, ref[i][1])
+    q_host = q.cpu().numpy()
+    for i in range(0, 40, 5):                                 # host-buffer entry point
+        s_h, i_h = sh.search_host(q_host[i], 10)
+        ok &= bool((torch.from_numpy(s_h).to(dev) == ref[i][0]).all()) and bool((torch.from_numpy(i_h).to(dev) == ref[i][1]).all())
     s3, i3 = sh.search(q[:3], 100)
     sh._xchg_saved, sh._xchg = sh._xchg, None
     s3r, i3r = sh.search(q[:3], 100)
@@ -86,13 +93,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
     ms_fused = timed(lambda: sh.search(q[:1], 10))
+    ms_stream = timed(lambda: sh.search(q[:1], 10, independent=True))
+    ms_one_kernel = timed(lambda: sh.search(q[:1], 10, one_kernel=True))
     sh._xchg = None
     ms_gather = timed(lambda: sh.search(q[:1], 10))
     sh._xchg = sh._xchg_saved
     ms_local = timed(lambda: index.search_keys(q[:1], 10))
     if rank == 0:
         print(json.dumps({"check": "sharded_multi_gpu", "world": world, "rows": n, "ok": bool(flag.item()),
-                          "ms_fused_exchange": ms_fused, "ms_allgather_merge": ms_gather, "ms_local_scan_only": ms_local}), flush=True)
+                          "ms_two_kernel_exchange": ms_fused, "ms_two_kernel_independent_stream": ms_stream,
+                          "ms_one_kernel_exchange": ms_one_kernel, "ms_allgather_merge": ms_gather, "ms_local_scan_only": ms_local}), flush=True)
     sh.close()
     dist.destroy_process_group()
     return 0 if flag.item() else 1

@@ -57,7 +57,7 @@ def test_no_gpu_calls_fail_loudly_not_silently():
     import torch
 
     import theoremsearch_b200 as ts
-    assert ts._lib.lib.ts_abi_version() == 1
+    assert ts._lib.lib.ts_abi_version() == 2
     if torch.cuda.is_available():
         pytest.skip("GPU present: the loud-failure path is for CPU-only hosts")
     with pytest.raises(ts.TheoremSearchError):

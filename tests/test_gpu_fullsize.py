@@ -86,6 +86,32 @@ def test_planted_neighbours_tensor_core_path_bitwise_equal(env):
     assert torch.all(sb[:, 1:] <= sb[:, :-1])
 
 
+def test_configs2_shape_4096_queries_top100_bitwise_equal_single_query(env):
+    """BASELINE.json configs[2] at its own shape (compare_embeddings.py:61,105 scaled up): 4096 queries x top-100
+    over 10M x 1024 through K3 — many m-blocks per n-block, every threshold chunk (1024 rows, then x3 growth),
+    candidate buffers near `batch.cap`. 72 of the 4096 result rows (spread over every 256-query n-block, plus the
+    planted query) must equal the single-query scan (K2) bit for bit — scores and ids, all 100 positions."""
+    ts, index, q, others = env
+    g = torch.Generator(device="cuda").manual_seed(4096)
+    batch = torch.randn((4096, D), generator=g, device="cuda")
+    batch[777] = q
+    sb, ib = index.search(batch, 100)
+    fixups = ts.last_batched_fixups()
+    assert fixups >= 0
+    print(f"configs[2] batch: {fixups} of 4096 queries failed the certificate and were re-scanned exactly")
+    assert ib[777].tolist()[:11] == expected_top()
+    picks = sorted({777, 0, 4095} | {b * 256 + o for b in range(16) for o in (3, 97, 130, 255)} | {1000, 2049, 3333})
+    assert len(picks) >= 64
+    for j in picks:
+        s1, i1 = index.search(batch[j], 100)                                  # K2, KPL = 4 instance
+        assert torch.equal(sb[j], s1[0]) and torch.equal(ib[j], i1[0]), j
+    assert torch.all(sb[:, 1:] <= sb[:, :-1])
+    ids = ib.cpu().numpy()
+    assert all(len(set(row.tolist())) == 100 for row in ids[::64])
+    sb2, ib2 = index.search(batch, 100)                                       # repeat runs are bit-identical
+    assert torch.equal(sb, sb2) and torch.equal(ib, ib2)
+
+
 def test_small_batches_cost_about_one_corpus_pass(env):
     """2..16 queries go through K3 with a narrow n-block and must stay near ONE pass over the 20 GB corpus
     (3.3 ms vs 2.85 ms for one query) — a guard against path-selection regressions (a dense-score path meant

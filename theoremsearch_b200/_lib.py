@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libtheoremsearch.so")
 
 TS_F32, TS_BF16, TS_FP8_E4M3, TS_F16 = 0, 1, 2, 3
 TS_MAX_K = 1024
+TS_SHARDED_INDEPENDENT, TS_SHARDED_ONE_KERNEL = 1, 2
 TS_MAX_DIM = 2048
 
 TS_OK = 0
@@ -74,7 +75,11 @@ SIGNATURES = {
     "ts_xchg_handle": (_i, [_p, _p]),
     "ts_xchg_connect": (_i, [_p, _p]),
     "ts_xchg_error": (_i, [_p]),
-    "ts_search_sharded": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _sz, _p]),
+    "ts_xchg_set_timeout_ms": (_i, [_p, _i64]),
+    "ts_xchg_reset": (_i, [_p]),
+    "ts_xchg_seq": (C.c_uint32, [_p]),
+    "ts_search_sharded": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _sz, _i, _p]),
+    "ts_search_sharded_host": (_i, [_p, _p, _p, _i, _i, _i, _p, _i64, _p, _p, _p]),
     "ts_pack_key": (_u64, [C.c_float, C.c_uint32]),
     "ts_unpack_key": (None, [_u64, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "ts_ctx_create": (_i, [C.POINTER(_p), _p, _i, _i]),

@@ -40,7 +40,9 @@ int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64
     p.tickets = nullptr;
     memset(&p.fin, 0, sizeof(p.fin));
     memset(&p.xchg, 0, sizeof(p.xchg));
+    p.pdl = 0;
     if (fused != nullptr) {
+        p.pdl = fused->pdl;
         p.q_raw = fused->q_raw;
         p.q_dtype = fused->q_dtype;
         p.q_normalize = fused->q_normalize;

@@ -58,21 +58,14 @@ struct ScanParams {
     // receive area over NVLink, waits for the peers' keys and merges the world lists — no NCCL call, no
     // second kernel
     XchgDev xchg;
+    // programmatic dependent launch (the sharded stream, ts_search_sharded): bit 0 = this grid was launched
+    // with programmatic stream serialisation — it lets its successor launch at once and waits for its
+    // predecessor (the previous query's exchange kernel, the reader of part_keys) only before it writes
+    // part_keys; bit 1 = queries / mask / corpus may have been written by the kernel that precedes this one
+    // on the stream: wait for it before touching anything (the safe default; without it the scan of query
+    // n+1 streams the corpus while query n's exchange kernel is still merging)
+    int pdl;
 };
-
-__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns2() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 
 __device__ __forceinline__ float load_query_elem(const void* base, int dtype, size_t idx) {
     if (dtype == TS_F32) return __ldg(reinterpret_cast<const float*>(base) + idx);
@@ -96,11 +89,13 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)W * stages * tile_bytes);
     uint64_t* my_bars = bars + warp * stages;
 
+    if (p.pdl & 1) griddep_launch_dependents();
     if (lane == 0) {
         for (int s = 0; s < stages; ++s) mbar_init(&my_bars[s], 1);
         fence_mbar_init();
     }
     __syncwarp();
+    if (p.pdl & 2) griddep_wait();
 
     const int64_t num_tiles = (p.n_rows + R - 1) / R;
     const int64_t gw = (int64_t)blockIdx.x * W + warp;
@@ -240,6 +235,7 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
     __syncthreads();
     if (warp == 0) {
         for (int w = 1; w < W; ++w) merge_sorted_into<KPL>(list, lists + (size_t)w * (KPL * 32), k, k, lane);
+        if (p.pdl & 1) griddep_wait();   // the previous query's exchange kernel has read part_keys
         uint64_t* out = p.part_keys + ((size_t)wi * gridDim.x + blockIdx.x) * k;
 #pragma unroll
         for (int j = 0; j < KPL; ++j) {
@@ -273,49 +269,9 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
             if (p.xchg.world == 0) {
                 merge_lists<KPL>(mp, wi, qi, lists, W);
             } else {
-                // ---- fused exchange. 1) this shard's top-k (local rows) into its own slot of the own area
-                const XchgDev& x = p.xchg;
-                const uint32_t par = x.seq & 1u;
-                const size_t slot_sz = (size_t)x.max_k;
-                const size_t my_slot = (((size_t)par * x.world + x.rank) * x.max_nq + qi) * slot_sz;
-                mp.out_keys = x.my_slots + my_slot - (size_t)qi * slot_sz;   // merge_lists adds qi * out_stride
-                mp.out_stride = (int64_t)slot_sz;
-                mp.out_scores = nullptr;
-                mp.out_ids = nullptr;
-                merge_lists<KPL>(mp, wi, qi, lists, W);
-                // 2) rebased to global rows and stored into every peer's area (NVLink stores), then the flags
-                __threadfence();
-                __syncthreads();
-                for (int i = threadIdx.x; i < k; i += blockDim.x) {
-                    const uint64_t key = rebase_key(__ldcg(x.my_slots + my_slot + i), x.base);
-                    for (int g = 0; g < x.world; ++g) x.peer_slots[g][my_slot + i] = key;
-                }
-                __threadfence_system();
-                __syncthreads();
-                const size_t flag_idx = ((size_t)par * x.world + x.rank) * x.max_nq + qi;
-                if ((int)threadIdx.x < x.world) st_release_sys_u32(x.peer_flags[threadIdx.x] + flag_idx, x.seq);
-                // 3) wait for every rank's keys (bounded: a dead peer must not hang the GPU)
-                if ((int)threadIdx.x < x.world) {
-                    const uint32_t* f = x.my_flags + ((size_t)par * x.world + threadIdx.x) * x.max_nq + qi;
-                    const unsigned long long t0 = globaltimer_ns2();
-                    while (ld_acquire_sys_u32(f) != x.seq) {
-                        if (globaltimer_ns2() - t0 > 4000000000ull) {   // 4 s
-                            *x.error = 1;
-                            break;
-                        }
-                    }
-                }
-                __threadfence_system();
-                __syncthreads();
-                // 4) merge the world lists (already global rows) and emit the final result
-                MergeParams fp = p.fin;
-                fp.keys = x.my_slots + (size_t)par * x.world * x.max_nq * slot_sz;
-                fp.nlists = x.world;
-                fp.k = k;
-                fp.stride_list = (int64_t)x.max_nq * slot_sz;
-                fp.stride_query = (int64_t)slot_sz;
-                fp.list_base = nullptr;
-                merge_lists<KPL>(fp, qi, qi, lists, W);
+                // ---- fused exchange (one-kernel form): this CTA also pushes the shard's keys to the peers,
+                // waits for theirs and merges the world lists
+                exchange_and_merge<KPL>(p.xchg, p.fin, mp, wi, qi, k, lists, W);
             }
         }
     }
@@ -366,7 +322,21 @@ static int launch_r(const ts_index* ix, const ScanParams& p0, int nq, int nparts
         const int64_t tiles = (p.n_rows + R - 1) / R;
         grid = (int)std::min<int64_t>(nparts, std::max<int64_t>(1, (tiles + c.warps * 4 - 1) / (c.warps * 4)));
     }
-    kern<<<dim3(grid, p.qcount ? std::min(nq, 8) : nq), c.warps * 32, c.smem, s>>>(p);
+    if (p.pdl & 1) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid, p.qcount ? std::min(nq, 8) : nq);
+        cfg.blockDim = dim3(c.warps * 32);
+        cfg.dynamicSmemBytes = c.smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        TS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    } else {
+        kern<<<dim3(grid, p.qcount ? std::min(nq, 8) : nq), c.warps * 32, c.smem, s>>>(p);
+    }
     TS_LAUNCH_CHECK();
     if (ev1) TS_CHECK_CUDA(cudaEventRecord(ev1, s));
     return TS_OK;

@@ -75,4 +75,70 @@ int launch_merge(const uint64_t* keys, int nlists, int nq, int k, bool query_maj
                                 out_ids, s);
 }
 
+// ---- exchange kernel of the sharded exact search (ts_search_sharded, two-kernel form) ----------------------
+// One CTA per query. Launched with programmatic stream serialisation right behind the scan kernel of the
+// same query: it becomes resident while the scan is still streaming (256 threads and 2-64 KB of shared
+// memory fit beside the scan's CTA), immediately lets ITS successor — the scan of the next query — launch,
+// and then sleeps in griddepcontrol.wait until the scan has completed and its per-CTA lists are visible.
+// The next scan therefore starts filling SMs the moment this query's scan CTAs retire, while this CTA
+// merges, pushes the keys to the peers over NVLink, waits for theirs and writes the result: neither the
+// launch gap nor the cross-GPU wait sits on the scan stream's critical path.
+template <int KPL>
+__global__ void __launch_bounds__(256) xchg_finish_kernel(const MergeParams local, const MergeParams fin,
+                                                           const XchgDev x) {
+    extern __shared__ __align__(16) uint8_t merge_smem[];
+    uint64_t* lists = reinterpret_cast<uint64_t*>(merge_smem);  // [8][KPL*32]
+    griddep_launch_dependents();
+    griddep_wait();
+    const int qi = blockIdx.x;
+    exchange_and_merge<KPL>(x, fin, local, qi, qi, local.k, lists, 8);
+}
+
+int launch_xchg_finish(const uint64_t* part_keys, int nparts, int nq, int k, const XchgDev& x, const int64_t* id_map,
+                       float* out_scores, int64_t* out_ids, cudaStream_t s) {
+    TS_REQUIRE(k >= 1 && k <= TS_MAX_K && nq >= 1, TS_ERR_BAD_ARG, "xchg_finish: nq=%d k=%d", nq, k);
+    MergeParams local;
+    memset(&local, 0, sizeof(local));
+    local.keys = part_keys;
+    local.nlists = nparts;
+    local.nq = nq;
+    local.k = k;
+    local.stride_list = k;
+    local.stride_query = (int64_t)nparts * k;
+    MergeParams fin;
+    memset(&fin, 0, sizeof(fin));
+    fin.nq = nq;
+    fin.k = k;
+    fin.id_map = id_map;
+    fin.out_scores = out_scores;
+    fin.out_ids = out_ids;
+    fin.out_stride = k;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nq);
+    cfg.blockDim = dim3(256);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (k <= 32) {
+        cfg.dynamicSmemBytes = 8 * 32 * 8;
+        TS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, xchg_finish_kernel<1>, local, fin, x));
+    } else if (k <= 128) {
+        cfg.dynamicSmemBytes = 8 * 128 * 8;
+        TS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, xchg_finish_kernel<4>, local, fin, x));
+    } else if (k <= 256) {
+        cfg.dynamicSmemBytes = 8 * 256 * 8;
+        TS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, xchg_finish_kernel<8>, local, fin, x));
+    } else {
+        cfg.dynamicSmemBytes = 8 * 1024 * 8;
+        TS_CHECK_CUDA(cudaFuncSetAttribute(xchg_finish_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           8 * 1024 * 8));
+        TS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, xchg_finish_kernel<32>, local, fin, x));
+    }
+    TS_LAUNCH_CHECK();
+    return TS_OK;
+}
+
 }  // namespace ts

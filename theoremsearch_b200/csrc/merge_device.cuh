@@ -180,4 +180,92 @@ __device__ __forceinline__ void merge_lists(const MergeParams& p, int qi, int qo
     __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------- peer exchange
+__device__ __forceinline__ void griddep_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns2() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// The cross-GPU step of the sharded exact search, run by ALL threads of one CTA for query `qi`:
+//   1) merge this shard's per-CTA lists (`local`, work item `wi`) into the shard's top-k (local rows), parked
+//      in this rank's own slot of its own receive area;
+//   2) rebase the keys to global rows and store them into EVERY rank's receive area (plain stores through the
+//      CUDA-IPC mappings: NVLink for the peers), system-scope fence, then raise the (rank, query) sequence flag
+//      in every area with st.release.sys;
+//   3) wait (ld.acquire.sys, bounded by x.timeout_ns) until all `world` flags of this query carry x.seq;
+//   4) merge the world lists and write the final (scores, ids) — or, if a peer did not arrive in time, raise the
+//      sticky error flag (host-mapped memory: the host sees it without synchronising) and write a poisoned
+//      result (-inf, -1) so that a stale or partial merge can never pass for an answer.
+// Slots and flags are double-buffered by sequence parity: a rank finishes query s only after every rank has
+// pushed s, so nobody can be more than one query ahead of a reader.
+template <int KPL>
+__device__ __forceinline__ void exchange_and_merge(const XchgDev& x, const MergeParams& fin, MergeParams local, int wi,
+                                                   int qi, int k, uint64_t* lists, int nwarps) {
+    __shared__ int s_timed_out;
+    const uint32_t par = x.seq & 1u;
+    const size_t slot_sz = (size_t)x.max_k;
+    const size_t my_slot = (((size_t)par * x.world + x.rank) * x.max_nq + qi) * slot_sz;
+    local.out_keys = x.my_slots + my_slot - (size_t)qi * slot_sz;   // merge_lists adds qi * out_stride
+    local.out_stride = (int64_t)slot_sz;
+    local.out_scores = nullptr;
+    local.out_ids = nullptr;
+    local.id_map = nullptr;
+    if (threadIdx.x == 0) s_timed_out = 0;
+    merge_lists<KPL>(local, wi, qi, lists, nwarps);
+    __threadfence();
+    __syncthreads();
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const uint64_t key = rebase_key(__ldcg(x.my_slots + my_slot + i), x.base);
+        for (int g = 0; g < x.world; ++g) x.peer_slots[g][my_slot + i] = key;
+    }
+    __threadfence_system();
+    __syncthreads();
+    const size_t flag_idx = ((size_t)par * x.world + x.rank) * x.max_nq + qi;
+    if ((int)threadIdx.x < x.world) {
+        if (!x.debug_no_flag) st_release_sys_u32(x.peer_flags[threadIdx.x] + flag_idx, x.seq);
+        const uint32_t* f = x.my_flags + ((size_t)par * x.world + threadIdx.x) * x.max_nq + qi;
+        const unsigned long long t0 = globaltimer_ns2();
+        while (ld_acquire_sys_u32(f) != x.seq) {
+            if (globaltimer_ns2() - t0 > x.timeout_ns) {
+                s_timed_out = 1;
+                *reinterpret_cast<volatile int*>(x.error) = 1;
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (s_timed_out) {
+        for (int i = threadIdx.x; i < k; i += blockDim.x) {
+            if (fin.out_keys) fin.out_keys[(size_t)qi * fin.out_stride + i] = 0ull;
+            if (fin.out_scores) fin.out_scores[(size_t)qi * k + i] = -INFINITY;
+            if (fin.out_ids) fin.out_ids[(size_t)qi * k + i] = -1;
+        }
+        __syncthreads();
+        return;
+    }
+    MergeParams w = fin;
+    w.keys = x.my_slots + (size_t)par * x.world * x.max_nq * slot_sz;
+    w.nlists = x.world;
+    w.k = k;
+    w.stride_list = (int64_t)x.max_nq * slot_sz;
+    w.stride_query = (int64_t)slot_sz;
+    w.list_base = nullptr;     // already global rows
+    merge_lists<KPL>(w, qi, qi, lists, nwarps);
+}
+
 }  // namespace ts

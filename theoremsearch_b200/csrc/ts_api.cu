@@ -88,6 +88,7 @@ int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k,
     f.out_scores = out_scores;
     f.out_ids = out_ids;
     memset(&f.xchg, 0, sizeof(f.xchg));
+    f.pdl = 0;
     return launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, w.part_keys, w.nparts,
                             s, ev0, ev1, nullptr, nullptr, &f);
 }
@@ -98,7 +99,7 @@ using namespace ts;
 
 extern "C" {
 
-int ts_abi_version(void) { return 1; }
+int ts_abi_version(void) { return 2; }
 
 const char* ts_last_error(void) { return t_error.c_str(); }
 
@@ -526,6 +527,10 @@ int ts_xchg_create(ts_xchg** out, int device, int world, int rank, int max_nq, i
     x->rank = rank;
     x->max_nq = max_nq;
     x->max_k = max_k;
+    if (const char* env = getenv("TS_XCHG_TIMEOUT_MS")) {
+        const long long ms = atoll(env);
+        if (ms > 0) x->timeout_ns = (unsigned long long)ms * 1000000ull;
+    }
     x->bytes = xchg_slot_count(x) * sizeof(uint64_t) + xchg_flag_count(x) * sizeof(uint32_t);
     cudaError_t e = cudaMalloc(&x->base, x->bytes);
     if (e == cudaSuccess) e = cudaMemset(x->base, 0, x->bytes);
@@ -533,8 +538,11 @@ int ts_xchg_create(ts_xchg** out, int device, int world, int rank, int max_nq, i
     if (e == cudaSuccess) e = cudaMalloc(&x->d_peer_flags, 16 * sizeof(void*));
     if (e == cudaSuccess) e = cudaMalloc(&x->d_tickets, (size_t)max_nq * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(x->d_tickets, 0, (size_t)max_nq * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&x->d_error, sizeof(int));
-    if (e == cudaSuccess) e = cudaMemset(x->d_error, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&x->h_error, sizeof(int), cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        *x->h_error = 0;
+        e = cudaHostGetDevicePointer((void**)&x->d_error, x->h_error, 0);
+    }
     if (e != cudaSuccess) {
         set_error("xchg_create: allocation failed: %s", cudaGetErrorString(e));
         ts_xchg_destroy(x);
@@ -558,7 +566,15 @@ void ts_xchg_destroy(ts_xchg* x) {
     cudaFree(x->d_peer_slots);
     cudaFree(x->d_peer_flags);
     cudaFree(x->d_tickets);
-    cudaFree(x->d_error);
+    cudaFreeHost(x->h_error);
+    cudaFreeHost(x->h_queries);
+    cudaFreeHost(x->h_scores);
+    cudaFreeHost(x->h_ids);
+    cudaFree(x->d_queries);
+    cudaFree(x->d_scores);
+    cudaFree(x->d_ids);
+    cudaFree(x->workspace);
+    if (x->stream) cudaStreamDestroy(x->stream);
     delete x;
 }
 
@@ -597,20 +613,41 @@ int ts_xchg_connect(ts_xchg* x, const void* all_handles) {
 }
 
 int ts_xchg_error(const ts_xchg* x) {
-    if (!x) return -1;
-    DeviceGuard g(x->device);
-    int v = -1;
-    if (cudaMemcpy(&v, x->d_error, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    return v;
+    if (!x || !x->h_error) return -1;
+    return *reinterpret_cast<volatile int*>(x->h_error);   // host-mapped: no device synchronisation
 }
+
+int ts_xchg_set_timeout_ms(ts_xchg* x, int64_t ms) {
+    TS_REQUIRE(x != nullptr && ms > 0, TS_ERR_BAD_ARG, "xchg_set_timeout_ms: ms=%lld", (long long)ms);
+    x->timeout_ns = (unsigned long long)ms * 1000000ull;
+    return TS_OK;
+}
+
+int ts_xchg_reset(ts_xchg* x) {
+    TS_REQUIRE(x != nullptr, TS_ERR_BAD_ARG, "xchg_reset: NULL handle");
+    DeviceGuard g(x->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "xchg_reset: cannot select CUDA device %d", x->device);
+    TS_CHECK_CUDA(cudaDeviceSynchronize());
+    TS_CHECK_CUDA(cudaMemset(x->base, 0, x->bytes));
+    TS_CHECK_CUDA(cudaMemset(x->d_tickets, 0, (size_t)x->max_nq * sizeof(uint32_t)));
+    TS_CHECK_CUDA(cudaDeviceSynchronize());
+    *reinterpret_cast<volatile int*>(x->h_error) = 0;
+    x->seq = 0;
+    return TS_OK;
+}
+
+uint32_t ts_xchg_seq(const ts_xchg* x) { return x ? x->seq : 0u; }
 
 int ts_search_sharded(ts_index* ix, ts_xchg* x, const void* queries, int q_dtype, int nq, int k, int normalize_queries,
                       const uint32_t* allow_mask, int64_t shard_base, const int64_t* id_map, float* out_scores,
-                      int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream) {
+                      int64_t* out_ids, void* workspace, size_t workspace_bytes, int flags, void* stream) {
     TS_REQUIRE(ix != nullptr && x != nullptr, TS_ERR_BAD_ARG, "search_sharded: NULL handle");
     TS_REQUIRE(x->connected, TS_ERR_STATE, "search_sharded: ts_xchg_connect has not been called");
     TS_REQUIRE(x->device == ix->device, TS_ERR_BAD_ARG, "search_sharded: index on device %d, exchange on %d", ix->device,
                x->device);
+    TS_REQUIRE(*reinterpret_cast<volatile int*>(x->h_error) == 0, TS_ERR_STATE,
+               "search_sharded: an earlier search timed out waiting for a peer (its result was poisoned with -inf / -1); "
+               "bring every rank to a barrier and call ts_xchg_reset before searching again");
     TS_REQUIRE(nq >= 1 && nq <= x->max_nq, TS_ERR_CAPACITY, "search_sharded: nq=%d outside [1, %d]", nq, x->max_nq);
     TS_REQUIRE(k >= 1 && k <= x->max_k, TS_ERR_CAPACITY, "search_sharded: k=%d outside [1, %d]", k, x->max_k);
     TS_REQUIRE(!use_batched(ix, nq), TS_ERR_UNSUPPORTED,
@@ -626,29 +663,90 @@ int ts_search_sharded(ts_index* ix, ts_xchg* x, const void* queries, int q_dtype
     SearchWs w = carve_ws(ix, nq, k, workspace);
     TS_REQUIRE(workspace_bytes >= w.bytes, TS_ERR_CAPACITY, "search_sharded: workspace %zu < %zu bytes", workspace_bytes,
                w.bytes);
-    // the exchange context owns self-cleaning tickets: the whole search is ONE stream operation (the kernel)
+    XchgDev xd;
+    xd.peer_slots = x->d_peer_slots;
+    xd.peer_flags = x->d_peer_flags;
+    xd.my_slots = x->slots;
+    xd.my_flags = x->flags;
+    xd.error = x->d_error;
+    xd.world = x->world;
+    xd.rank = x->rank;
+    xd.max_nq = x->max_nq;
+    xd.max_k = x->max_k;
+    xd.seq = ++x->seq;
+    xd.base = shard_base;
+    xd.timeout_ns = x->timeout_ns;
+    xd.debug_no_flag = tunables().xchg_debug_no_flag;
     ScanFused f;
     f.q_raw = queries;
     f.q_dtype = q_dtype;
     f.q_normalize = normalize_queries;
-    f.tickets = x->d_tickets;
     f.id_map = id_map;
     f.out_keys = nullptr;
-    f.out_scores = out_scores;
-    f.out_ids = out_ids;
-    f.xchg.peer_slots = x->d_peer_slots;
-    f.xchg.peer_flags = x->d_peer_flags;
-    f.xchg.my_slots = x->slots;
-    f.xchg.my_flags = x->flags;
-    f.xchg.error = x->d_error;
-    f.xchg.world = x->world;
-    f.xchg.rank = x->rank;
-    f.xchg.max_nq = x->max_nq;
-    f.xchg.max_k = x->max_k;
-    f.xchg.seq = ++x->seq;
-    f.xchg.base = shard_base;
-    return launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, w.part_keys, w.nparts, s,
-                            nullptr, nullptr, nullptr, nullptr, &f);
+    if (flags & TS_SHARDED_ONE_KERNEL) {
+        // the exchange context owns self-cleaning tickets: the whole search is ONE stream operation (the kernel)
+        f.tickets = x->d_tickets;
+        f.out_scores = out_scores;
+        f.out_ids = out_ids;
+        f.xchg = xd;
+        f.pdl = 0;
+        return launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, w.part_keys, w.nparts, s,
+                                nullptr, nullptr, nullptr, nullptr, &f);
+    }
+    // two kernels chained by programmatic dependent launch: the scan writes its per-CTA lists, the exchange
+    // kernel (resident early, asleep until the scan completes) merges, exchanges and writes the result while
+    // the NEXT search's scan already streams the corpus
+    f.tickets = nullptr;
+    f.out_scores = nullptr;
+    f.out_ids = nullptr;
+    memset(&f.xchg, 0, sizeof(f.xchg));
+    f.pdl = 1 | ((flags & TS_SHARDED_INDEPENDENT) ? 0 : 2);
+    int rc = launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, w.part_keys, w.nparts, s,
+                              nullptr, nullptr, nullptr, nullptr, &f);
+    if (rc) return rc;
+    return launch_xchg_finish(w.part_keys, w.nparts, nq, k, xd, id_map, out_scores, out_ids, s);
+}
+
+int ts_search_sharded_host(ts_index* ix, ts_xchg* x, const float* queries, int nq, int k, int normalize_queries,
+                           const uint32_t* allow_mask, int64_t shard_base, const int64_t* id_map, float* out_scores,
+                           int64_t* out_ids) {
+    TS_REQUIRE(ix != nullptr && x != nullptr, TS_ERR_BAD_ARG, "search_sharded_host: NULL handle");
+    TS_REQUIRE(nq >= 1 && nq <= x->max_nq, TS_ERR_CAPACITY, "search_sharded_host: nq=%d outside [1, %d]", nq, x->max_nq);
+    TS_REQUIRE(k >= 1 && k <= x->max_k, TS_ERR_CAPACITY, "search_sharded_host: k=%d outside [1, %d]", k, x->max_k);
+    TS_REQUIRE(queries && out_scores && out_ids, TS_ERR_BAD_ARG, "search_sharded_host: NULL buffer");
+    DeviceGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "search_sharded_host: cannot select CUDA device %d", ix->device);
+    if (x->stream == nullptr || x->host_dim != ix->dim) {   // first call: stream, pinned staging, device buffers
+        TS_REQUIRE(x->stream == nullptr, TS_ERR_BAD_ARG, "search_sharded_host: the exchange was set up for dim %d", x->host_dim);
+        const size_t qb = (size_t)x->max_nq * ix->dim * sizeof(float);
+        const size_t sb = (size_t)x->max_nq * x->max_k * sizeof(float);
+        const size_t ib = (size_t)x->max_nq * x->max_k * sizeof(int64_t);
+        x->workspace_bytes = carve_ws(ix, x->max_nq, x->max_k, nullptr).bytes;
+        TS_CHECK_CUDA(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
+        TS_CHECK_CUDA(cudaMallocHost(&x->h_queries, qb));
+        TS_CHECK_CUDA(cudaMallocHost(&x->h_scores, sb));
+        TS_CHECK_CUDA(cudaMallocHost(&x->h_ids, ib));
+        TS_CHECK_CUDA(cudaMalloc(&x->d_queries, qb));
+        TS_CHECK_CUDA(cudaMalloc(&x->d_scores, sb));
+        TS_CHECK_CUDA(cudaMalloc(&x->d_ids, ib));
+        TS_CHECK_CUDA(cudaMalloc(&x->workspace, x->workspace_bytes));
+        x->host_dim = ix->dim;
+    }
+    const size_t qb = (size_t)nq * ix->dim * sizeof(float);
+    memcpy(x->h_queries, queries, qb);
+    TS_CHECK_CUDA(cudaMemcpyAsync(x->d_queries, x->h_queries, qb, cudaMemcpyHostToDevice, x->stream));
+    int rc = ts_search_sharded(ix, x, x->d_queries, TS_F32, nq, k, normalize_queries, allow_mask, shard_base, id_map,
+                               x->d_scores, x->d_ids, x->workspace, x->workspace_bytes, 0, x->stream);
+    if (rc) return rc;
+    const size_t n = (size_t)nq * k;
+    TS_CHECK_CUDA(cudaMemcpyAsync(x->h_scores, x->d_scores, n * sizeof(float), cudaMemcpyDeviceToHost, x->stream));
+    TS_CHECK_CUDA(cudaMemcpyAsync(x->h_ids, x->d_ids, n * sizeof(int64_t), cudaMemcpyDeviceToHost, x->stream));
+    TS_CHECK_CUDA(cudaStreamSynchronize(x->stream));
+    memcpy(out_scores, x->h_scores, n * sizeof(float));
+    memcpy(out_ids, x->h_ids, n * sizeof(int64_t));
+    TS_REQUIRE(*reinterpret_cast<volatile int*>(x->h_error) == 0, TS_ERR_STATE,
+               "search_sharded_host: timed out waiting for a peer's keys; the result was poisoned (-inf / -1)");
+    return TS_OK;
 }
 
 // ------------------------------------------------------------------------------------ tunables
@@ -672,6 +770,7 @@ static int* tunable_slot(const char* name) {
     if (!strcmp(name, "ivf.timeline")) return &t.ivf_timeline;
     if (!strcmp(name, "ivf.group_min_nq")) return &t.ivf_group_min_nq;
     if (!strcmp(name, "ivf.group_mma")) return &t.ivf_group_mma;
+    if (!strcmp(name, "xchg.debug_no_flag")) return &t.xchg_debug_no_flag;
     if (!strcmp(name, "ivf.group_min_lists")) return &t.ivf_group_min_lists;
     return nullptr;
 }

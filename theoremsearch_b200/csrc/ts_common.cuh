@@ -92,6 +92,7 @@ struct Tunables {
     int ivf_timeline = 0;       // 1 = K4b CTAs record globaltimer stamps per phase (ts_debug_ivf_timeline)
     int ivf_group_min_nq = 16;  // batches at least this large take the list-major scan (K4d); 0 = never (sweep: profiles/sweep_ivf_batch_r1.txt)
     int ivf_group_min_lists = 0;  // K4d needs at least this many lists (and query-list pairs); 0 = 4 x SM count
+    int xchg_debug_no_flag = 0; // test hook: the sharded exchange does not raise its own flag, so its wait times out
     int ivf_group_mma = 1;      // K4d scoring: 1 / 2 = mma.sync f16 tensor-core variant with 8 / 16 queries per group,
                                 // 0 = packed HFMA2 on the CUDA cores (4 queries per group)
 };
@@ -358,9 +359,23 @@ struct ts_xchg {
     uint64_t** d_peer_slots = nullptr;   // device array [world]
     uint32_t** d_peer_flags = nullptr;   // device array [world]
     uint32_t* d_tickets = nullptr;    // [max_nq] last-CTA tickets: zero at creation, left zero by every kernel (no per-call memset)
-    int* d_error = nullptr;           // device flag: 1 = a peer did not arrive within the time-out
+    int* h_error = nullptr;           // sticky flag in pinned, device-mapped host memory: 1 = a peer did not arrive
+                                      // within the time-out; the host reads it without synchronising
+    int* d_error = nullptr;           // the device-side address of h_error
     uint32_t seq = 0;                 // searches issued so far (identical on every rank)
+    unsigned long long timeout_ns = 10000000000ull;   // 10 s: covers lazy module loads and per-rank host skew
     bool connected = false;
+    // host-buffer path (ts_search_sharded_host): stream, pinned staging, device buffers, workspace
+    cudaStream_t stream = nullptr;
+    float* h_queries = nullptr;
+    float* h_scores = nullptr;
+    int64_t* h_ids = nullptr;
+    float* d_queries = nullptr;
+    float* d_scores = nullptr;
+    int64_t* d_ids = nullptr;
+    void* workspace = nullptr;
+    size_t workspace_bytes = 0;
+    int host_dim = 0;
 };
 
 struct ts_ctx {
@@ -411,10 +426,12 @@ struct XchgDev {
     uint32_t* const* peer_flags;   // [world] every rank's flag area (mapped)
     uint64_t* my_slots;
     uint32_t* my_flags;
-    int* error;
+    int* error;                    // sticky time-out flag in host-mapped memory
     int world, rank, max_nq, max_k;
     uint32_t seq;
     int64_t base;                  // global row of this shard's row 0
+    unsigned long long timeout_ns; // bound on the wait for the peers' flags
+    int debug_no_flag;             // test hook ("xchg.debug_no_flag"): do not raise the own flag -> the wait times out
 };
 struct ScanFused {
     const void* q_raw;      // caller's queries [nq, dim] (nullptr: read prepared fp32 queries instead)
@@ -425,12 +442,17 @@ struct ScanFused {
     float* out_scores;
     int64_t* out_ids;
     XchgDev xchg;           // world > 0: exchange the shard results with the peers inside the kernel
+    int pdl;                // ScanParams::pdl
 };
 int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64_t n_rows,
                      const float* queries_f32, int nq, int k, const uint32_t* allow_mask,
                      uint64_t* part_keys, int nparts, cudaStream_t s, cudaEvent_t ev0,
                      cudaEvent_t ev1, const int* qlist = nullptr, const int* qcount = nullptr,
                      const ScanFused* fused = nullptr);
+// exchange kernel of the two-kernel sharded search (k5_merge.cu): merges the scan's per-CTA lists, exchanges the
+// shard's keys with the peers, merges the world lists. Launched with programmatic stream serialisation.
+int launch_xchg_finish(const uint64_t* part_keys, int nparts, int nq, int k, const XchgDev& x, const int64_t* id_map,
+                       float* out_scores, int64_t* out_ids, cudaStream_t s);
 // K5: lists[nlists][nq][k] (list-major) or [nq][nlists][k] (query-major) -> top-k
 int launch_merge(const uint64_t* keys, int nlists, int nq, int k, bool query_major,
                  const int64_t* list_base, const int64_t* id_map, uint64_t* out_keys,

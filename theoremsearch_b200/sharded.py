@@ -21,6 +21,11 @@ from ._lib import check, lib
 from .index import _TORCH_TO_TS, TheoremIndex, _stream_ptr, merge_topk
 
 
+class PeerExchangeTimeout(_lib.TheoremSearchError):
+    """A rank waited longer than the exchange time-out for a peer's keys. The affected result holds
+    score = -inf / id = -1 in every position; call ``ShardedIndex.resync()`` on every rank to recover."""
+
+
 def shard_bounds(n_rows: int, world_size: int) -> list[tuple[int, int]]:
     """Contiguous shards [g*N/G, (g+1)*N/G)."""
     return [((g * n_rows) // world_size, ((g + 1) * n_rows) // world_size) for g in range(world_size)]
@@ -123,30 +128,91 @@ class ShardedIndex:
         return (self._xchg is not None and nq <= self._xchg_limits[0] and k <= self._xchg_limits[1]
                 and nq < _lib.get_tunable("batch.min_nq"))
 
-    def _search_fused(self, queries, k: int, normalize: bool, allow_mask):
+    def _search_fused(self, queries, k: int, normalize: bool, allow_mask, independent: bool = False,
+                      one_kernel: bool = False):
         ix = self.local
         q = ix._prep_queries(queries)
         nq = q.shape[0]
         scores = torch.empty((nq, k), dtype=torch.float32, device=ix.device)
         ids = torch.empty((nq, k), dtype=torch.int64, device=ix.device)
         ws = ix._workspace(nq, k)
-        check(lib.ts_search_sharded(ix.handle, self._xchg, q.data_ptr(), _TORCH_TO_TS[q.dtype], nq, int(k),
-                                    int(normalize), ix._mask_ptr(allow_mask), int(self.lo),
-                                    self.id_map.data_ptr() if self.id_map is not None else None,
-                                    scores.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(),
-                                    _stream_ptr(ix.device)))
+        flags = (_lib.TS_SHARDED_INDEPENDENT if independent else 0) | (_lib.TS_SHARDED_ONE_KERNEL if one_kernel else 0)
+        try:
+            check(lib.ts_search_sharded(ix.handle, self._xchg, q.data_ptr(), _TORCH_TO_TS[q.dtype], nq, int(k),
+                                        int(normalize), ix._mask_ptr(allow_mask), int(self.lo),
+                                        self.id_map.data_ptr() if self.id_map is not None else None,
+                                        scores.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(), flags,
+                                        _stream_ptr(ix.device)))
+        except _lib.TheoremSearchError as e:
+            if e.code == -6 and self.peer_exchange_error():
+                raise PeerExchangeTimeout(e.code, _lib.last_error()) from None
+            raise
         q.record_stream(torch.cuda.current_stream(ix.device))
         return scores, ids
 
+    def search_host(self, queries: np.ndarray, k: int, normalize: bool = True,
+                    allow_mask: Optional[torch.Tensor] = None):
+        """End-to-end call with HOST buffers, the sharded counterpart of ``TheoremIndex.search_host``: numpy
+        fp32 queries in, numpy (scores [nq, k], ids [nq, k]) out on every rank; staging, H2D, scan + exchange,
+        D2H and the synchronise happen inside ``ts_search_sharded_host``."""
+        q = np.ascontiguousarray(np.asarray(queries, dtype=np.float32))
+        if q.ndim == 1:
+            q = q[None, :]
+        nq = q.shape[0]
+        if q.shape[1] != self.local.dim:
+            raise _lib.TheoremSearchError(-1, f"queries must be [nq, {self.local.dim}], got {q.shape}")
+        if not self._fused_ok(nq, k):
+            s, i = self.search(torch.from_numpy(q).to(self.local.device), k, normalize, allow_mask)
+            return s.cpu().numpy(), i.cpu().numpy()
+        scores = np.empty((nq, k), dtype=np.float32)
+        ids = np.empty((nq, k), dtype=np.int64)
+        try:
+            check(lib.ts_search_sharded_host(self.local.handle, self._xchg, q.ctypes.data, nq, int(k), int(normalize),
+                                             self.local._mask_ptr(allow_mask), int(self.lo),
+                                             self.id_map.data_ptr() if self.id_map is not None else None,
+                                             scores.ctypes.data, ids.ctypes.data))
+        except _lib.TheoremSearchError as e:
+            if e.code == -6 and self.peer_exchange_error():
+                raise PeerExchangeTimeout(e.code, _lib.last_error()) from None
+            raise
+        return scores, ids
+
     def peer_exchange_error(self) -> bool:
+        """True once a search on this rank gave up waiting for a peer (its result was poisoned with -inf / -1).
+        Reads a host-mapped flag: no device synchronisation, cheap enough to poll after every result."""
         return self._xchg is not None and int(lib.ts_xchg_error(self._xchg)) != 0
 
+    def set_exchange_timeout(self, seconds: float) -> None:
+        check(lib.ts_xchg_set_timeout_ms(self._xchg, int(seconds * 1000)))
+
+    def resync(self) -> None:
+        """Collective recovery after ``PeerExchangeTimeout`` or after the ranks' call sequences diverged (one rank
+        raised between two searches): barrier, clear every rank's receive area / sequence counter / error flag,
+        barrier. A rank that timed out stops pushing keys, so its peers time out on their next search too and
+        every rank ends up here."""
+        if self._xchg is None:
+            return
+        torch.cuda.synchronize(self.local.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        check(lib.ts_xchg_reset(self._xchg))
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
     def search(self, queries: torch.Tensor, k: int, normalize: bool = True,
-               allow_mask: Optional[torch.Tensor] = None):
-        """Replicated queries [nq, D] -> global (scores [nq, k], ids [nq, k]) on every rank."""
+               allow_mask: Optional[torch.Tensor] = None, independent: bool = False, one_kernel: bool = False):
+        """Replicated queries [nq, D] -> global (scores [nq, k], ids [nq, k]) on every rank.
+
+        With the peer exchange enabled a small batch is a scan kernel plus an exchange kernel chained by
+        programmatic dependent launch (``ts_search_sharded``). ``independent=True`` promises that the queries /
+        mask are not produced by the kernel enqueued just before this call on the current stream; the scan then
+        starts streaming the corpus while the previous search's exchange kernel is still merging, so a stream
+        of searches runs at the local scan rate. ``one_kernel=True`` selects the form where the scan kernel's
+        last CTA does the exchange itself. Raises ``PeerExchangeTimeout`` if an EARLIER search timed out waiting
+        for a peer (the flag is sticky; see ``resync``)."""
         nq = 1 if queries.dim() == 1 else queries.shape[0]
         if self._fused_ok(nq, k):
-            return self._search_fused(queries, k, normalize, allow_mask)
+            return self._search_fused(queries, k, normalize, allow_mask, independent, one_kernel)
         keys = self._local_search(queries, k, normalize, allow_mask)          # [nq, k] packed keys
         if self.world == 1:
             gathered = keys.unsqueeze(0)
