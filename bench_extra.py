@@ -5,6 +5,7 @@ configs and tuning sweeps.  Each sub-command prints one JSON line per measuremen
   python bench_extra.py batched   [--rows 10000000 --nq 4096 --k 100]     configs[2]: K3 tcgen05 GEMM + top-k
   python bench_extra.py small-batch [--rows 10000000]                     nq = 1..4096 latency curve
   python bench_extra.py sweep-scan [--rows 10000000]                      K2 tunables sweep
+  python bench_extra.py shard-stream [--rows 1250000 --iters 400]          per-query cost of every sharded search form at the shard size (1 GPU)
   python bench_extra.py k1                                                K1 normalise+quantise throughput
   python bench_extra.py torch-compare                                     library comparator: torch.topk(corpus @ q) vs K2
   python bench_extra.py cfg0                                              configs[0] (73 queries x 100k x 1024 fp32, top-10):
@@ -526,9 +527,42 @@ def cmd_sharded(a):
         os._exit(0)
 
 
+def cmd_shard_stream(a):
+    """One GPU holding ONE shard of the N-way sharded corpus (default 1.25M rows = 10M / 8), world = 1 exchange:
+    the per-step cost of every search form at the shard size, without a second GPU. Isolates what the
+    programmatic-dependent-launch chain buys (launch gap, merge tail) from cross-GPU skew."""
+    from theoremsearch_b200.sharded import ShardedIndex
+    dev = torch.device("cuda", 0)
+    index = build(a.rows, a.dim, dev)
+    sh = ShardedIndex(index, a.rows).enable_peer_exchange(max_nq=1, max_k=32)
+    q = synthetic.make_queries(256, a.dim, dev)
+    torch.cuda.synchronize()
+    it = itertools.count()
+    forms = {
+        "plain ts_search (one kernel, last-CTA merge)": lambda: index.search(q[next(it) % 256:][:1], a.k),
+        "sharded one-kernel": lambda: sh.search(q[next(it) % 256:][:1], a.k, one_kernel=True),
+        "sharded scan+exchange (PDL), dependent": lambda: sh.search(q[next(it) % 256:][:1], a.k),
+        "sharded scan+exchange (PDL), independent stream": lambda: sh.search(q[next(it) % 256:][:1], a.k, independent=True),
+    }
+    bytes_ = a.rows * a.dim * 2
+    out = {"bench": "shard-stream", "rows": a.rows, "dim": a.dim, "k": a.k, "iters": a.iters}
+    for name, fn in forms.items():
+        ms = timed(fn, 20, a.iters)
+        out[name] = {"ms_per_query": ms, "gbs": bytes_ / (ms * 1e-3) / 1e9}
+    for i in range(3):
+        index.search_host(q[i].cpu().numpy(), a.k, timing=True)
+    km = []
+    for i in range(50):
+        index.search_host(q[i].cpu().numpy(), a.k, timing=True)
+        km.append(index.last_kernel_ms)
+    out["scan_kernel_alone_ms (events around the kernel)"] = sum(km) / len(km)
+    print(json.dumps(out), flush=True)
+    sh.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("cmd", choices=["batched", "sweep-scan", "small-batch", "ivf", "sharded", "ivf-q1", "ivf-q1-sweep", "fp8-scan", "k1", "cfg0", "torch-compare"])
+    ap.add_argument("cmd", choices=["batched", "sweep-scan", "small-batch", "ivf", "sharded", "ivf-q1", "ivf-q1-sweep", "fp8-scan", "k1", "cfg0", "torch-compare", "shard-stream"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--dim", type=int, default=1024)
     ap.add_argument("--nq", type=int, default=4096)
@@ -553,7 +587,7 @@ def main():
     a = ap.parse_args()
     if a.k is None:
         a.k = 100 if a.cmd == "batched" else 10
-    {"batched": cmd_batched, "sweep-scan": cmd_sweep_scan, "small-batch": cmd_small_batch, "ivf": cmd_ivf, "sharded": cmd_sharded, "ivf-q1": cmd_ivf_q1, "ivf-q1-sweep": cmd_ivf_q1_sweep, "fp8-scan": cmd_fp8_scan, "k1": cmd_k1, "cfg0": cmd_cfg0, "torch-compare": cmd_torch_compare}[a.cmd](a)
+    {"batched": cmd_batched, "sweep-scan": cmd_sweep_scan, "small-batch": cmd_small_batch, "ivf": cmd_ivf, "sharded": cmd_sharded, "ivf-q1": cmd_ivf_q1, "ivf-q1-sweep": cmd_ivf_q1_sweep, "fp8-scan": cmd_fp8_scan, "k1": cmd_k1, "cfg0": cmd_cfg0, "torch-compare": cmd_torch_compare, "shard-stream": cmd_shard_stream}[a.cmd](a)
 
 
 if __name__ == "__main__":

@@ -27,16 +27,82 @@ def _as_ranked(ranked) -> np.ndarray:
     r = np.asarray(ranked)
     if r.ndim != 2:
         raise ValueError(f"ranked must be [num_queries, >=k] doc ids, got shape {r.shape}")
-    return r
+    return r.astype(np.int64, copy=False)
 
 
-def _correct_doc(rels_dict: dict) -> int:
-    return next(d for d, v in rels_dict.items() if v == 1)  # compare_embeddings.py:111
+class _Judged:
+    """The [Q, k] ranking joined ONCE with the relevance judgements — every metric below is array arithmetic on
+    these tables, where the reference walks a dict per query per rank inside each of its six metric loops.
+
+    ``qrels``: {query -> {doc -> relevance}} (compare_embeddings.py:175-182). All (query, doc, relevance) triples
+    are flattened into one sorted key table; the relevance of every ranked entry is a single ``searchsorted``.
+    ``pos`` is each entry's 1-based rank among the VALID entries of its row (-1 padding and ranks past ``k``
+    are invalid and carry relevance 0)."""
+
+    def __init__(self, ranked, qrels, k: Optional[int]):
+        r = _as_ranked(ranked)
+        self.nq = r.shape[0]
+        r = r if k is None else r[:, :k]
+        self.docs = r
+        self.valid = r >= 0
+        self.pos = np.cumsum(self.valid, axis=1)
+        per_query = [qrels.get(q) or {} for q in range(self.nq)]
+        self.judged = np.array([bool(d) for d in per_query], dtype=bool)
+        counts = np.array([len(d) for d in per_query], dtype=np.int64)
+        self.owner = np.repeat(np.arange(self.nq), counts)
+        self.doc_of = np.fromiter((doc for d in per_query for doc in d), dtype=np.int64, count=int(counts.sum()))
+        self.rel_of = np.fromiter((v for d in per_query for v in d.values()), dtype=float, count=int(counts.sum()))
+        self.starts = np.concatenate([[0], np.cumsum(counts)])
+        span = int(max(self.doc_of.max(initial=0), r.max(initial=0))) + 2
+        keys = self.owner * span + self.doc_of
+        order = np.argsort(keys, kind="stable")
+        keys, rel_sorted = keys[order], self.rel_of[order]
+        want = (np.arange(self.nq)[:, None] * span + np.where(self.valid, r, span - 1)).reshape(-1)
+        at = np.minimum(np.searchsorted(keys, want), max(len(keys) - 1, 0))
+        found = (keys[at] == want) if len(keys) else np.zeros(want.shape, dtype=bool)
+        rel = np.where(found, rel_sorted[at] if len(keys) else 0.0, 0.0).reshape(r.shape)
+        self.rel = np.where(self.valid, rel, 0.0)
+
+    def correct_doc(self) -> np.ndarray:
+        """Per query, the first judged doc (in judgement order) with relevance exactly 1 (compare_embeddings.py:111)."""
+        is_one = self.rel_of == 1
+        first = np.full(self.nq, -1, dtype=np.int64)
+        idx = np.flatnonzero(is_one)
+        if idx.size:
+            q_of, where = np.unique(self.owner[idx], return_index=True)
+            first[q_of] = self.doc_of[idx[where]]
+        if (first < 0).any():
+            raise StopIteration(f"query {int(np.flatnonzero(first < 0)[0])} has no document of relevance 1")
+        return first
+
+    def found_rank(self) -> np.ndarray:
+        """1-based rank of each query's correct doc inside the cut ranking, 0 where it is absent."""
+        match = self.valid & (self.docs == self.correct_doc()[:, None])
+        return np.where(match.any(axis=1), self.pos[np.arange(self.nq), match.argmax(axis=1)], 0)
+
+    def ideal(self, k: Optional[int]) -> np.ndarray:
+        """[Q, width] judged relevances of each query sorted descending and cut at k (zero padded)."""
+        width = int((self.starts[1:] - self.starts[:-1]).max(initial=0))
+        width = width if k is None else min(width, k)
+        out = np.zeros((self.nq, max(width, 1)))
+        order = np.lexsort((-self.rel_of, self.owner))              # by query, then relevance descending
+        slot = np.arange(len(order)) - self.starts[self.owner[order]]
+        keep = slot < out.shape[1]
+        out[self.owner[order][keep], slot[keep]] = self.rel_of[order][keep]
+        return out
 
 
-def _cut(order: np.ndarray, k: Optional[int]) -> np.ndarray:
-    order = order if k is None else order[:k]
-    return order[order >= 0]
+def _seq_sum(terms: np.ndarray) -> np.ndarray:
+    """Row sums accumulated left to right (the reference adds term by term; np.sum would add pairwise)."""
+    return np.cumsum(terms, axis=1)[:, -1] if terms.shape[1] else np.zeros(terms.shape[0])
+
+
+def _gain(rel: np.ndarray, gain: str) -> np.ndarray:
+    if gain == "exp":
+        return np.exp2(rel) - 1.0
+    if gain == "linear":
+        return rel
+    raise ValueError(f"Unknown gain scheme: {gain}")
 
 
 def rank_concepts(q_emb, corpus, k: int, dtype: str = "f32") -> np.ndarray:
@@ -52,137 +118,90 @@ def rank_concepts(q_emb, corpus, k: int, dtype: str = "f32") -> np.ndarray:
 
 
 def precision_at_k(ranked, qrels, k: int = 5) -> float:
-    """compare_embeddings.py:95-119 — hit / k, averaged."""
-    r = _as_ranked(ranked)
-    vals = []
-    for q in range(r.shape[0]):
-        hit = 1 if _correct_doc(qrels[q]) in _cut(r[q], k) else 0
-        vals.append(hit / k)
-    return float(np.mean(vals))
+    """compare_embeddings.py:95-119 — (correct doc among the first k) / k, averaged over queries."""
+    return float(np.mean((_Judged(ranked, qrels, k).found_rank() > 0) / k))
 
 
 def hit_at_k(ranked, qrels, k: int = 5) -> float:
     """compare_embeddings.py:122-141."""
-    r = _as_ranked(ranked)
-    return float(np.mean([1 if _correct_doc(qrels[q]) in _cut(r[q], k) else 0 for q in range(r.shape[0])]))
+    return float(np.mean((_Judged(ranked, qrels, k).found_rank() > 0).astype(np.int64)))
 
 
 def mrr_at_k(ranked, qrels, k: Optional[int] = None) -> float:
     """compare_embeddings.py:143-173.  With ``k=None`` the reference walks the full ranking; here the
     walk ends at the width of ``ranked`` (reciprocal ranks below 1/width count as 0)."""
-    r = _as_ranked(ranked)
-    rrs = []
-    for q in range(r.shape[0]):
-        row = _cut(r[q], k)
-        m = np.where(row == _correct_doc(qrels[q]))[0]
-        rrs.append(1.0 / (int(m[0]) + 1) if m.size else 0.0)
-    return float(np.mean(rrs))
+    rank = _Judged(ranked, qrels, k).found_rank()
+    return float(np.mean(np.where(rank > 0, 1.0 / np.maximum(rank, 1), 0.0)))
 
 
 def _generate_qrels(queries, slogans):
     """compare_embeddings.py:175-182: 0.5 for every slogan of the query's paper, else 0."""
-    return {i: {j: 0.5 if slogans[j][1] == queries[i][1] else 0 for j in range(len(slogans))}
-            for i in range(len(queries))}
+    paper_of_slogan = np.array([s[1] for s in slogans], dtype=object)
+    return {i: dict(enumerate(np.where(paper_of_slogan == q[1], 0.5, 0).tolist())) for i, q in enumerate(queries)}
 
 
-def _rels(order: np.ndarray, rels_dict: dict, k: Optional[int], default: float = 0.0) -> np.ndarray:
-    return np.array([rels_dict.get(int(d), default) for d in _cut(order, k)], dtype=float)
-
-
-def _dcg_from_rels(rels: np.ndarray, gain: str = "exp") -> float:
-    """compare_embeddings.py:196-213."""
-    if rels.size == 0:
-        return 0.0
-    if gain == "exp":
-        gains = np.power(2.0, rels) - 1.0
-    elif gain == "linear":
-        gains = rels
-    else:
-        raise ValueError(f"Unknown gain scheme: {gain}")
-    return float(np.sum(gains / np.log2(np.arange(2, rels.size + 2))))
+def _discounted(gains: np.ndarray, pos: np.ndarray) -> np.ndarray:
+    """sum_i gain_i / log2(rank_i + 1), rank 1-based (compare_embeddings.py:196-213)."""
+    return _seq_sum(gains / np.log2(np.maximum(pos, 1) + 1.0))
 
 
 def ndcg_at_k(ranked, qrels, k: int = 10, gain: str = "exp") -> float:
-    """compare_embeddings.py:216-243."""
-    r = _as_ranked(ranked)
-    out = []
-    for q in range(r.shape[0]):
-        rels_dict = qrels.get(q, {})
-        dcg = _dcg_from_rels(_rels(r[q], rels_dict, k), gain)
-        ideal = np.sort(np.array(list(rels_dict.values()), dtype=float))[::-1]
-        if k is not None:
-            ideal = ideal[:k]
-        idcg = _dcg_from_rels(ideal, gain)
-        out.append(0.0 if idcg == 0.0 else dcg / idcg)
-    return float(np.mean(out))
+    """compare_embeddings.py:216-243: DCG of the ranking over the DCG of the judged relevances sorted descending."""
+    j = _Judged(ranked, qrels, k)
+    dcg = _discounted(np.where(j.valid, _gain(j.rel, gain), 0.0), j.pos)
+    ideal = j.ideal(k)
+    idcg = _discounted(_gain(ideal, gain), np.arange(1, ideal.shape[1] + 1)[None, :])
+    return float(np.mean(np.where(idcg == 0.0, 0.0, dcg / np.where(idcg == 0.0, 1.0, idcg))))
 
 
 def _max_rel(qrels) -> float:
-    m = 0.0
-    for rels_dict in qrels.values():
-        if rels_dict:
-            m = max(m, max(rels_dict.values()))
-    return m
+    return max((max(d.values()) for d in qrels.values() if d), default=0.0) or 0.0
+
+
+def _scale(qrels, max_rel: Optional[float]) -> Optional[float]:
+    """2^max_rel, the normaliser of the graded gains; None when nothing is relevant (the metric is then 0)."""
+    if max_rel is None:
+        max_rel = max(0.0, _max_rel(qrels))
+        if max_rel <= 0.0:
+            return None
+    return 2.0 ** max_rel
 
 
 def err_at_k(ranked, qrels, k: int = 10, max_rel: Optional[float] = None) -> float:
-    """compare_embeddings.py:257-311 (expected reciprocal rank, cascade model)."""
-    r = _as_ranked(ranked)
-    if max_rel is None:
-        max_rel = _max_rel(qrels)
-        if max_rel <= 0.0:
-            return 0.0
-    denom = 2.0 ** max_rel
-    errs = []
-    for q in range(r.shape[0]):
-        rels_dict = qrels.get(q, None)
-        if not rels_dict:
-            errs.append(0.0)
-            continue
-        rels = _rels(r[q], rels_dict, k)
-        if rels.size == 0:
-            errs.append(0.0)
-            continue
-        ps = (np.power(2.0, rels) - 1.0) / denom
-        err_q, not_sat = 0.0, 1.0
-        for i, p in enumerate(ps, start=1):
-            if p > 0.0:
-                err_q += not_sat * p * (1.0 / i)
-            not_sat *= (1.0 - p)
-            if p > 0.0 and not_sat <= 1e-12:
-                break
-        errs.append(err_q)
-    return float(np.mean(errs)) if errs else 0.0
+    """compare_embeddings.py:257-311 — expected reciprocal rank under the cascade model: the user stops at rank i
+    with probability p_i = (2^rel_i - 1) / 2^max_rel having passed every earlier rank; the walk is abandoned once
+    the probability of still reading drops to 1e-12."""
+    scale = _scale(qrels, max_rel)
+    if scale is None:
+        return 0.0
+    j = _Judged(ranked, qrels, k)
+    if j.nq == 0:
+        return 0.0
+    stop = (np.exp2(j.rel) - 1.0) / scale
+    still_reading = np.cumprod(1.0 - stop, axis=1)
+    reached = np.concatenate([np.ones((j.nq, 1)), still_reading[:, :-1]], axis=1)
+    gave_up = (stop > 0.0) & (still_reading <= 1e-12)
+    live = (np.cumsum(gave_up, axis=1) - gave_up) == 0            # nothing before this rank ended the walk
+    terms = np.where(live & (stop > 0.0), reached * stop * (1.0 / np.maximum(j.pos, 1)), 0.0)
+    return float(np.mean(np.where(j.judged, _seq_sum(terms), 0.0)))
 
 
 def q_measure_at_k(ranked, qrels, k: int = 10, max_rel: Optional[float] = None) -> float:
-    """compare_embeddings.py:315-371."""
-    r = _as_ranked(ranked)
-    if max_rel is None:
-        max_rel = _max_rel(qrels)
-        if max_rel <= 0.0:
-            return 0.0
-    denom = 2.0 ** max_rel
-    scores = []
-    for q in range(r.shape[0]):
-        rels_dict = qrels.get(q, None)
-        if not rels_dict:
-            scores.append(0.0)
-            continue
-        gains_all = (np.power(2.0, np.array(list(rels_dict.values()), dtype=float)) - 1.0) / denom
-        cg_star = gains_all.sum()
-        if cg_star <= 0.0:
-            scores.append(0.0)
-            continue
-        gains_k = (np.power(2.0, _rels(r[q], rels_dict, k)) - 1.0) / denom
-        cg = q_sum = 0.0
-        for i, g in enumerate(gains_k, start=1):
-            if g <= 0.0:
-                continue
-            cg += g
-            q_sum += g * (cg / i)
-        scores.append(q_sum / cg_star)
-    return float(np.mean(scores)) if scores else 0.0
+    """compare_embeddings.py:315-371 — sum over relevant ranks of gain_i * (cumulative gain_i / i), over the total
+    gain of everything judged for the query."""
+    scale = _scale(qrels, max_rel)
+    if scale is None:
+        return 0.0
+    j = _Judged(ranked, qrels, k)
+    if j.nq == 0:
+        return 0.0
+    total = np.zeros(j.nq)
+    np.add.at(total, j.owner, (np.exp2(j.rel_of) - 1.0) / scale)
+    g = (np.exp2(j.rel) - 1.0) / scale
+    g = np.where(g > 0.0, g, 0.0)
+    blended = _seq_sum(g * (np.cumsum(g, axis=1) / np.maximum(j.pos, 1)))
+    ok = j.judged & (total > 0.0)
+    return float(np.mean(np.where(ok, blended / np.where(ok, total, 1.0), 0.0)))
 
 
 def evaluate_rankings(ranked, qrels, top_k_report: int = 3) -> dict:

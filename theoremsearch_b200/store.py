@@ -235,38 +235,53 @@ class TheoremStore:
         return [self.result_row(cand[j][1], cand[j][0], weighted[j]) for j in order]
 
 
+def _showcase_keep(items: Sequence[dict], filters: dict) -> np.ndarray:
+    """Which pool entries pass the showcase app's post-filter (app_showcase_model.py:104-121), as one boolean
+    vector: every criterion is evaluated column-wise over the whole pool, the criteria are AND-ed."""
+    n = len(items)
+    keep = np.ones(n, dtype=bool)
+    source = np.array([it["source"] for it in items], dtype=object)
+    on_arxiv = source == "arXiv"
+    keep &= np.isin(source, list(filters["sources"]))
+    if filters["types"]:
+        keep &= np.isin(np.array([it["type"].lower() for it in items], dtype=object), list(filters["types"]))
+    if filters["tags"]:
+        keep &= np.isin(np.array([it["primary_math_tag"] for it in items], dtype=object), list(filters["tags"]))
+    if filters["authors"]:
+        wanted = list(filters["authors"])
+        keep &= np.fromiter((any(w in it["authors"] for w in wanted) for it in items), dtype=bool, count=n)
+    lo, hi = filters["citation_range"]
+    cites = np.array([it["citations"] for it in items])
+    keep &= (cites >= lo) & (cites <= hi)
+    if filters["year_range"]:                      # the year window binds arXiv entries only
+        y0, y1 = filters["year_range"]
+        year = np.array([it.get("year", 0) for it in items])
+        keep &= ~on_arxiv | ((year >= y0) & (year <= y1))
+    status = filters["journal_status"]
+    if status in ("Journal Article", "Preprint Only"):   # so does the journal / preprint switch
+        published = np.array([bool(it.get("journal_published", False)) for it in items], dtype=bool)
+        keep &= ~on_arxiv | (published if status == "Journal Article" else ~published)
+    return keep
+
+
 def search_showcase(query, model, theorems_data, embeddings_db, filters: dict, pool: int = 200) -> list[dict]:
-    """``app_showcase_model.search_and_display`` (reference :82-129) up to rendering: take the
-    top ``min(200, N)`` by cosine, then POST-filter that pool in rank order until ``top_k``
-    survive.  Kept for drop-in fidelity; ``TheoremStore.search`` pre-filters instead (exact)."""
+    """``app_showcase_model.search_and_display`` (reference :82-129) up to rendering: the top ``min(200, N)``
+    rows by cosine form a pool, the pool is POST-filtered and its first ``top_k`` survivors (in rank order) are
+    returned.  Kept for drop-in fidelity; ``TheoremStore.search`` pre-filters instead (exact among eligible rows)."""
     if not query or not filters["sources"]:
         return []
     query_emb = model.encode(query, convert_to_tensor=True)                    # :92
     q = np.asarray(query_emb.detach().cpu().numpy() if hasattr(query_emb, "detach") else query_emb,
                    dtype=np.float32).reshape(-1)
-    k = min(pool, len(theorems_data))                                          # :96
-    scores, idxs = embeddings_db.search_host(q, k, normalize=True)
-    out = []
-    for s, idx in zip(scores[0], idxs[0]):
-        if idx < 0:
-            break
-        item = theorems_data[int(idx)]
-        type_match = not filters["types"] or item["type"].lower() in filters["types"]
-        tag_match = not filters["tags"] or item["primary_math_tag"] in filters["tags"]
-        author_match = not filters["authors"] or any(a in item["authors"] for a in filters["authors"])
-        source_match = item["source"] in filters["sources"]
-        citation_match = filters["citation_range"][0] <= item["citations"] <= filters["citation_range"][1]
-        year_match = True
-        if filters["year_range"] and item["source"] == "arXiv":
-            year_match = filters["year_range"][0] <= item.get("year", 0) <= filters["year_range"][1]
-        journal_match = True
-        if item["source"] == "arXiv":
-            if filters["journal_status"] == "Journal Article":
-                journal_match = item.get("journal_published", False)
-            elif filters["journal_status"] == "Preprint Only":
-                journal_match = not item.get("journal_published", False)
-        if all([type_match, tag_match, author_match, source_match, year_match, citation_match, journal_match]):
-            out.append({"info": item, "similarity": float(s)})
-        if len(out) >= filters["top_k"]:
-            break
-    return out
+    scores, idxs = embeddings_db.search_host(q, min(pool, len(theorems_data)), normalize=True)   # :93-96
+    valid = idxs[0] >= 0
+    rows, sims = idxs[0][valid], scores[0][valid]
+    if rows.size == 0:
+        return []
+    items = [theorems_data[int(r)] for r in rows]
+    keep = _showcase_keep(items, filters)
+    top_k = int(filters["top_k"])
+    # the reference stops once it HAS top_k results, testing after each pool entry: with top_k < 1 that is after
+    # the first entry, whatever it was
+    chosen = np.flatnonzero(keep)[:top_k] if top_k >= 1 else np.flatnonzero(keep[:1])
+    return [{"info": items[j], "similarity": float(sims[j])} for j in chosen]
