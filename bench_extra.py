@@ -560,9 +560,66 @@ def cmd_shard_stream(a):
     sh.close()
 
 
+def cmd_scan_timeline(a):
+    """Per-CTA phase stamps of consecutive K2 launches at the shard size (tunable scan.timeline): where a
+    query's time goes besides streaming — start-up, the spread of the CTAs' finishing times, the merge tail —
+    and how far the next launch's CTAs overlap the previous launch's tail, for every search form."""
+    import ctypes as C
+    import numpy as np
+    from theoremsearch_b200 import _lib
+    from theoremsearch_b200.sharded import ShardedIndex
+    dev = torch.device("cuda", 0)
+    index = build(a.rows, a.dim, dev)
+    sh = ShardedIndex(index, a.rows).enable_peer_exchange(max_nq=1, max_k=32)
+    q = synthetic.make_queries(64, a.dim, dev)
+    torch.cuda.synchronize()
+    forms = {"plain": lambda i: index.search(q[i:i + 1], a.k),
+             "one_kernel": lambda i: sh.search(q[i:i + 1], a.k, one_kernel=True),
+             "pdl_dependent": lambda i: sh.search(q[i:i + 1], a.k),
+             "pdl_independent": lambda i: sh.search(q[i:i + 1], a.k, independent=True)}
+    n = 148
+    out = {"bench": "scan-timeline", "rows": a.rows, "stamps": ["entry", "query_ready", "first_tile", "warp0_done",
+                                                                "cta_done", "list_written", "final_merge_done"]}
+    for name, fn in forms.items():
+        for i in range(20):
+            fn(i)
+        torch.cuda.synchronize()
+        _lib.set_tunable("scan.timeline", 1)
+        for i in range(20, 36):
+            fn(i)
+        torch.cuda.synchronize()
+        _lib.set_tunable("scan.timeline", 0)
+        tl = []
+        for back in range(4):
+            buf = np.zeros((n, 8), dtype=np.uint64)
+            _lib.check(_lib.lib.ts_debug_scan_timeline(buf.ctypes.data, back, n))
+            tl.append(buf.astype(np.int64))
+        tl = tl[::-1]                       # oldest first: launches L-3 .. L
+        t0 = int(tl[1][:, 0].min())         # reference: first CTA entry of launch L-2
+        rep = {}
+        for li, lab in ((1, "launch_n"), (2, "launch_n_plus_1")):
+            d = tl[li][:, :7] - t0
+            rep[lab] = {st: {"min": int(d[:, j].min()), "p50": int(np.median(d[:, j])), "p95": int(np.percentile(d[:, j], 95)),
+                             "max": int(d[:, j].max())} for j, st in enumerate(out["stamps"][:6])}
+            last = tl[li][:, 6]
+            rep[lab]["final_merge_done"] = int(last[last > 0].max() - t0) if (last > t0).any() else None
+        rep["period_ns (entry min of n+1 minus entry min of n)"] = int(tl[2][:, 0].min() - tl[1][:, 0].min())
+        rep["cta_busy_ns p50 (entry -> list_written)"] = int(np.median(tl[1][:, 5] - tl[1][:, 0]))
+        rep["cta_stream_ns p50 (first_tile -> cta_done)"] = int(np.median(tl[1][:, 4] - tl[1][:, 2]))
+        rep["spread_cta_done_ns (max - min)"] = int(tl[1][:, 4].max() - tl[1][:, 4].min())
+        rep["spread_entry_ns (max - min)"] = int(tl[1][:, 0].max() - tl[1][:, 0].min())
+        # per-SM gap between the end of launch n's CTA and the entry of launch n+1's CTA on the same SM
+        sm_n = {int(r[7]): int(r[5]) for r in tl[1]}
+        gaps = [int(r[0]) - sm_n[int(r[7])] for r in tl[2] if int(r[7]) in sm_n]
+        rep["same_sm_gap_ns (n+1 entry - n list_written)"] = {"p50": int(np.median(gaps)), "min": int(min(gaps)), "max": int(max(gaps))}
+        out[name] = rep
+    print(json.dumps(out), flush=True)
+    sh.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("cmd", choices=["batched", "sweep-scan", "small-batch", "ivf", "sharded", "ivf-q1", "ivf-q1-sweep", "fp8-scan", "k1", "cfg0", "torch-compare", "shard-stream"])
+    ap.add_argument("cmd", choices=["batched", "sweep-scan", "small-batch", "ivf", "sharded", "ivf-q1", "ivf-q1-sweep", "fp8-scan", "k1", "cfg0", "torch-compare", "shard-stream", "scan-timeline"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--dim", type=int, default=1024)
     ap.add_argument("--nq", type=int, default=4096)
@@ -587,7 +644,7 @@ def main():
     a = ap.parse_args()
     if a.k is None:
         a.k = 100 if a.cmd == "batched" else 10
-    {"batched": cmd_batched, "sweep-scan": cmd_sweep_scan, "small-batch": cmd_small_batch, "ivf": cmd_ivf, "sharded": cmd_sharded, "ivf-q1": cmd_ivf_q1, "ivf-q1-sweep": cmd_ivf_q1_sweep, "fp8-scan": cmd_fp8_scan, "k1": cmd_k1, "cfg0": cmd_cfg0, "torch-compare": cmd_torch_compare, "shard-stream": cmd_shard_stream}[a.cmd](a)
+    {"batched": cmd_batched, "sweep-scan": cmd_sweep_scan, "small-batch": cmd_small_batch, "ivf": cmd_ivf, "sharded": cmd_sharded, "ivf-q1": cmd_ivf_q1, "ivf-q1-sweep": cmd_ivf_q1_sweep, "fp8-scan": cmd_fp8_scan, "k1": cmd_k1, "cfg0": cmd_cfg0, "torch-compare": cmd_torch_compare, "shard-stream": cmd_shard_stream, "scan-timeline": cmd_scan_timeline}[a.cmd](a)
 
 
 if __name__ == "__main__":

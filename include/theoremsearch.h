@@ -318,6 +318,12 @@ TS_API int ts_get_tunable(const char* name, int* value);
  * boundaries; this copies [n_ctas][12] stamps to HOST memory. Synchronises the device. */
 TS_API int ts_debug_ivf_timeline(uint64_t* out_host, int n_ctas);
 
+/* With tunable "scan.timeline" = 1 every K2 launch records, per CTA, %globaltimer (ns) at: 0 entry, 1 query
+ * ready, 2 first tile landed, 3 warp 0 done, 4 all warps done, 5 CTA list written, 6 (last CTA) final merge
+ * done; slot 7 = SM id. Copies the [n_ctas][8] stamps of the launch `launches_back` launches ago (0 = latest,
+ * ring of 8) to HOST memory. Synchronises the device. */
+TS_API int ts_debug_scan_timeline(uint64_t* out_host, int launches_back, int n_ctas);
+
 /* How many queries of the most recent batched (K3) search failed the exactness certificate or
  * overflowed their candidate buffer and were therefore re-scanned by the exact K2 path.
  * Synchronises the device; -1 if no batched search has run. Valid until the caller frees or

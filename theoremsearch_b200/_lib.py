@@ -103,6 +103,7 @@ SIGNATURES = {
     "ts_get_tunable": (_i, [C.c_char_p, C.POINTER(_i)]),
     "ts_debug_last_batched_fixups": (_i, []),
     "ts_debug_ivf_timeline": (_i, [_p, _i]),
+    "ts_debug_scan_timeline": (_i, [_p, _i, _i]),
 }
 
 

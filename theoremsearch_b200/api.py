@@ -54,7 +54,15 @@ def cos_sim_topk(queries, corpus_index: TheoremIndex, k: int, normalize_queries:
     """(scores float32 [Q, k], ids int64 [Q, k]) sorted by score desc then id asc.  A 1-D query
     returns 1-D rows so ``idx.item()`` / ``scores[i].item()`` consumers (test_app.py:85-88) work."""
     one_d = (queries.ndim if hasattr(queries, "ndim") else np.asarray(queries).ndim) == 1
-    if getattr(corpus_index, "scan_dtype", None) == "fp8" and 2 * k <= TS_IVF_MAX_CANDIDATES:
+    fp8 = getattr(corpus_index, "scan_dtype", None) == "fp8" and 2 * k <= TS_IVF_MAX_CANDIDATES
+    if fp8 and not corpus_index.fp8_scan_ready:
+        # rows were added since the e4m3 copy was made: refresh it (one pass over the corpus) unless real IVF
+        # lists have taken its place, in which case the exact bf16 scan answers
+        if corpus_index.nlist <= 1:
+            corpus_index.build_fp8_shadow()
+        else:
+            fp8 = False
+    if fp8:
         scores, ids = corpus_index.search_fp8(queries, k, rescore_k=min(TS_IVF_MAX_CANDIDATES, max(128, 2 * k)),
                                               normalize=normalize_queries, allow_mask=allow_mask)
     else:

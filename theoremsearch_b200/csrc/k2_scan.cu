@@ -2,12 +2,28 @@
 // translation units (k2_scan_{bf16,f32}_{small,large}.cu) so that the build parallelises.
 #include "k2_scan_impl.cuh"
 
+#include <atomic>
+
 namespace ts {
 
 int launch_scan_bf16_small(const ts_index*, const ScanParams&, int nchunk, int nq, int nparts, cudaStream_t, cudaEvent_t, cudaEvent_t);
 int launch_scan_bf16_large(const ts_index*, const ScanParams&, int nchunk, int nq, int nparts, cudaStream_t, cudaEvent_t, cudaEvent_t);
 int launch_scan_f32_small(const ts_index*, const ScanParams&, int nchunk, int nq, int nparts, cudaStream_t, cudaEvent_t, cudaEvent_t);
 int launch_scan_f32_large(const ts_index*, const ScanParams&, int nchunk, int nq, int nparts, cudaStream_t, cudaEvent_t, cudaEvent_t);
+
+// "scan.timeline": a ring of 8 launches x 1024 CTAs x 8 stamps (ts_debug_scan_timeline)
+__device__ unsigned long long g_scan_timeline[8 * 1024 * 8];
+static std::atomic<unsigned> g_timeline_launch{0};
+
+int debug_scan_timeline(uint64_t* out_host, int launches_back, int n_ctas) {
+    TS_REQUIRE(out_host != nullptr && launches_back >= 0 && launches_back < 8 && n_ctas >= 1 && n_ctas <= 1024,
+               TS_ERR_BAD_ARG, "debug_scan_timeline: bad argument");
+    TS_CHECK_CUDA(cudaDeviceSynchronize());
+    const unsigned slot = (g_timeline_launch.load() - 1u - (unsigned)launches_back) & 7u;
+    TS_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_scan_timeline, (size_t)n_ctas * 8 * sizeof(uint64_t),
+                                       (size_t)slot * 1024 * 8 * sizeof(uint64_t)));
+    return TS_OK;
+}
 
 int scan_nparts(const ts_index* ix) {
     int ctas = tunables().scan_ctas_per_sm < 1 ? 1 : tunables().scan_ctas_per_sm;
@@ -41,6 +57,12 @@ int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64
     memset(&p.fin, 0, sizeof(p.fin));
     memset(&p.xchg, 0, sizeof(p.xchg));
     p.pdl = 0;
+    p.timeline = nullptr;
+    if (tunables().scan_timeline) {
+        unsigned long long* base = nullptr;
+        TS_CHECK_CUDA(cudaGetSymbolAddress((void**)&base, g_scan_timeline));
+        p.timeline = base + (size_t)(g_timeline_launch.fetch_add(1) & 7u) * 1024 * 8;
+    }
     if (fused != nullptr) {
         p.pdl = fused->pdl;
         p.q_raw = fused->q_raw;

@@ -65,7 +65,17 @@ struct ScanParams {
     // on the stream: wait for it before touching anything (the safe default; without it the scan of query
     // n+1 streams the corpus while query n's exchange kernel is still merging)
     int pdl;
+    // diagnostics ("scan.timeline"): [gridDim.x][8] %globaltimer stamps of this launch, or nullptr
+    unsigned long long* timeline;
 };
+
+__device__ __forceinline__ void scan_stamp(const ScanParams& p, int slot) {
+    if (p.timeline != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.timeline[(size_t)blockIdx.x * 8 + slot] = t;
+    }
+}
 
 __device__ __forceinline__ float load_query_elem(const void* base, int dtype, size_t idx) {
     if (dtype == TS_F32) return __ldg(reinterpret_cast<const float*>(base) + idx);
@@ -89,6 +99,12 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)W * stages * tile_bytes);
     uint64_t* my_bars = bars + warp * stages;
 
+    scan_stamp(p, 0);                                  // 0: CTA entry
+    if (p.timeline != nullptr && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.timeline[(size_t)blockIdx.x * 8 + 7] = smid;
+    }
     if (p.pdl & 1) griddep_launch_dependents();
     if (lane == 0) {
         for (int s = 0; s < stages; ++s) mbar_init(&my_bars[s], 1);
@@ -174,6 +190,8 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
     WarpTopK<KPL> list;
     list.clear();
     uint64_t thr = 0ull;  // current k-th key of this warp's list (0 while it has < k entries)
+    scan_stamp(p, 1);                                  // 1: query in registers, scan loop starts
+    bool first_tile = true;
 
     for (int64_t tile = gw; tile < num_tiles; tile += tw) {
         const int64_t row0 = tile * R;
@@ -185,6 +203,10 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
         if (p.mask != nullptr && allowed) allowed = (__ldg(p.mask + (row >> 5)) >> (row & 31)) & 1u;
 
         mbar_wait(&my_bars[s], parity);
+        if (first_tile) {
+            scan_stamp(p, 2);                          // 2: warp 0's first tile has landed
+            first_tile = false;
+        }
 
         const uint8_t* slot = my_slots + (size_t)s * tile_bytes;
         float acc[R];
@@ -228,7 +250,9 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
 
     // ---- CTA merge: warps park their lists in smem (the pipeline has drained: every issued
     // copy was waited on), warp 0 folds them into its own and writes the CTA's k best.
+    scan_stamp(p, 3);                                  // 3: warp 0 finished its tiles
     __syncthreads();
+    scan_stamp(p, 4);                                  // 4: every warp of the CTA finished
     uint64_t* lists = reinterpret_cast<uint64_t*>(smem);  // [W][KPL*32]
 #pragma unroll
     for (int j = 0; j < KPL; ++j) lists[(size_t)warp * (KPL * 32) + j * 32 + lane] = list.key[j];
@@ -244,6 +268,7 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
         }
     }
     __syncthreads();  // the list area aliases the TMA slots of the next work item
+    scan_stamp(p, 5);                                  // 5: CTA list written
     if (p.tickets != nullptr) {
         // ---- fused final merge: the last CTA of this work item to arrive folds all gridDim.x lists.
         // One gpu-scope fence on each side of the ticket, by thread 0 only: the barriers order the other
@@ -273,6 +298,7 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
                 // waits for theirs and merges the world lists
                 exchange_and_merge<KPL>(p.xchg, p.fin, mp, wi, qi, k, lists, W);
             }
+            scan_stamp(p, 6);                          // 6: (last CTA only) final merge / exchange done
         }
     }
     }  // work items

@@ -412,22 +412,31 @@ __global__ void init_batch_state_kernel(uint64_t* cand, uint32_t* count, float* 
 
 // ---------------------------------------------------------------------------------- query rounding
 // q32 (normalised fp32, what K2 dots with) -> bf16 copy for the tensor cores, plus
-// qerr[q] = ||q32 - bf16(q32)||_2: by Cauchy-Schwarz |<q32,c> - <q16,c>| <= qerr * ||c||.
+// qerr[q], a bound (per unit of ||c||) on how far a row's exact-path score can sit above its GEMM score:
+//   ||q32 - bf16(q32)||_2        Cauchy-Schwarz: |<q32,c> - <q16,c>| <= that * ||c||
+// + 2 * dim_pad * 2^-23 * ||q16||  fp32 accumulation of dim_pad products, in whatever order the tensor core uses and
+//                                allowing truncation instead of rounding (error <= n * 2^-23 * sum|q_i c_i| <=
+//                                n * 2^-23 * ||q|| ||c||), once for the excluded row's GEMM score and once for the
+//                                threshold score it was compared with.
 __global__ void __launch_bounds__(256) round_queries_kernel(const float* __restrict__ q32, int nq, int dim_pad,
                                                             __nv_bfloat16* __restrict__ q16, float* __restrict__ qerr) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
-    float e2 = 0.f;
+    float e2 = 0.f, n2 = 0.f;
     for (int i = lane; i < dim_pad; i += 32) {
         const float v = q32[(size_t)q * dim_pad + i];
         const __nv_bfloat16 b = __float2bfloat16_rn(v);
         q16[(size_t)q * dim_pad + i] = b;
-        const float d = v - __bfloat162float(b);
+        const float bf = __bfloat162float(b);
+        const float d = v - bf;
         e2 = fmaf(d, d, e2);
+        n2 = fmaf(bf, bf, n2);
     }
     e2 = warp_sum(e2);
-    if (lane == 0) qerr[q] = sqrtf(e2) * 1.0001f + 1e-30f;
+    n2 = warp_sum(n2);
+    if (lane == 0)
+        qerr[q] = sqrtf(e2) * 1.0001f + 2.0f * (float)dim_pad * 1.1920929e-7f * sqrtf(n2) * 1.0001f + 1e-30f;
 }
 
 // ---------------------------------------------------------------------------------- K3c rescore + certify
@@ -485,7 +494,7 @@ __global__ void __launch_bounds__(256) rescore_certify_kernel(uint64_t* cand, si
         bool ok = overflow[q] == 0;
         if (ok && worst_kept != 0ull) {
             const uint64_t kth = rs_buf[k - 1];
-            const float bound = key_score(worst_kept) + qerr[q] * sqrtf(*max_norm2) + 2e-6f;
+            const float bound = key_score(worst_kept) + qerr[q] * sqrtf(*max_norm2) + 2e-6f;   // + the exact path's own rounding
             ok = kth != 0ull && key_score(kth) > bound;   // NaN bound -> not certified -> re-scan
         }
         flags[q] = ok ? 0 : 1;

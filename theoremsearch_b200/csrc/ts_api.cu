@@ -491,6 +491,17 @@ int ts_search_host(ts_ctx* c, const float* queries, int nq, int k, int normalize
     ts_index* ix = c->index;
     DeviceGuard g(ix->device);
     TS_REQUIRE(g.ok, TS_ERR_CUDA, "search_host: cannot select CUDA device %d", ix->device);
+    // the batched path's workspace depends on the index SIZE (dense small-corpus path): rows added since the ctx
+    // was created may need more than it was sized for
+    const size_t need = ts_workspace_bytes(ix, nq, k);
+    if (need > c->workspace_bytes) {
+        TS_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(c->workspace);
+        c->workspace = nullptr;
+        c->workspace_bytes = 0;
+        TS_CHECK_CUDA(cudaMalloc(&c->workspace, need));
+        c->workspace_bytes = need;
+    }
     const size_t qb = (size_t)nq * ix->dim * sizeof(float);
     memcpy(c->h_queries, queries, qb);
     TS_CHECK_CUDA(cudaMemcpyAsync(c->d_queries, c->h_queries, qb, cudaMemcpyHostToDevice, c->stream));
@@ -771,10 +782,14 @@ static int* tunable_slot(const char* name) {
     if (!strcmp(name, "ivf.group_min_nq")) return &t.ivf_group_min_nq;
     if (!strcmp(name, "ivf.group_mma")) return &t.ivf_group_mma;
     if (!strcmp(name, "xchg.debug_no_flag")) return &t.xchg_debug_no_flag;
+    if (!strcmp(name, "scan.timeline")) return &t.scan_timeline;
     if (!strcmp(name, "ivf.group_min_lists")) return &t.ivf_group_min_lists;
     return nullptr;
 }
 int ts_debug_last_batched_fixups(void) { return debug_last_batched_fixups(); }
+int ts_debug_scan_timeline(uint64_t* out_host, int launches_back, int n_ctas) {
+    return debug_scan_timeline(out_host, launches_back, n_ctas);
+}
 
 int ts_set_tunable(const char* name, int value) {
     int* s = tunable_slot(name);

@@ -92,6 +92,7 @@ struct Tunables {
     int ivf_timeline = 0;       // 1 = K4b CTAs record globaltimer stamps per phase (ts_debug_ivf_timeline)
     int ivf_group_min_nq = 16;  // batches at least this large take the list-major scan (K4d); 0 = never (sweep: profiles/sweep_ivf_batch_r1.txt)
     int ivf_group_min_lists = 0;  // K4d needs at least this many lists (and query-list pairs); 0 = 4 x SM count
+    int scan_timeline = 0;      // 1 = K2 CTAs record %globaltimer stamps per phase (ts_debug_scan_timeline)
     int xchg_debug_no_flag = 0; // test hook: the sharded exchange does not raise its own flag, so its wait times out
     int ivf_group_mma = 1;      // K4d scoring: 1 / 2 = mma.sync f16 tensor-core variant with 8 / 16 queries per group,
                                 // 0 = packed HFMA2 on the CUDA cores (4 queries per group)
@@ -419,6 +420,7 @@ int launch_prepare_queries(const void* q, int q_dtype, int nq, int dim, int dim_
                            float* out_f32, cudaStream_t s);
 // K2: per-CTA candidate lists part_keys[nq][nparts][k]
 int scan_nparts(const ts_index* ix);
+int debug_scan_timeline(uint64_t* out_host, int launches_back, int n_ctas);
 // Optional fused stages of K2: in-kernel query normalisation and in-kernel final merge.
 // device view of a ts_xchg for one search (world == 0: no exchange)
 struct XchgDev {

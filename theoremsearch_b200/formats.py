@@ -135,7 +135,8 @@ def save_index(index: TheoremIndex, path: str) -> None:
     list_dtype = int(lib.ts_ivf_list_dtype(index.handle))
     header = {"version": 1, "dim": index.dim, "dtype": index.dtype, "rows": n, "row_bytes": row_bytes,
               "has_ids": has_ids, "nlist": nlist if nlist > 0 else 0,
-              "ivf_list_dtype": {_lib.TS_BF16: "bf16", _lib.TS_FP8_E4M3: "fp8"}.get(list_dtype)}
+              "ivf_list_dtype": {_lib.TS_BF16: "bf16", _lib.TS_FP8_E4M3: "fp8"}.get(list_dtype),
+              "scan_dtype": getattr(index, "scan_dtype", index.dtype)}
     hj = json.dumps(header).encode()
     tmp = path + ".tmp"
     with open(tmp, "wb") as f:
@@ -192,4 +193,6 @@ def load_index(path: str, device: int | str | torch.device = 0, capacity: Option
             index.ivf_set_centroids(cent)
             if h.get("ivf_list_dtype"):
                 index.ivf_build(h["ivf_list_dtype"])
+        if h.get("scan_dtype") == "fp8" and index.fp8_scan_ready:
+            index.scan_dtype = "fp8"
     return index

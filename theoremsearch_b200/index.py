@@ -262,6 +262,8 @@ class TheoremIndex:
                   seed: int = 0) -> "TheoremIndex":
         """Spherical k-means -> ``nlist`` centroids (pgvector ivfflat's training step).  ``sample``:
         CUDA fp32 [n, dim], or None to train on every (len/n_sample)-th stored row in place."""
+        if int(nlist) != 1:
+            self.scan_dtype = self.dtype     # real IVF lists replace the one-list e4m3 scan copy
         ptr, n = None, int(n_sample)
         if sample is not None:
             sample = sample.to(self.device, torch.float32).contiguous()
@@ -272,6 +274,8 @@ class TheoremIndex:
         return self
 
     def ivf_set_centroids(self, centroids: torch.Tensor) -> "TheoremIndex":
+        if int(centroids.shape[0]) != 1:
+            self.scan_dtype = self.dtype
         c = centroids.to(self.device, torch.float32).contiguous()
         if c.dim() != 2 or c.shape[1] != self.dim:
             raise _lib.TheoremSearchError(-1, f"centroids must be [nlist, {self.dim}], got {tuple(c.shape)}")
@@ -318,8 +322,17 @@ class TheoremIndex:
     def build_fp8_shadow(self) -> "TheoremIndex":
         """An e4m3 copy of the whole corpus (one inverted list holding every row, in row order) for
         BASELINE.json's "optionally fp8-e4m3, rescored in fp32" single-query scan: half the bytes per query."""
+        if self.nlist > 1:
+            raise _lib.TheoremSearchError(
+                -6, f"build_fp8_shadow: the index holds {self.nlist} IVF lists; the e4m3 scan copy is the one-list "
+                    "special case of the same structure and would replace them")
         self.ivf_train(1, n_sample=1, iters=0)
         return self.ivf_build("fp8")
+
+    @property
+    def fp8_scan_ready(self) -> bool:
+        """True while the one-list e4m3 scan copy covers every stored row (``add`` invalidates it)."""
+        return self.nlist == 1 and int(lib.ts_ivf_list_dtype(self._h)) == _lib.TS_FP8_E4M3
 
     def search_fp8(self, queries, k: int, rescore_k: int = 128, normalize: bool = True,
                    allow_mask: Optional[torch.Tensor] = None):
