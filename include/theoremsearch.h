@@ -80,8 +80,8 @@ TS_API uint64_t ts_kernel_launches(void);
  * the pgvector table `theorem_embedding_qwen(slogan_id BIGINT, embedding vector(1024))`
  * (rds_schema.sql:50-53). */
 
-/* Allocate an empty index for `capacity` rows of `dim` elements stored as `dtype`
- * (TS_BF16 or TS_F32) on CUDA device `device`. */
+/* Allocate an empty index with room for `capacity` rows of `dim` elements stored as `dtype`
+ * (TS_BF16 or TS_F32) on CUDA device `device`; the room grows on demand (see "mutation"). */
 TS_API int ts_index_create(ts_index** out, int device, int dim, int dtype, int64_t capacity);
 
 /* Free the index and everything it owns. NULL is a no-op. */
@@ -99,6 +99,33 @@ TS_API int ts_index_add(ts_index* index, const void* rows, int src_dtype, int64_
 /* Same, rows/ids in HOST memory; staged through pinned buffers in chunks. Synchronises. */
 TS_API int ts_index_add_host(ts_index* index, const void* rows, int src_dtype, int64_t n,
                              int normalize, const int64_t* ids);
+
+/* ---- mutation ------------------------------------------------------------------------
+ * The table this index replaces has no fixed size and is written with
+ *     INSERT ... ON CONFLICT (slogan_id) DO UPDATE SET embedding = EXCLUDED.embedding
+ * (ec2/generate_embeddings/__main__.py:84-101). `capacity` is therefore only the initial reservation:
+ * ts_index_add / ts_index_upsert grow the row store geometrically when it is full (the old and the new
+ * allocation are resident together while the rows are copied across, device to device).
+ * Built IVF lists stay valid across add / upsert, as pgvector's ivfflat accepts inserts after its build:
+ * new and replaced rows are filed under the existing centroids in per-list OVERFLOW segments (scanned with
+ * their list), a replaced row's old list entry is tombstoned, and once tombstones + overflow exceed a tenth
+ * of the corpus the lists are re-packed from scratch. Until the re-pack, batched ANN searches take the
+ * per-query list scan (K4b) instead of the list-major scan (K4d).
+ * add / upsert / reserve / train / build are exclusive with searches on the same index. */
+
+/* Make room for at least `capacity` rows (never shrinks). Synchronises the device. */
+TS_API int ts_index_reserve(ts_index* index, int64_t capacity);
+
+/* Upsert n rows (DEVICE, row-major [n, dim] of src_dtype) keyed by ids (HOST int64[n]): a row whose id is
+ * already stored is replaced in place, any other is appended. An id that occurs more than once in the batch
+ * keeps its last occurrence (what row-by-row execution would leave). An index whose rows were added without
+ * ids treats the row position as the id. *n_replaced (may be NULL) receives the number of distinct stored
+ * rows that were replaced. Synchronises `stream` before returning. */
+TS_API int ts_index_upsert(ts_index* index, const void* rows, int src_dtype, int64_t n, int normalize,
+                           const int64_t* ids_host, int64_t* n_replaced, void* stream);
+/* Same with the rows in HOST memory (staged in chunks, in order). */
+TS_API int ts_index_upsert_host(ts_index* index, const void* rows, int src_dtype, int64_t n, int normalize,
+                                const int64_t* ids_host, int64_t* n_replaced);
 
 TS_API int64_t ts_index_size(const ts_index* index);     /* rows added so far */
 TS_API int64_t ts_index_capacity(const ts_index* index);
@@ -294,6 +321,11 @@ TS_API int ts_ivf_search_host(ts_ctx* ctx, const float* queries, int nq, int k, 
                               int normalize_queries, const uint32_t* allow_mask, float* out_scores,
                               int64_t* out_ids);
 TS_API int ts_ivf_nlist(const ts_index* index);
+/* Rows filed in overflow lists / tombstoned list positions since the last build or re-pack (either may be NULL). */
+TS_API int ts_ivf_pending(const ts_index* index, int64_t* overflow_rows, int64_t* dead_positions);
+/* Re-pack the lists now (same centroids, every stored row re-filed): clears overflow and tombstones. No-op on
+ * pristine lists. Synchronises. */
+TS_API int ts_ivf_repack(ts_index* index, void* stream);
 /* Storage dtype of the built lists (TS_BF16 / TS_FP8_E4M3), -1 if the lists are not built. */
 TS_API int ts_ivf_list_dtype(const ts_index* index);
 /* Copy list sizes (int64[nlist]) to a device buffer — for balance diagnostics. */

@@ -204,6 +204,25 @@ def ids_match_within_eps(got_ids: np.ndarray, ref_scores_all: np.ndarray, ref_id
 
 
 # --------------------------------------------------------------------------------------
+# corpus writes (ec2/generate_embeddings/__main__.py:84-101 -> ec2/rds/upsert.py:29-52)
+# --------------------------------------------------------------------------------------
+def upsert_rows(table: dict, ids: Sequence[int], rows: np.ndarray) -> int:
+    """``INSERT INTO theorem_embedding_x (slogan_id, embedding) VALUES ... ON CONFLICT (slogan_id) DO UPDATE SET
+    embedding = EXCLUDED.embedding`` run by ``cur.executemany`` — one statement per row, in order: an existing
+    id has its embedding replaced (its place in the table kept), a new id is appended, a repeated id ends up with
+    its last embedding.  ``table``: {id: row} in insertion order (a Python dict).  Returns how many distinct
+    PRE-EXISTING ids were overwritten."""
+    before = set(table)
+    hit = set()
+    for i, r in zip(ids, rows):
+        i = int(i)
+        if i in before:
+            hit.add(i)
+        table[i] = np.asarray(r, dtype=np.float32)
+    return len(hit)
+
+
+# --------------------------------------------------------------------------------------
 # reference call shapes
 # --------------------------------------------------------------------------------------
 def search_theorems_topk(query_embedding, embeddings_db, k: int = 5):

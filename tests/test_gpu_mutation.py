@@ -1,0 +1,175 @@
+"""Index mutation as the reference's writer does it (ec2/generate_embeddings/__main__.py:84-101: upsert keyed by
+slogan_id into a table without a fixed size): an upsert stream must leave the index EQUAL to one rebuilt from
+scratch from the final table — exact search bit for bit, IVF search through overflow lists and tombstones equal to
+the IVF search over freshly packed lists with the same centroids — and the row store must grow on demand."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ts():
+    import theoremsearch_b200 as ts
+    assert torch.cuda.is_available()
+    return ts
+
+
+def _stream(rng, table, n_batches, batch, dim, id_space):
+    """Random upsert batches over `id_space` ids (so existing ids recur), some ids repeated inside a batch."""
+    for _ in range(n_batches):
+        ids = rng.integers(0, id_space, size=batch)
+        ids[batch // 2] = ids[0]                       # an in-batch duplicate: the later row must win
+        rows = rng.standard_normal((batch, dim)).astype(np.float32)
+        yield ids.astype(np.int64), rows
+
+
+def _rebuild(ts, table, dim, dtype="bf16"):
+    ids = np.fromiter(table.keys(), dtype=np.int64, count=len(table))
+    rows = np.stack(list(table.values())) if table else np.zeros((0, dim), np.float32)
+    return ts.build_index(rows, ids=ids, dtype=dtype), ids, rows
+
+
+@pytest.mark.parametrize("dim,host_rows", [(256, False), (1024, True), (100, False)])
+def test_upsert_stream_equals_rebuild_from_scratch(ts, dim, host_rows):
+    rng = np.random.default_rng(dim)
+    table = {}
+    index = ts.TheoremIndex(dim, 64, dtype="bf16")              # far too small on purpose: it must grow
+    first_ids = np.arange(1000, 1300, dtype=np.int64)
+    first = rng.standard_normal((300, dim)).astype(np.float32)
+    assert oracle.upsert_rows(table, first_ids, first) == 0
+    assert index.upsert(first if host_rows else torch.from_numpy(first).cuda(), first_ids) == 0
+    for ids, rows in _stream(rng, table, 12, 97, dim, 1600):
+        want = oracle.upsert_rows(table, ids + 1000, rows)
+        got = index.upsert(rows if host_rows else torch.from_numpy(rows).cuda(), ids + 1000)
+        assert got == want
+    assert len(index) == len(table) and index.capacity >= len(index)
+    fresh, ids_all, rows_all = _rebuild(ts, table, dim)
+    assert torch.equal(index.get_rows(), fresh.get_rows())      # same rows, same places
+    q = torch.from_numpy(oracle.synthetic_queries(9, dim))
+    for qq in (q[:1], q):                                       # scan path and tensor-core path
+        s0, i0 = fresh.search(qq, 10)
+        s1, i1 = index.search(qq, 10)
+        assert torch.equal(s0, s1) and torch.equal(i0, i1)
+    # and against the oracle on the final table
+    stored = oracle.bf16_round(oracle.normalize_f64(rows_all))
+    o_s, o_i = oracle.exact_search(oracle.normalize_f64(q.numpy()), stored, 10, ids=ids_all)
+    s1, i1 = index.search(q, 10)
+    assert np.array_equal(i1.cpu().numpy(), o_i)
+    assert np.max(np.abs(s1.cpu().numpy() - o_s)) < 1e-5
+
+
+def test_rows_without_ids_use_their_position_as_id(ts):
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((50, 64)).astype(np.float32)
+    index = ts.build_index(x)                                    # no ids: id == row
+    y = rng.standard_normal((3, 64)).astype(np.float32)
+    assert index.upsert(y, [5, 50, 7]) == 2                      # rows 5 and 7 replaced, id 50 == next row: appended
+    assert len(index) == 51
+    x2 = np.concatenate([x, y[1:2]])
+    x2[5], x2[7] = y[0], y[2]
+    fresh = ts.build_index(x2)
+    assert torch.equal(index.get_rows(), fresh.get_rows())
+    s0, i0 = fresh.search(torch.from_numpy(y), 5)
+    s1, i1 = index.search(torch.from_numpy(y), 5)
+    assert torch.equal(s0, s1) and torch.equal(i0, i1)
+    assert i1[:, 0].tolist() == [5, 50, 7]
+    # an id that is not the next row position switches the index to an explicit id table
+    assert index.upsert(y[:1], [9000]) == 0
+    s2, i2 = index.search(torch.from_numpy(y[:1]), 2)
+    assert sorted(i2[0].tolist()) == [5, 9000] and s2[0, 0] == s2[0, 1]
+
+
+def test_add_grows_capacity_and_keeps_results(ts):
+    x = oracle.synthetic_rows(0, 5000, 128, seed=11)
+    index = ts.TheoremIndex(128, 10, dtype="bf16")
+    for lo in range(0, 5000, 700):
+        index.add(torch.from_numpy(x[lo:lo + 700]).cuda())
+    assert len(index) == 5000 and index.capacity >= 5000
+    fresh = ts.build_index(x)
+    q = torch.from_numpy(oracle.synthetic_queries(4, 128))
+    s0, i0 = fresh.search(q, 10)
+    s1, i1 = index.search(q, 10)
+    assert torch.equal(s0, s1) and torch.equal(i0, i1)
+    sh, ih = index.search_host(q.numpy(), 10)                    # the host ctx re-sizes its workspace too
+    assert np.array_equal(ih, i0.cpu().numpy())
+
+
+@pytest.mark.parametrize("list_dtype", ["bf16", "fp8"])
+def test_ivf_lists_stay_valid_across_upserts(ts, list_dtype):
+    """Overflow lists + tombstones: (a) probing every list equals the exact search on the mutated corpus (bf16
+    lists), (b) a realistic probe budget equals the same search over freshly packed lists with the same
+    centroids, (c) re-pack clears the pending state without changing a result."""
+    dim, n0, nlist = 256, 40_000, 64
+    rng = np.random.default_rng(5)
+    table = {}
+    ids0 = np.arange(n0, dtype=np.int64) * 3
+    x0 = oracle.synthetic_rows(0, n0, dim, seed=21)
+    oracle.upsert_rows(table, ids0, x0)
+    index = ts.build_index(x0, ids=ids0)
+    index.ivf_train(nlist, n_sample=20_000, iters=4, seed=0)
+    index.ivf_build(list_dtype)
+    assert index.ivf_pending() == (0, 0)
+    for ids, rows in _stream(rng, table, 6, 301, dim, 2 * n0):   # ~half replace (ids divisible by 3), half append
+        oracle.upsert_rows(table, ids, rows)
+        index.upsert(torch.from_numpy(rows).cuda(), ids)
+    ovf, dead = index.ivf_pending()
+    assert ovf > 0 and dead > 0 and ovf + dead < n0 // 10        # incremental state, no automatic re-pack yet
+    fresh, ids_all, rows_all = _rebuild(ts, table, dim)
+    fresh.ivf_set_centroids(index.ivf_centroids())
+    fresh.ivf_build(list_dtype)
+    q = torch.from_numpy(oracle.synthetic_queries(40, dim))
+    if list_dtype == "bf16":
+        s_e, i_e = index.search(q, 10)
+        for qq, se, ie in ((q, s_e, i_e), (q[:1], s_e[:1], i_e[:1])):
+            s_a, i_a = index.ivf_search(qq, 10, nprobe=nlist, rescore_k=10)
+            assert torch.equal(se, s_a) and torch.equal(ie, i_a)
+    for qq in (q, q[:1]):                                        # batch (per-query scan while mutated) and latency mode
+        s_m, i_m = index.ivf_search(qq, 10, nprobe=8, rescore_k=100)
+        s_f, i_f = fresh.ivf_search(qq, 10, nprobe=8, rescore_k=100)
+        assert torch.equal(s_m, s_f) and torch.equal(i_m, i_f)
+    sizes = index.ivf_list_sizes()
+    assert int(sizes.sum()) == len(index) + dead                 # tombstones still occupy their slots
+    index.ivf_repack()
+    assert index.ivf_pending() == (0, 0)
+    assert int(index.ivf_list_sizes().sum()) == len(index)
+    off, rows = index.ivf_lists()
+    assert sorted(rows.cpu().tolist()) == list(range(len(index)))
+    s_r, i_r = index.ivf_search(q, 10, nprobe=8, rescore_k=100)
+    s_f, i_f = fresh.ivf_search(q, 10, nprobe=8, rescore_k=100)
+    assert torch.equal(s_r, s_f) and torch.equal(i_r, i_f)
+
+
+def test_heavy_churn_triggers_the_automatic_repack(ts):
+    dim, n0 = 128, 20_000
+    x0 = oracle.synthetic_rows(0, n0, dim, seed=31)
+    index = ts.build_index(x0)
+    index.ivf_train(32, n_sample=n0, iters=3, seed=0)
+    index.ivf_build("fp8")
+    more = oracle.synthetic_rows(n0, 1500, dim, seed=31)
+    index.add(torch.from_numpy(more).cuda())
+    assert index.ivf_pending() == (1500, 0)
+    index.add(torch.from_numpy(oracle.synthetic_rows(n0 + 1500, 3000, dim, seed=31)).cuda())   # churn past the re-pack threshold
+    assert index.ivf_pending() == (0, 0) and len(index) == n0 + 4500
+    q = torch.from_numpy(oracle.synthetic_queries(3, dim))
+    s_e, i_e = index.search(q, 5)
+    s_a, i_a = index.ivf_search(q, 5, nprobe=32, rescore_k=200)
+    assert torch.equal(i_e, i_a) and torch.equal(s_e, s_a)
+
+
+def test_fp8_scan_copy_follows_added_rows(ts):
+    """build_index(dtype='fp8') then add(): cos_sim_topk must keep answering, with the new rows."""
+    x = oracle.synthetic_rows(0, 30_000, 256, seed=41)
+    index = ts.build_index(x, dtype="fp8")
+    extra = oracle.synthetic_rows(30_000, 2_000, 256, seed=41)
+    index.add(torch.from_numpy(extra).cuda())
+    assert index.fp8_scan_ready
+    q = torch.from_numpy(extra[1234])                            # a new row as the query: it must come back first
+    s, i = ts.cos_sim_topk(q, index, 10)
+    assert int(i[0]) == 30_000 + 1234
+    s_e, i_e = index.search(q, 10)
+    assert float(s[0]) == float(s_e[0, 0])                       # re-scored exactly
+    assert len(set(i.tolist()) & set(i_e[0].tolist())) >= 9      # e4m3 candidate selection: recall, not identity

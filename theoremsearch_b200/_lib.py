@@ -53,6 +53,11 @@ SIGNATURES = {
     "ts_index_destroy": (None, [_p]),
     "ts_index_add": (_i, [_p, _p, _i, _i64, _i, _p, _p]),
     "ts_index_add_host": (_i, [_p, _p, _i, _i64, _i, _p]),
+    "ts_index_reserve": (_i, [_p, _i64]),
+    "ts_index_upsert": (_i, [_p, _p, _i, _i64, _i, _p, _p, _p]),
+    "ts_index_upsert_host": (_i, [_p, _p, _i, _i64, _i, _p, _p]),
+    "ts_ivf_pending": (_i, [_p, _p, _p]),
+    "ts_ivf_repack": (_i, [_p, _p]),
     "ts_index_size": (_i64, [_p]),
     "ts_index_capacity": (_i64, [_p]),
     "ts_index_dim": (_i, [_p]),

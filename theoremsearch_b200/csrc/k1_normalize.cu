@@ -86,7 +86,8 @@ template <typename SRC, typename DST, int NP>
 __global__ void __launch_bounds__(256, NP <= 16 ? 2 : 1) normalize_cast_kernel(const SRC* __restrict__ src, int64_t n,
                                                              int dim, int dim_pad, int normalize,
                                                              DST* __restrict__ dst,
-                                                             float* __restrict__ max_norm2) {
+                                                             float* __restrict__ max_norm2,
+                                                             const int64_t* __restrict__ dst_rows) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -94,7 +95,14 @@ __global__ void __launch_bounds__(256, NP <= 16 ? 2 : 1) normalize_cast_kernel(c
     float warp_max = 0.f;                 // running max over this warp's rows: ONE atomic per warp at the end
     for (int64_t row = warp0; row < n; row += nwarps) {
         const SRC* x = src + row * (int64_t)dim;
-        DST* y = dst + row * (int64_t)dim_pad;
+        // upsert: source row `row` lands in stored row dst_rows[row] (negative = superseded by a later source row
+        // with the same id, skipped); append / build: rows land contiguously
+        int64_t out_row = row;
+        if (dst_rows != nullptr) {
+            out_row = dst_rows[row];
+            if (out_row < 0) continue;
+        }
+        DST* y = dst + out_row * (int64_t)dim_pad;
         float2 v[NP];
         load_row_pairs<SRC, NP>(x, lane, dim, vec_ok, v);
         if (normalize) {
@@ -160,15 +168,15 @@ __global__ void __launch_bounds__(256) dequant_rows_kernel(const SRC* __restrict
 
 template <typename SRC, int NP>
 static int launch_nc_nj(const void* src, int64_t n, int dim, int dim_pad, int normalize, void* dst,
-                        int dst_dtype, cudaStream_t s, float* max_norm2) {
+                        int dst_dtype, cudaStream_t s, float* max_norm2, const int64_t* dst_rows) {
     int64_t blocks64 = (n + 7) / 8;
     int blocks = (int)(blocks64 > 148 * 32 ? 148 * 32 : blocks64);
     if (dst_dtype == TS_BF16) {
         normalize_cast_kernel<SRC, __nv_bfloat16, NP><<<blocks, 256, 0, s>>>(
-            (const SRC*)src, n, dim, dim_pad, normalize, (__nv_bfloat16*)dst, max_norm2);
+            (const SRC*)src, n, dim, dim_pad, normalize, (__nv_bfloat16*)dst, max_norm2, dst_rows);
     } else if (dst_dtype == TS_F32) {
         normalize_cast_kernel<SRC, float, NP><<<blocks, 256, 0, s>>>((const SRC*)src, n, dim, dim_pad,
-                                                                     normalize, (float*)dst, max_norm2);
+                                                                     normalize, (float*)dst, max_norm2, dst_rows);
     } else {
         set_error("normalize_cast: unsupported destination dtype %d", dst_dtype);
         return TS_ERR_UNSUPPORTED;
@@ -179,22 +187,23 @@ static int launch_nc_nj(const void* src, int64_t n, int dim, int dim_pad, int no
 
 template <typename SRC>
 static int launch_nc(const void* src, int64_t n, int dim, int dim_pad, int normalize, void* dst,
-                     int dst_dtype, cudaStream_t s, float* max_norm2) {
+                     int dst_dtype, cudaStream_t s, float* max_norm2, const int64_t* dst_rows) {
     if (n == 0) return TS_OK;
-    if (dim_pad <= 256) return launch_nc_nj<SRC, 4>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
-    if (dim_pad <= 512) return launch_nc_nj<SRC, 8>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
-    if (dim_pad <= 768) return launch_nc_nj<SRC, 12>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
-    if (dim_pad <= 1024) return launch_nc_nj<SRC, 16>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
-    return launch_nc_nj<SRC, 32>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
+    if (dim_pad <= 256) return launch_nc_nj<SRC, 4>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2, dst_rows);
+    if (dim_pad <= 512) return launch_nc_nj<SRC, 8>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2, dst_rows);
+    if (dim_pad <= 768) return launch_nc_nj<SRC, 12>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2, dst_rows);
+    if (dim_pad <= 1024) return launch_nc_nj<SRC, 16>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2, dst_rows);
+    return launch_nc_nj<SRC, 32>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2, dst_rows);
 }
 
 int launch_normalize_cast(const void* src, int src_dtype, int64_t n, int dim, int dim_pad,
-                          int normalize, void* dst, int dst_dtype, cudaStream_t s, float* max_norm2) {
+                          int normalize, void* dst, int dst_dtype, cudaStream_t s, float* max_norm2,
+                          const int64_t* dst_rows) {
     switch (src_dtype) {
-        case TS_F32: return launch_nc<float>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
+        case TS_F32: return launch_nc<float>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2, dst_rows);
         case TS_BF16:
-            return launch_nc<__nv_bfloat16>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
-        case TS_F16: return launch_nc<__half>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2);
+            return launch_nc<__nv_bfloat16>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2, dst_rows);
+        case TS_F16: return launch_nc<__half>(src, n, dim, dim_pad, normalize, dst, dst_dtype, s, max_norm2, dst_rows);
         default:
             set_error("normalize_cast: unsupported source dtype %d", src_dtype);
             return TS_ERR_BAD_ARG;

@@ -57,6 +57,8 @@ int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64
     memset(&p.fin, 0, sizeof(p.fin));
     memset(&p.xchg, 0, sizeof(p.xchg));
     p.pdl = 0;
+    p.ring_gate = nullptr;
+    p.ring_need = 0;
     p.timeline = nullptr;
     if (tunables().scan_timeline) {
         unsigned long long* base = nullptr;
@@ -65,6 +67,8 @@ int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64
     }
     if (fused != nullptr) {
         p.pdl = fused->pdl;
+        p.ring_gate = fused->ring_gate;
+        p.ring_need = fused->ring_need;
         p.q_raw = fused->q_raw;
         p.q_dtype = fused->q_dtype;
         p.q_normalize = fused->q_normalize;

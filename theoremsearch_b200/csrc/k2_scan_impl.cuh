@@ -59,12 +59,15 @@ struct ScanParams {
     // second kernel
     XchgDev xchg;
     // programmatic dependent launch (the sharded stream, ts_search_sharded): bit 0 = this grid was launched
-    // with programmatic stream serialisation — it lets its successor launch at once and waits for its
-    // predecessor (the previous query's exchange kernel, the reader of part_keys) only before it writes
-    // part_keys; bit 1 = queries / mask / corpus may have been written by the kernel that precedes this one
-    // on the stream: wait for it before touching anything (the safe default; without it the scan of query
-    // n+1 streams the corpus while query n's exchange kernel is still merging)
+    // with programmatic stream serialisation and lets its successor launch at once; bit 1 = queries / mask /
+    // corpus may have been written by the kernel that precedes this one on the stream: wait for it before
+    // touching anything (the safe default; without it the scan of query n+1 streams the corpus while query
+    // n's exchange kernel is still merging). part_keys then points into a ring of 4 per-search buffers; before
+    // a CTA writes its list it checks that the exchange kernel which last read this ring slot (search
+    // ring_need) has finished: *ring_gate is the sequence number of the last finished exchange.
     int pdl;
+    const uint32_t* ring_gate;
+    uint32_t ring_need;
     // diagnostics ("scan.timeline"): [gridDim.x][8] %globaltimer stamps of this launch, or nullptr
     unsigned long long* timeline;
 };
@@ -162,6 +165,62 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
         // max((float)sqrt, 1e-12).
         const size_t qoff = (size_t)qi * p.dim;
         float den = 1.0f;
+        if (p.q_dtype == TS_F32) {
+            // fp32 queries (the common case): every load of a phase is independent and issued back to back —
+            // one L2 round trip per phase. (A rolled loop of dependent-latency loads cost 10-13 us here, during
+            // which the warp's two TMA slots sat full: 3 % of a 1.25M-row shard's scan.)
+            const float* qv = reinterpret_cast<const float*>(p.q_raw) + qoff;
+            if (p.q_normalize) {
+                constexpr int NP = NCHUNK * CN / 2;            // pairs per lane: (2l, 2l+1) + 64j
+                const bool vec2 = ((p.dim & 1) == 0) && ((reinterpret_cast<uintptr_t>(qv) & 7u) == 0);
+                float2 v[NP];
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    const int i = 2 * lane + 64 * j;
+                    v[j] = make_float2(0.f, 0.f);
+                    if (vec2) {
+                        if (i < p.dim) v[j] = __ldg(reinterpret_cast<const float2*>(qv + i));
+                    } else {
+                        if (i < p.dim) v[j].x = __ldg(qv + i);
+                        if (i + 1 < p.dim) v[j].y = __ldg(qv + i + 1);
+                    }
+                }
+                double ss = 0.0;
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {                 // zeros past dim leave ss unchanged (K1 does the same)
+                    const double a = (double)v[j].x, b = (double)v[j].y;
+                    ss = fma(a, a, ss);
+                    ss = fma(b, b, ss);
+                }
+                ss = warp_sum(ss);
+                den = fmaxf((float)sqrt(ss), 1e-12f);
+            }
+            const bool vec4 = ((p.dim & 3) == 0) && ((reinterpret_cast<uintptr_t>(qv) & 15u) == 0);
+#pragma unroll
+            for (int j = 0; j < NCHUNK; ++j) {
+                const int e0 = (j * 32 + lane) * CN;
+#pragma unroll
+                for (int i = 0; i < CN; i += 4) {
+                    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (vec4) {
+                        if (e0 + i < p.dim) f = __ldg(reinterpret_cast<const float4*>(qv + e0 + i));
+                    } else {
+                        if (e0 + i < p.dim) f.x = __ldg(qv + e0 + i);
+                        if (e0 + i + 1 < p.dim) f.y = __ldg(qv + e0 + i + 1);
+                        if (e0 + i + 2 < p.dim) f.z = __ldg(qv + e0 + i + 2);
+                        if (e0 + i + 3 < p.dim) f.w = __ldg(qv + e0 + i + 3);
+                    }
+                    q[j * CN + i] = f.x;
+                    q[j * CN + i + 1] = f.y;
+                    q[j * CN + i + 2] = f.z;
+                    q[j * CN + i + 3] = f.w;
+                }
+            }
+            if (p.q_normalize) {
+#pragma unroll
+                for (int i = 0; i < NCHUNK * CN; ++i) q[i] = __fdiv_rn(q[i], den);
+            }
+        } else {
         if (p.q_normalize) {
             double ss = 0.0;
             for (int i = 2 * lane; i < p.dim; i += 64) {   // K1's order: lane l owns pairs (2l, 2l+1) + 64j
@@ -184,6 +243,7 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
                 if (p.q_normalize) v = __fdiv_rn(v, den);
                 q[j * CN + i] = v;
             }
+        }
         }
     }
 
@@ -259,7 +319,9 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
     __syncthreads();
     if (warp == 0) {
         for (int w = 1; w < W; ++w) merge_sorted_into<KPL>(list, lists + (size_t)w * (KPL * 32), k, k, lane);
-        if (p.pdl & 1) griddep_wait();   // the previous query's exchange kernel has read part_keys
+        if (p.ring_gate != nullptr) {    // (never waits in practice: the slot's reader is four searches back)
+            while ((int32_t)(ld_acquire_gpu_u32(p.ring_gate) - p.ring_need) < 0) __nanosleep(200);
+        }
         uint64_t* out = p.part_keys + ((size_t)wi * gridDim.x + blockIdx.x) * k;
 #pragma unroll
         for (int j = 0; j < KPL; ++j) {

@@ -456,6 +456,11 @@ __global__ void list_sizes_kernel(const int64_t* __restrict__ offsets, int nlist
     if (c < nlist) out[c] = offsets[c + 1] - offsets[c];
 }
 
+__global__ void add_list_sizes_kernel(const int64_t* __restrict__ offsets, int nlist, int64_t* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < nlist) out[c] += offsets[c + 1] - offsets[c];
+}
+
 // ---------------------------------------------------------------------------------- K4b list scan
 struct ListScanParams {
     const uint8_t* list_data;     // [n, row_bytes] rows in list order
@@ -467,7 +472,8 @@ struct ListScanParams {
     int nprobe;
     const float* queries;         // [nq, dim_pad] fp32 normalised
     const uint32_t* mask;         // allow bitmask over CORPUS rows (SQL WHERE before ORDER BY/LIMIT) or nullptr
-    const uint32_t* list_rows;    // [n] corpus row of every list position (only read when mask != nullptr)
+    const uint32_t* list_rows;    // [n] corpus row of every list position (only read when mask != nullptr or has_dead)
+    int has_dead;                 // some positions are tombstones (list_rows[pos] == TS_DEAD_ROW): skip them
     int k;                        // candidates kept per query (rescore_k)
     uint64_t* part_keys;          // [nq][gridDim.x][k]
     uint32_t* tickets;            // [nq] zero on entry, left zero
@@ -635,9 +641,10 @@ __global__ void __launch_bounds__(512, 1) list_scan_kernel(const ListScanParams 
         const int left = s_len[jc] - tc * R;
         const int64_t pos = s_start[jc] + (int64_t)tc * R + my_row;
         bool mine = leader && my_row < left;
-        if (p.mask != nullptr && mine) {   // filtered search: position -> corpus row -> allow bit
+        if ((p.mask != nullptr || p.has_dead) && mine) {   // position -> corpus row -> tombstone? -> allow bit
             const uint32_t row = __ldg(p.list_rows + pos);
-            mine = (__ldg(p.mask + (row >> 5)) >> (row & 31)) & 1u;
+            mine = row != TS_DEAD_ROW;
+            if (mine && p.mask != nullptr) mine = (__ldg(p.mask + (row >> 5)) >> (row & 31)) & 1u;
         }
         float scale = 1.0f;
         if (ELEM == 1 && mine) scale = __ldg(p.scales + pos);
@@ -1025,6 +1032,11 @@ static void ivf_free_lists(ts_index* ix) {
     ix->list_rows = nullptr;
     ix->list_data = nullptr;
     ix->list_scales = nullptr;
+    cudaFree(ix->pos_of_row);
+    cudaFree(ix->ovf_set);
+    ix->pos_of_row = nullptr;
+    ix->ovf_set = nullptr;
+    ix->list_cap = ix->built_n = ix->ovf_n = ix->ivf_dead = ix->ovf_cap = 0;
     ix->ivf_built = false;
 }
 static void ivf_free_centroids(ts_index* ix) {
@@ -1093,6 +1105,181 @@ static int sort_by_list(const uint32_t* assign, int64_t n, int nlist, uint32_t* 
     g_launches.fetch_add(1, std::memory_order_relaxed);
     list_offsets_kernel<<<(nlist + 1 + 255) / 256, 256, 0, s>>>(sorted_assign, n, nlist, offsets);
     TS_LAUNCH_CHECK();
+    return TS_OK;
+}
+
+// ---------------------------------------------------------------------------------- incremental upkeep
+__global__ void invert_rows_kernel(const uint32_t* __restrict__ list_rows, int64_t n, int64_t first_pos,
+                                   uint32_t* __restrict__ pos_of_row) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t row = list_rows[first_pos + i];
+        if (row != TS_DEAD_ROW) pos_of_row[row] = (uint32_t)(first_pos + i);
+    }
+}
+// Replaced rows: the main-list position holding the old content dies; the row joins the overflow set (rows already
+// in the overflow just stay there — their content is re-gathered below).
+__global__ void tombstone_kernel(const uint32_t* __restrict__ replaced, int64_t n, uint32_t* __restrict__ pos_of_row,
+                                 int64_t built_n, uint32_t* __restrict__ list_rows, uint32_t* __restrict__ ovf_set,
+                                 unsigned int* __restrict__ moved) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t row = replaced[i];
+        const uint32_t pos = pos_of_row[row];
+        if ((int64_t)pos < built_n && list_rows[pos] == row) {
+            list_rows[pos] = TS_DEAD_ROW;
+            ovf_set[atomicAdd(moved, 1u)] = row;
+        }
+    }
+}
+__global__ void iota_from_kernel(uint32_t* out, int64_t n, uint32_t first) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = first + (uint32_t)i;
+}
+__global__ void gather_rows_kernel(const uint8_t* __restrict__ corpus, uint32_t row_bytes, const uint32_t* __restrict__ rows,
+                                   int64_t n, uint8_t* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += (int64_t)gridDim.x * 8) {
+        const uint8_t* src = corpus + (size_t)rows[i] * row_bytes;
+        for (uint32_t off = lane * 16u; off < row_bytes; off += 512u)
+            *reinterpret_cast<uint4*>(dst + (size_t)i * row_bytes + off) = __ldg(reinterpret_cast<const uint4*>(src + off));
+    }
+}
+// members[j] indexes the (ascending) overflow set: overflow position j holds corpus row ovf_set[members[j]]
+__global__ void overflow_rows_kernel(const uint32_t* __restrict__ ovf_set, const uint32_t* __restrict__ members, int64_t m,
+                                     int64_t built_n, uint32_t* __restrict__ list_rows, uint32_t* __restrict__ pos_of_row) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t row = ovf_set[members[j]];
+        list_rows[built_n + j] = row;
+        pos_of_row[row] = (uint32_t)(built_n + j);
+    }
+}
+__global__ void overflow_offsets_kernel(const int64_t* __restrict__ tmp_offsets, int nlist, int64_t built_n,
+                                        int64_t* __restrict__ list_offsets) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l <= nlist) list_offsets[nlist + l] = built_n + tmp_offsets[l];
+}
+// probe (score, list l) -> probes (score, l) and (score, nlist + l): the main list and its overflow list
+__global__ void expand_probes_kernel(const uint64_t* __restrict__ in, int64_t n, int nlist, uint64_t* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = in[i];
+        out[2 * i] = key;
+        out[2 * i + 1] = key ? pack_key(key_score(key), key_row(key) + (uint32_t)nlist) : 0ull;
+    }
+}
+
+template <typename T>
+static int grow_buffer(T** buf, size_t old_count, size_t new_count) {
+    T* fresh = nullptr;
+    TS_CHECK_CUDA(cudaMalloc(&fresh, std::max<size_t>(new_count, 1) * sizeof(T)));
+    if (*buf != nullptr && old_count > 0) {
+        cudaError_t e = cudaMemcpy(fresh, *buf, old_count * sizeof(T), cudaMemcpyDeviceToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(fresh);
+            TS_CHECK_CUDA(e);
+        }
+    }
+    cudaFree(*buf);
+    *buf = fresh;
+    return TS_OK;
+}
+
+void ivf_free_all(ts_index* ix) {
+    ivf_free_lists(ix);
+    ivf_free_centroids(ix);
+}
+
+int ivf_apply_mutation(ts_index* ix, const uint32_t* replaced_rows, int64_t n_replaced, int64_t app_first, int64_t app_n,
+                       cudaStream_t s) {
+    if (!ix->ivf_built || (n_replaced == 0 && app_n == 0)) return TS_OK;
+    // Past a tenth of the corpus in tombstones + overflow the lists are re-packed from scratch (one K4a pass over
+    // all rows: ~1 s per 40M rows); below that only the overflow lists are rebuilt, O(overflow).
+    const int64_t churn = ix->ivf_dead + ix->ovf_n + n_replaced + app_n;
+    if (churn > std::max<int64_t>(4096, ix->size / 10)) return ts_ivf_build(ix, ix->list_dtype, s);
+    TS_CHECK_CUDA(cudaStreamSynchronize(s));
+    const int64_t m_max = ix->ovf_n + n_replaced + app_n;
+    if (m_max > ix->ovf_cap) {
+        const int64_t cap = std::max<int64_t>(m_max, 2 * ix->ovf_cap);
+        int rc = grow_buffer(&ix->ovf_set, (size_t)ix->ovf_n, (size_t)cap);
+        if (rc) return rc;
+        ix->ovf_cap = cap;
+    }
+    if (ix->built_n + m_max > ix->list_cap) {
+        const int64_t cap = std::max<int64_t>(ix->built_n + m_max, ix->list_cap + ix->list_cap / 8);
+        const size_t used = (size_t)(ix->built_n + ix->ovf_n);
+        int rc = grow_buffer(&ix->list_rows, used, (size_t)cap);
+        if (!rc) rc = grow_buffer((uint8_t**)&ix->list_data, used * ix->list_row_bytes, (size_t)cap * ix->list_row_bytes);
+        if (!rc && ix->list_scales) rc = grow_buffer(&ix->list_scales, used, (size_t)cap);
+        if (rc) return rc;
+        ix->list_cap = cap;
+    }
+    TempBufs tmp;
+    int rc;
+    // 1. tombstones; replaced main-list rows join the overflow set
+    unsigned int moved = 0;
+    if (n_replaced > 0) {
+        unsigned int* d_moved = nullptr;
+        if ((rc = tmp.get(&d_moved, 1))) return rc;
+        TS_CHECK_CUDA(cudaMemsetAsync(d_moved, 0, sizeof(unsigned int), s));
+        tombstone_kernel<<<(int)std::min<int64_t>((n_replaced + 255) / 256, 1024), 256, 0, s>>>(
+            replaced_rows, n_replaced, ix->pos_of_row, ix->built_n, ix->list_rows, ix->ovf_set + ix->ovf_n, d_moved);
+        TS_LAUNCH_CHECK();
+        TS_CHECK_CUDA(cudaMemcpyAsync(&moved, d_moved, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+        TS_CHECK_CUDA(cudaStreamSynchronize(s));
+        ix->ivf_dead += moved;
+    }
+    int64_t m = ix->ovf_n + moved;
+    if (app_n > 0) {
+        iota_from_kernel<<<(int)std::min<int64_t>((app_n + 255) / 256, 1024), 256, 0, s>>>(ix->ovf_set + m, app_n,
+                                                                                          (uint32_t)app_first);
+        TS_LAUNCH_CHECK();
+        m += app_n;
+    }
+    if (m == 0) return TS_OK;
+    TS_REQUIRE(m < (int64_t)1 << 31, TS_ERR_UNSUPPORTED, "ivf: more than 2^31-1 overflow rows");
+    // 2. the overflow set in ascending row order (so rows ascend inside every overflow list, like the main lists)
+    uint32_t* sorted_set = nullptr;
+    if ((rc = tmp.get(&sorted_set, (size_t)m))) return rc;
+    {
+        size_t tbytes = 0;
+        TS_CHECK_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tbytes, ix->ovf_set, sorted_set, (int)m, 0, 32, s));
+        uint8_t* t = nullptr;
+        if ((rc = tmp.get(&t, tbytes))) return rc;
+        TS_CHECK_CUDA(cub::DeviceRadixSort::SortKeys(t, tbytes, ix->ovf_set, sorted_set, (int)m, 0, 32, s));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        TS_CHECK_CUDA(cudaMemcpyAsync(ix->ovf_set, sorted_set, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    }
+    // 3. file them under the existing centroids: gather -> K4a -> (list, row) order
+    uint8_t* rows = nullptr;
+    uint32_t *assign = nullptr, *sorted_assign = nullptr, *iota = nullptr, *members = nullptr;
+    int64_t* offsets = nullptr;
+    if ((rc = tmp.get(&rows, (size_t)m * ix->row_bytes())) || (rc = tmp.get(&assign, (size_t)m)) ||
+        (rc = tmp.get(&sorted_assign, (size_t)m)) || (rc = tmp.get(&iota, (size_t)m)) || (rc = tmp.get(&members, (size_t)m)) ||
+        (rc = tmp.get(&offsets, (size_t)ix->nlist + 1)))
+        return rc;
+    const int gblocks = (int)std::min<int64_t>((m + 7) / 8, 148 * 16);
+    gather_rows_kernel<<<gblocks, 256, 0, s>>>((const uint8_t*)ix->data, (uint32_t)ix->row_bytes(), ix->ovf_set, m, rows);
+    TS_LAUNCH_CHECK();
+    rc = launch_assign(ix->device, rows, m, ix->row_bytes(), ix->centroids_bf16, ix->nlist, ix->dim_pad, assign, nullptr, s);
+    if (rc) return rc;
+    rc = sort_by_list(assign, m, ix->nlist, sorted_assign, iota, members, offsets, tmp, s);
+    if (rc) return rc;
+    overflow_rows_kernel<<<(int)std::min<int64_t>((m + 255) / 256, 1024), 256, 0, s>>>(ix->ovf_set, members, m, ix->built_n,
+                                                                                      ix->list_rows, ix->pos_of_row);
+    TS_LAUNCH_CHECK();
+    if (ix->list_dtype == TS_BF16)
+        gather_quantize_kernel<2><<<gblocks, 256, 0, s>>>((const uint8_t*)ix->data, (uint32_t)ix->row_bytes(),
+                                                          ix->list_rows + ix->built_n, m, ix->dim_pad, ix->list_row_bytes,
+                                                          (uint8_t*)ix->list_data + (size_t)ix->built_n * ix->list_row_bytes,
+                                                          nullptr);
+    else
+        gather_quantize_kernel<1><<<gblocks, 256, 0, s>>>((const uint8_t*)ix->data, (uint32_t)ix->row_bytes(),
+                                                          ix->list_rows + ix->built_n, m, ix->dim_pad, ix->list_row_bytes,
+                                                          (uint8_t*)ix->list_data + (size_t)ix->built_n * ix->list_row_bytes,
+                                                          ix->list_scales + ix->built_n);
+    TS_LAUNCH_CHECK();
+    overflow_offsets_kernel<<<(ix->nlist + 1 + 255) / 256, 256, 0, s>>>(offsets, ix->nlist, ix->built_n, ix->list_offsets);
+    TS_LAUNCH_CHECK();
+    TS_CHECK_CUDA(cudaStreamSynchronize(s));   // temporaries are freed on return
+    ix->ovf_n = m;
     return TS_OK;
 }
 
@@ -1203,7 +1390,8 @@ int ts_ivf_build(ts_index* ix, int list_dtype, void* stream) {
     int rc;
     if ((rc = tmp.get(&assign, (size_t)n)) || (rc = tmp.get(&sorted_assign, (size_t)n)) || (rc = tmp.get(&iota, (size_t)n)))
         return rc;
-    TS_CHECK_CUDA(cudaMalloc(&ix->list_offsets, ((size_t)ix->nlist + 1) * sizeof(int64_t)));
+    TS_CHECK_CUDA(cudaMalloc(&ix->list_offsets, (2 * (size_t)ix->nlist + 1) * sizeof(int64_t)));
+    TS_CHECK_CUDA(cudaMalloc(&ix->pos_of_row, std::max<size_t>((size_t)ix->capacity, 1) * sizeof(uint32_t)));
     TS_CHECK_CUDA(cudaMalloc(&ix->list_rows, std::max<size_t>((size_t)n, 1) * sizeof(uint32_t)));
     TS_CHECK_CUDA(cudaMalloc(&ix->list_data, std::max<size_t>((size_t)n, 1) * lrow));
     if (list_dtype == TS_FP8_E4M3)
@@ -1226,13 +1414,33 @@ int ts_ivf_build(ts_index* ix, int list_dtype, void* stream) {
                                                              ix->list_rows, n, ix->dim_pad, lrow, (uint8_t*)ix->list_data,
                                                              ix->list_scales);
         TS_LAUNCH_CHECK();
+        invert_rows_kernel<<<1024, 256, 0, s>>>(ix->list_rows, n, 0, ix->pos_of_row);
+        TS_LAUNCH_CHECK();
     }
     TS_CHECK_CUDA(cudaStreamSynchronize(s));
+    ix->list_cap = std::max<int64_t>(n, 1);
+    ix->built_n = n;
+    ix->ovf_n = 0;
+    ix->ivf_dead = 0;
     ix->ivf_built = true;
     return TS_OK;
 }
 
 int ts_ivf_nlist(const ts_index* ix) { return ix ? ix->nlist : -1; }
+
+int ts_ivf_repack(ts_index* ix, void* stream) {
+    TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "ivf_repack: index is NULL");
+    TS_REQUIRE(ix->ivf_built, TS_ERR_STATE, "ivf_repack: lists are not built (call ts_ivf_build)");
+    if (ix->ovf_n == 0 && ix->ivf_dead == 0) return TS_OK;
+    return ts_ivf_build(ix, ix->list_dtype, stream);
+}
+
+int ts_ivf_pending(const ts_index* ix, int64_t* overflow_rows, int64_t* dead_positions) {
+    TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "ivf_pending: index is NULL");
+    if (overflow_rows) *overflow_rows = ix->ivf_built ? ix->ovf_n : 0;
+    if (dead_positions) *dead_positions = ix->ivf_built ? ix->ivf_dead : 0;
+    return TS_OK;
+}
 
 int ts_debug_ivf_timeline(uint64_t* out_host, int n_ctas) {
     TS_REQUIRE(out_host != nullptr && n_ctas >= 1 && n_ctas <= 148, TS_ERR_BAD_ARG, "debug_ivf_timeline: bad argument");
@@ -1248,12 +1456,20 @@ int ts_ivf_list_sizes(const ts_index* ix, int64_t* out, void* stream) {
     TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_list_sizes: cannot select CUDA device %d", ix->device);
     list_sizes_kernel<<<(ix->nlist + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ix->list_offsets, ix->nlist, out);
     TS_LAUNCH_CHECK();
+    if (ix->ovf_n > 0) {   // + the overflow lists (tombstoned positions still count until the re-pack)
+        add_list_sizes_kernel<<<(ix->nlist + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ix->list_offsets + ix->nlist,
+                                                                                         ix->nlist, out);
+        TS_LAUNCH_CHECK();
+    }
     return TS_OK;
 }
 
 int ts_ivf_get_lists(const ts_index* ix, int64_t* offsets_out, int64_t* rows_out, void* stream) {
     TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "ivf_get_lists: index is NULL");
     TS_REQUIRE(ix->ivf_built, TS_ERR_STATE, "ivf_get_lists: lists are not built (call ts_ivf_build)");
+    TS_REQUIRE(ix->ovf_n == 0 && ix->ivf_dead == 0, TS_ERR_STATE,
+               "ivf_get_lists: rows were added or replaced since the build (%lld in overflow lists, %lld tombstones); "
+               "call ts_ivf_repack first", (long long)ix->ovf_n, (long long)ix->ivf_dead);
     DeviceGuard g(ix->device);
     TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_get_lists: cannot select CUDA device %d", ix->device);
     cudaStream_t s = (cudaStream_t)stream;
@@ -1270,8 +1486,9 @@ int ts_ivf_get_lists(const ts_index* ix, int64_t* offsets_out, int64_t* rows_out
 int ts_ivf_get_list_data(const ts_index* ix, int64_t first, int64_t n, float* out, void* stream) {
     TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "ivf_get_list_data: index is NULL");
     TS_REQUIRE(ix->ivf_built, TS_ERR_STATE, "ivf_get_list_data: lists are not built (call ts_ivf_build)");
-    TS_REQUIRE(first >= 0 && n >= 0 && first + n <= ix->size, TS_ERR_BAD_ARG, "ivf_get_list_data: [%lld, %lld) outside [0, %lld)",
-               (long long)first, (long long)(first + n), (long long)ix->size);
+    TS_REQUIRE(first >= 0 && n >= 0 && first + n <= ix->built_n + ix->ovf_n, TS_ERR_BAD_ARG,
+               "ivf_get_list_data: [%lld, %lld) outside [0, %lld)", (long long)first, (long long)(first + n),
+               (long long)(ix->built_n + ix->ovf_n));
     if (n == 0) return TS_OK;
     TS_REQUIRE(out != nullptr, TS_ERR_BAD_ARG, "ivf_get_list_data: out is NULL");
     DeviceGuard g(ix->device);
@@ -1315,6 +1532,7 @@ static int ivf_parts(const ts_index* ix, int nq) {
 static bool ivf_use_grouped(const ts_index* ix, int nq, int kc, int nprobe) {
     const int m = tunables().ivf_group_min_nq;
     if (m <= 0 || nq < m || !ivf_grouped_supported(ix, kc)) return false;
+    if (ix->ovf_n > 0 || ix->ivf_dead > 0) return false;   // overflow lists / tombstones: per-query scan until the re-pack
     const int64_t pairs = (int64_t)nq * std::min(nprobe, ix->nlist);
     const int min_lists = tunables().ivf_group_min_lists > 0 ? tunables().ivf_group_min_lists : 4 * sm_count(ix->device);
     return ix->nlist >= min_lists && pairs >= min_lists;
@@ -1324,6 +1542,7 @@ struct IvfWs {
     void* grouped;
     float* q32;
     uint64_t* probes;
+    uint64_t* probes2;
     void* coarse;
     size_t coarse_bytes;
     uint64_t* part_keys;
@@ -1342,6 +1561,7 @@ static IvfWs carve_ivf(const ts_index* ix, int nq, int kc, int nprobe, void* bas
     };
     w.q32 = (float*)take((size_t)nq * ix->dim_pad * 4);
     w.probes = (uint64_t*)take((size_t)nq * nprobe * 8);
+    w.probes2 = (uint64_t*)take((size_t)nq * nprobe * 2 * 8);   // (main list, overflow list) per probe, when rows were added
     w.coarse_bytes = ts_workspace_bytes(&view, nq, nprobe);
     w.coarse = take(w.coarse_bytes);
     w.part_keys = (uint64_t*)take((size_t)nq * ivf_parts(ix, nq) * kc * 8);
@@ -1397,9 +1617,18 @@ static int ivf_search_impl(ts_index* ix, const void* queries, int q_dtype, int n
     p.list_offsets = ix->list_offsets;
     p.probes = w.probes;
     p.nprobe = nprobe;
+    if (ix->ovf_n > 0) {   // rows added since the build: every probed list brings its overflow list along
+        const int64_t np = (int64_t)nq * nprobe;
+        expand_probes_kernel<<<(int)std::min<int64_t>((np + 255) / 256, 1024), 256, 0, s>>>(w.probes, np, ix->nlist,
+                                                                                         w.probes2);
+        TS_LAUNCH_CHECK();
+        p.probes = w.probes2;
+        p.nprobe = 2 * nprobe;
+    }
     p.queries = w.q32;
     p.mask = allow_mask;
     p.list_rows = ix->list_rows;
+    p.has_dead = ix->ivf_dead > 0 ? 1 : 0;
     p.k = kc;
     p.part_keys = w.part_keys;
     p.tickets = w.tickets;

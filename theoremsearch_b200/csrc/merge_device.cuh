@@ -194,6 +194,14 @@ __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long globaltimer_ns2() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -211,7 +219,22 @@ __device__ __forceinline__ unsigned long long globaltimer_ns2() {
 //      sticky error flag (host-mapped memory: the host sees it without synchronising) and write a poisoned
 //      result (-inf, -1) so that a stale or partial merge can never pass for an answer.
 // Slots and flags are double-buffered by sequence parity: a rank finishes query s only after every rank has
-// pushed s, so nobody can be more than one query ahead of a reader.
+// pushed s, so nobody can be more than one query ahead of a reader. Exchanges of one rank run strictly in
+// sequence: step 0 waits until *x.done_seq == seq - 1 (the exchange kernels of consecutive searches are chained
+// by programmatic dependent launch, which orders their starts, not their completions) and the last step
+// publishes *x.done_seq = seq, which also releases the scan kernel's ring slot (k2_scan_impl.cuh).
+// The queries of one search finish in separate CTAs: the last of them publishes the search as done.
+__device__ __forceinline__ void xchg_publish_done(const XchgDev& x) {
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (x.nq == 1 || atomicAdd(x.done_count, 1u) == (unsigned)x.nq - 1u) {
+            if (x.nq > 1) *x.done_count = 0u;
+            __threadfence();
+            st_release_gpu_u32(x.done_seq, x.seq);
+        }
+    }
+}
+
 template <int KPL>
 __device__ __forceinline__ void exchange_and_merge(const XchgDev& x, const MergeParams& fin, MergeParams local, int wi,
                                                    int qi, int k, uint64_t* lists, int nwarps) {
@@ -224,7 +247,17 @@ __device__ __forceinline__ void exchange_and_merge(const XchgDev& x, const Merge
     local.out_scores = nullptr;
     local.out_ids = nullptr;
     local.id_map = nullptr;
-    if (threadIdx.x == 0) s_timed_out = 0;
+    if (threadIdx.x == 0) {
+        s_timed_out = 0;
+        const unsigned long long t0 = globaltimer_ns2();
+        while ((int32_t)(ld_acquire_gpu_u32(x.done_seq) - (x.seq - 1u)) < 0) {
+            if (globaltimer_ns2() - t0 > x.timeout_ns) {
+                s_timed_out = 1;
+                *reinterpret_cast<volatile int*>(x.error) = 1;
+                break;
+            }
+        }
+    }
     merge_lists<KPL>(local, wi, qi, lists, nwarps);
     __threadfence();
     __syncthreads();
@@ -256,6 +289,7 @@ __device__ __forceinline__ void exchange_and_merge(const XchgDev& x, const Merge
             if (fin.out_ids) fin.out_ids[(size_t)qi * k + i] = -1;
         }
         __syncthreads();
+        xchg_publish_done(x);
         return;
     }
     MergeParams w = fin;
@@ -266,6 +300,7 @@ __device__ __forceinline__ void exchange_and_merge(const XchgDev& x, const Merge
     w.stride_query = (int64_t)slot_sz;
     w.list_base = nullptr;     // already global rows
     merge_lists<KPL>(w, qi, qi, lists, nwarps);
+    xchg_publish_done(x);
 }
 
 }  // namespace ts

@@ -89,6 +89,8 @@ int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k,
     f.out_ids = out_ids;
     memset(&f.xchg, 0, sizeof(f.xchg));
     f.pdl = 0;
+    f.ring_gate = nullptr;
+    f.ring_need = 0;
     return launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, w.part_keys, w.nparts,
                             s, ev0, ev1, nullptr, nullptr, &f);
 }
@@ -176,6 +178,9 @@ void ts_index_destroy(ts_index* ix) {
     cudaFree(ix->list_data);
     cudaFree(ix->list_scales);
     cudaFree(ix->centroid_max_norm2);
+    cudaFree(ix->pos_of_row);
+    cudaFree(ix->ovf_set);
+    delete ix->id_map_host;
     delete ix;
 }
 
@@ -190,11 +195,13 @@ int ts_index_add(ts_index* ix, const void* rows, int src_dtype, int64_t n, int n
     TS_REQUIRE(n >= 0, TS_ERR_BAD_ARG, "index_add: n=%lld", (long long)n);
     if (n == 0) return TS_OK;
     TS_REQUIRE(rows != nullptr, TS_ERR_BAD_ARG, "index_add: rows is NULL");
-    TS_REQUIRE(ix->size + n <= ix->capacity, TS_ERR_CAPACITY, "index_add: %lld + %lld rows exceed capacity %lld",
-               (long long)ix->size, (long long)n, (long long)ix->capacity);
     DeviceGuard g(ix->device);
     TS_REQUIRE(g.ok, TS_ERR_CUDA, "index_add: cannot select CUDA device %d", ix->device);
     cudaStream_t s = (cudaStream_t)stream;
+    if (ix->size + n > ix->capacity) {   // the pgvector table this replaces has no fixed size (rds_schema.sql:50-53)
+        int grc = index_make_room(ix, n);
+        if (grc) return grc;
+    }
     if (ids != nullptr && !ix->has_ids) {
         // first explicit ids: materialise the id table, rows added so far keep id = row
         TS_CHECK_CUDA(cudaMalloc(&ix->ids, (size_t)std::max<int64_t>(ix->capacity, 1) * sizeof(int64_t)));
@@ -217,9 +224,11 @@ int ts_index_add(ts_index* ix, const void* rows, int src_dtype, int64_t n, int n
     int rc = launch_normalize_cast(rows, src_dtype, n, ix->dim, ix->dim_pad, normalize, dst, ix->dtype, s,
                                    ix->max_norm2);
     if (rc) return rc;
+    const int64_t first = ix->size;
     ix->size += n;
-    ix->ivf_built = false;
-    return TS_OK;
+    ix->id_map_valid = false;
+    // built IVF lists stay valid: the new rows are filed in overflow lists (re-packed once they reach a tenth of the corpus)
+    return ivf_apply_mutation(ix, nullptr, 0, first, n, s);
 }
 
 int ts_index_add_host(ts_index* ix, const void* rows, int src_dtype, int64_t n, int normalize,
@@ -350,10 +359,12 @@ int ts_index_append_raw_host(ts_index* ix, const void* rows, int64_t n, const in
     TS_REQUIRE(n >= 0, TS_ERR_BAD_ARG, "index_append_raw_host: n=%lld", (long long)n);
     if (n == 0) return TS_OK;
     TS_REQUIRE(rows != nullptr, TS_ERR_BAD_ARG, "index_append_raw_host: rows is NULL");
-    TS_REQUIRE(ix->size + n <= ix->capacity, TS_ERR_CAPACITY, "index_append_raw_host: %lld + %lld rows exceed capacity %lld",
-               (long long)ix->size, (long long)n, (long long)ix->capacity);
     DeviceGuard g(ix->device);
     TS_REQUIRE(g.ok, TS_ERR_CUDA, "index_append_raw_host: cannot select CUDA device %d", ix->device);
+    if (ix->size + n > ix->capacity) {
+        int grc = index_make_room(ix, n);
+        if (grc) return grc;
+    }
     if (ids != nullptr && !ix->has_ids) {
         TS_CHECK_CUDA(cudaMalloc(&ix->ids, (size_t)std::max<int64_t>(ix->capacity, 1) * sizeof(int64_t)));
         if (ix->size > 0) {
@@ -375,9 +386,10 @@ int ts_index_append_raw_host(ts_index* ix, const void* rows, int64_t n, const in
     int rc = launch_max_norm2(dst, ix->dtype, n, ix->dim_pad, ix->max_norm2, nullptr);
     if (rc) return rc;
     TS_CHECK_CUDA(cudaDeviceSynchronize());
+    const int64_t first = ix->size;
     ix->size += n;
-    ix->ivf_built = false;
-    return TS_OK;
+    ix->id_map_valid = false;
+    return ivf_apply_mutation(ix, nullptr, 0, first, n, nullptr);
 }
 
 int ts_ivf_list_dtype(const ts_index* ix) { return (ix && ix->ivf_built) ? ix->list_dtype : -1; }
@@ -549,6 +561,8 @@ int ts_xchg_create(ts_xchg** out, int device, int world, int rank, int max_nq, i
     if (e == cudaSuccess) e = cudaMalloc(&x->d_peer_flags, 16 * sizeof(void*));
     if (e == cudaSuccess) e = cudaMalloc(&x->d_tickets, (size_t)max_nq * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(x->d_tickets, 0, (size_t)max_nq * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&x->d_done, 2 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(x->d_done, 0, 2 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&x->h_error, sizeof(int), cudaHostAllocMapped);
     if (e == cudaSuccess) {
         *x->h_error = 0;
@@ -577,6 +591,8 @@ void ts_xchg_destroy(ts_xchg* x) {
     cudaFree(x->d_peer_slots);
     cudaFree(x->d_peer_flags);
     cudaFree(x->d_tickets);
+    cudaFree(x->d_done);
+    cudaFree(x->part_ring);
     cudaFreeHost(x->h_error);
     cudaFreeHost(x->h_queries);
     cudaFreeHost(x->h_scores);
@@ -641,6 +657,7 @@ int ts_xchg_reset(ts_xchg* x) {
     TS_CHECK_CUDA(cudaDeviceSynchronize());
     TS_CHECK_CUDA(cudaMemset(x->base, 0, x->bytes));
     TS_CHECK_CUDA(cudaMemset(x->d_tickets, 0, (size_t)x->max_nq * sizeof(uint32_t)));
+    TS_CHECK_CUDA(cudaMemset(x->d_done, 0, 2 * sizeof(uint32_t)));
     TS_CHECK_CUDA(cudaDeviceSynchronize());
     *reinterpret_cast<volatile int*>(x->h_error) = 0;
     x->seq = 0;
@@ -680,6 +697,9 @@ int ts_search_sharded(ts_index* ix, ts_xchg* x, const void* queries, int q_dtype
     xd.my_slots = x->slots;
     xd.my_flags = x->flags;
     xd.error = x->d_error;
+    xd.done_seq = x->d_done;
+    xd.done_count = x->d_done + 1;
+    xd.nq = nq;
     xd.world = x->world;
     xd.rank = x->rank;
     xd.max_nq = x->max_nq;
@@ -701,21 +721,35 @@ int ts_search_sharded(ts_index* ix, ts_xchg* x, const void* queries, int q_dtype
         f.out_ids = out_ids;
         f.xchg = xd;
         f.pdl = 0;
+        f.ring_gate = nullptr;
+        f.ring_need = 0;
         return launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, w.part_keys, w.nparts, s,
                                 nullptr, nullptr, nullptr, nullptr, &f);
     }
     // two kernels chained by programmatic dependent launch: the scan writes its per-CTA lists, the exchange
     // kernel (resident early, asleep until the scan completes) merges, exchanges and writes the result while
     // the NEXT search's scan already streams the corpus
+    // The per-CTA lists go into a ring of four buffers owned by the exchange (search seq uses slot seq % 4), so a
+    // scan never has to wait for the previous search's exchange kernel before it can write its lists.
+    if (x->part_ring == nullptr || x->ring_nparts != w.nparts) {
+        TS_CHECK_CUDA(cudaDeviceSynchronize());
+        cudaFree(x->part_ring);
+        x->part_ring = nullptr;
+        TS_CHECK_CUDA(cudaMalloc(&x->part_ring, (size_t)4 * x->max_nq * w.nparts * x->max_k * sizeof(uint64_t)));
+        x->ring_nparts = w.nparts;
+    }
+    uint64_t* part = x->part_ring + (size_t)(xd.seq & 3u) * x->max_nq * w.nparts * x->max_k;
     f.tickets = nullptr;
     f.out_scores = nullptr;
     f.out_ids = nullptr;
     memset(&f.xchg, 0, sizeof(f.xchg));
     f.pdl = 1 | ((flags & TS_SHARDED_INDEPENDENT) ? 0 : 2);
-    int rc = launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, w.part_keys, w.nparts, s,
+    f.ring_gate = x->d_done;
+    f.ring_need = xd.seq - 4u;
+    int rc = launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, part, w.nparts, s,
                               nullptr, nullptr, nullptr, nullptr, &f);
     if (rc) return rc;
-    return launch_xchg_finish(w.part_keys, w.nparts, nq, k, xd, id_map, out_scores, out_ids, s);
+    return launch_xchg_finish(part, w.nparts, nq, k, xd, id_map, out_scores, out_ids, s);
 }
 
 int ts_search_sharded_host(ts_index* ix, ts_xchg* x, const float* queries, int nq, int k, int normalize_queries,

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 
 #include "../../include/theoremsearch.h"
 
@@ -342,6 +343,22 @@ struct ts_index {
     uint32_t list_row_bytes = 0;        // bytes per row of list_data (multiple of 16)
     float* centroid_max_norm2 = nullptr;  // device scalar: max ||centroid_bf16||^2
     bool ivf_built = false;
+    // Incremental IVF state (pgvector's ivfflat accepts inserts after the build; so does this):
+    // the list arrays hold `built_n` positions of packed main lists followed by `ovf_n` positions of OVERFLOW
+    // lists — rows added or replaced since the build, filed under the same centroids and packed the same way.
+    // Overflow list l is virtual list nlist + l: list_offsets has 2*nlist + 1 entries and simply continues, so
+    // the scan kernels see one more list per probe and need no other change. A replaced row's old position is
+    // tombstoned (list_rows[pos] = TS_DEAD_ROW) and its new content filed in the overflow.
+    int64_t list_cap = 0;            // rows the list arrays (list_rows / list_data / list_scales) can hold
+    int64_t built_n = 0;
+    int64_t ovf_n = 0;
+    int64_t ivf_dead = 0;            // tombstoned positions among the main lists
+    uint32_t* pos_of_row = nullptr;  // [capacity] list position of every corpus row
+    uint32_t* ovf_set = nullptr;     // [ovf_cap] corpus rows filed in the overflow lists, ascending
+    int64_t ovf_cap = 0;
+    // id -> row (host side; upserts arrive from the host writer, ec2/generate_embeddings/__main__.py:84-101)
+    std::unordered_map<int64_t, int64_t>* id_map_host = nullptr;
+    bool id_map_valid = false;
 
     size_t elem_bytes() const { return dtype == TS_F32 ? 4 : 2; }
     size_t row_bytes() const { return (size_t)dim_pad * elem_bytes(); }
@@ -363,6 +380,9 @@ struct ts_xchg {
     int* h_error = nullptr;           // sticky flag in pinned, device-mapped host memory: 1 = a peer did not arrive
                                       // within the time-out; the host reads it without synchronising
     int* d_error = nullptr;           // the device-side address of h_error
+    uint32_t* d_done = nullptr;       // [2]: sequence number of the last finished exchange, per-search query counter
+    uint64_t* part_ring = nullptr;    // [4][max_nq][ring_nparts][max_k] per-CTA lists of the last four searches
+    int ring_nparts = 0;
     uint32_t seq = 0;                 // searches issued so far (identical on every rank)
     unsigned long long timeout_ns = 10000000000ull;   // 10 s: covers lazy module loads and per-rank host skew
     bool connected = false;
@@ -398,15 +418,25 @@ struct ts_ctx {
     float last_ms = -1.f;
 };
 
+#define TS_DEAD_ROW 0xFFFFFFFFu
+
 // internal kernel entry points (one per .cu)
 namespace ts {
+// IVF upkeep after rows were replaced in place (device list of corpus rows) and/or appended ([app_first,
+// app_first + app_n)): tombstones, overflow lists, automatic re-pack (k4_ivf.cu). No-op unless lists are built.
+int ivf_apply_mutation(ts_index* ix, const uint32_t* replaced_rows, int64_t n_replaced, int64_t app_first,
+                       int64_t app_n, cudaStream_t s);
+void ivf_free_all(ts_index* ix);
+// grow the row capacity (data, ids, pos_of_row); synchronises the device
+int index_reserve(ts_index* ix, int64_t capacity);
+int index_make_room(ts_index* ix, int64_t extra);
 // exact search over `ix` (K2 or K3 by batch size); exactly one of out_keys / (out_scores, out_ids) is used
 int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k, int normalize_queries,
                 const uint32_t* allow_mask, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
                 void* workspace, size_t workspace_bytes, cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1);
 int launch_normalize_cast(const void* src, int src_dtype, int64_t n, int dim, int dim_pad,
                           int normalize, void* dst, int dst_dtype, cudaStream_t s,
-                          float* max_norm2 = nullptr);
+                          float* max_norm2 = nullptr, const int64_t* dst_rows = nullptr);
 // K4d: list-major batched IVF scan (k4_ivf_grouped.cu)
 bool ivf_grouped_supported(const ts_index* ix, int kc);
 size_t ivf_grouped_workspace_bytes(const ts_index* ix, int nq, int nprobe);
@@ -429,7 +459,9 @@ struct XchgDev {
     uint64_t* my_slots;
     uint32_t* my_flags;
     int* error;                    // sticky time-out flag in host-mapped memory
-    int world, rank, max_nq, max_k;
+    uint32_t* done_seq;            // sequence number of this rank's last finished exchange
+    uint32_t* done_count;          // queries of the current search finished so far (nq > 1)
+    int world, rank, max_nq, max_k, nq;
     uint32_t seq;
     int64_t base;                  // global row of this shard's row 0
     unsigned long long timeout_ns; // bound on the wait for the peers' flags
@@ -445,6 +477,8 @@ struct ScanFused {
     int64_t* out_ids;
     XchgDev xchg;           // world > 0: exchange the shard results with the peers inside the kernel
     int pdl;                // ScanParams::pdl
+    const uint32_t* ring_gate;   // ScanParams::ring_gate / ring_need
+    uint32_t ring_need;
 };
 int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64_t n_rows,
                      const float* queries_f32, int nq, int k, const uint32_t* allow_mask,

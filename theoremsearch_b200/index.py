@@ -97,7 +97,8 @@ class TheoremIndex:
     # -------------------------------------------------------------------------------- building
     def add(self, rows, ids=None, normalize: bool = True) -> "TheoremIndex":
         """Append rows [n, dim]. CUDA tensors are consumed in place (K1 on the current stream);
-        numpy arrays / CPU tensors go through the chunked host path. ``ids``: int64 [n]."""
+        numpy arrays / CPU tensors go through the chunked host path. ``ids``: int64 [n]. The store grows when
+        it is full; built IVF lists stay valid (new rows go to overflow lists)."""
         if isinstance(rows, torch.Tensor) and rows.is_cuda:
             if rows.device != self.device:
                 raise _lib.TheoremSearchError(-1, f"rows on {rows.device}, index on {self.device}")
@@ -138,6 +139,48 @@ class TheoremIndex:
         check(lib.ts_index_add_host(self._h, ptr, code, n, int(normalize),
                                     id_arr.ctypes.data if id_arr is not None else None))
         return self
+
+    def reserve(self, capacity: int) -> "TheoremIndex":
+        """Make room for ``capacity`` rows now (``add`` / ``upsert`` also grow the store on demand)."""
+        check(lib.ts_index_reserve(self._h, int(capacity)))
+        return self
+
+    def upsert(self, rows, ids, normalize: bool = True) -> int:
+        """``INSERT ... ON CONFLICT (slogan_id) DO UPDATE SET embedding = EXCLUDED.embedding`` — the reference
+        writer's statement (ec2/generate_embeddings/__main__.py:84-101 through ec2/rds/upsert.py:29-52, executed
+        row by row): a row whose id is already stored is replaced in place, any other is appended; a repeated id
+        keeps its last occurrence. ``rows`` [n, dim]: CUDA tensor (consumed in place), CPU tensor or numpy;
+        ``ids``: n int64 values (host). Built IVF lists stay valid. Returns the number of stored rows replaced."""
+        id_arr = np.ascontiguousarray(np.asarray(ids.cpu() if isinstance(ids, torch.Tensor) else ids, dtype=np.int64))
+        replaced = C.c_int64(0)
+        if isinstance(rows, torch.Tensor) and rows.is_cuda:
+            if rows.device != self.device:
+                raise _lib.TheoremSearchError(-1, f"rows on {rows.device}, index on {self.device}")
+            if rows.dim() != 2 or rows.shape[1] != self.dim:
+                raise _lib.TheoremSearchError(-1, f"rows must be [n, {self.dim}], got {tuple(rows.shape)}")
+            if rows.dtype not in _TORCH_TO_TS:
+                rows = rows.to(torch.float32)
+            rows = rows.contiguous()
+            if id_arr.shape != (rows.shape[0],):
+                raise _lib.TheoremSearchError(-1, f"ids must be [{rows.shape[0]}], got {id_arr.shape}")
+            check(lib.ts_index_upsert(self._h, rows.data_ptr(), _TORCH_TO_TS[rows.dtype], rows.shape[0], int(normalize),
+                                      id_arr.ctypes.data, C.byref(replaced), _stream_ptr(self.device)))
+            return int(replaced.value)
+        arr = rows.detach().cpu() if isinstance(rows, torch.Tensor) else rows
+        if isinstance(arr, torch.Tensor):
+            if arr.dtype not in _TORCH_TO_TS:
+                arr = arr.to(torch.float32)
+            code, arr = _TORCH_TO_TS[arr.dtype], arr.contiguous()
+            n, d, ptr = arr.shape[0], arr.shape[1], arr.data_ptr()
+        else:
+            arr = np.ascontiguousarray(np.asarray(arr, dtype=np.float32))
+            if arr.ndim != 2:
+                raise _lib.TheoremSearchError(-1, f"rows must be 2-D, got shape {arr.shape}")
+            code, (n, d), ptr = TS_F32, arr.shape, arr.ctypes.data
+        if d != self.dim or id_arr.shape != (n,):
+            raise _lib.TheoremSearchError(-1, f"rows must be [n, {self.dim}] with n ids, got {(n, d)} and {id_arr.shape}")
+        check(lib.ts_index_upsert_host(self._h, ptr, code, n, int(normalize), id_arr.ctypes.data, C.byref(replaced)))
+        return int(replaced.value)
 
     def get_rows(self, first: int = 0, n: Optional[int] = None) -> torch.Tensor:
         """Stored rows dequantised to fp32 (device tensor) — the oracle's 'same inputs'."""
@@ -297,6 +340,17 @@ class TheoremIndex:
         code = {"fp8": _lib.TS_FP8_E4M3, "fp8_e4m3": _lib.TS_FP8_E4M3, "e4m3": _lib.TS_FP8_E4M3, "bf16": TS_BF16}[list_dtype]
         check(lib.ts_ivf_build(self._h, code, _stream_ptr(self.device)))
         self._ws = {}
+        return self
+
+    def ivf_pending(self) -> tuple[int, int]:
+        """(rows filed in overflow lists, tombstoned list positions) since the last build / re-pack."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        check(lib.ts_ivf_pending(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def ivf_repack(self) -> "TheoremIndex":
+        """Re-file every row under the current centroids now (clears overflow lists and tombstones)."""
+        check(lib.ts_ivf_repack(self._h, _stream_ptr(self.device)))
         return self
 
     def ivf_lists(self):
