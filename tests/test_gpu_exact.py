@@ -214,8 +214,10 @@ def test_caller_ids_and_incremental_add(ts):
     q = oracle.normalize_f64(oracle.synthetic_queries(2, d))
     s, i = index.search(torch.from_numpy(q), 10, normalize=False)
     check_against_oracle(ts, index, q, 10, s, i, ids=ids)
-    with pytest.raises(ts.TheoremSearchError):
-        index.add(rows[:1], normalize=False)  # over capacity
+    index.add(rows[:1], ids=np.array([5], dtype=np.int64), normalize=False)  # past the initial reservation: it grows
+    assert len(index) == 5001 and index.capacity >= 5001
+    s2, i2 = index.search(torch.from_numpy(rows[:1]), 2, normalize=False)
+    assert i2[0].tolist() == [int(ids[0]), 5] and s2[0, 0] == s2[0, 1]     # the duplicate, tie -> lower row first
 
 
 def test_allow_mask_is_applied_before_topk(ts):

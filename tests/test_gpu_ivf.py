@@ -232,10 +232,14 @@ def test_shared_centroids_and_state_errors(ts):
     c.ivf_train(32, sample=torch.from_numpy(x[::2]).cuda(), iters=3, seed=1)
     c.ivf_build("fp8")
     assert int(c.ivf_list_sizes().sum()) == 4000
-    # adding rows invalidates the lists
+    # adding rows keeps the lists valid (pgvector's ivfflat accepts inserts after its build): the new rows sit in
+    # overflow lists and are found; the full story is tests/test_gpu_mutation.py
     c.add(x[:10])
-    with pytest.raises(ts.TheoremSearchError):
-        c.ivf_search(torch.zeros(1, 256), 5)
+    assert c.ivf_pending() == (10, 0) and int(c.ivf_list_sizes().sum()) == 4010
+    s, i = c.ivf_search(torch.from_numpy(x[3:4]), 2, nprobe=32, rescore_k=16)
+    assert i[0].tolist() == [3, 4003] and s[0, 0] == s[0, 1]      # the original row and its added duplicate
+    with pytest.raises(ts.TheoremSearchError):                    # the packed layout is not exportable while mutated
+        c.ivf_lists()
 
 
 def test_fp8_exhaustive_scan_mode(ts):
