@@ -168,8 +168,9 @@ TS_API size_t ts_workspace_bytes(const ts_index* index, int nq, int k);
  * allow_mask: optional device bitmask, bit r of word r/32 set = row r is eligible (the SQL WHERE
  * of streamlit_app.py:175-243 applied BEFORE ORDER BY/LIMIT); NULL = all rows.
  * out_scores: device float[nq, k]; out_ids: device int64[nq, k] (caller ids, or rows if none).
- * Dispatch: nq == 1 (and any nq on an fp32 index) -> K2 bandwidth-bound scan; nq >= 2 on a bf16 index ->
- * K3 tcgen05 GEMM (results bit-identical to K2). */
+ * Dispatch: nq == 1 -> K2 bandwidth-bound scan; nq >= 2 -> K3 tcgen05 GEMM (kind::f16 on a bf16 index,
+ * kind::tf32 on an fp32 index — the reference's own storage precision, rds_schema.sql:50-53), candidates
+ * re-scored and certified so that results are bit-identical to K2's. */
 TS_API int ts_search(ts_index* index, const void* queries, int q_dtype, int nq, int k,
                      int normalize_queries, const uint32_t* allow_mask, float* out_scores,
                      int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream);

@@ -180,3 +180,53 @@ def test_dense_small_corpus_path_equals_chunked_path(ts):
         assert torch.equal(s_dm, s_cm) and torch.equal(i_dm, i_cm)
     s10, i10 = index.search(q, 10)
     check_against_oracle(ts, index, oracle.normalize_f64(q.numpy()), 10, s10, i10)
+
+
+# ------------------------------------------------------------------------------------------ fp32 corpora (TF32 GEMM)
+@pytest.mark.parametrize("n,d,nq,k", [
+    (5000, 1024, 4, 10), (20000, 1024, 73, 10), (4097, 768, 33, 100), (3000, 100, 16, 5), (2000, 8, 8, 3),
+    (300_000, 256, 40, 10),      # > 2^18 rows: the chunked threshold path, not the dense small-corpus path
+    (127, 1024, 5, 10), (1000, 1024, 20, 1000),
+])
+def test_fp32_corpus_batches_take_the_tf32_gemm_and_stay_exact(ts, n, d, nq, k):
+    """An fp32-stored corpus is the reference's own precision (pg `vector(1024)`, rds_schema.sql:50-53;
+    compare_embeddings.py:61 on fp32 tensors). Batches now read the rows ONCE through tcgen05 kind::tf32; the
+    candidates are re-scored in fp32 in K2's summation order and certified against the TF32 truncation bound, so the
+    result must be the single-query scan's bit for bit, and the fp64 oracle's within 1e-5."""
+    rows = unit_rows(n, d, seed=n + d + 2)
+    index = ts.build_index(rows, dtype="f32", normalize=False)
+    q_raw = oracle.synthetic_queries(nq, d, seed=500 + nq)
+    before = ts.kernel_launches()
+    s, i = index.search(torch.from_numpy(q_raw), k, normalize=True)
+    torch.cuda.synchronize()
+    assert ts.kernel_launches() - before >= 6, "the GEMM path is a chain of kernels; the per-query scan is one launch"
+    assert ts.last_batched_fixups() >= 0
+    check_against_oracle(ts, index, prepared(q_raw), k, s, i)
+    for j in sorted({0, nq // 2, nq - 1}):
+        s1, i1 = index.search(torch.from_numpy(q_raw[j]), k, normalize=True)       # K2 on fp32 rows
+        assert torch.equal(s[j], s1[0]) and torch.equal(i[j], i1[0])
+    ts.set_tunable("batch.tf32", 0)                                                # round 1's path: nq K2 passes
+    try:
+        before = ts.kernel_launches()
+        s0, i0 = index.search(torch.from_numpy(q_raw), k, normalize=True)
+        assert ts.kernel_launches() - before <= 2
+    finally:
+        ts.set_tunable("batch.tf32", 1)
+    assert torch.equal(s, s0) and torch.equal(i, i0)
+
+
+def test_fp32_corpus_near_duplicates_fail_the_tf32_certificate_and_are_fixed_up(ts):
+    """Rows that differ from each other by less than the TF32 truncation error cannot be ranked by the GEMM:
+    the certificate must send those queries to the exact re-scan, and the result must still be exact."""
+    d, n = 1024, 6000
+    rows = unit_rows(n, d, seed=77)
+    base = rows[100].copy()
+    rng = np.random.default_rng(1)
+    for r in range(200, 500):                         # 300 rows within ~1e-4 of each other
+        v = base + 1e-4 * rng.standard_normal(d).astype(np.float32)
+        rows[r] = v / np.linalg.norm(v)
+    index = ts.build_index(rows, dtype="f32", normalize=False)
+    q = np.stack([base, rows[300], unit_rows(1, d, seed=5)[0]])
+    s, i = index.search(torch.from_numpy(q), 10, normalize=True)
+    assert ts.last_batched_fixups() >= 2
+    check_against_oracle(ts, index, prepared(q), 10, s, i)

@@ -110,11 +110,17 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
         : "memory");
 }
 
-template <bool PAIR>
+// TF32 = true: both operands are fp32 rows (an fp32-stored corpus — the reference's own precision, pg
+//               `vector(1024)`, rds_schema.sql:50-53 — and the fp32 queries themselves), multiplied as TF32
+//               (tcgen05 kind::tf32, K = 8 per instruction). A k-block is still one 128-byte swizzle span per row
+//               (32 fp32 instead of 64 bf16), so the smem ring, the descriptors and the expect-tx bytes are unchanged.
+template <bool PAIR, bool TF32>
 __global__ void __launch_bounds__(k3::THREADS, 1)
 batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const BatchParams p) {
     using namespace k3;
+    static_assert(!(PAIR && TF32), "the CTA-pair kernel is bf16 only");
+    constexpr int KB_ELEMS = TF32 ? BK / 2 : BK;           // elements per k-block (one 128-byte span per row)
     constexpr int NST = PAIR ? 6 : STAGES;                 // smem ring depth
     constexpr int BSLOT = PAIR ? B_BYTES / 2 : B_BYTES;    // bytes reserved per stage for this CTA's part of B
     constexpr int TILE_ROWS = PAIR ? 2 * BM : BM;
@@ -189,12 +195,12 @@ batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     mbar_wait_wd(&empty[stage], phase ^ 1u);
                     if constexpr (PAIR) {
                         if (leader) mbar_expect_tx(&full[stage], 2u * (A_BYTES + b_rows * (BK * 2)));
-                        tma_load_2d_pair(smem_a + (size_t)stage * A_BYTES, &tmap_a, kb * BK, row0, &full[stage], pol_a);
-                        tma_load_2d_pair(smem_b + (size_t)stage * BSLOT, &tmap_b, kb * BK, b0, &full[stage], pol_b);
+                        tma_load_2d_pair(smem_a + (size_t)stage * A_BYTES, &tmap_a, kb * KB_ELEMS, row0, &full[stage], pol_a);
+                        tma_load_2d_pair(smem_b + (size_t)stage * BSLOT, &tmap_b, kb * KB_ELEMS, b0, &full[stage], pol_b);
                     } else {
                         mbar_expect_tx(&full[stage], A_BYTES + b_rows * (BK * 2));
-                        tma_load_2d(smem_a + (size_t)stage * A_BYTES, &tmap_a, kb * BK, row0, &full[stage], pol_a);
-                        tma_load_2d(smem_b + (size_t)stage * BSLOT, &tmap_b, kb * BK, b0, &full[stage], pol_b);
+                        tma_load_2d(smem_a + (size_t)stage * A_BYTES, &tmap_a, kb * KB_ELEMS, row0, &full[stage], pol_a);
+                        tma_load_2d(smem_b + (size_t)stage * BSLOT, &tmap_b, kb * KB_ELEMS, b0, &full[stage], pol_b);
                     }
                     if (++stage == NST) {
                         stage = 0;
@@ -206,8 +212,10 @@ batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread; in PAIR mode only in the leader CTA) =====================
         if (lane == 0 && leader) {
-            // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) |
+            // instruction descriptor: D=f32 at [4,6), A / B format at [7,10) / [10,13) (1 = bf16, 2 = tf32), both
+            // K-major, N>>3 at [17,23), M>>4 at [24,29)
+            constexpr uint32_t FMT = TF32 ? 2u : 1u;
+            const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(p.bn >> 3) << 17) |
                                    ((uint32_t)(TILE_ROWS >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
@@ -228,6 +236,8 @@ batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         // +32 bytes per UMMA_K step inside the 128-byte swizzle span (address field is >>4)
                         if constexpr (PAIR)
                             umma_bf16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        else if constexpr (TF32)
+                            umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
                         else
                             umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
                     }
@@ -439,6 +449,24 @@ __global__ void __launch_bounds__(256) round_queries_kernel(const float* __restr
         qerr[q] = sqrtf(e2) * 1.0001f + 2.0f * (float)dim_pad * 1.1920929e-7f * sqrtf(n2) * 1.0001f + 1e-30f;
 }
 
+// fp32 corpus (TF32 GEMM): the queries go to the tensor core as they are; the tensor core drops the low 13
+// mantissa bits of BOTH operands (relative error < 2^-10 each), so |<q,c> - tf32 score| <= (2^-9 + 2^-20) ||q|| ||c||,
+// plus the same accumulation allowance as above.
+__global__ void __launch_bounds__(256) tf32_query_error_kernel(const float* __restrict__ q32, int nq, int dim_pad,
+                                                               float* __restrict__ qerr) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    float n2 = 0.f;
+    for (int i = lane; i < dim_pad; i += 32) {
+        const float v = q32[(size_t)q * dim_pad + i];
+        n2 = fmaf(v, v, n2);
+    }
+    n2 = warp_sum(n2);
+    if (lane == 0)
+        qerr[q] = sqrtf(n2) * 1.0001f * (1.9550e-3f + 2.0f * (float)dim_pad * 1.1920929e-7f) + 1e-30f;
+}
+
 // ---------------------------------------------------------------------------------- K3c rescore + certify
 // One CTA per query. The GEMM ranked candidates with bf16-ROUNDED queries; the exact path (K2)
 // scores with the fp32 query. Re-score the kp best candidates with the fp32 query using K2's exact
@@ -447,6 +475,7 @@ __global__ void __launch_bounds__(256) round_queries_kernel(const float* __restr
 // fp32-query score <= b + qerr*max||row||; if the k-th rescored score beats that bound the top-k is
 // provably the exact one, otherwise (or if a candidate buffer overflowed) the query is flagged and
 // re-scanned by K2.
+template <int ELEM>   // bytes per stored corpus element: 2 = bf16 rows, 4 = fp32 rows
 __global__ void __launch_bounds__(256) rescore_certify_kernel(uint64_t* cand, size_t cand_stride, int kp, int k,
                                                               const float* __restrict__ q32,
                                                               const uint8_t* __restrict__ corpus, uint32_t row_bytes,
@@ -470,6 +499,14 @@ __global__ void __launch_bounds__(256) rescore_certify_kernel(uint64_t* cand, si
             float acc = 0.f;
             for (uint32_t off = (uint32_t)lane * 16u; off < row_bytes; off += 512u) {   // K2's chunk order
                 const uint4 v = __ldg(reinterpret_cast<const uint4*>(r + off));
+                if constexpr (ELEM == 4) {
+                    const float4 qa = __ldg(reinterpret_cast<const float4*>(qv + off / 4));
+                    acc = fmaf(__uint_as_float(v.x), qa.x, acc);
+                    acc = fmaf(__uint_as_float(v.y), qa.y, acc);
+                    acc = fmaf(__uint_as_float(v.z), qa.z, acc);
+                    acc = fmaf(__uint_as_float(v.w), qa.w, acc);
+                    continue;
+                }
                 const float4 qa = __ldg(reinterpret_cast<const float4*>(qv + off / 2));
                 const float4 qb = __ldg(reinterpret_cast<const float4*>(qv + off / 2 + 4));
                 acc = fmaf(__uint_as_float(v.x << 16), qa.x, acc);
@@ -642,7 +679,8 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
                           const uint32_t* allow_mask, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
                           void* workspace, size_t workspace_bytes, cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1) {
     using namespace k3;
-    TS_REQUIRE(ix->dtype == TS_BF16, TS_ERR_UNSUPPORTED, "batched: corpus must be stored as bf16");
+    TS_REQUIRE(ix->dtype == TS_BF16 || ix->dtype == TS_F32, TS_ERR_UNSUPPORTED, "batched: corpus must be stored as bf16 or fp32");
+    const bool f32 = ix->dtype == TS_F32;     // fp32 rows: TF32 GEMM on the rows and the fp32 queries themselves
     const Tunables& t = tunables();
     const int k_out = k;          // what the caller asked for
     k = batched_kp(k_out);        // what the GEMM stage keeps per query (kp)
@@ -677,27 +715,33 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
 
     int rc = launch_prepare_queries(queries, q_dtype, nq, ix->dim, ix->dim_pad, normalize, q32, s);
     if (rc) return rc;
-    round_queries_kernel<<<(nq + 7) / 8, 256, 0, s>>>(q32, nq, ix->dim_pad, q16, qerr);
+    if (f32) tf32_query_error_kernel<<<(nq + 7) / 8, 256, 0, s>>>(q32, nq, ix->dim_pad, qerr);
+    else round_queries_kernel<<<(nq + 7) / 8, 256, 0, s>>>(q32, nq, ix->dim_pad, q16, qerr);
     TS_LAUNCH_CHECK();
     init_batch_state_kernel<<<256, 256, 0, s>>>(cand, count, thr, overflow, nq, nq_pad, k, cap);
     TS_LAUNCH_CHECK();
 
     CUtensorMap tmap_a, tmap_b;
-    rc = make_tmap_bf16_rows(&tmap_a, ix->data, (uint64_t)ix->size, (uint64_t)ix->dim_pad, ix->row_bytes(), BM);
+    rc = make_tmap_rows(&tmap_a, ix->data, (uint64_t)ix->size, (uint64_t)ix->dim_pad, ix->row_bytes(), BM, f32);
     if (rc) return rc;
     // CTA pairs pay off once the batch is tensor-bound; small batches (HBM-bound) keep single CTAs, which
     // spread the corpus stream over all 148 SMs' TMA queues.
-    const bool pair = t.batch_cta_pair != 0 && nq >= t.batch_pair_min_nq && !dense;   // the dense pass uses single CTAs
-    rc = make_tmap_bf16_rows(&tmap_b, q16, (uint64_t)nq, (uint64_t)ix->dim_pad, (uint64_t)ix->dim_pad * 2,
-                             pair ? bn / 2 : bn);
+    const bool pair = t.batch_cta_pair != 0 && nq >= t.batch_pair_min_nq && !dense && !f32;   // the dense pass uses single CTAs
+    if (f32)
+        rc = make_tmap_rows(&tmap_b, q32, (uint64_t)nq, (uint64_t)ix->dim_pad, (uint64_t)ix->dim_pad * 4, bn, true);
+    else
+        rc = make_tmap_rows(&tmap_b, q16, (uint64_t)nq, (uint64_t)ix->dim_pad, (uint64_t)ix->dim_pad * 2,
+                            pair ? bn / 2 : bn, false);
     if (rc) return rc;
 
     static bool attr_set[64] = {false};   // function attributes are per device
     const int dslot = ix->device & 63;
     if (!attr_set[dslot]) {
-        TS_CHECK_CUDA(cudaFuncSetAttribute(batched_gemm_topk_kernel<false>,
+        TS_CHECK_CUDA(cudaFuncSetAttribute(batched_gemm_topk_kernel<false, false>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        TS_CHECK_CUDA(cudaFuncSetAttribute(batched_gemm_topk_kernel<true>,
+        TS_CHECK_CUDA(cudaFuncSetAttribute(batched_gemm_topk_kernel<true, false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        TS_CHECK_CUDA(cudaFuncSetAttribute(batched_gemm_topk_kernel<false, true>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         TS_CHECK_CUDA(cudaFuncSetAttribute(compact_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            64 * 1024));
@@ -712,7 +756,7 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
     p.nq = nq;
     p.k = k;
     p.cap = cap;
-    p.num_k_blocks = (ix->dim_pad + BK - 1) / BK;
+    p.num_k_blocks = f32 ? (ix->dim_pad + BK / 2 - 1) / (BK / 2) : (ix->dim_pad + BK - 1) / BK;
     p.num_n_blocks = num_n_blocks;
     p.bn = bn;
     p.thr = thr;
@@ -740,7 +784,8 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
         p.row_end = ix->size;
         p.num_m_blocks = (int)((ix->size + BM - 1) / BM);
         const int tiles = p.num_m_blocks * p.num_n_blocks;
-        batched_gemm_topk_kernel<false><<<tiles < sms ? tiles : sms, THREADS, SMEM_BYTES, s>>>(tmap_a, tmap_b, p);
+        if (f32) batched_gemm_topk_kernel<false, true><<<tiles < sms ? tiles : sms, THREADS, SMEM_BYTES, s>>>(tmap_a, tmap_b, p);
+        else batched_gemm_topk_kernel<false, false><<<tiles < sms ? tiles : sms, THREADS, SMEM_BYTES, s>>>(tmap_a, tmap_b, p);
         TS_LAUNCH_CHECK();
         dense_select_kernel<<<nq, 256, 0, s>>>(dscores, p.dense_stride, ix->size, k, cand, (size_t)k + cap, overflow);
         TS_LAUNCH_CHECK();
@@ -769,10 +814,11 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            TS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, batched_gemm_topk_kernel<true>, tmap_a, tmap_b, p));
+            TS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, batched_gemm_topk_kernel<true, false>, tmap_a, tmap_b, p));
         } else {
             const int grid = tiles < sms ? tiles : sms;
-            batched_gemm_topk_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>(tmap_a, tmap_b, p);
+            if (f32) batched_gemm_topk_kernel<false, true><<<grid, THREADS, SMEM_BYTES, s>>>(tmap_a, tmap_b, p);
+            else batched_gemm_topk_kernel<false, false><<<grid, THREADS, SMEM_BYTES, s>>>(tmap_a, tmap_b, p);
         }
         TS_LAUNCH_CHECK();
         compact_candidates_kernel<<<nq, 256, sort_smem, s>>>(cand, count, thr, overflow, k, cap);
@@ -784,9 +830,14 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
     const size_t cstride = (size_t)k + cap;
     int PR = 64;
     while (PR < k) PR <<= 1;
-    rescore_certify_kernel<<<nq, 256, (size_t)PR * 8, s>>>(cand, cstride, k, k_out, q32, (const uint8_t*)ix->data,
-                                                           (uint32_t)ix->row_bytes(), ix->dim_pad, qerr, ix->max_norm2,
-                                                           overflow, flags);
+    if (f32)
+        rescore_certify_kernel<4><<<nq, 256, (size_t)PR * 8, s>>>(cand, cstride, k, k_out, q32, (const uint8_t*)ix->data,
+                                                                  (uint32_t)ix->row_bytes(), ix->dim_pad, qerr,
+                                                                  ix->max_norm2, overflow, flags);
+    else
+        rescore_certify_kernel<2><<<nq, 256, (size_t)PR * 8, s>>>(cand, cstride, k, k_out, q32, (const uint8_t*)ix->data,
+                                                                  (uint32_t)ix->row_bytes(), ix->dim_pad, qerr,
+                                                                  ix->max_norm2, overflow, flags);
     TS_LAUNCH_CHECK();
     // Fix-up: queries that could not be certified (or overflowed) are re-scanned exactly by K2.
     // The work list lives on the device; with nothing flagged these launches exit immediately.

@@ -49,9 +49,10 @@ static SearchWs carve_ws(const ts_index* ix, int nq, int k, void* base) {
     return w;
 }
 
-// nq >= batch.min_nq on a bf16 corpus goes to K3 (tcgen05 GEMM); everything else to K2.
+// nq >= batch.min_nq goes to K3 (tcgen05 GEMM: kind::f16 on bf16 rows, kind::tf32 on fp32 rows); a single query to K2.
 static bool use_batched(const ts_index* ix, int nq) {
-    return ix->dtype == TS_BF16 && nq >= tunables().batch_min_nq && ix->size > 0;
+    if (ix->dtype == TS_F32 && !tunables().batch_tf32) return false;
+    return (ix->dtype == TS_BF16 || ix->dtype == TS_F32) && nq >= tunables().batch_min_nq && ix->size > 0;
 }
 
 int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k,
@@ -398,7 +399,7 @@ int ts_ivf_list_dtype(const ts_index* ix) { return (ix && ix->ivf_built) ? ix->l
 size_t ts_workspace_bytes(const ts_index* ix, int nq, int k) {
     if (!ix || nq < 0 || k < 1) return 0;
     const size_t scan = carve_ws(ix, std::max(nq, 1), k, nullptr).bytes;
-    const size_t batched = ix->dtype == TS_BF16 ? batched_workspace_bytes(ix, std::max(nq, 1), k) : 0;
+    const size_t batched = batched_workspace_bytes(ix, std::max(nq, 1), k);
     return std::max(scan, batched);
 }
 
@@ -807,6 +808,7 @@ static int* tunable_slot(const char* name) {
     if (!strcmp(name, "batch.first_chunk")) return &t.batch_first_chunk;
     if (!strcmp(name, "batch.growth")) return &t.batch_growth;
     if (!strcmp(name, "batch.dense")) return &t.batch_dense;
+    if (!strcmp(name, "batch.tf32")) return &t.batch_tf32;
     if (!strcmp(name, "batch.cta_pair")) return &t.batch_cta_pair;
     if (!strcmp(name, "batch.pair_min_nq")) return &t.batch_pair_min_nq;
     if (!strcmp(name, "ivf.warps")) return &t.ivf_warps;

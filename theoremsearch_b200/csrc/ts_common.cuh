@@ -83,6 +83,7 @@ struct Tunables {
     int batch_first_chunk = 1024;  // rows of the first K3 chunk (every row passes thr = -inf)
     int batch_growth = 3;       // next chunk = growth x rows already seen
     int batch_dense = 1;        // small corpora (nq * N * 4 B <= 1 GiB): dense score matrix + select instead of chunked filtering
+    int batch_tf32 = 1;         // fp32-stored corpora: batches take the TF32 GEMM (0 = one K2 pass per query, as in round 1)
     int batch_cta_pair = 0;     // 1 = use the cta_group::2 kernel (CTA pairs) for large batches. Measured on B200
                                 // (4096 x 10M x 1024, 40 iterations, power-capped ~1.36 GHz): pairs 74.9 ms vs
                                 // single CTAs 71.8 ms, so single CTAs are the default; the pair kernel stays tested.

@@ -46,6 +46,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// fp32 operands, read by the tensor core as TF32 (the low 13 mantissa bits are ignored): K = 8 per instruction
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // K-major, SWIZZLE_128B operand tile whose rows are 128 bytes apart: 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t umma_smem_desc(const void* smem) {
     uint64_t d = (uint64_t)((smem_u32(smem) >> 4) & 0x3FFFu);
@@ -86,19 +95,26 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     return fn;
 }
 
-inline int make_tmap_bf16_rows(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_bytes,
-                               uint32_t box_rows) {
+// rows of `cols` elements (bf16, or fp32 when f32 = true), `row_bytes` apart; one box = box_rows rows x one
+// 128-byte swizzle span (64 bf16 / 32 fp32); columns past `cols` read as zero
+inline int make_tmap_rows(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_bytes,
+                          uint32_t box_rows, bool f32) {
     auto enc = get_encode_fn();
     TS_REQUIRE(enc != nullptr, TS_ERR_CUDA, "batched: cuTensorMapEncodeTiled entry point unavailable");
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {row_bytes};
-    cuuint32_t box[2] = {(cuuint32_t)umma::BK, box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)(f32 ? umma::BK / 2 : umma::BK), box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     TS_REQUIRE(r == CUDA_SUCCESS, TS_ERR_CUDA, "batched: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
     return TS_OK;
+}
+inline int make_tmap_bf16_rows(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_bytes,
+                               uint32_t box_rows) {
+    return make_tmap_rows(map, base, rows, cols, row_bytes, box_rows, false);
 }
 
 
