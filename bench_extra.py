@@ -48,16 +48,43 @@ def build(rows, dim, dev):
     return index
 
 
+_CLOCKS = None     # bench.ClockSampler of this process; every timed region samples SM clocks / throttle reasons
+
+
+class _Sampling:
+    """`with _Sampling():` samples clocks for the enclosed timed region (no-op before main() set the sampler up)."""
+
+    def __enter__(self):
+        if _CLOCKS is not None:
+            _CLOCKS.__enter__()
+
+    def __exit__(self, *a):
+        if _CLOCKS is not None:
+            _CLOCKS.__exit__(*a)
+
+
+_json_dumps = json.dumps
+
+
+def _dumps_with_clocks(obj, *a, **k):
+    """Every result line carries the clocks of the most recent timed region (a number without them is unusable)."""
+    if isinstance(obj, dict) and "bench" in obj and "clocks" not in obj and _CLOCKS is not None:
+        obj = dict(obj)
+        obj["clocks"] = _CLOCKS.summary()
+    return _json_dumps(obj, *a, **k)
+
+
 def timed(fn, warmup, iters):
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
+    with _Sampling():
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
 
 
@@ -160,10 +187,12 @@ def cmd_cfg0(a):
 
     for name, index in (("f32_rows", index32), ("bf16_rows", index16)):
         it = itertools.cycle(range(nq))
-        lat = wall(lambda: index.search_host(queries[next(it)], k), 10, 3 * nq)
+        with _Sampling():
+            lat = wall(lambda: index.search_host(queries[next(it)], k), 10, 3 * nq)
         out[f"gpu_{name}_single_p50_ms"] = float(np.median(lat) * 1e3)
         out[f"gpu_{name}_single_qps"] = float(1.0 / lat.mean())
-        lat = wall(lambda: index.search_host(queries, k), 3, 20)
+        with _Sampling():
+            lat = wall(lambda: index.search_host(queries, k), 3, 200)
         out[f"gpu_{name}_batch73_ms"] = float(np.median(lat) * 1e3)
         out[f"gpu_{name}_batch73_qps"] = float(nq / np.median(lat))
 
@@ -642,6 +671,10 @@ def main():
     ap.add_argument("--recall-sweep", type=int, nargs="*", default=[])
     ap.add_argument("--profile-nq", type=int, default=1, help="ivf-q1: queries per call (1 = latency mode)")
     a = ap.parse_args()
+    global _CLOCKS
+    from bench import ClockSampler
+    _CLOCKS = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    json.dumps = _dumps_with_clocks
     if a.k is None:
         a.k = 100 if a.cmd == "batched" else 10
     {"batched": cmd_batched, "sweep-scan": cmd_sweep_scan, "small-batch": cmd_small_batch, "ivf": cmd_ivf, "sharded": cmd_sharded, "ivf-q1": cmd_ivf_q1, "ivf-q1-sweep": cmd_ivf_q1_sweep, "fp8-scan": cmd_fp8_scan, "k1": cmd_k1, "cfg0": cmd_cfg0, "torch-compare": cmd_torch_compare, "shard-stream": cmd_shard_stream, "scan-timeline": cmd_scan_timeline}[a.cmd](a)

@@ -419,3 +419,36 @@ def test_ivf_host_buffer_entry_point(ts):
     assert np.array_equal(i_h, i_d.cpu().numpy()) and np.array_equal(s_h, s_d.cpu().numpy())
     s_1, i_1 = index.ivf_search_host(q[3], 10, nprobe=8, rescore_k=100, normalize=False)
     assert np.array_equal(i_1[0], i_h[3])
+
+
+@pytest.mark.parametrize("mode,d", [(3, 1024), (4, 1024), (3, 768), (3, 100), (4, 264), (1, 1024), (0, 1024)])
+def test_list_major_scoring_variants_agree_with_the_per_query_scan(ts, mode, d):
+    """K4d's scoring back ends — tcgen05 kind::f8f6f4 with 16 / 8 queries per group (modes 3 / 4: e4m3 rows straight
+    into the tensor cores, two-term e4m3 queries), legacy mma.sync (1), CUDA cores (0) — must hand the exact
+    re-score the same candidates the per-query scan (K4b) does: same top-10 after re-scoring, exact scores."""
+    x = clustered_rows(40000, d, 90, 0.9, seed=7 + d)
+    index = built(ts, x, 128, "fp8")
+    q = torch.from_numpy(oracle.normalize_f64(clustered_rows(300, d, 90, 0.9, seed=7 + d)))
+    old_mode, old_nq = ts.get_tunable("ivf.group_mma"), ts.get_tunable("ivf.group_min_nq")
+    try:
+        ts.set_tunable("ivf.group_mma", mode)
+        index._ws = {}
+        s_g, i_g = index.ivf_search(q, 10, nprobe=16, rescore_k=100)      # list-major, this back end
+        ts.set_tunable("ivf.group_min_nq", 0)
+        index._ws = {}
+        s_c, i_c = index.ivf_search(q, 10, nprobe=16, rescore_k=100)      # per-query scan
+    finally:
+        ts.set_tunable("ivf.group_mma", old_mode)
+        ts.set_tunable("ivf.group_min_nq", old_nq)
+        index._ws = {}
+    assert oracle.recall_at_k(i_g.cpu().numpy(), i_c.cpu().numpy()) >= 0.995
+    same = (i_g == i_c).all(dim=1)
+    assert same.sum() >= 290 and torch.equal(s_g[same], s_c[same])
+    # every list probed: equal to the exact search up to e4m3 candidate selection
+    s_e, i_e = index.search(q[:64], 10)
+    ts.set_tunable("ivf.group_mma", mode)
+    try:
+        s_a, i_a = index.ivf_search(q[:64], 10, nprobe=128, rescore_k=200)
+    finally:
+        ts.set_tunable("ivf.group_mma", old_mode)
+    assert oracle.recall_at_k(i_a.cpu().numpy(), i_e.cpu().numpy()) >= 0.99

@@ -26,6 +26,7 @@
 
 #include "merge_device.cuh"
 #include "scan_device.cuh"
+#include "umma_device.cuh"
 
 namespace ts {
 
@@ -507,6 +508,301 @@ __global__ void __launch_bounds__(g4m::warps_for(NT) * 32, 1) ivf_grouped_mma_ke
     }
 }
 
+// ---------------------------------------------------------------------------------- G4 on tcgen05 (the default)
+// Blackwell's tensor cores multiply e4m3 natively (tcgen05.mma kind::f8f6f4, fp32 accumulation in TMEM), so the list
+// rows go from HBM to the MMA untouched: no conversion instructions, no register staging.
+//   * A (rows): 128-row x 128-byte k-blocks of the list by 2-D TMA (a u8 tensor map over list_data, SWIZZLE_128B)
+//     into an 8-stage smem ring — one full 128-row tile of D = 1024 in flight per SM.
+//   * B (queries): a group of QB <= 16 queries. Queries are quantised ONCE per batch to TWO e4m3 terms with one
+//     fp32 scale per query — q / s = hi + lo / 16 — and both terms are MMA columns (N = 2 * QB), so the query side
+//     carries ~8 mantissa bits while the row side stays single e4m3; the candidate ranking is as good as with fp16
+//     queries. Two loader warps copy the group's 2 * QB byte rows into smem in the 128-byte-swizzled K-major layout
+//     the UMMA descriptor expects (double-buffered: the next item's queries load while this item streams).
+//   * D: 128 rows x 2 * QB fp32 columns in TMEM, double-buffered; four epilogue warps read it back (thread = row),
+//     fold hi + lo / 16, apply query scale x row scale (and the allow mask / tombstones) and store to the dense
+//     score buffer — for a fixed query a warp's 32 rows are 32 consecutive floats, one coalesced store.
+//   * persistent CTAs (one per SM) walk the work items with a fixed stride; every role derives the item's
+//     geometry itself, the pipeline never drains between items.
+// Algorithmic bytes per item = list rows x row_bytes, read once per QB = 16 queries (K4b: once per query).
+namespace g4u {
+constexpr int NST = 8;                 // A ring stages (16 KB each)
+constexpr int A_BYTES = 128 * 128;
+constexpr int THREADS = 256;           // warp 0 TMA, warp 1 MMA + TMEM, warps 2-5 epilogue, warps 6-7 query loaders
+constexpr int LOADERS = 64;
+constexpr int KB_MAX = 8;              // k-blocks per row: row_bytes <= 1024
+}  // namespace g4u
+
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// q / s = hi + lo / 16 with hi, lo in e4m3 and s = max|q| / 448: out[q][0][*] = hi bytes, out[q][1][*] = lo bytes
+// (row_bytes each, zero padded), qscale[q] = s. One warp per query.
+__global__ void __launch_bounds__(256) quantize_queries_e4m3x2_kernel(const float* __restrict__ q32, int nq, int dim_pad,
+                                                                      uint32_t row_bytes, uint8_t* __restrict__ out,
+                                                                      float* __restrict__ qscale) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const float* src = q32 + (size_t)q * dim_pad;
+    float amax = 0.f;
+    for (int i = lane; i < dim_pad; i += 32) amax = fmaxf(amax, fabsf(src[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, o));
+    const float scale = amax > 0.f ? __fdiv_rn(amax, 448.0f) : 1.0f;
+    if (lane == 0) qscale[q] = scale;
+    uint8_t* hi = out + (size_t)q * 2 * row_bytes;
+    uint8_t* lo = hi + row_bytes;
+    for (int i = lane; i < (int)row_bytes; i += 32) {
+        uint8_t h = 0, l = 0;
+        if (i < dim_pad) {
+            const float x = __fdiv_rn(src[i], scale);
+            h = (uint8_t)__nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E4M3);
+            const __half_raw hr = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)h, __NV_E4M3);
+            const float back = __half2float(*reinterpret_cast<const __half*>(&hr));
+            l = (uint8_t)__nv_cvt_float_to_fp8((x - back) * 16.0f, __NV_SATFINITE, __NV_E4M3);
+        }
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
+struct UmmaItem {
+    int nqg;          // queries in this group
+    uint32_t s0;      // first table slot of the group
+    int64_t start;    // first list position
+    int len, tiles;   // rows, 128-row tiles
+};
+__device__ __forceinline__ UmmaItem umma_item(const GroupedParams& p, uint32_t item, int qb) {
+    UmmaItem it;
+    const int l = (int)p.item_list[item];
+    const int grp = (int)(item - p.item_start[l]);
+    const int c = (int)p.cnt[l];
+    it.nqg = (c - grp * qb < qb) ? (c - grp * qb) : qb;
+    it.s0 = p.slot_start[l] + (uint32_t)grp * qb;
+    it.start = p.list_offsets[l];
+    it.len = (int)(p.list_offsets[l + 1] - it.start);
+    it.tiles = (it.len + 127) / 128;
+    return it;
+}
+
+template <int QB>
+__global__ void __launch_bounds__(g4u::THREADS, 1)
+ivf_grouped_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const GroupedParams p, const uint8_t* __restrict__ q8,
+                        const float* __restrict__ qscale, int has_dead) {
+    using namespace g4u;
+    constexpr int N = 2 * QB;                       // MMA columns: hi and lo term of every query
+    constexpr int B_KB_BYTES = N * 128;             // one k-block of the query operand
+    constexpr int TMEM_COLS = (2 * N < 32) ? 32 : 2 * N;
+    extern __shared__ uint8_t smem_raw[];
+    if (p.totals[1] != 0u) return;                  // score buffer too small for this batch: K4b does the work
+    const uint32_t n_items = p.totals[0];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int KB = (int)((p.row_bytes + 127) / 128);
+    uint8_t* smem_a = smem;                                            // [NST][128 rows][128 B]
+    uint8_t* smem_b = smem + (size_t)NST * A_BYTES;                    // [2][KB_MAX][N rows][128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)2 * KB_MAX * B_KB_BYTES);
+    uint64_t* full = bars;                 // [NST]
+    uint64_t* empty = bars + NST;          // [NST]
+    uint64_t* tmem_full = bars + 2 * NST;  // [2]
+    uint64_t* tmem_empty = tmem_full + 2;  // [2]
+    uint64_t* b_full = tmem_empty + 2;     // [2]
+    uint64_t* b_empty = b_full + 2;        // [2]
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(b_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 128);
+            mbar_init(&b_full[s], LOADERS);
+            mbar_init(&b_empty[s], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const uint64_t pol = l2_policy_evict_first();
+            int stage = 0;
+            uint32_t phase = 0;
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const UmmaItem it = umma_item(p, item, QB);
+                for (int tile = 0; tile < it.tiles; ++tile) {
+                    const int row0 = (int)(it.start + (int64_t)tile * 128);
+                    for (int kb = 0; kb < KB; ++kb) {
+                        mbar_wait_wd(&empty[stage], phase ^ 1u);
+                        mbar_expect_tx(&full[stage], A_BYTES);
+                        tma_load_2d(smem_a + (size_t)stage * A_BYTES, &tmap_a, kb * 128, row0, &full[stage], pol);
+                        if (++stage == NST) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor: D = f32 at [4,6); A / B format at [7,10) / [10,13): 0 = e4m3; K-major; N>>3 at
+            // [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t tcount = 0, icount = 0;
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++icount) {
+                const UmmaItem it = umma_item(p, item, QB);
+                const int bbuf = (int)(icount & 1u);
+                mbar_wait_wd(&b_full[bbuf], (icount >> 1) & 1u);
+                tcgen05_fence_after();
+                const uint8_t* bq = smem_b + (size_t)bbuf * KB_MAX * B_KB_BYTES;
+                for (int tile = 0; tile < it.tiles; ++tile, ++tcount) {
+                    const int acc = (int)(tcount & 1u);
+                    mbar_wait_wd(&tmem_empty[acc], ((tcount >> 1) & 1u) ^ 1u);
+                    tcgen05_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+                    for (int kb = 0; kb < KB; ++kb) {
+                        mbar_wait_wd(&full[stage], phase);
+                        tcgen05_fence_after();
+                        const uint64_t da = umma_smem_desc(smem_a + (size_t)stage * A_BYTES);
+                        const uint64_t db = umma_smem_desc(bq + (size_t)kb * B_KB_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)   // K = 32 e4m3 = 32 bytes per instruction: +2 in the >>4 address field
+                            umma_f8(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        tcgen05_commit(&empty[stage]);
+                        if (kb == KB - 1) tcgen05_commit(&tmem_full[acc]);
+                        if (++stage == NST) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+                tcgen05_commit(&b_empty[bbuf]);   // the item's MMAs have read the queries: the buffer may be refilled
+            }
+        }
+    } else if (warp < 6) {
+        // ===================== epilogue: TMEM -> scaled scores -> dense score buffer =====================
+        const int lane_base = 32 * (warp & 3);            // TMEM lanes this warp may touch
+        uint32_t tcount = 0;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const UmmaItem it = umma_item(p, item, QB);
+            unsigned long long obase[QB];
+            float qs[QB];
+#pragma unroll
+            for (int qq = 0; qq < QB; ++qq) {
+                obase[qq] = 0ull;
+                qs[qq] = 0.f;
+                if (qq < it.nqg) {
+                    const uint32_t e = p.inv[it.s0 + qq];
+                    obase[qq] = p.pair_off[e];
+                    qs[qq] = __ldg(qscale + e / (uint32_t)p.nprobe);
+                }
+            }
+            for (int tile = 0; tile < it.tiles; ++tile, ++tcount) {
+                const int acc = (int)(tcount & 1u);
+                const int r = tile * 128 + lane_base + lane;           // row inside the list
+                const bool valid = r < it.len;
+                float rscale = 0.f;
+                bool allowed = valid;
+                if (valid) {
+                    rscale = __ldg(p.scales + it.start + r);
+                    if (p.mask != nullptr || has_dead) {
+                        const uint32_t row = __ldg(p.list_rows + it.start + r);
+                        allowed = row != TS_DEAD_ROW;
+                        if (allowed && p.mask != nullptr) allowed = (__ldg(p.mask + (row >> 5)) >> (row & 31)) & 1u;
+                    }
+                }
+                mbar_wait_wd(&tmem_full[acc], (tcount >> 1) & 1u);
+                tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(acc * N);
+                uint32_t v[N];
+                if constexpr (N == 32) {
+                    tmem_ld_32x32b_x32(taddr, v);
+                } else {
+                    tmem_ld_32x32b_x16(taddr, v);
+                }
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                mbar_arrive(&tmem_empty[acc]);                         // accumulator drained: the next tile may start
+                if (valid) {
+#pragma unroll
+                    for (int qq = 0; qq < QB; ++qq) {
+                        if (qq < it.nqg) {
+                            const float sc = fmaf(__uint_as_float(v[QB + qq]), 0.0625f, __uint_as_float(v[qq])) * (qs[qq] * rscale);
+                            p.scores[obase[qq] + (unsigned long long)r] = allowed ? sc : -INFINITY;
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== query loaders: the group's 2 * QB byte rows -> swizzled K-major smem =====================
+        const int lt = threadIdx.x - 192;                 // 0..63
+        uint32_t icount = 0;
+        const int chunks_per_row = KB * 8;                // 16-byte chunks
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++icount) {
+            const UmmaItem it = umma_item(p, item, QB);
+            const int bbuf = (int)(icount & 1u);
+            mbar_wait_wd(&b_empty[bbuf], ((icount >> 1) & 1u) ^ 1u);
+            uint8_t* bq = smem_b + (size_t)bbuf * KB_MAX * B_KB_BYTES;
+            for (int c = lt; c < N * chunks_per_row; c += LOADERS) {
+                const int n = c / chunks_per_row, ch = c % chunks_per_row;    // operand row, 16-byte chunk in the row
+                const int qq = n < QB ? n : n - QB;
+                uint4 val = make_uint4(0u, 0u, 0u, 0u);
+                if (qq < it.nqg && (uint32_t)ch * 16u < p.row_bytes) {
+                    const uint32_t e = p.inv[it.s0 + qq];
+                    const size_t qi = (size_t)(e / (uint32_t)p.nprobe);
+                    val = __ldg(reinterpret_cast<const uint4*>(q8 + (qi * 2 + (n < QB ? 0 : 1)) * p.row_bytes + (size_t)ch * 16));
+                }
+                const int kb = ch >> 3, ci = ch & 7;
+                // SWIZZLE_128B, K-major: 8-row groups 1024 B apart, rows 128 B apart, chunk index XOR (row mod 8)
+                uint8_t* dst = bq + (size_t)kb * B_KB_BYTES + (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 +
+                               (size_t)((ci ^ (n & 7)) * 16);
+                *reinterpret_cast<uint4*>(dst) = val;
+            }
+            fence_proxy_async();                          // generic-proxy stores -> visible to the tensor core's reads
+            mbar_arrive(&b_full[bbuf]);
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
 // Per query: best k keys over the score runs of its probed lists. The whole CTA walks the runs 1024 rows at a
 // time (one 16-byte load per thread, the next step's load issued before the current one is consumed); keys that
 // beat the running threshold are appended to one shared buffer (warp-aggregated slot allocation); when the buffer
@@ -602,6 +898,7 @@ size_t ivf_grouped_workspace_bytes(const ts_index* ix, int nq, int nprobe) {
     b += 256;                              // totals
     b += g_al(np * 4) * 3;                 // inv, pair_len, pair_pos0
     b += g_al(np * 8);                     // pair_off
+    b += g_al((size_t)nq * 2 * ix->list_row_bytes) + g_al((size_t)nq * 4);   // two-term e4m3 queries + their scales
     b += g_al(ivf_grouped_score_cap(ix, nq, nprobe) * 4);
     return b;
 }
@@ -635,6 +932,8 @@ int launch_ivf_grouped(const ts_index* ix, const uint64_t* probes, const float* 
     uint32_t* pair_len = (uint32_t*)take(np * 4);
     uint32_t* pair_pos0 = (uint32_t*)take(np * 4);
     unsigned long long* pair_off = (unsigned long long*)take(np * 8);
+    uint8_t* q8 = (uint8_t*)take((size_t)nq * 2 * ix->list_row_bytes);
+    float* qscale = (float*)take((size_t)nq * 4);
     const size_t cap = ivf_grouped_score_cap(ix, nq, nprobe);
     float* scores = (float*)take(cap * 4);
     *flag_out = totals + 1;
@@ -643,8 +942,12 @@ int launch_ivf_grouped(const ts_index* ix, const uint64_t* probes, const float* 
     const int pb = (int)std::min<size_t>((np + 255) / 256, 148 * 8);
     ivf_invert_count_kernel<<<pb, 256, 0, s>>>(probes, (int)np, cnt);
     TS_LAUNCH_CHECK();
-    const bool use_mma = tunables().ivf_group_mma != 0;
-    const int qb = use_mma ? (tunables().ivf_group_mma >= 2 ? 16 : 8) : g4::QB;
+    // ivf.group_mma: 3 / 4 = tcgen05 kind::f8f6f4 with 16 / 8 queries per group (3 is the default), 1 / 2 = legacy
+    // mma.sync with 8 / 16, 0 = CUDA cores with 4
+    const int mode = tunables().ivf_group_mma;
+    const bool use_umma = mode >= 3;
+    const bool use_mma = mode == 1 || mode == 2;
+    const int qb = use_umma ? (mode == 3 ? 16 : 8) : use_mma ? (mode == 2 ? 16 : 8) : g4::QB;
     ivf_invert_scan_kernel<<<1, 1024, 0, s>>>(cnt, ix->list_offsets, ix->nlist, slot_start, item_start, base, totals,
                                               (unsigned long long)cap, qb);
     TS_LAUNCH_CHECK();
@@ -674,7 +977,34 @@ int launch_ivf_grouped(const ts_index* ix, const uint64_t* probes, const float* 
     p.totals = totals;
     p.scores = scores;
     p.stages = 2;
-    if (use_mma) {
+    if (use_umma) {
+        quantize_queries_e4m3x2_kernel<<<(nq + 7) / 8, 256, 0, s>>>(q32, nq, ix->dim_pad, p.row_bytes, q8, qscale);
+        TS_LAUNCH_CHECK();
+        CUtensorMap tmap;
+        {
+            auto enc = get_encode_fn();
+            TS_REQUIRE(enc != nullptr, TS_ERR_CUDA, "ivf grouped scan: cuTensorMapEncodeTiled entry point unavailable");
+            cuuint64_t dims[2] = {(cuuint64_t)p.row_bytes, (cuuint64_t)std::max<int64_t>(ix->built_n + ix->ovf_n, 1)};
+            cuuint64_t strides[1] = {(cuuint64_t)p.row_bytes};
+            cuuint32_t box[2] = {128, 128};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>((const void*)p.list_data), dims,
+                             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            TS_REQUIRE(r == CUDA_SUCCESS, TS_ERR_CUDA, "ivf grouped scan: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+        }
+        const int n_cols = 2 * qb;
+        const size_t smem = (size_t)g4u::NST * g4u::A_BYTES + (size_t)2 * g4u::KB_MAX * n_cols * 128 + 32 * sizeof(uint64_t) + 1024;
+        const unsigned grid = (unsigned)std::min<size_t>(max_items, (size_t)sm_count(ix->device));
+        const int has_dead = ix->ivf_dead > 0 ? 1 : 0;
+        if (qb == 16) {
+            TS_CHECK_CUDA(cudaFuncSetAttribute(ivf_grouped_umma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ivf_grouped_umma_kernel<16><<<grid, g4u::THREADS, smem, s>>>(tmap, p, q8, qscale, has_dead);
+        } else {
+            TS_CHECK_CUDA(cudaFuncSetAttribute(ivf_grouped_umma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ivf_grouped_umma_kernel<8><<<grid, g4u::THREADS, smem, s>>>(tmap, p, q8, qscale, has_dead);
+        }
+    } else if (use_mma) {
         const int nt = qb / 8;
         const int warps = g4m::warps_for(nt);
         const size_t tile_bytes = (size_t)g4m::R * (p.row_bytes + 16);

@@ -96,7 +96,8 @@ struct Tunables {
     int ivf_group_min_lists = 0;  // K4d needs at least this many lists (and query-list pairs); 0 = 4 x SM count
     int scan_timeline = 0;      // 1 = K2 CTAs record %globaltimer stamps per phase (ts_debug_scan_timeline)
     int xchg_debug_no_flag = 0; // test hook: the sharded exchange does not raise its own flag, so its wait times out
-    int ivf_group_mma = 1;      // K4d scoring: 1 / 2 = mma.sync f16 tensor-core variant with 8 / 16 queries per group,
+    int ivf_group_mma = 3;      // K4d scoring: 3 / 4 = tcgen05 kind::f8f6f4 (e4m3 rows straight into the tensor cores, two-term
+                                // e4m3 queries) with 16 / 8 queries per group; 1 / 2 = legacy mma.sync f16 variant with 8 / 16;
                                 // 0 = packed HFMA2 on the CUDA cores (4 queries per group)
 };
 Tunables& tunables();
