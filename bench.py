@@ -298,13 +298,14 @@ def ivf_section(ts, args, dev, clocks, peaks):
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    # unique bytes the list-major scan must read: every (list, group of <= 8 probing queries) streams the list once
+    # unique bytes the list-major scan must read: every (list, group of <= QB probing queries) streams the list once
     cent = ts.build_index(index.ivf_centroids(), dtype="bf16", normalize=False, device=dev)
     _, probes = cent.search(q, 32)
     cnt = torch.bincount(probes.reshape(-1), minlength=args.ivf_nlist)
     sizes = index.ivf_list_sizes()
     row_bytes = ((args.dim + 15) // 16) * 16 + 4
-    unique = int((((cnt + 7) // 8) * sizes).sum().item()) * row_bytes
+    qbw = {0: 4, 1: 8, 2: 16, 3: 16, 4: 8}.get(ts.get_tunable("ivf.group_mma"), 8)   # queries per (list, group) work item
+    unique = int((((cnt + qbw - 1) // qbw) * sizes).sum().item()) * row_bytes
     per_query_equiv = int((cnt * sizes).sum().item()) * row_bytes
     cent.close()
     # single-query latency (device time, mean over 200 distinct queries)
@@ -323,7 +324,8 @@ def ivf_section(ts, args, dev, clocks, peaks):
            "recall_queries": nq_recall, "batch_queries": 4096, "batch_ms": ms, "qps": 4096 / (ms * 1e-3),
            "unique_bytes": unique, "per_query_scan_bytes_if_not_grouped": per_query_equiv,
            "frac_hbm": unique / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-           "frac_hbm_note": "unique (list, 8-query group) bytes / WHOLE batch time (coarse + scan + select + re-score) / measured HBM peak",
+           "queries_per_group": qbw,
+           "frac_hbm_note": "unique (list, query-group) bytes / WHOLE batch time (coarse + scan + select + re-score) / measured HBM peak",
            "single_query_ms": q1_ms, "clocks": clocks.summary()}
     index.close()
     return out

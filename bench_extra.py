@@ -286,6 +286,10 @@ def cmd_ivf(a):
     if a.data == "clustered":
         centers = synthetic.fill_index_clustered(index, a.rows, a.centers or a.nlist, a.sigma, seed=0)
         q_all = synthetic.make_clustered_queries(max(a.nq, a.nq_recall), centers, a.sigma)
+    elif a.data == "hier":
+        model = synthetic.HierarchicalCorpus(a.dim, n_leaves=10 * a.nlist, device=dev, seed=0)
+        model.fill(index, a.rows)
+        q_all = model.queries(max(a.nq, a.nq_recall), seed=3_000_000)
     else:
         synthetic.fill_index(index, 0, a.rows, seed=0)
         q_all = synthetic.make_queries(max(a.nq, a.nq_recall), a.dim, dev)
@@ -342,8 +346,27 @@ def cmd_ivf(a):
     out["batch_nq"] = a.nq
     out["batch_ms"] = ms_b
     out["batch_qps"] = a.nq / (ms_b * 1e-3)
-    out["batch_list_scan_gbs"] = a.nq * scan_bytes / (ms_b * 1e-3) / 1e9
-    out["batch_frac_of_measured_hbm"] = out["batch_list_scan_gbs"] / pk["hbm_gbs"]
+    # what the list-major scan must READ: every (list, group of <= QB probing queries) streams the list once
+    # (nq x per-query bytes would count a list once per query although it is read once per group)
+    cent_ix = ts.build_index(index.ivf_centroids(), dtype="bf16", normalize=False, device=dev)
+    _, probes_b = cent_ix.search(qb, min(a.nprobe, a.nlist))
+    cnt = torch.bincount(probes_b.reshape(-1), minlength=a.nlist)
+    cent_ix.close()
+    lrow = ((a.dim + 15) // 16) * 16 + 4 if a.list_dtype == "fp8" else a.dim * 2
+    sizes_i = index.ivf_list_sizes()
+    out["batch_bytes_if_read_per_query"] = int((cnt * sizes_i).sum().item()) * lrow
+    out["batch_by_scoring_backend"] = {}
+    for mode in (a.mma_modes or [ts.get_tunable("ivf.group_mma")]):
+        qbw = {0: 4, 1: 8, 2: 16, 3: 16, 4: 8}[mode]
+        ts.set_tunable("ivf.group_mma", mode)
+        index._ws = {}
+        ms_m = timed(lambda: index.ivf_search(qb, a.k, nprobe=a.nprobe, rescore_k=a.rescore), 2, 8)
+        unique = int((((cnt + qbw - 1) // qbw) * sizes_i).sum().item()) * lrow
+        _, ids_m = index.ivf_search(qr, a.k, nprobe=a.nprobe, rescore_k=a.rescore)
+        out["batch_by_scoring_backend"][str(mode)] = {
+            "queries_per_group": qbw, "batch_ms": ms_m, "qps": a.nq / (ms_m * 1e-3), "unique_list_bytes": unique,
+            "whole_batch_frac_of_measured_hbm": unique / (ms_m * 1e-3) / 1e9 / pk["hbm_gbs"],
+            "recall_at_k": recall_at_k(ids_m, exact_ids), "clocks": _CLOCKS.summary() if _CLOCKS else None}
     out["tunables"] = a.tunable
     print(json.dumps(out), flush=True)
 
@@ -662,7 +685,9 @@ def main():
     ap.add_argument("--nprobe", type=int, default=32)
     ap.add_argument("--rescore", type=int, default=100)
     ap.add_argument("--list-dtype", default="fp8", choices=["fp8", "bf16"])
-    ap.add_argument("--data", default="clustered", choices=["clustered", "gaussian"])
+    ap.add_argument("--data", default="clustered", choices=["clustered", "gaussian", "hier"])
+    ap.add_argument("--mma-modes", type=int, nargs="*", default=[],
+                    help="ivf: time the batch with each K4d scoring back end (ivf.group_mma value)")
     ap.add_argument("--centers", type=int, default=0)
     ap.add_argument("--sigma", type=float, default=1.0)
     ap.add_argument("--train-sample", type=int, default=2_000_000)
