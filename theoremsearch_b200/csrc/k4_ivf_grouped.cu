@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(1024) ivf_invert_scan_kernel(const uint32_t* _
         base[nlist] = carry[2];
         totals[0] = (uint32_t)carry[1];
         totals[1] = carry[2] > score_cap ? 1u : 0u;
+        totals[2] = 0u;   // work-item counter of the persistent scan kernel (dynamic scheduling)
     }
 }
 
@@ -521,8 +522,10 @@ __global__ void __launch_bounds__(g4m::warps_for(NT) * 32, 1) ivf_grouped_mma_ke
 //   * D: 128 rows x 2 * QB fp32 columns in TMEM, double-buffered; four epilogue warps read it back (thread = row),
 //     fold hi + lo / 16, apply query scale x row scale (and the allow mask / tombstones) and store to the dense
 //     score buffer — for a fixed query a warp's 32 rows are 32 consecutive floats, one coalesced store.
-//   * persistent CTAs (one per SM) walk the work items with a fixed stride; every role derives the item's
-//     geometry itself, the pipeline never drains between items.
+//   * persistent CTAs (one per SM) claim work items from a global counter (lists differ in length by 30x: a fixed
+//     stride left the SMs 14 % idle at the tail — ncu: smsp cycles active 86 % of elapsed): the TMA thread claims
+//     the next item one item ahead and publishes it through a small smem ring that the other roles follow;
+//     every role derives the item's geometry itself, the pipeline never drains between items.
 // Algorithmic bytes per item = list rows x row_bytes, read once per QB = 16 queries (K4b: once per query).
 namespace g4u {
 constexpr int NST = 8;                 // A ring stages (16 KB each)
@@ -530,6 +533,9 @@ constexpr int A_BYTES = 128 * 128;
 constexpr int THREADS = 256;           // warp 0 TMA, warp 1 MMA + TMEM, warps 2-5 epilogue, warps 6-7 query loaders
 constexpr int LOADERS = 64;
 constexpr int KB_MAX = 8;              // k-blocks per row: row_bytes <= 1024
+constexpr int SR = 8;                  // scheduler ring entries (items claimed ahead of their consumers)
+constexpr int SCHED_CONSUMERS = 7;     // MMA thread + 4 epilogue warps + 2 loader warps
+constexpr uint32_t NO_ITEM = 0xFFFFFFFFu;
 }  // namespace g4u
 
 __device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -621,7 +627,18 @@ ivf_grouped_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const Groupe
     uint64_t* tmem_empty = tmem_full + 2;  // [2]
     uint64_t* b_full = tmem_empty + 2;     // [2]
     uint64_t* b_empty = b_full + 2;        // [2]
-    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(b_empty + 2);
+    uint64_t* sched_full = b_empty + 2;    // [SR]
+    uint64_t* sched_empty = sched_full + SR;   // [SR]
+    uint32_t* sched_item = reinterpret_cast<uint32_t*>(sched_empty + SR);   // [SR]
+    uint32_t* tmem_ptr_s = sched_item + SR;
+    uint32_t* item_counter = const_cast<uint32_t*>(p.totals) + 2;
+    // the i-th item of this CTA, as published by the TMA thread (NO_ITEM = no more work)
+    auto next_item = [&](uint32_t i) -> uint32_t {
+        const int slot = (int)(i % SR);
+        mbar_wait_wd(&sched_full[slot], (i / SR) & 1u);
+        return *reinterpret_cast<volatile uint32_t*>(&sched_item[slot]);
+    };
+    auto release_item = [&](uint32_t i) { mbar_arrive(&sched_empty[i % SR]); };
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -636,6 +653,10 @@ ivf_grouped_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const Groupe
             mbar_init(&tmem_empty[s], 128);
             mbar_init(&b_full[s], LOADERS);
             mbar_init(&b_empty[s], 1);
+        }
+        for (int s = 0; s < SR; ++s) {
+            mbar_init(&sched_full[s], 1);
+            mbar_init(&sched_empty[s], SCHED_CONSUMERS);
         }
         fence_mbar_init();
     }
@@ -655,7 +676,15 @@ ivf_grouped_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const Groupe
             const uint64_t pol = l2_policy_evict_first();
             int stage = 0;
             uint32_t phase = 0;
-            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            uint32_t claimed = atomicAdd(item_counter, 1u);
+            for (uint32_t i = 0;; ++i) {
+                const uint32_t item = claimed < n_items ? claimed : NO_ITEM;
+                const int slot = (int)(i % SR);
+                mbar_wait_wd(&sched_empty[slot], ((i / SR) & 1u) ^ 1u);
+                sched_item[slot] = item;
+                mbar_arrive(&sched_full[slot]);          // (mbarrier arrive has release semantics: the store above is visible)
+                if (item == NO_ITEM) break;
+                claimed = atomicAdd(item_counter, 1u);   // the NEXT item: the round trip hides behind this item's copies
                 const UmmaItem it = umma_item(p, item, QB);
                 for (int tile = 0; tile < it.tiles; ++tile) {
                     const int row0 = (int)(it.start + (int64_t)tile * 128);
@@ -679,9 +708,12 @@ ivf_grouped_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const Groupe
             const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
-            uint32_t tcount = 0, icount = 0;
-            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++icount) {
+            uint32_t tcount = 0;
+            for (uint32_t icount = 0;; ++icount) {
+                const uint32_t item = next_item(icount);
+                if (item == NO_ITEM) break;
                 const UmmaItem it = umma_item(p, item, QB);
+                release_item(icount);
                 const int bbuf = (int)(icount & 1u);
                 mbar_wait_wd(&b_full[bbuf], (icount >> 1) & 1u);
                 tcgen05_fence_after();
@@ -714,8 +746,12 @@ ivf_grouped_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const Groupe
         // ===================== epilogue: TMEM -> scaled scores -> dense score buffer =====================
         const int lane_base = 32 * (warp & 3);            // TMEM lanes this warp may touch
         uint32_t tcount = 0;
-        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (uint32_t icount = 0;; ++icount) {
+            const uint32_t item = next_item(icount);
+            if (item == NO_ITEM) break;
             const UmmaItem it = umma_item(p, item, QB);
+            __syncwarp();
+            if (lane == 0) release_item(icount);
             unsigned long long obase[QB];
             float qs[QB];
 #pragma unroll
@@ -768,10 +804,13 @@ ivf_grouped_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const Groupe
     } else {
         // ===================== query loaders: the group's 2 * QB byte rows -> swizzled K-major smem =====================
         const int lt = threadIdx.x - 192;                 // 0..63
-        uint32_t icount = 0;
         const int chunks_per_row = KB * 8;                // 16-byte chunks
-        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++icount) {
+        for (uint32_t icount = 0;; ++icount) {
+            const uint32_t item = next_item(icount);
+            if (item == NO_ITEM) break;
             const UmmaItem it = umma_item(p, item, QB);
+            __syncwarp();
+            if (lane == 0) release_item(icount);
             const int bbuf = (int)(icount & 1u);
             mbar_wait_wd(&b_empty[bbuf], ((icount >> 1) & 1u) ^ 1u);
             uint8_t* bq = smem_b + (size_t)bbuf * KB_MAX * B_KB_BYTES;
@@ -994,7 +1033,7 @@ int launch_ivf_grouped(const ts_index* ix, const uint64_t* probes, const float* 
             TS_REQUIRE(r == CUDA_SUCCESS, TS_ERR_CUDA, "ivf grouped scan: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
         }
         const int n_cols = 2 * qb;
-        const size_t smem = (size_t)g4u::NST * g4u::A_BYTES + (size_t)2 * g4u::KB_MAX * n_cols * 128 + 32 * sizeof(uint64_t) + 1024;
+        const size_t smem = (size_t)g4u::NST * g4u::A_BYTES + (size_t)2 * g4u::KB_MAX * n_cols * 128 + 64 * sizeof(uint64_t) + 1024;
         const unsigned grid = (unsigned)std::min<size_t>(max_items, (size_t)sm_count(ix->device));
         const int has_dead = ix->ivf_dead > 0 ? 1 : 0;
         if (qb == 16) {
