@@ -676,15 +676,28 @@ ivf_grouped_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const Groupe
             const uint64_t pol = l2_policy_evict_first();
             int stage = 0;
             uint32_t phase = 0;
-            uint32_t claimed = atomicAdd(item_counter, 1u);
-            for (uint32_t i = 0;; ++i) {
-                const uint32_t item = claimed < n_items ? claimed : NO_ITEM;
+            // Items are claimed two ahead and PUBLISHED one ahead of the copies: the loader warps need an item's id a
+            // whole item early (metadata + 32 KB of query bytes + the swizzled smem writes must be done before the
+            // item's first MMA), and the claim's atomic round trip hides behind the current item's copies.
+            auto claim = [&]() -> uint32_t {
+                const uint32_t c = atomicAdd(item_counter, 1u);
+                return c < n_items ? c : NO_ITEM;
+            };
+            auto publish = [&](uint32_t i, uint32_t item) {
                 const int slot = (int)(i % SR);
                 mbar_wait_wd(&sched_empty[slot], ((i / SR) & 1u) ^ 1u);
                 sched_item[slot] = item;
                 mbar_arrive(&sched_full[slot]);          // (mbarrier arrive has release semantics: the store above is visible)
-                if (item == NO_ITEM) break;
-                claimed = atomicAdd(item_counter, 1u);   // the NEXT item: the round trip hides behind this item's copies
+            };
+            uint32_t c_a = claim(), c_b = claim();
+            publish(0, c_a);
+            for (uint32_t i = 0;; ++i) {
+                const uint32_t item = c_a;
+                if (item == NO_ITEM) break;              // its sentinel has been published already
+                publish(i + 1, c_b);
+                const uint32_t c_c = c_b == NO_ITEM ? NO_ITEM : claim();
+                c_a = c_b;
+                c_b = c_c;
                 const UmmaItem it = umma_item(p, item, QB);
                 for (int tile = 0; tile < it.tiles; ++tile) {
                     const int row0 = (int)(it.start + (int64_t)tile * 128);
@@ -847,6 +860,33 @@ ivf_grouped_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const Groupe
 // beat the running threshold are appended to one shared buffer (warp-aggregated slot allocation); when the buffer
 // could overflow in the next step the CTA sorts it cooperatively, keeps the best k and raises the threshold to the
 // k-th key. After the first compaction only ~k ln(n / 1024) more keys ever pass, so a query costs two CTA sorts.
+// Warp-per-query form (the default): the query's score runs are walked by one warp with float4 loads against a float
+// threshold, candidates go through a register-resident WarpSelect (warp_select_run) — no shared memory, no barriers, no
+// CTA sorts; 4096 queries run as 4096 independent warps. 0.93 ms -> see profiles/launches_ivf_batch_r2*.csv.
+template <int KPL>
+__global__ void __launch_bounds__(256) ivf_select_warp_kernel(const float* __restrict__ scores,
+                                                              const unsigned long long* __restrict__ pair_off,
+                                                              const uint32_t* __restrict__ pair_len,
+                                                              const uint32_t* __restrict__ pair_pos0, int nq, int nprobe, int k,
+                                                              const uint32_t* __restrict__ totals, uint64_t* __restrict__ cand) {
+    if (totals[1] != 0u) return;
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    WarpSelect<KPL> sel;
+    sel.init();
+    for (int j = 0; j < nprobe; ++j) {
+        const size_t e = (size_t)q * nprobe + j;
+        const int len = (int)pair_len[e];
+        if (len == 0) continue;
+        warp_select_run<KPL>(sel, scores + pair_off[e], len, pair_pos0[e], k, lane);
+    }
+    sel.flush(k, lane);
+#pragma unroll
+    for (int j = 0; j < KPL; ++j)
+        if (j * 32 + lane < k) cand[(size_t)q * k + j * 32 + lane] = sel.best.key[j];
+}
+
 constexpr int SEL_CAP = 3072;   // keys the buffer holds (24 KB); a step appends at most 1024
 __global__ void __launch_bounds__(256) ivf_select_kernel(const float* __restrict__ scores,
                                                          const unsigned long long* __restrict__ pair_off,
@@ -1070,7 +1110,14 @@ int launch_ivf_grouped(const ts_index* ix, const uint64_t* probes, const float* 
     }
     TS_LAUNCH_CHECK();
 
-    ivf_select_kernel<<<nq, 256, 0, s>>>(scores, pair_off, pair_len, pair_pos0, nprobe, kc, totals, cand);
+    if (tunables().ivf_select_warp == 0)
+        ivf_select_kernel<<<nq, 256, 0, s>>>(scores, pair_off, pair_len, pair_pos0, nprobe, kc, totals, cand);
+    else if (kc <= 32)
+        ivf_select_warp_kernel<1><<<(nq + 7) / 8, 256, 0, s>>>(scores, pair_off, pair_len, pair_pos0, nq, nprobe, kc, totals, cand);
+    else if (kc <= 128)
+        ivf_select_warp_kernel<4><<<(nq + 7) / 8, 256, 0, s>>>(scores, pair_off, pair_len, pair_pos0, nq, nprobe, kc, totals, cand);
+    else
+        ivf_select_warp_kernel<8><<<(nq + 7) / 8, 256, 0, s>>>(scores, pair_off, pair_len, pair_pos0, nq, nprobe, kc, totals, cand);
     TS_LAUNCH_CHECK();
     return TS_OK;
 }

@@ -201,4 +201,37 @@ struct WarpSelect {
     }
 };
 
+// One warp selects the best k keys of a run of `len` fp32 scores (positions pos0 .. pos0 + len - 1; -inf = masked).
+// Fast path: a lane loads four scores at once and compares them with the running threshold as FLOATS; only when
+// some lane of the warp has a candidate are keys packed and offered to the WarpSelect — after the first few hundred
+// rows that happens for ~k ln(n) / n of the steps. `run` must be 16-byte aligned; len is padded to 4 in memory.
+template <int KPL>
+__device__ __forceinline__ void warp_select_run(WarpSelect<KPL>& sel, const float* __restrict__ run, int len, uint32_t pos0,
+                                                int k, int lane) {
+    float thr_f = sel.thr ? key_score(sel.thr) : -INFINITY;
+    for (int r0 = 0; r0 < len; r0 += 512) {            // 4 x (32 lanes x float4) per iteration, loads issued together
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u * 128 + 4 * lane;
+            v[u] = (r < len) ? __ldg(reinterpret_cast<const float4*>(run + r)) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u * 128 + 4 * lane;
+            const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            bool any = false;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) any |= (r + i < len) && (f[i] >= thr_f) && (f[i] > -INFINITY);
+            if (!__any_sync(0xFFFFFFFFu, any)) continue;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool live = (r + i < len) && (f[i] > -INFINITY);
+                sel.offer(live ? pack_key(f[i], pos0 + (uint32_t)(r + i)) : 0ull, k, lane);
+            }
+            thr_f = sel.thr ? key_score(sel.thr) : -INFINITY;
+        }
+    }
+}
+
 }  // namespace ts

@@ -817,6 +817,7 @@ static int* tunable_slot(const char* name) {
     if (!strcmp(name, "ivf.timeline")) return &t.ivf_timeline;
     if (!strcmp(name, "ivf.group_min_nq")) return &t.ivf_group_min_nq;
     if (!strcmp(name, "ivf.group_mma")) return &t.ivf_group_mma;
+    if (!strcmp(name, "ivf.select_warp")) return &t.ivf_select_warp;
     if (!strcmp(name, "xchg.debug_no_flag")) return &t.xchg_debug_no_flag;
     if (!strcmp(name, "scan.timeline")) return &t.scan_timeline;
     if (!strcmp(name, "ivf.group_min_lists")) return &t.ivf_group_min_lists;

@@ -94,6 +94,7 @@ struct Tunables {
     int ivf_timeline = 0;       // 1 = K4b CTAs record globaltimer stamps per phase (ts_debug_ivf_timeline)
     int ivf_group_min_nq = 16;  // batches at least this large take the list-major scan (K4d); 0 = never (sweep: profiles/sweep_ivf_batch_r1.txt)
     int ivf_group_min_lists = 0;  // K4d needs at least this many lists (and query-list pairs); 0 = 4 x SM count
+    int ivf_select_warp = 1;    // K4d candidate selection: 1 = warp-per-query register select, 0 = CTA-per-query smem select
     int scan_timeline = 0;      // 1 = K2 CTAs record %globaltimer stamps per phase (ts_debug_scan_timeline)
     int xchg_debug_no_flag = 0; // test hook: the sharded exchange does not raise its own flag, so its wait times out
     int ivf_group_mma = 3;      // K4d scoring: 3 / 4 = tcgen05 kind::f8f6f4 (e4m3 rows straight into the tensor cores, two-term
