@@ -205,12 +205,16 @@ struct WarpSelect {
 // Fast path: a lane loads four scores at once and compares them with the running threshold as FLOATS; only when
 // some lane of the warp has a candidate are keys packed and offered to the WarpSelect — after the first few hundred
 // rows that happens for ~k ln(n) / n of the steps. `run` must be 16-byte aligned; len is padded to 4 in memory.
+__device__ __forceinline__ float pick4(const float4& v, int i) {   // register selects, never local memory
+    return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
 template <int KPL>
 __device__ __forceinline__ void warp_select_run(WarpSelect<KPL>& sel, const float* __restrict__ run, int len, uint32_t pos0,
                                                 int k, int lane) {
     float thr_f = sel.thr ? key_score(sel.thr) : -INFINITY;
     for (int r0 = 0; r0 < len; r0 += 512) {            // 4 x (32 lanes x float4) per iteration, loads issued together
         float4 v[4];
+        bool any = false;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int r = r0 + u * 128 + 4 * lane;
@@ -220,15 +224,22 @@ __device__ __forceinline__ void warp_select_run(WarpSelect<KPL>& sel, const floa
         for (int u = 0; u < 4; ++u) {
             const int r = r0 + u * 128 + 4 * lane;
             const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-            bool any = false;
 #pragma unroll
             for (int i = 0; i < 4; ++i) any |= (r + i < len) && (f[i] >= thr_f) && (f[i] > -INFINITY);
-            if (!__any_sync(0xFFFFFFFFu, any)) continue;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const bool live = (r + i < len) && (f[i] > -INFINITY);
-                sel.offer(live ? pack_key(f[i], pos0 + (uint32_t)(r + i)) : 0ull, k, lane);
-            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, any)) continue;
+        // slow path, ONE call site of offer(): its flush (a 128..256-key register sort + merge, ~2000 instructions)
+        // is inlined wherever offer() is called, and sixteen copies of it thrashed the instruction cache
+        // (dense select 1.55 ms instead of 0.1 ms)
+#pragma unroll 1
+        for (int t = 0; t < 16; ++t) {
+            const int u = t >> 2, i = t & 3;
+            const float4 vu = u == 0 ? v[0] : (u == 1 ? v[1] : (u == 2 ? v[2] : v[3]));
+            const float f = pick4(vu, i);
+            const int r = r0 + u * 128 + 4 * lane + i;
+            const bool live = (r < len) && (f >= thr_f) && (f > -INFINITY);
+            if (!__any_sync(0xFFFFFFFFu, live)) continue;
+            sel.offer(live ? pack_key(f, pos0 + (uint32_t)r) : 0ull, k, lane);
             thr_f = sel.thr ? key_score(sel.thr) : -INFINITY;
         }
     }
