@@ -503,12 +503,22 @@ def cmd_sharded(a):
     if a.data == "clustered":
         centers = synthetic.fill_index_clustered(index, hi - lo, a.centers or a.nlist, a.sigma, seed=0, first_row=lo)
         q_all = synthetic.make_clustered_queries(max(a.nq, a.nq_recall), centers, a.sigma)
+    elif a.data == "hier":
+        model = synthetic.HierarchicalCorpus(a.dim, n_leaves=10 * a.nlist, device=dev, seed=0)
+        model.fill(index, hi - lo, first_row=lo)
+        q_all = model.queries(max(a.nq, a.nq_recall), seed=3_000_000)
     else:
         synthetic.fill_index(index, lo, hi - lo, seed=0)
         q_all = synthetic.make_queries(max(a.nq, a.nq_recall), a.dim, dev)
     torch.cuda.synchronize()
     fill_s = time.time() - t0
     sh = ShardedIndex(index, a.rows)
+    peer = False
+    try:
+        sh.enable_peer_exchange(max_nq=1, max_k=32)
+        peer = True
+    except ts.TheoremSearchError:
+        pass
 
     def sync():
         if world > 1:
@@ -520,11 +530,12 @@ def cmd_sharded(a):
             fn()
         sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record()
-        sync()
+        with _Sampling():
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            sync()
         t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -535,7 +546,16 @@ def cmd_sharded(a):
            "fill_s": fill_s}
     q1 = [q_all[i:i + 1].contiguous() for i in range(64)]
     it = iter(itertools.cycle(range(64)))
-    ms1 = timed_max(lambda: sh.search(q1[next(it)], a.k), 10, 100)
+    ms1 = timed_max(lambda: sh.search(q1[next(it)], a.k, independent=peer), 10, 200)
+    out["exact_q1_form"] = ("device-initiated exchange, scan + exchange kernel (PDL), independent stream" if peer
+                            else "NCCL all-gather + merge kernel")
+    out["exact_q1_clocks"] = _CLOCKS.summary() if _CLOCKS else None
+    if peer:
+        out["exact_q1_dependent_ms"] = timed_max(lambda: sh.search(q1[next(it)], a.k), 10, 100)
+        out["exact_q1_one_kernel_ms"] = timed_max(lambda: sh.search(q1[next(it)], a.k, one_kernel=True), 10, 100)
+        saved, sh._xchg = sh._xchg, None
+        out["exact_q1_nccl_ms"] = timed_max(lambda: sh.search(q1[next(it)], a.k), 10, 100)
+        sh._xchg = saved
     out["exact_q1_ms"] = ms1
     out["exact_q1_qps"] = 1e3 / ms1
     out["exact_q1_aggregate_gbs"] = a.rows * a.dim * 2 / (ms1 * 1e-3) / 1e9
@@ -570,6 +590,7 @@ def cmd_sharded(a):
         out["ivf"] = ivf
     if rank == 0:
         print(json.dumps(out), flush=True)
+    sh.close()
     index.close()
     if world > 1:
         dist.barrier()
