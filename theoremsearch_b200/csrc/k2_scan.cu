@@ -79,6 +79,8 @@ int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64
         p.fin.out_scores = fused->out_scores;
         p.fin.out_ids = fused->out_ids;
         p.fin.out_stride = k;
+        p.fin.done_flag = fused->done_flag;
+        p.fin.done_value = fused->done_value;
         p.xchg = fused->xchg;
     }
     if (data_dtype == TS_BF16) {

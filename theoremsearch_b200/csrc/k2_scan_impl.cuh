@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
             } else {
                 // ---- fused exchange (one-kernel form): this CTA also pushes the shard's keys to the peers,
                 // waits for theirs and merges the world lists
+                mp.done_flag = nullptr;   // the shard-local merge is an intermediate step: only the world merge signals
                 exchange_and_merge<KPL>(p.xchg, p.fin, mp, wi, qi, k, lists, W);
             }
             scan_stamp(p, 6);                          // 6: (last CTA only) final merge / exchange done

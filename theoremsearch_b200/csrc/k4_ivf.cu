@@ -844,6 +844,8 @@ __global__ void __launch_bounds__(512, 1) list_scan_kernel(const ListScanParams 
         mp.out_stride = k;
         mp.qlist = nullptr;
         mp.qcount = nullptr;
+        mp.done_flag = nullptr;
+        mp.done_value = 0;
         merge_lists<KPL>(mp, qi, qi, cbuf, W);
     }
     IVF_STAMP(7);

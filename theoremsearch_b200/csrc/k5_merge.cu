@@ -48,6 +48,8 @@ int launch_merge_strided(const uint64_t* keys, int nlists, int nq, int k, int64_
     p.out_stride = out_stride ? out_stride : k;
     p.qlist = qlist;
     p.qcount = qcount;
+    p.done_flag = nullptr;
+    p.done_value = 0;
     const int grid = qcount ? std::min(nq, 64) : nq;
     if (k <= 32) {
         merge_topk_kernel<1><<<grid, 256, 8 * 32 * 8, s>>>(p);
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(256) xchg_finish_kernel(const MergeParams loca
 }
 
 int launch_xchg_finish(const uint64_t* part_keys, int nparts, int nq, int k, const XchgDev& x, const int64_t* id_map,
-                       float* out_scores, int64_t* out_ids, cudaStream_t s) {
+                       float* out_scores, int64_t* out_ids, cudaStream_t s, uint32_t* done_flag, uint32_t done_value) {
     TS_REQUIRE(k >= 1 && k <= TS_MAX_K && nq >= 1, TS_ERR_BAD_ARG, "xchg_finish: nq=%d k=%d", nq, k);
     MergeParams local;
     memset(&local, 0, sizeof(local));
@@ -113,6 +115,8 @@ int launch_xchg_finish(const uint64_t* part_keys, int nparts, int nq, int k, con
     fin.out_scores = out_scores;
     fin.out_ids = out_ids;
     fin.out_stride = k;
+    fin.done_flag = done_flag;
+    fin.done_value = done_value;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nq);
     cfg.blockDim = dim3(256);

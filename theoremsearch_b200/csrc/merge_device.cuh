@@ -18,7 +18,19 @@ struct MergeParams {
     int64_t out_stride;                 // elements between consecutive queries in out_keys
     const int* qlist;                   // fix-up mode: work item w reads lists of item w, writes query qlist[w]
     const int* qcount;                  // ... for w < *qcount
+    // host-buffer latency path (single query): the outputs above point into pinned, device-mapped HOST memory and,
+    // once they are written, *done_flag (also host-mapped) receives done_value — the host polls the flag instead
+    // of paying two D2H copies and a stream synchronise. nullptr: no signal.
+    uint32_t* done_flag;
+    uint32_t done_value;
 };
+
+__device__ __forceinline__ void merge_signal_done(const MergeParams& p) {
+    if (p.done_flag != nullptr && threadIdx.x == 0) {
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t*>(p.done_flag) = p.done_value;
+    }
+}
 
 // Descending bitonic sort of P keys (power of two, >= 64) in shared memory by every thread of the CTA.
 // A warp owns 64-key windows: all compare-exchange levels with stride <= 32 run in registers (two keys per
@@ -178,6 +190,7 @@ __device__ __forceinline__ void merge_lists(const MergeParams& p, int qi, int qo
         }
     }
     __syncthreads();
+    merge_signal_done(p);
 }
 
 // ---------------------------------------------------------------------------------------------- peer exchange
@@ -289,6 +302,7 @@ __device__ __forceinline__ void exchange_and_merge(const XchgDev& x, const Merge
             if (fin.out_ids) fin.out_ids[(size_t)qi * k + i] = -1;
         }
         __syncthreads();
+        merge_signal_done(fin);
         xchg_publish_done(x);
         return;
     }

@@ -27,6 +27,26 @@ Tunables& tunables() {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Poll a completion flag the device writes into mapped host memory. The result bytes were written (and fenced at
+// system scope) before the flag, so once the flag shows `value` the outputs beside it are final. After ~200 ms of
+// polling — a kernel that faulted never raises the flag — fall back to a stream synchronise, which reports the error.
+int wait_done_flag(const volatile uint32_t* flag, uint32_t value, cudaStream_t s, const char* what) {
+    for (uint64_t spins = 0; *flag != value; ++spins) {
+#if defined(__x86_64__) || defined(_M_X64)
+        __builtin_ia32_pause();
+#endif
+        if ((spins & 0xFFFFu) == 0xFFFFu) {
+            const cudaError_t q = cudaStreamQuery(s);
+            if (q == cudaSuccess) break;                       // the stream has drained: the flag write is done too
+            if (q != cudaErrorNotReady) {
+                set_error("%s: kernel failed: %s", what, cudaGetErrorString(q));
+                return TS_ERR_CUDA;
+            }
+        }
+    }
+    return TS_OK;
+}
+
 // Workspace layout for exact search: [prepared queries fp32 | per-CTA candidate keys]
 struct SearchWs {
     float* q_f32;
@@ -58,7 +78,7 @@ static bool use_batched(const ts_index* ix, int nq) {
 int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k,
                        int normalize_queries, const uint32_t* allow_mask, uint64_t* out_keys,
                        float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
-                       cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1) {
+                       cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1, uint32_t* done_flag, uint32_t done_value) {
     TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "search: index is NULL");
     TS_REQUIRE(nq >= 0, TS_ERR_BAD_ARG, "search: nq=%d", nq);
     TS_REQUIRE(k >= 1 && k <= TS_MAX_K, TS_ERR_BAD_ARG, "search: k=%d out of range [1, %d]", k, TS_MAX_K);
@@ -92,6 +112,8 @@ int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k,
     f.pdl = 0;
     f.ring_gate = nullptr;
     f.ring_need = 0;
+    f.done_flag = done_flag;     // only the single-query host path passes one (nq == 1: one merging CTA)
+    f.done_value = done_value;
     return launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, w.part_keys, w.nparts,
                             s, ev0, ev1, nullptr, nullptr, &f);
 }
@@ -448,8 +470,15 @@ int ts_ctx_create(ts_ctx** out, ts_index* ix, int max_nq, int max_k) {
     const size_t ib = (size_t)max_nq * max_k * sizeof(int64_t);
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_queries, qb);
-    if (e == cudaSuccess) e = cudaMallocHost(&c->h_scores, sb);
-    if (e == cudaSuccess) e = cudaMallocHost(&c->h_ids, ib);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&c->h_scores, sb, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&c->h_ids, ib, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&c->h_done, sizeof(uint32_t), cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        *c->h_done = 0u;
+        e = cudaHostGetDevicePointer((void**)&c->m_scores, c->h_scores, 0);
+    }
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&c->m_ids, c->h_ids, 0);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&c->m_done, c->h_done, 0);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_queries, qb);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_scores, sb);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_ids, ib);
@@ -473,6 +502,7 @@ void ts_ctx_destroy(ts_ctx* c) {
     cudaFreeHost(c->h_queries);
     cudaFreeHost(c->h_scores);
     cudaFreeHost(c->h_ids);
+    cudaFreeHost(c->h_done);
     cudaFree(c->d_queries);
     cudaFree(c->d_scores);
     cudaFree(c->d_ids);
@@ -518,9 +548,21 @@ int ts_search_host(ts_ctx* c, const float* queries, int nq, int k, int normalize
     const size_t qb = (size_t)nq * ix->dim * sizeof(float);
     memcpy(c->h_queries, queries, qb);
     TS_CHECK_CUDA(cudaMemcpyAsync(c->d_queries, c->h_queries, qb, cudaMemcpyHostToDevice, c->stream));
+    if (nq == 1 && !c->timing && !use_batched(ix, nq)) {
+        // latency path: the kernel's last CTA writes the k results into mapped host memory and raises a flag
+        const uint32_t seq = ++c->done_seq;
+        int rc1 = search_impl(ix, c->d_queries, TS_F32, 1, k, normalize_queries, allow_mask, nullptr, c->m_scores, c->m_ids,
+                              c->workspace, c->workspace_bytes, c->stream, nullptr, nullptr, c->m_done, seq);
+        if (rc1) return rc1;
+        rc1 = wait_done_flag(c->h_done, seq, c->stream, "search_host");
+        if (rc1) return rc1;
+        memcpy(out_scores, c->h_scores, (size_t)k * sizeof(float));
+        memcpy(out_ids, c->h_ids, (size_t)k * sizeof(int64_t));
+        return TS_OK;
+    }
     int rc = search_impl(ix, c->d_queries, TS_F32, nq, k, normalize_queries, allow_mask, nullptr, c->d_scores,
                          c->d_ids, c->workspace, c->workspace_bytes, c->stream, c->timing ? c->ev0 : nullptr,
-                         c->timing ? c->ev1 : nullptr);
+                         c->timing ? c->ev1 : nullptr, nullptr, 0);
     if (rc) return rc;
     const size_t n = (size_t)nq * k;
     TS_CHECK_CUDA(cudaMemcpyAsync(c->h_scores, c->d_scores, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -598,6 +640,7 @@ void ts_xchg_destroy(ts_xchg* x) {
     cudaFreeHost(x->h_queries);
     cudaFreeHost(x->h_scores);
     cudaFreeHost(x->h_ids);
+    cudaFreeHost(x->h_done);
     cudaFree(x->d_queries);
     cudaFree(x->d_scores);
     cudaFree(x->d_ids);
@@ -667,9 +710,12 @@ int ts_xchg_reset(ts_xchg* x) {
 
 uint32_t ts_xchg_seq(const ts_xchg* x) { return x ? x->seq : 0u; }
 
-int ts_search_sharded(ts_index* ix, ts_xchg* x, const void* queries, int q_dtype, int nq, int k, int normalize_queries,
-                      const uint32_t* allow_mask, int64_t shard_base, const int64_t* id_map, float* out_scores,
-                      int64_t* out_ids, void* workspace, size_t workspace_bytes, int flags, void* stream) {
+}  // extern "C"
+
+static int search_sharded_impl(ts_index* ix, ts_xchg* x, const void* queries, int q_dtype, int nq, int k, int normalize_queries,
+                               const uint32_t* allow_mask, int64_t shard_base, const int64_t* id_map, float* out_scores,
+                               int64_t* out_ids, void* workspace, size_t workspace_bytes, int flags, void* stream,
+                               uint32_t* done_flag, uint32_t done_value) {
     TS_REQUIRE(ix != nullptr && x != nullptr, TS_ERR_BAD_ARG, "search_sharded: NULL handle");
     TS_REQUIRE(x->connected, TS_ERR_STATE, "search_sharded: ts_xchg_connect has not been called");
     TS_REQUIRE(x->device == ix->device, TS_ERR_BAD_ARG, "search_sharded: index on device %d, exchange on %d", ix->device,
@@ -724,6 +770,8 @@ int ts_search_sharded(ts_index* ix, ts_xchg* x, const void* queries, int q_dtype
         f.pdl = 0;
         f.ring_gate = nullptr;
         f.ring_need = 0;
+        f.done_flag = done_flag;
+        f.done_value = done_value;
         return launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, w.part_keys, w.nparts, s,
                                 nullptr, nullptr, nullptr, nullptr, &f);
     }
@@ -750,7 +798,16 @@ int ts_search_sharded(ts_index* ix, ts_xchg* x, const void* queries, int q_dtype
     int rc = launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, part, w.nparts, s,
                               nullptr, nullptr, nullptr, nullptr, &f);
     if (rc) return rc;
-    return launch_xchg_finish(part, w.nparts, nq, k, xd, id_map, out_scores, out_ids, s);
+    return launch_xchg_finish(part, w.nparts, nq, k, xd, id_map, out_scores, out_ids, s, done_flag, done_value);
+}
+
+extern "C" {
+
+int ts_search_sharded(ts_index* ix, ts_xchg* x, const void* queries, int q_dtype, int nq, int k, int normalize_queries,
+                      const uint32_t* allow_mask, int64_t shard_base, const int64_t* id_map, float* out_scores,
+                      int64_t* out_ids, void* workspace, size_t workspace_bytes, int flags, void* stream) {
+    return search_sharded_impl(ix, x, queries, q_dtype, nq, k, normalize_queries, allow_mask, shard_base, id_map, out_scores,
+                               out_ids, workspace, workspace_bytes, flags, stream, nullptr, 0);
 }
 
 int ts_search_sharded_host(ts_index* ix, ts_xchg* x, const float* queries, int nq, int k, int normalize_queries,
@@ -770,8 +827,13 @@ int ts_search_sharded_host(ts_index* ix, ts_xchg* x, const float* queries, int n
         x->workspace_bytes = carve_ws(ix, x->max_nq, x->max_k, nullptr).bytes;
         TS_CHECK_CUDA(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
         TS_CHECK_CUDA(cudaMallocHost(&x->h_queries, qb));
-        TS_CHECK_CUDA(cudaMallocHost(&x->h_scores, sb));
-        TS_CHECK_CUDA(cudaMallocHost(&x->h_ids, ib));
+        TS_CHECK_CUDA(cudaHostAlloc((void**)&x->h_scores, sb, cudaHostAllocMapped));
+        TS_CHECK_CUDA(cudaHostAlloc((void**)&x->h_ids, ib, cudaHostAllocMapped));
+        TS_CHECK_CUDA(cudaHostAlloc((void**)&x->h_done, sizeof(uint32_t), cudaHostAllocMapped));
+        *x->h_done = 0u;
+        TS_CHECK_CUDA(cudaHostGetDevicePointer((void**)&x->m_scores, x->h_scores, 0));
+        TS_CHECK_CUDA(cudaHostGetDevicePointer((void**)&x->m_ids, x->h_ids, 0));
+        TS_CHECK_CUDA(cudaHostGetDevicePointer((void**)&x->m_done, x->h_done, 0));
         TS_CHECK_CUDA(cudaMalloc(&x->d_queries, qb));
         TS_CHECK_CUDA(cudaMalloc(&x->d_scores, sb));
         TS_CHECK_CUDA(cudaMalloc(&x->d_ids, ib));
@@ -781,10 +843,24 @@ int ts_search_sharded_host(ts_index* ix, ts_xchg* x, const float* queries, int n
     const size_t qb = (size_t)nq * ix->dim * sizeof(float);
     memcpy(x->h_queries, queries, qb);
     TS_CHECK_CUDA(cudaMemcpyAsync(x->d_queries, x->h_queries, qb, cudaMemcpyHostToDevice, x->stream));
+    const size_t n = (size_t)nq * k;
+    if (nq == 1) {
+        // latency path: the exchange kernel writes the k results into mapped host memory and raises a flag
+        const uint32_t seq = ++x->done_seq;
+        int rc1 = search_sharded_impl(ix, x, x->d_queries, TS_F32, 1, k, normalize_queries, allow_mask, shard_base, id_map,
+                                      x->m_scores, x->m_ids, x->workspace, x->workspace_bytes, 0, x->stream, x->m_done, seq);
+        if (rc1) return rc1;
+        rc1 = wait_done_flag(x->h_done, seq, x->stream, "search_sharded_host");
+        if (rc1) return rc1;
+        memcpy(out_scores, x->h_scores, n * sizeof(float));
+        memcpy(out_ids, x->h_ids, n * sizeof(int64_t));
+        TS_REQUIRE(*reinterpret_cast<volatile int*>(x->h_error) == 0, TS_ERR_STATE,
+                   "search_sharded_host: timed out waiting for a peer's keys; the result was poisoned (-inf / -1)");
+        return TS_OK;
+    }
     int rc = ts_search_sharded(ix, x, x->d_queries, TS_F32, nq, k, normalize_queries, allow_mask, shard_base, id_map,
                                x->d_scores, x->d_ids, x->workspace, x->workspace_bytes, 0, x->stream);
     if (rc) return rc;
-    const size_t n = (size_t)nq * k;
     TS_CHECK_CUDA(cudaMemcpyAsync(x->h_scores, x->d_scores, n * sizeof(float), cudaMemcpyDeviceToHost, x->stream));
     TS_CHECK_CUDA(cudaMemcpyAsync(x->h_ids, x->d_ids, n * sizeof(int64_t), cudaMemcpyDeviceToHost, x->stream));
     TS_CHECK_CUDA(cudaStreamSynchronize(x->stream));

@@ -400,6 +400,11 @@ struct ts_xchg {
     void* workspace = nullptr;
     size_t workspace_bytes = 0;
     int host_dim = 0;
+    float* m_scores = nullptr;        // device addresses of the mapped h_scores / h_ids / h_done (see ts_ctx)
+    int64_t* m_ids = nullptr;
+    uint32_t* h_done = nullptr;
+    uint32_t* m_done = nullptr;
+    uint32_t done_seq = 0;
 };
 
 struct ts_ctx {
@@ -419,6 +424,13 @@ struct ts_ctx {
     bool timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = -1.f;
+    // single-query latency path: the final merge writes (scores, ids) straight into pinned, device-mapped host
+    // memory and raises a mapped flag the host polls (no D2H copies, no stream synchronise)
+    float* m_scores = nullptr;        // device address of h_scores
+    int64_t* m_ids = nullptr;         // device address of h_ids
+    uint32_t* h_done = nullptr;       // mapped flag (host address) and its device address
+    uint32_t* m_done = nullptr;
+    uint32_t done_seq = 0;
 };
 
 #define TS_DEAD_ROW 0xFFFFFFFFu
@@ -436,7 +448,8 @@ int index_make_room(ts_index* ix, int64_t extra);
 // exact search over `ix` (K2 or K3 by batch size); exactly one of out_keys / (out_scores, out_ids) is used
 int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k, int normalize_queries,
                 const uint32_t* allow_mask, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
-                void* workspace, size_t workspace_bytes, cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1);
+                void* workspace, size_t workspace_bytes, cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1, uint32_t* done_flag = nullptr,
+                uint32_t done_value = 0);
 int launch_normalize_cast(const void* src, int src_dtype, int64_t n, int dim, int dim_pad,
                           int normalize, void* dst, int dst_dtype, cudaStream_t s,
                           float* max_norm2 = nullptr, const int64_t* dst_rows = nullptr);
@@ -482,6 +495,8 @@ struct ScanFused {
     int pdl;                // ScanParams::pdl
     const uint32_t* ring_gate;   // ScanParams::ring_gate / ring_need
     uint32_t ring_need;
+    uint32_t* done_flag = nullptr;   // MergeParams::done_flag / done_value (host-mapped completion flag)
+    uint32_t done_value = 0;
 };
 int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64_t n_rows,
                      const float* queries_f32, int nq, int k, const uint32_t* allow_mask,
@@ -491,7 +506,10 @@ int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64
 // exchange kernel of the two-kernel sharded search (k5_merge.cu): merges the scan's per-CTA lists, exchanges the
 // shard's keys with the peers, merges the world lists. Launched with programmatic stream serialisation.
 int launch_xchg_finish(const uint64_t* part_keys, int nparts, int nq, int k, const XchgDev& x, const int64_t* id_map,
-                       float* out_scores, int64_t* out_ids, cudaStream_t s);
+                       float* out_scores, int64_t* out_ids, cudaStream_t s, uint32_t* done_flag = nullptr,
+                       uint32_t done_value = 0);
+// host-side wait for a device-written completion flag in mapped memory (falls back to a stream synchronise)
+int wait_done_flag(const volatile uint32_t* flag, uint32_t value, cudaStream_t s, const char* what);
 // K5: lists[nlists][nq][k] (list-major) or [nq][nlists][k] (query-major) -> top-k
 int launch_merge(const uint64_t* keys, int nlists, int nq, int k, bool query_major,
                  const int64_t* list_base, const int64_t* id_map, uint64_t* out_keys,
