@@ -289,8 +289,7 @@ class TheoremIndex:
             raise _lib.TheoremSearchError(-1, f"queries must be [nq, {self.dim}], got {q.shape}")
         nq = q.shape[0]
         ctx = self._get_ctx(nq, k)
-        if timing:
-            check(lib.ts_ctx_set_timing(ctx, 1))
+        check(lib.ts_ctx_set_timing(ctx, 1 if timing else 0))
         scores = np.empty((nq, k), dtype=np.float32)
         ids = np.empty((nq, k), dtype=np.int64)
         check(lib.ts_search_host(ctx, q.ctypes.data, nq, int(k), int(normalize), self._mask_ptr(allow_mask),
