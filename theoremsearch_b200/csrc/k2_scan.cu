@@ -59,6 +59,7 @@ int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64
     p.pdl = 0;
     p.ring_gate = nullptr;
     p.ring_need = 0;
+    p.q_out = nullptr;
     p.timeline = nullptr;
     if (tunables().scan_timeline) {
         unsigned long long* base = nullptr;
@@ -79,6 +80,7 @@ int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64
         p.fin.out_scores = fused->out_scores;
         p.fin.out_ids = fused->out_ids;
         p.fin.out_stride = k;
+        p.q_out = fused->q_out;
         p.fin.done_flag = fused->done_flag;
         p.fin.done_value = fused->done_value;
         p.xchg = fused->xchg;

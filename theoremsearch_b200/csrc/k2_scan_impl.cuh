@@ -70,6 +70,9 @@ struct ScanParams {
     uint32_t ring_need;
     // diagnostics ("scan.timeline"): [gridDim.x][8] %globaltimer stamps of this launch, or nullptr
     unsigned long long* timeline;
+    // optional: the prepared (normalised, zero padded) fp32 queries are also written here [nq, dim_pad] — the IVF
+    // coarse scan hands them to the list scan and the re-score, saving a separate preparation launch
+    float* q_out;
 };
 
 __device__ __forceinline__ void scan_stamp(const ScanParams& p, int slot) {
@@ -247,6 +250,16 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
         }
     }
 
+    if (p.q_out != nullptr && blockIdx.x == 0 && warp == 0) {
+        float* qo = p.q_out + (size_t)qi * p.dim_pad;
+#pragma unroll
+        for (int j = 0; j < NCHUNK; ++j) {
+            const int e0 = (j * 32 + lane) * CN;
+#pragma unroll
+            for (int i = 0; i < CN; ++i)
+                if (e0 + i < p.dim_pad) qo[e0 + i] = q[j * CN + i];
+        }
+    }
     WarpTopK<KPL> list;
     list.clear();
     uint64_t thr = 0ull;  // current k-th key of this warp's list (0 while it has < k entries)

@@ -461,6 +461,115 @@ __global__ void add_list_sizes_kernel(const int64_t* __restrict__ offsets, int n
     if (c < nlist) out[c] += offsets[c + 1] - offsets[c];
 }
 
+// ---------------------------------------------------------------------------------- K4c rescore
+// One CTA per query: candidates (list positions) -> corpus rows -> exact fp32-query scores in K2's
+// summation order -> bitonic sort -> top-k.
+// The body is a device function run by ALL threads of a CTA for query q: the stand-alone kernel below wraps it, and
+// the list scan's last CTA calls it directly for small batches (one launch fewer on the single-query latency path).
+// Needs blockDim.x >= P (the candidates padded to a power of two >= 64) and P * 8 bytes of shared memory at rs_buf.
+template <int ELEM>
+__device__ __forceinline__ void ivf_rescore_body(const uint64_t* __restrict__ cand, int kc, int k, int q,
+                                                 const uint32_t* __restrict__ list_rows,
+                                                 const float* __restrict__ q32,
+                                                 const uint8_t* __restrict__ corpus, uint32_t row_bytes,
+                                                 int dim_pad, const int64_t* __restrict__ id_map,
+                                                 uint64_t* __restrict__ out_keys, float* __restrict__ out_scores,
+                                                 int64_t* __restrict__ out_ids, uint64_t* rs_buf) {
+    constexpr int CN = Chunk<ELEM>::N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    int P = 64;
+    while (P < kc) P <<= 1;
+    const float* qv = q32 + (size_t)q * dim_pad;
+    // warp w owns candidates w, w + nwarps, ...; lane i looks up the i-th of them (key -> list position ->
+    // corpus row), so all of a warp's dependent lookups are in flight together; rows are then scored four at
+    // a time (their loads are independent and overlap), each by the whole warp in K2's summation order.
+    {
+        const int jm = warp + lane * nwarps;
+        const uint64_t mykey = (jm < kc) ? cand[(size_t)q * kc + jm] : 0ull;
+        const uint32_t myrow = mykey ? list_rows[key_row(mykey)] : 0u;
+        const unsigned live = __ballot_sync(0xFFFFFFFFu, mykey != 0ull);
+        uint64_t outkey = 0ull;
+        for (int c0 = 0; c0 < 32 && warp + c0 * nwarps < P; c0 += 4) {
+            if (((live >> c0) & 0xFu) == 0u) continue;
+            uint32_t row[4];
+            const uint8_t* r[4];
+            float acc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                row[u] = __shfl_sync(0xFFFFFFFFu, myrow, (c0 + u) & 31);   // dead slots read row 0: harmless
+                r[u] = corpus + (size_t)row[u] * row_bytes;
+                acc[u] = 0.f;
+            }
+#pragma unroll 2
+            for (uint32_t off = (uint32_t)lane * 16u; off < row_bytes; off += 512u) {   // K2's chunk order
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(r[u] + off));
+                float ql[CN];
+#pragma unroll
+                for (int i = 0; i < CN; i += 4) {
+                    const float4 f = __ldg(reinterpret_cast<const float4*>(qv + off / ELEM + i));
+                    ql[i] = f.x;
+                    ql[i + 1] = f.y;
+                    ql[i + 2] = f.z;
+                    ql[i + 3] = f.w;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc[u] = Chunk<ELEM>::dot(v[u], ql, acc[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xFFFFFFFFu, acc[u], o);   // == K2's reduce tree
+                if (lane == c0 + u && ((live >> (c0 + u)) & 1u)) outkey = pack_key(acc[u], row[u]);
+            }
+        }
+        if (jm < P) rs_buf[jm] = outkey;
+    }
+    __syncthreads();
+    // rank by counting: P <= 256 keys, one per thread, unique (distinct rows) or 0 — a key's rank is the number
+    // of larger keys; 128 x 128 compares cost a fraction of a 28-level bitonic network's barriers
+    {
+        const int i = threadIdx.x;
+        const uint64_t key = (i < P) ? rs_buf[i] : 0ull;
+        const int nnz = __syncthreads_count(key != 0ull);
+        if (key != 0ull) {
+            int rank = 0;
+#pragma unroll 8
+            for (int j = 0; j < P; ++j) rank += (rs_buf[j] > key) ? 1 : 0;
+            if (rank < k) {
+                const size_t o = (size_t)q * k + rank;
+                if (out_keys) out_keys[o] = key;
+                if (out_scores) out_scores[o] = key_score(key);
+                if (out_ids) {
+                    const uint32_t row = key_row(key);
+                    out_ids[o] = id_map ? id_map[row] : (int64_t)row;
+                }
+            }
+        }
+        for (int r = nnz + i; r < k; r += blockDim.x) {   // fewer eligible rows than k: padding
+            const size_t o = (size_t)q * k + r;
+            if (out_keys) out_keys[o] = 0ull;
+            if (out_scores) out_scores[o] = -INFINITY;
+            if (out_ids) out_ids[o] = -1;
+        }
+    }
+}
+
+template <int ELEM>
+__global__ void __launch_bounds__(1024) ivf_rescore_kernel(const uint64_t* __restrict__ cand, int kc, int k,
+                                                           const uint32_t* __restrict__ list_rows,
+                                                           const float* __restrict__ q32,
+                                                           const uint8_t* __restrict__ corpus, uint32_t row_bytes,
+                                                           int dim_pad, const int64_t* __restrict__ id_map,
+                                                           uint64_t* __restrict__ out_keys, float* __restrict__ out_scores,
+                                                           int64_t* __restrict__ out_ids) {
+    extern __shared__ uint64_t rs_buf_dyn[];
+    ivf_rescore_body<ELEM>(cand, kc, k, (int)blockIdx.x, list_rows, q32, corpus, row_bytes, dim_pad, id_map, out_keys,
+                           out_scores, out_ids, rs_buf_dyn);
+}
+
 // ---------------------------------------------------------------------------------- K4b list scan
 struct ListScanParams {
     const uint8_t* list_data;     // [n, row_bytes] rows in list order
@@ -481,6 +590,14 @@ struct ListScanParams {
     const uint32_t* run_flag;     // non-null: run only if *run_flag != 0 (fallback of the list-major path K4d)
     int stages;
     unsigned long long* timeline; // diagnostics: [gridDim.x][8] globaltimer stamps of query 0, or nullptr
+    // fused exact re-score (K4c inside the last CTA of the query; small batches): k_out > 0 enables it
+    int k_out;                    // final k (0 = stop at the candidates, a separate K4c launch follows)
+    const uint8_t* corpus;        // stored bf16 rows
+    uint32_t corpus_row_bytes;
+    const int64_t* id_map;
+    uint64_t* fin_keys;           // [nq][k_out] any of the three may be nullptr
+    float* fin_scores;
+    int64_t* fin_ids;
 };
 
 __device__ unsigned long long g_ivf_timeline[148 * 12];
@@ -849,6 +966,12 @@ __global__ void __launch_bounds__(512, 1) list_scan_kernel(const ListScanParams 
         merge_lists<KPL>(mp, qi, qi, cbuf, W);
     }
     IVF_STAMP(7);
+    if (p.k_out > 0) {
+        // exact re-score of the k candidates by this CTA (they were written to dst by this CTA: visible after the barrier)
+        __syncthreads();
+        ivf_rescore_body<2>(p.out_keys, k, p.k_out, qi, p.list_rows, p.queries, p.corpus, p.corpus_row_bytes, p.dim_pad,
+                            p.id_map, p.fin_keys, p.fin_scores, p.fin_ids, cbuf);
+    }
 }
 
 // A query spread over several CTAs whose warps would each see only a few hundred rows is latency-bound
@@ -882,6 +1005,12 @@ static int launch_list_scan_r(const ts_index* ix, ListScanParams p, int nq, int 
     const size_t select_bytes = std::max<size_t>((size_t)warps * 2 * KPL * 32 * 8, 4096 * 8);
     if (smem < select_bytes) smem = select_bytes;
     p.stages = stages;
+    if (p.k_out > 0) {
+        int P = 64;
+        while (P < p.k) P <<= 1;
+        TS_REQUIRE(warps * 32 >= P, TS_ERR_UNSUPPORTED, "ivf list scan: %d threads cannot re-score %d candidates in place "
+                   "(set tunable ivf.fuse_rescore = 0)", warps * 32, p.k);
+    }
     p.timeline = nullptr;
     if (t.ivf_timeline) TS_CHECK_CUDA(cudaGetSymbolAddress((void**)&p.timeline, g_ivf_timeline));
     auto kern = list_scan_kernel<ELEM, NCHUNK, KPL, R>;
@@ -927,101 +1056,6 @@ static int launch_list_scan(const ts_index* ix, const ListScanParams& p, int nq,
     }
     set_error("ivf list scan: no kernel for list dtype %d dim %d", ix->list_dtype, ix->dim);
     return TS_ERR_UNSUPPORTED;
-}
-
-// ---------------------------------------------------------------------------------- K4c rescore
-// One CTA per query: candidates (list positions) -> corpus rows -> exact fp32-query scores in K2's
-// summation order -> bitonic sort -> top-k.
-template <int ELEM>
-__global__ void __launch_bounds__(1024) ivf_rescore_kernel(const uint64_t* __restrict__ cand, int kc, int k,
-                                                           const uint32_t* __restrict__ list_rows,
-                                                           const float* __restrict__ q32,
-                                                           const uint8_t* __restrict__ corpus, uint32_t row_bytes,
-                                                           int dim_pad, const int64_t* __restrict__ id_map,
-                                                           uint64_t* __restrict__ out_keys, float* __restrict__ out_scores,
-                                                           int64_t* __restrict__ out_ids) {
-    constexpr int CN = Chunk<ELEM>::N;
-    extern __shared__ uint64_t rs_buf[];
-    const int q = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nwarps = blockDim.x >> 5;
-    int P = 64;
-    while (P < kc) P <<= 1;
-    const float* qv = q32 + (size_t)q * dim_pad;
-    // warp w owns candidates w, w + nwarps, ...; lane i looks up the i-th of them (key -> list position ->
-    // corpus row), so all of a warp's dependent lookups are in flight together; rows are then scored four at
-    // a time (their loads are independent and overlap), each by the whole warp in K2's summation order.
-    {
-        const int jm = warp + lane * nwarps;
-        const uint64_t mykey = (jm < kc) ? cand[(size_t)q * kc + jm] : 0ull;
-        const uint32_t myrow = mykey ? list_rows[key_row(mykey)] : 0u;
-        const unsigned live = __ballot_sync(0xFFFFFFFFu, mykey != 0ull);
-        uint64_t outkey = 0ull;
-        for (int c0 = 0; c0 < 32 && warp + c0 * nwarps < P; c0 += 4) {
-            if (((live >> c0) & 0xFu) == 0u) continue;
-            uint32_t row[4];
-            const uint8_t* r[4];
-            float acc[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                row[u] = __shfl_sync(0xFFFFFFFFu, myrow, (c0 + u) & 31);   // dead slots read row 0: harmless
-                r[u] = corpus + (size_t)row[u] * row_bytes;
-                acc[u] = 0.f;
-            }
-#pragma unroll 2
-            for (uint32_t off = (uint32_t)lane * 16u; off < row_bytes; off += 512u) {   // K2's chunk order
-                uint4 v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(r[u] + off));
-                float ql[CN];
-#pragma unroll
-                for (int i = 0; i < CN; i += 4) {
-                    const float4 f = __ldg(reinterpret_cast<const float4*>(qv + off / ELEM + i));
-                    ql[i] = f.x;
-                    ql[i + 1] = f.y;
-                    ql[i + 2] = f.z;
-                    ql[i + 3] = f.w;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) acc[u] = Chunk<ELEM>::dot(v[u], ql, acc[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xFFFFFFFFu, acc[u], o);   // == K2's reduce tree
-                if (lane == c0 + u && ((live >> (c0 + u)) & 1u)) outkey = pack_key(acc[u], row[u]);
-            }
-        }
-        if (jm < P) rs_buf[jm] = outkey;
-    }
-    __syncthreads();
-    // rank by counting: P <= 256 keys, one per thread, unique (distinct rows) or 0 — a key's rank is the number
-    // of larger keys; 128 x 128 compares cost a fraction of a 28-level bitonic network's barriers
-    {
-        const int i = threadIdx.x;
-        const uint64_t key = (i < P) ? rs_buf[i] : 0ull;
-        const int nnz = __syncthreads_count(key != 0ull);
-        if (key != 0ull) {
-            int rank = 0;
-#pragma unroll 8
-            for (int j = 0; j < P; ++j) rank += (rs_buf[j] > key) ? 1 : 0;
-            if (rank < k) {
-                const size_t o = (size_t)q * k + rank;
-                if (out_keys) out_keys[o] = key;
-                if (out_scores) out_scores[o] = key_score(key);
-                if (out_ids) {
-                    const uint32_t row = key_row(key);
-                    out_ids[o] = id_map ? id_map[row] : (int64_t)row;
-                }
-            }
-        }
-        for (int r = nnz + i; r < k; r += blockDim.x) {   // fewer eligible rows than k: padding
-            const size_t o = (size_t)q * k + r;
-            if (out_keys) out_keys[o] = 0ull;
-            if (out_scores) out_scores[o] = -INFINITY;
-            if (out_ids) out_ids[o] = -1;
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------- host: state
@@ -1597,20 +1631,15 @@ static int ivf_search_impl(ts_index* ix, const void* queries, int q_dtype, int n
     TS_REQUIRE(workspace_bytes >= w.bytes, TS_ERR_CAPACITY, "ivf_search: workspace %zu < %zu bytes", workspace_bytes,
                w.bytes);
     // 1. coarse: exact top-nprobe over the centroid table (K2 for a few queries, K3 for a batch)
-    // (queries are normalised once, by K1's kernel; the coarse scan then takes them as given, which skips
-    // its per-warp fp64 norm — tens of microseconds of a single-query search on this fp64-poor part)
+    // (the coarse scan normalises the raw queries itself and also writes the prepared fp32 copy the list scan and
+    // the re-score read — no separate preparation launch; a batch (K3) prepares them with K1's kernel)
     ts_index view = centroid_view(ix);
-    int rc = launch_prepare_queries(queries, q_dtype, nq, ix->dim, ix->dim_pad, normalize, w.q32, s);
-    if (rc) return rc;
-    if (ix->dim == ix->dim_pad)
-        rc = search_impl(&view, w.q32, TS_F32, nq, nprobe, 0, nullptr, w.probes, nullptr, nullptr, w.coarse,
-                         w.coarse_bytes, s, nullptr, nullptr);
-    else   // padded rows: the prepared copy has another stride than the scan's raw-query reader expects
-        rc = search_impl(&view, queries, q_dtype, nq, nprobe, normalize, nullptr, w.probes, nullptr, nullptr, w.coarse,
-                         w.coarse_bytes, s, nullptr, nullptr);
+    // both ticket arrays are zeroed up front so that the coarse scan and the list scan are adjacent launches
+    TS_CHECK_CUDA(cudaMemsetAsync(w.tickets, 0, (size_t)nq * sizeof(uint32_t), s));
+    int rc = search_impl(&view, queries, q_dtype, nq, nprobe, normalize, nullptr, w.probes, nullptr, nullptr, w.coarse,
+                         w.coarse_bytes, s, nullptr, nullptr, nullptr, 0, w.q32);
     if (rc) return rc;
     // 2. scan the probed lists, keep kc candidates per query
-    TS_CHECK_CUDA(cudaMemsetAsync(w.tickets, 0, (size_t)nq * sizeof(uint32_t), s));
     ListScanParams p;
     p.list_data = (const uint8_t*)ix->list_data;
     p.row_bytes = ix->list_row_bytes;
@@ -1637,6 +1666,16 @@ static int ivf_search_impl(ts_index* ix, const void* queries, int q_dtype, int n
     p.out_keys = w.cand;
     p.run_flag = nullptr;
     p.stages = 0;
+    p.k_out = 0;
+    p.corpus = (const uint8_t*)ix->data;
+    p.corpus_row_bytes = (uint32_t)ix->row_bytes();
+    p.id_map = ix->has_ids ? ix->ids : nullptr;
+    p.fin_keys = out_keys;
+    p.fin_scores = out_scores;
+    p.fin_ids = out_ids;
+    // small batches (the latency path): the list scan's last CTA re-scores its candidates itself — one launch fewer
+    const bool fuse_rescore = w.grouped == nullptr && nq < 64 && tunables().ivf_fuse_rescore != 0;
+    if (fuse_rescore) p.k_out = k;
     if (w.grouped != nullptr) {
         // large batch: list-major scan (each probed list read once per 4 queries); K4b below runs only if the
         // score buffer turned out too small for this batch (decided on the device)
@@ -1645,6 +1684,7 @@ static int ivf_search_impl(ts_index* ix, const void* queries, int q_dtype, int n
     }
     rc = launch_list_scan(ix, p, nq, ivf_parts(ix, nq), s);
     if (rc) return rc;
+    if (fuse_rescore) return TS_OK;
     // 3. exact re-score of the survivors against the stored corpus rows
     int P = 64;
     while (P < kc) P <<= 1;

@@ -78,7 +78,8 @@ static bool use_batched(const ts_index* ix, int nq) {
 int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k,
                        int normalize_queries, const uint32_t* allow_mask, uint64_t* out_keys,
                        float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
-                       cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1, uint32_t* done_flag, uint32_t done_value) {
+                       cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1, uint32_t* done_flag, uint32_t done_value,
+                       float* q_out) {
     TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "search: index is NULL");
     TS_REQUIRE(nq >= 0, TS_ERR_BAD_ARG, "search: nq=%d", nq);
     TS_REQUIRE(k >= 1 && k <= TS_MAX_K, TS_ERR_BAD_ARG, "search: k=%d out of range [1, %d]", k, TS_MAX_K);
@@ -89,9 +90,14 @@ int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k,
     TS_REQUIRE(workspace != nullptr, TS_ERR_BAD_ARG, "search: workspace is NULL");
     DeviceGuard g(ix->device);
     TS_REQUIRE(g.ok, TS_ERR_CUDA, "search: cannot select CUDA device %d", ix->device);
-    if (use_batched(ix, nq))
+    if (use_batched(ix, nq)) {
+        if (q_out != nullptr) {   // the caller wants the prepared queries too (IVF): K3 keeps its own copy internally
+            int prc = launch_prepare_queries(queries, q_dtype, nq, ix->dim, ix->dim_pad, normalize_queries, q_out, s);
+            if (prc) return prc;
+        }
         return launch_batched_search(ix, queries, q_dtype, nq, k, normalize_queries, allow_mask, out_keys,
                                      out_scores, out_ids, workspace, workspace_bytes, s, ev0, ev1);
+    }
     SearchWs w = carve_ws(ix, nq, k, workspace);
     TS_REQUIRE(workspace_bytes >= w.bytes, TS_ERR_CAPACITY, "search: workspace %zu < %zu bytes",
                workspace_bytes, w.bytes);
@@ -114,6 +120,7 @@ int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k,
     f.ring_need = 0;
     f.done_flag = done_flag;     // only the single-query host path passes one (nq == 1: one merging CTA)
     f.done_value = done_value;
+    f.q_out = q_out;
     return launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, w.part_keys, w.nparts,
                             s, ev0, ev1, nullptr, nullptr, &f);
 }
@@ -894,6 +901,7 @@ static int* tunable_slot(const char* name) {
     if (!strcmp(name, "ivf.group_min_nq")) return &t.ivf_group_min_nq;
     if (!strcmp(name, "ivf.group_mma")) return &t.ivf_group_mma;
     if (!strcmp(name, "ivf.select_warp")) return &t.ivf_select_warp;
+    if (!strcmp(name, "ivf.fuse_rescore")) return &t.ivf_fuse_rescore;
     if (!strcmp(name, "xchg.debug_no_flag")) return &t.xchg_debug_no_flag;
     if (!strcmp(name, "scan.timeline")) return &t.scan_timeline;
     if (!strcmp(name, "ivf.group_min_lists")) return &t.ivf_group_min_lists;

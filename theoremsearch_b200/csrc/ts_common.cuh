@@ -94,6 +94,7 @@ struct Tunables {
     int ivf_timeline = 0;       // 1 = K4b CTAs record globaltimer stamps per phase (ts_debug_ivf_timeline)
     int ivf_group_min_nq = 16;  // batches at least this large take the list-major scan (K4d); 0 = never (sweep: profiles/sweep_ivf_batch_r1.txt)
     int ivf_group_min_lists = 0;  // K4d needs at least this many lists (and query-list pairs); 0 = 4 x SM count
+    int ivf_fuse_rescore = 1;   // small IVF batches: the list scan's last CTA re-scores its candidates (no separate K4c launch)
     int ivf_select_warp = 1;    // K4d candidate selection: 1 = warp-per-query register select, 0 = CTA-per-query smem select
     int scan_timeline = 0;      // 1 = K2 CTAs record %globaltimer stamps per phase (ts_debug_scan_timeline)
     int xchg_debug_no_flag = 0; // test hook: the sharded exchange does not raise its own flag, so its wait times out
@@ -449,7 +450,7 @@ int index_make_room(ts_index* ix, int64_t extra);
 int search_impl(ts_index* ix, const void* queries, int q_dtype, int nq, int k, int normalize_queries,
                 const uint32_t* allow_mask, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
                 void* workspace, size_t workspace_bytes, cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1, uint32_t* done_flag = nullptr,
-                uint32_t done_value = 0);
+                uint32_t done_value = 0, float* q_out = nullptr);
 int launch_normalize_cast(const void* src, int src_dtype, int64_t n, int dim, int dim_pad,
                           int normalize, void* dst, int dst_dtype, cudaStream_t s,
                           float* max_norm2 = nullptr, const int64_t* dst_rows = nullptr);
@@ -497,6 +498,7 @@ struct ScanFused {
     uint32_t ring_need;
     uint32_t* done_flag = nullptr;   // MergeParams::done_flag / done_value (host-mapped completion flag)
     uint32_t done_value = 0;
+    float* q_out = nullptr;          // ScanParams::q_out
 };
 int launch_scan_topk(const ts_index* ix, const void* data, int data_dtype, int64_t n_rows,
                      const float* queries_f32, int nq, int k, const uint32_t* allow_mask,
