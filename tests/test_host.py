@@ -6,6 +6,7 @@ import os
 
 import numpy as np
 import pytest
+import torch
 
 import theoremsearch_b200 as ts
 from oracle import oracle
@@ -298,3 +299,48 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("configs[1]") and d["gpu_launches"] == 0
+
+
+# --------------------------------------------------------------------------------------- round 2 additions
+def test_oracle_upsert_rows_is_row_by_row_on_conflict_do_update():
+    """ec2/rds/upsert.py:29-52 runs one INSERT ... ON CONFLICT DO UPDATE per row (executemany): existing ids keep their
+    place and take the new embedding, new ids append in order, a repeated id ends with its last embedding."""
+    table = {}
+    assert oracle.upsert_rows(table, [7, 3, 9], np.array([[1.0], [2.0], [3.0]])) == 0
+    assert list(table) == [7, 3, 9]
+    n = oracle.upsert_rows(table, [3, 11, 3, 7], np.array([[20.0], [40.0], [21.0], [10.0]]))
+    assert n == 2                                        # ids 3 and 7 existed
+    assert list(table) == [7, 3, 9, 11]                  # places kept, 11 appended
+    assert [float(table[i][0]) for i in table] == [10.0, 21.0, 3.0, 40.0]
+
+
+def test_hierarchical_corpus_generator_is_deterministic_and_structured():
+    from theoremsearch_b200 import synthetic
+    m = synthetic.HierarchicalCorpus(64, n_leaves=80, device="cpu", seed=0, n_blobs=4, rank=8, n_bases=2)
+    a, b = m.rows(500, seed=5), m.rows(500, seed=5)
+    assert torch.equal(a, b) and a.shape == (500, 64)
+    q = m.queries(20)
+    assert q.shape == (20, 64) and not torch.equal(q[:10], m.queries(10, seed=1))
+    # rows of one blob are far closer to each other than to rows of another blob
+    x = torch.nn.functional.normalize(m.rows(2000, seed=9), dim=1)
+    sims = x @ x.T
+    assert float(sims.topk(2, dim=1).values[:, 1].mean()) > 0.5 > float(sims.mean())
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` on a tiny corpus: one JSON line, the steps / warm-up it was given, nothing
+    extrapolated, the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--rows", "20000",
+                          "--steps", "3", "--warmup", "4"], capture_output=True, text=True, check=True, timeout=300).stdout
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["steps"] == 3 and d["warmup"] == 4 and d["extrapolated"] is False
+    assert d["rows_timed"] == 20000 and d["unit"] == "queries/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert abs(d["ms_per_step"] * d["value"] - 1000.0) < 1e-6
