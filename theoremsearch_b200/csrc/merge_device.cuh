@@ -95,11 +95,95 @@ __device__ __forceinline__ uint64_t rebase_key(uint64_t key, int64_t base) {
 // Merge work item `qi` (its p.nlists lists) and write output row `qo`. Called by ALL threads of a
 // CTA with `nwarps` warps; `lists` is smem scratch [nwarps][KPL*32]. Lists are read with ld.global.cg
 // (L2) so a CTA may merge keys other CTAs of the same grid wrote just before (after a fence).
+// Write output position `pos` of query row `qo` (key 0 = empty slot).
+__device__ __forceinline__ void merge_emit(const MergeParams& p, int qo, int pos, uint64_t key) {
+    const size_t o = (size_t)qo * p.k + pos;
+    if (p.out_keys) p.out_keys[(size_t)qo * p.out_stride + pos] = key;
+    if (p.out_scores) p.out_scores[o] = key ? key_score(key) : -INFINITY;
+    if (p.out_ids) {
+        int64_t id = -1;
+        if (key) {
+            const uint32_t row = key_row(key);
+            id = p.id_map ? p.id_map[row] : (int64_t)row;
+        }
+        p.out_ids[o] = id;
+    }
+}
+
+// k <= 32, 16..256 lists (the 148 per-CTA lists of a scan): the pruned merge. The k-th largest list HEAD T is a lower
+// bound on the k-th best key overall (the k largest heads are k distinct keys >= T), so only keys >= T can be in
+// the result — typically ~2k of the nlists * k keys, held by ~k lists. Two L2 round trips (heads; the qualifying
+// lists) and two rank-by-counting passes in shared memory replace ~nlists/nwarps dependent register merges per
+// warp plus a serial fold of the warps' lists: ~3 us instead of ~9 us for 148 lists. Returns false (nothing
+// written) when more keys survive than the 256-entry buffer holds — the caller then runs the general merge.
+constexpr int MERGE_PRUNE_MAX = 256;
+__device__ __forceinline__ bool merge_lists_pruned(const MergeParams& p, int qi, int qo, uint64_t* surv /* [>= 256] */) {
+    __shared__ uint64_t s_heads[MERGE_PRUNE_MAX];
+    __shared__ unsigned long long s_T;
+    __shared__ int s_cnt;
+    const int k = p.k, nl = p.nlists;
+    auto list_ptr = [&](int l) { return p.keys + (int64_t)l * p.stride_list + (int64_t)qi * p.stride_query; };
+    uint64_t head = 0ull;
+    int64_t base = 0;
+    const int l = threadIdx.x;                       // thread l owns list l (blockDim.x >= 256 >= nl)
+    if (l < nl) {
+        base = p.list_base ? p.list_base[l] : 0;
+        head = rebase_key(__ldcg(list_ptr(l)), base);
+    }
+    if (l < MERGE_PRUNE_MAX) s_heads[l] = head;
+    if (threadIdx.x == 0) {
+        s_T = 0ull;                                  // fewer than k non-empty lists: every key survives
+        s_cnt = 0;
+    }
+    __syncthreads();
+    if (head != 0ull) {                              // rank of this head among the heads (unique keys)
+        int rank = 0;
+#pragma unroll 4
+        for (int j = 0; j < nl; ++j) rank += (s_heads[j] > head) ? 1 : 0;
+        if (rank == k - 1) s_T = head;
+    }
+    __syncthreads();
+    const uint64_t T = s_T;
+    if (head != 0ull && head >= T) {                 // a qualifying list: fetch it whole (independent loads), keep keys >= T
+        const uint64_t* src = list_ptr(l);
+        uint64_t v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (j < k) ? __ldcg(src + j) : 0ull;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const uint64_t key = rebase_key(v[j], base);
+            if (key != 0ull && key >= T) {
+                const int pos = atomicAdd(&s_cnt, 1);
+                if (pos < MERGE_PRUNE_MAX) surv[pos] = key;
+            }
+        }
+    }
+    __syncthreads();
+    const int cnt = s_cnt;
+    if (cnt > MERGE_PRUNE_MAX) return false;         // uniform: the buffer overflowed, nothing has been written
+    if ((int)threadIdx.x < cnt) {
+        const uint64_t key = surv[threadIdx.x];
+        int rank = 0;
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) rank += (surv[j] > key) ? 1 : 0;
+        if (rank < k) merge_emit(p, qo, rank, key);
+    }
+    for (int pos = cnt + (int)threadIdx.x; pos < k; pos += blockDim.x) merge_emit(p, qo, pos, 0ull);   // padding
+    __syncthreads();
+    merge_signal_done(p);
+    return true;
+}
+
 template <int KPL>
 __device__ __forceinline__ void merge_lists(const MergeParams& p, int qi, int qo, uint64_t* lists, int nwarps) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int k = p.k;
+    if constexpr (KPL == 1) {
+        if (p.nlists >= 16 && p.nlists <= MERGE_PRUNE_MAX && blockDim.x >= MERGE_PRUNE_MAX && nwarps * 32 >= MERGE_PRUNE_MAX) {
+            if (merge_lists_pruned(p, qi, qo, lists)) return;
+        }
+    }
     WarpTopK<KPL> list;
     list.clear();
     auto list_ptr = [&](int l) { return p.keys + (int64_t)l * p.stride_list + (int64_t)qi * p.stride_query; };
