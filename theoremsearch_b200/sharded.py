@@ -2,8 +2,9 @@
 
 New surface with no reference counterpart (the reference has no distributed code at all,
 SURVEY §2); specified by BASELINE.json: GPU g holds rows [g*N/G, (g+1)*N/G), every GPU scans its
-shard for the (replicated) queries, ONE all-gather of the k x 8-byte packed (score,row) keys
-goes over NVLink, and K5 merges the G lists on every rank.  No corpus bytes cross NVLink.
+shard for the (replicated) queries, the k x 8-byte packed (score,row) keys of every GPU are exchanged
+over NVLink — by the GPUs themselves for small batches (stores into CUDA-IPC mapped peer memory), by
+ONE NCCL all-gather for large ones — and merged on every rank.  No corpus bytes cross NVLink.
 """
 from __future__ import annotations
 
@@ -68,10 +69,11 @@ class ShardedIndex:
 
     # -------------------------------------------------------------------------------- fused peer exchange
     def enable_peer_exchange(self, max_nq: int = 3, max_k: int = 256) -> "ShardedIndex":
-        """Set up the in-kernel exchange (``ts_search_sharded``): every rank allocates a receive area,
+        """Set up the device-initiated exchange (``ts_search_sharded``): every rank allocates a receive area,
         the CUDA-IPC handles are all-gathered once (host-side plumbing), peers are mapped.  Afterwards
-        small-batch searches need no collective call at all: the scan kernel's last CTA stores its k keys
-        into the peers' memory over NVLink, waits for theirs and merges."""
+        small-batch searches need no collective call at all: an exchange kernel chained to the scan by
+        programmatic dependent launch stores the shard's k keys into the peers' memory over NVLink, waits
+        for theirs and merges, while the next search's scan already streams the corpus."""
         if self._xchg is not None:
             return self
         dev = self.local.device
