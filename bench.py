@@ -100,7 +100,7 @@ class ClockSampler:
     def _run(self):
         while not self._stop.is_set():
             self._sample()
-            time.sleep(0.002)
+            time.sleep(0.01)      # NVML queries take driver locks: sampling harder than this perturbs latency-bound loops
 
     def __enter__(self):
         self.samples, self.reasons = [], set()
