@@ -212,13 +212,23 @@ template <int KPL>
 __device__ __forceinline__ void warp_select_run(WarpSelect<KPL>& sel, const float* __restrict__ run, int len, uint32_t pos0,
                                                 int k, int lane) {
     float thr_f = sel.thr ? key_score(sel.thr) : -INFINITY;
+    const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    // software-pipelined: the next 512 scores are requested before the current ones are examined (a warp walks its run
+    // alone, so without this every step waits out a full DRAM round trip: 4096 queries x 78k scores took 0.45 ms)
+    float4 nxt[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int r = u * 128 + 4 * lane;
+        nxt[u] = (r < len) ? __ldg(reinterpret_cast<const float4*>(run + r)) : ninf4;
+    }
     for (int r0 = 0; r0 < len; r0 += 512) {            // 4 x (32 lanes x float4) per iteration, loads issued together
         float4 v[4];
         bool any = false;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int r = r0 + u * 128 + 4 * lane;
-            v[u] = (r < len) ? __ldg(reinterpret_cast<const float4*>(run + r)) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            v[u] = nxt[u];
+            const int rn = r0 + 512 + u * 128 + 4 * lane;
+            nxt[u] = (rn < len) ? __ldg(reinterpret_cast<const float4*>(run + rn)) : ninf4;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
