@@ -173,10 +173,13 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
             // one L2 round trip per phase. (A rolled loop of dependent-latency loads cost 10-13 us here, during
             // which the warp's two TMA slots sat full: 3 % of a 1.25M-row shard's scan.)
             const float* qv = reinterpret_cast<const float*>(p.q_raw) + qoff;
+            // both views of the query are requested at once (ONE L2 round trip): the pair view K1's norm is summed
+            // in, and the chunk view the scan multiplies with
+            constexpr int NP = NCHUNK * CN / 2;            // pairs per lane: (2l, 2l+1) + 64j
+            const bool vec2 = ((p.dim & 1) == 0) && ((reinterpret_cast<uintptr_t>(qv) & 7u) == 0);
+            const bool vec4 = ((p.dim & 3) == 0) && ((reinterpret_cast<uintptr_t>(qv) & 15u) == 0);
+            float2 v[NP];
             if (p.q_normalize) {
-                constexpr int NP = NCHUNK * CN / 2;            // pairs per lane: (2l, 2l+1) + 64j
-                const bool vec2 = ((p.dim & 1) == 0) && ((reinterpret_cast<uintptr_t>(qv) & 7u) == 0);
-                float2 v[NP];
 #pragma unroll
                 for (int j = 0; j < NP; ++j) {
                     const int i = 2 * lane + 64 * j;
@@ -188,17 +191,7 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
                         if (i + 1 < p.dim) v[j].y = __ldg(qv + i + 1);
                     }
                 }
-                double ss = 0.0;
-#pragma unroll
-                for (int j = 0; j < NP; ++j) {                 // zeros past dim leave ss unchanged (K1 does the same)
-                    const double a = (double)v[j].x, b = (double)v[j].y;
-                    ss = fma(a, a, ss);
-                    ss = fma(b, b, ss);
-                }
-                ss = warp_sum(ss);
-                den = fmaxf((float)sqrt(ss), 1e-12f);
             }
-            const bool vec4 = ((p.dim & 3) == 0) && ((reinterpret_cast<uintptr_t>(qv) & 15u) == 0);
 #pragma unroll
             for (int j = 0; j < NCHUNK; ++j) {
                 const int e0 = (j * 32 + lane) * CN;
@@ -220,6 +213,15 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
                 }
             }
             if (p.q_normalize) {
+                double ss = 0.0;
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {                 // zeros past dim leave ss unchanged (K1 does the same)
+                    const double a = (double)v[j].x, b = (double)v[j].y;
+                    ss = fma(a, a, ss);
+                    ss = fma(b, b, ss);
+                }
+                ss = warp_sum(ss);
+                den = fmaxf((float)sqrt(ss), 1e-12f);
 #pragma unroll
                 for (int i = 0; i < NCHUNK * CN; ++i) q[i] = __fdiv_rn(q[i], den);
             }
