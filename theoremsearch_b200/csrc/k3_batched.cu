@@ -53,6 +53,7 @@ struct BatchParams {
     int nq, k, cap;
     int num_k_blocks;
     int num_m_blocks, num_n_blocks;
+    int a_policy;                 // L2 policy of the corpus-tile loads: 0 = evict_first, 1 = evict_normal, 2 = evict_last
     int bn;                       // queries per n-block actually used (multiple of 32, <= BN): UMMA N, TMA box rows
     const float* thr;             // [num_n_blocks * bn] running k-th best score per query (-inf initially)
     uint32_t* count;              // [nq] candidates appended in this chunk
@@ -185,7 +186,8 @@ batched_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (warp == 0) {
         // ===================== TMA producer (every CTA loads its own rows / its half of B) =====================
         if (lane == 0) {
-            const uint64_t pol_a = l2_policy_evict_first();  // corpus tile: streamed (L2 holds it for the n-blocks in flight)
+            // corpus tile: streamed once per n-block; the other n-blocks of the same rows read it within microseconds
+            const uint64_t pol_a = p.a_policy == 0 ? l2_policy_evict_first() : (p.a_policy == 1 ? l2_policy_evict_normal() : l2_policy_evict_last());
             const uint64_t pol_b = l2_policy_evict_last();   // query block: re-read by every corpus tile
             const uint32_t b_rows = PAIR ? (uint32_t)p.bn / 2 : (uint32_t)p.bn;
             int stage = 0;
@@ -791,6 +793,7 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
     p.mask = allow_mask;
     p.dense = nullptr;
     p.dense_stride = 0;
+    p.a_policy = t.batch_a_policy;
     const int sms = sm_count(ix->device);
 
     // chunk schedule: first chunk fills the buffers (every row passes thr = -inf), then chunks

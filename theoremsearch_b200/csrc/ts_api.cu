@@ -892,6 +892,7 @@ static int* tunable_slot(const char* name) {
     if (!strcmp(name, "batch.growth")) return &t.batch_growth;
     if (!strcmp(name, "batch.dense")) return &t.batch_dense;
     if (!strcmp(name, "batch.tf32")) return &t.batch_tf32;
+    if (!strcmp(name, "batch.a_policy")) return &t.batch_a_policy;
     if (!strcmp(name, "batch.cta_pair")) return &t.batch_cta_pair;
     if (!strcmp(name, "batch.pair_min_nq")) return &t.batch_pair_min_nq;
     if (!strcmp(name, "ivf.warps")) return &t.ivf_warps;

@@ -83,10 +83,13 @@ struct Tunables {
     int batch_first_chunk = 1024;  // rows of the first K3 chunk (every row passes thr = -inf)
     int batch_growth = 3;       // next chunk = growth x rows already seen
     int batch_dense = 1;        // small corpora (nq * N * 4 B <= 1 GiB): dense score matrix + select instead of chunked filtering
+    int batch_a_policy = 2;     // K3 corpus-tile L2 policy: 0 evict_first, 1 evict_normal, 2 evict_last. With evict_first the 16 n-blocks
+                                // of a corpus tile re-fetched it from DRAM (ncu: 15.7 GB read for a 7.4 GB chunk, 26 GB with CTA pairs) and
+                                // DRAM traffic costs power under the cap: 71.9 -> 70.8 ms (single CTAs), 76.0 -> 70.2 ms (pairs)
     int batch_tf32 = 1;         // fp32-stored corpora: batches take the TF32 GEMM (0 = one K2 pass per query, as in round 1)
-    int batch_cta_pair = 0;     // 1 = use the cta_group::2 kernel (CTA pairs) for large batches. Measured on B200
-                                // (4096 x 10M x 1024, 40 iterations, power-capped ~1.36 GHz): pairs 74.9 ms vs
-                                // single CTAs 71.8 ms, so single CTAs are the default; the pair kernel stays tested.
+    int batch_cta_pair = 1;     // large batches use the cta_group::2 kernel (CTA pairs: 256-row tiles, each CTA stages half of the
+                                // query block). Round 2, 4096 x 10M x 1024, 10 iterations, power-capped: pairs 70.2 ms vs single CTAs
+                                // 70.8 ms with the corpus tiles kept in L2 (profiles/k3_sweep_r2b.txt); ncu on the large chunk: 33.1 vs 35.4 ms
     int batch_pair_min_nq = 512;  // batches at least this large use CTA pairs
     int ivf_warps = 0;          // K4b warps per CTA; 0 = auto (latency mode 16, throughput mode 8)
     int ivf_tile_rows = 0;      // K4b rows per TMA tile (4 or 8, e4m3 D<=1024 lists only); 0 = auto
@@ -311,6 +314,11 @@ __device__ __forceinline__ void tma_load_1d_hint(void* smem_dst, const void* gme
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
