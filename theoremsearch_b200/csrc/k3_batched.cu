@@ -793,7 +793,7 @@ int launch_batched_search(const ts_index* ix, const void* queries, int q_dtype, 
     p.mask = allow_mask;
     p.dense = nullptr;
     p.dense_stride = 0;
-    p.a_policy = t.batch_a_policy;
+    p.a_policy = num_n_blocks > 1 ? t.batch_a_policy : 0;   // one n-block: every corpus tile is read exactly once
     const int sms = sm_count(ix->device);
 
     // chunk schedule: first chunk fills the buffers (every row passes thr = -inf), then chunks
