@@ -57,6 +57,12 @@ def _worker(rank, world, port, n, d, k, out_dir):
     s, i = sh.search(torch.from_numpy(q), k, normalize=False)
     np.save(os.path.join(out_dir, f"ids_{rank}.npy"), i.numpy())
     np.save(os.path.join(out_dir, f"scores_{rank}.npy"), s.numpy())
+    # host-buffer entry point without a peer exchange: the gather + merge form, numpy in / numpy out
+    s_h, i_h = sh.search_host(q.astype(np.float32), k, normalize=False)
+    assert np.array_equal(i_h, i.numpy()) and np.array_equal(s_h, s.numpy())
+    assert not sh.peer_exchange_error()
+    sh.resync()                                               # a no-op without an exchange, must not dead-lock or raise
+    sh.close()
     dist.barrier()
     dist.destroy_process_group()
 

@@ -161,10 +161,11 @@ class ShardedIndex:
         if q.ndim == 1:
             q = q[None, :]
         nq = q.shape[0]
-        if q.shape[1] != self.local.dim:
+        if self.local is not None and q.shape[1] != self.local.dim:
             raise _lib.TheoremSearchError(-1, f"queries must be [nq, {self.local.dim}], got {q.shape}")
-        if not self._fused_ok(nq, k):
-            s, i = self.search(torch.from_numpy(q).to(self.local.device), k, normalize, allow_mask)
+        if not self._fused_ok(nq, k):     # batches, or no peer exchange: the gather + merge form, copied back
+            qt = torch.from_numpy(q)
+            s, i = self.search(qt.to(self.local.device) if self.local is not None else qt, k, normalize, allow_mask)
             return s.cpu().numpy(), i.cpu().numpy()
         scores = np.empty((nq, k), dtype=np.float32)
         ids = np.empty((nq, k), dtype=np.int64)
