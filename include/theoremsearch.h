@@ -109,8 +109,7 @@ TS_API int ts_index_add_host(ts_index* index, const void* rows, int src_dtype, i
  * Built IVF lists stay valid across add / upsert, as pgvector's ivfflat accepts inserts after its build:
  * new and replaced rows are filed under the existing centroids in per-list OVERFLOW segments (scanned with
  * their list), a replaced row's old list entry is tombstoned, and once tombstones + overflow exceed a tenth
- * of the corpus the lists are re-packed from scratch. Until the re-pack, batched ANN searches take the
- * per-query list scan (K4b) instead of the list-major scan (K4d).
+ * of the corpus the lists are re-packed from scratch.
  * add / upsert / reserve / train / build are exclusive with searches on the same index. */
 
 /* Make room for at least `capacity` rows (never shrinks). Synchronises the device. */

@@ -131,6 +131,23 @@ def test_ivf_lists_stay_valid_across_upserts(ts, list_dtype):
         s_m, i_m = index.ivf_search(qq, 10, nprobe=8, rescore_k=100)
         s_f, i_f = fresh.ivf_search(qq, 10, nprobe=8, rescore_k=100)
         assert torch.equal(s_m, s_f) and torch.equal(i_m, i_f)
+    if list_dtype == "fp8":
+        # the list-major batch scan (K4d, tcgen05) over main + overflow lists with tombstones skipped in its epilogue
+        ts.set_tunable("ivf.group_min_lists", 1)
+        try:
+            index._ws, fresh._ws = {}, {}
+            before = ts.kernel_launches()
+            s_g, i_g = index.ivf_search(q, 10, nprobe=8, rescore_k=100)
+            assert ts.kernel_launches() - before >= 12               # coarse K3 chain + invert kernels + scan + select
+            s_h, i_h = fresh.ivf_search(q, 10, nprobe=8, rescore_k=100)
+            assert oracle.recall_at_k(i_g.cpu().numpy(), i_h.cpu().numpy()) >= 0.995
+            same = (i_g == i_h).all(dim=1)
+            assert same.sum() >= 38 and torch.equal(s_g[same], s_h[same])
+            s_m, i_m = index.ivf_search(q, 10, nprobe=8, rescore_k=100)
+            assert torch.equal(s_g, s_m) and torch.equal(i_g, i_m)   # deterministic
+        finally:
+            ts.set_tunable("ivf.group_min_lists", 0)
+            index._ws, fresh._ws = {}, {}
     sizes = index.ivf_list_sizes()
     assert int(sizes.sum()) == len(index) + dead                 # tombstones still occupy their slots
     index.ivf_repack()

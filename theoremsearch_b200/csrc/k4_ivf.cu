@@ -1568,7 +1568,9 @@ static int ivf_parts(const ts_index* ix, int nq) {
 static bool ivf_use_grouped(const ts_index* ix, int nq, int kc, int nprobe) {
     const int m = tunables().ivf_group_min_nq;
     if (m <= 0 || nq < m || !ivf_grouped_supported(ix, kc)) return false;
-    if (ix->ovf_n > 0 || ix->ivf_dead > 0) return false;   // overflow lists / tombstones: per-query scan until the re-pack
+    // overflow lists are ordinary (virtual) lists for the list-major scan; tombstones are skipped by the tcgen05 back
+    // end's epilogue only — the older back ends fall back to the per-query scan until the re-pack
+    if (ix->ivf_dead > 0 && tunables().ivf_group_mma < 3) return false;
     const int64_t pairs = (int64_t)nq * std::min(nprobe, ix->nlist);
     const int min_lists = tunables().ivf_group_min_lists > 0 ? tunables().ivf_group_min_lists : 4 * sm_count(ix->device);
     return ix->nlist >= min_lists && pairs >= min_lists;
@@ -1679,7 +1681,8 @@ static int ivf_search_impl(ts_index* ix, const void* queries, int q_dtype, int n
     if (w.grouped != nullptr) {
         // large batch: list-major scan (each probed list read once per 4 queries); K4b below runs only if the
         // score buffer turned out too small for this batch (decided on the device)
-        rc = launch_ivf_grouped(ix, w.probes, w.q32, nq, nprobe, kc, allow_mask, w.grouped, w.cand, &p.run_flag, s);
+        rc = launch_ivf_grouped(ix, p.probes, w.q32, nq, nprobe, ix->ovf_n > 0 ? 2 : 1, kc, allow_mask, w.grouped, w.cand,
+                                &p.run_flag, s);
         if (rc) return rc;
     }
     rc = launch_list_scan(ix, p, nq, ivf_parts(ix, nq), s);

@@ -967,8 +967,10 @@ size_t ivf_grouped_score_cap(const ts_index* ix, int nq, int nprobe) {
     return (size_t)want;
 }
 
+// Sized for the mutated index as well: overflow lists double the list count (virtual lists nlist .. 2 nlist - 1) and
+// the probes per query; the score buffer follows the real probe count (overflow lists hold < 10 % of the rows).
 size_t ivf_grouped_workspace_bytes(const ts_index* ix, int nq, int nprobe) {
-    const size_t np = (size_t)nq * nprobe, nl = (size_t)ix->nlist;
+    const size_t np = (size_t)nq * nprobe * 2, nl = (size_t)ix->nlist * 2;
     size_t b = 0;
     b += g_al(nl * 4) * 2;                 // cnt, cursor
     b += g_al((nl + 1) * 4) * 2;           // slot_start, item_start
@@ -988,36 +990,42 @@ bool ivf_grouped_supported(const ts_index* ix, int kc) {
 
 // Enqueues G1..G5. cand[nq][kc] receives the candidates unless the device-side capacity flag trips; `flag_out`
 // points at that flag (1 = the caller's K4b launch must do the work instead).
-int launch_ivf_grouped(const ts_index* ix, const uint64_t* probes, const float* q32, int nq, int nprobe, int kc,
+// `vmul` = 2 when the index carries overflow lists: `probes` then holds 2 * nprobe keys per query (every probed list and
+// its overflow list) and lists are numbered 0 .. 2 nlist - 1.
+int launch_ivf_grouped(const ts_index* ix, const uint64_t* probes, const float* q32, int nq, int nprobe_real, int vmul, int kc,
                        const uint32_t* allow_mask, void* workspace, uint64_t* cand, const uint32_t** flag_out,
                        cudaStream_t s) {
-    const size_t np = (size_t)nq * nprobe, nl = (size_t)ix->nlist;
-    TS_REQUIRE(np < ((size_t)1 << 31), TS_ERR_UNSUPPORTED, "ivf grouped scan: nq * nprobe = %zu too large", np);
+    const int nprobe = nprobe_real * vmul;                   // probes per query as the kernels see them
+    const int nlist_v = ix->nlist * vmul;
+    const size_t np_max = (size_t)nq * nprobe_real * 2, nl_max = (size_t)ix->nlist * 2;   // the carve-out is the same for both
+    const size_t np = (size_t)nq * nprobe, nl = (size_t)nlist_v;
+    TS_REQUIRE(np_max < ((size_t)1 << 31), TS_ERR_UNSUPPORTED, "ivf grouped scan: nq * nprobe = %zu too large", np_max);
     char* w = (char*)workspace;
     auto take = [&](size_t bytes) {
         char* p = w;
         w += g_al(bytes);
         return p;
     };
-    uint32_t* cnt = (uint32_t*)take(nl * 4);
-    uint32_t* cursor = (uint32_t*)take(nl * 4);
-    uint32_t* slot_start = (uint32_t*)take((nl + 1) * 4);
-    uint32_t* item_start = (uint32_t*)take((nl + 1) * 4);
+    uint32_t* cnt = (uint32_t*)take(nl_max * 4);
+    uint32_t* cursor = (uint32_t*)take(nl_max * 4);
+    uint32_t* slot_start = (uint32_t*)take((nl_max + 1) * 4);
+    uint32_t* item_start = (uint32_t*)take((nl_max + 1) * 4);
+    const size_t max_items_alloc = np_max / g4::QB + std::min(nl_max, np_max) + 1;
     const size_t max_items = np / g4::QB + std::min(nl, np) + 1;   // upper bound on sum ceil(cnt/QB)
-    uint32_t* item_list = (uint32_t*)take(max_items * 4);
-    unsigned long long* base = (unsigned long long*)take((nl + 1) * 8);
+    uint32_t* item_list = (uint32_t*)take(max_items_alloc * 4);
+    unsigned long long* base = (unsigned long long*)take((nl_max + 1) * 8);
     uint32_t* totals = (uint32_t*)take(256);
-    uint32_t* inv = (uint32_t*)take(np * 4);
-    uint32_t* pair_len = (uint32_t*)take(np * 4);
-    uint32_t* pair_pos0 = (uint32_t*)take(np * 4);
-    unsigned long long* pair_off = (unsigned long long*)take(np * 8);
+    uint32_t* inv = (uint32_t*)take(np_max * 4);
+    uint32_t* pair_len = (uint32_t*)take(np_max * 4);
+    uint32_t* pair_pos0 = (uint32_t*)take(np_max * 4);
+    unsigned long long* pair_off = (unsigned long long*)take(np_max * 8);
     uint8_t* q8 = (uint8_t*)take((size_t)nq * 2 * ix->list_row_bytes);
     float* qscale = (float*)take((size_t)nq * 4);
-    const size_t cap = ivf_grouped_score_cap(ix, nq, nprobe);
+    const size_t cap = ivf_grouped_score_cap(ix, nq, nprobe_real);
     float* scores = (float*)take(cap * 4);
     *flag_out = totals + 1;
 
-    TS_CHECK_CUDA(cudaMemsetAsync(cnt, 0, g_al(nl * 4) * 2, s));   // cnt and cursor are adjacent
+    TS_CHECK_CUDA(cudaMemsetAsync(cnt, 0, g_al(nl_max * 4) * 2, s));   // cnt and cursor are adjacent
     const int pb = (int)std::min<size_t>((np + 255) / 256, 148 * 8);
     ivf_invert_count_kernel<<<pb, 256, 0, s>>>(probes, (int)np, cnt);
     TS_LAUNCH_CHECK();
@@ -1027,13 +1035,13 @@ int launch_ivf_grouped(const ts_index* ix, const uint64_t* probes, const float* 
     const bool use_umma = mode >= 3;
     const bool use_mma = mode == 1 || mode == 2;
     const int qb = use_umma ? (mode == 3 ? 16 : 8) : use_mma ? (mode == 2 ? 16 : 8) : g4::QB;
-    ivf_invert_scan_kernel<<<1, 1024, 0, s>>>(cnt, ix->list_offsets, ix->nlist, slot_start, item_start, base, totals,
+    ivf_invert_scan_kernel<<<1, 1024, 0, s>>>(cnt, ix->list_offsets, nlist_v, slot_start, item_start, base, totals,
                                               (unsigned long long)cap, qb);
     TS_LAUNCH_CHECK();
     ivf_invert_fill_kernel<<<pb, 256, 0, s>>>(probes, (int)np, slot_start, base, ix->list_offsets, cursor, inv, pair_off,
                                               pair_len, pair_pos0);
     TS_LAUNCH_CHECK();
-    ivf_item_table_kernel<<<(ix->nlist + 255) / 256, 256, 0, s>>>(cnt, item_start, ix->nlist, item_list, qb);
+    ivf_item_table_kernel<<<(nlist_v + 255) / 256, 256, 0, s>>>(cnt, item_start, nlist_v, item_list, qb);
     TS_LAUNCH_CHECK();
 
     GroupedParams p;
@@ -1044,7 +1052,7 @@ int launch_ivf_grouped(const ts_index* ix, const uint64_t* probes, const float* 
     p.list_offsets = ix->list_offsets;
     p.queries = q32;
     p.nprobe = nprobe;
-    p.nlist = ix->nlist;
+    p.nlist = nlist_v;
     p.mask = allow_mask;
     p.list_rows = ix->list_rows;
     p.cnt = cnt;

@@ -465,7 +465,7 @@ int launch_normalize_cast(const void* src, int src_dtype, int64_t n, int dim, in
 // K4d: list-major batched IVF scan (k4_ivf_grouped.cu)
 bool ivf_grouped_supported(const ts_index* ix, int kc);
 size_t ivf_grouped_workspace_bytes(const ts_index* ix, int nq, int nprobe);
-int launch_ivf_grouped(const ts_index* ix, const uint64_t* probes, const float* q32, int nq, int nprobe, int kc,
+int launch_ivf_grouped(const ts_index* ix, const uint64_t* probes, const float* q32, int nq, int nprobe_real, int vmul, int kc,
                        const uint32_t* allow_mask, void* workspace, uint64_t* cand, const uint32_t** flag_out,
                        cudaStream_t s);
 int launch_max_norm2(const void* rows, int dtype, int64_t n, int dim_pad, float* out, cudaStream_t s);
