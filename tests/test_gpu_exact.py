@@ -288,6 +288,58 @@ def test_merge_topk_matches_oracle(ts, nshards, nq, k):
     assert torch.equal(i1, i) and torch.equal(s1, s)
 
 
+def _keys_tensor(scores, rows):
+    """[L, Q, k] (score, local row) -> packed keys as K2 / K5 exchange them (row < 0 = empty slot)."""
+    out = np.zeros(scores.shape, dtype=np.uint64)
+    for idx in np.ndindex(*scores.shape):
+        if rows[idx] >= 0:
+            out[idx] = oracle.pack_key(float(scores[idx]), int(rows[idx]))
+    return torch.from_numpy(out.view(np.int64)).cuda()
+
+
+@pytest.mark.parametrize("case", ["random", "one_list_holds_everything", "staircase_overflows_the_prune_buffer",
+                                   "few_non_empty_lists", "ties_across_lists"])
+@pytest.mark.parametrize("nlists,k", [(148, 10), (64, 32), (17, 1), (256, 5)])
+def test_pruned_merge_of_many_lists_equals_the_oracle(ts, case, nlists, k):
+    """K5 with 16..256 lists and k <= 32 takes the pruned merge (only keys >= the k-th largest list head survive) —
+    the same code K2's last CTA runs over its 148 per-CTA lists on every search. Adversarial layouts: every winner in
+    one list, a staircase that leaves more than 256 survivors (the general merge must take over), almost-empty
+    inputs (no k-th head exists), equal scores in different lists (lower global row first)."""
+    rng = np.random.default_rng(nlists * 100 + k)
+    nq = 3
+    scores = np.full((nlists, nq, k), -np.inf, dtype=np.float32)
+    rows = np.full((nlists, nq, k), -1, dtype=np.int64)
+    base = np.arange(nlists, dtype=np.int64) * 1000
+    for q in range(nq):
+        for l in range(nlists):
+            if case == "random":
+                n = int(rng.integers(0, k + 1))
+                sc = rng.standard_normal(n)
+            elif case == "one_list_holds_everything":
+                n = k
+                sc = rng.standard_normal(n) + (100.0 if l == (7 * q + 3) % nlists else 0.0)
+            elif case == "staircase_overflows_the_prune_buffer":
+                n = k
+                sc = l + rng.random(n) * 0.9                     # list l beats list l - 1 entirely
+            elif case == "few_non_empty_lists":
+                n = k if l in (1, nlists - 2) else 0
+                sc = rng.standard_normal(n)
+            else:                                                # ties: the same few score values everywhere
+                n = k
+                sc = rng.integers(0, 4, size=n).astype(np.float64)
+            sc = np.sort(np.asarray(sc, dtype=np.float32))[::-1]
+            rr = rng.permutation(900)[:n]
+            if case == "ties_across_lists":                      # within a list: equal scores sorted by row ascending
+                order = np.lexsort((rr, -sc))
+                sc, rr = sc[order], rr[order]
+            scores[l, q, :n], rows[l, q, :n] = sc, rr
+    keys = _keys_tensor(scores, rows)
+    s, i = ts.merge_topk(keys, k, shard_base=base.tolist())
+    want_s, want_r = oracle.merge_shards(list(scores.astype(np.float64)), list(rows), base.tolist(), k)
+    assert np.array_equal(i.cpu().numpy(), want_r)
+    assert np.array_equal(s.cpu().numpy().astype(np.float64), want_s)
+
+
 def test_errors_are_loud(ts):
     with pytest.raises(ts.TheoremSearchError):
         ts.TheoremIndex(4096, 10)          # dim too large
