@@ -112,6 +112,11 @@ TS_API int ts_index_add_host(ts_index* index, const void* rows, int src_dtype, i
  * of the corpus the lists are re-packed from scratch.
  * add / upsert / reserve / train / build are exclusive with searches on the same index. */
 
+/* 1 if the row store is virtual-memory mapped (a reserved address range into which physical memory is mapped as the
+ * index grows: growth copies no row and needs no second allocation, ts_index_data() never changes), 0 if it is a
+ * plain allocation that is copied on growth (driver entry points unavailable, or tunable "store.no_vmm"). */
+TS_API int ts_index_grows_in_place(const ts_index* index);
+
 /* Make room for at least `capacity` rows (never shrinks). Synchronises the device. */
 TS_API int ts_index_reserve(ts_index* index, int64_t capacity);
 

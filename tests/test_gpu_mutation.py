@@ -83,12 +83,26 @@ def test_rows_without_ids_use_their_position_as_id(ts):
     assert sorted(i2[0].tolist()) == [5, 9000] and s2[0, 0] == s2[0, 1]
 
 
-def test_add_grows_capacity_and_keeps_results(ts):
+@pytest.mark.parametrize("no_vmm", [0, 1])
+def test_add_grows_capacity_and_keeps_results(ts, no_vmm):
+    """The row store grows on demand. Default: virtual-memory mapped, grows in place (the data pointer never moves, no
+    row is copied); `store.no_vmm = 1`: plain allocation, copied on growth. Same results either way."""
+    from theoremsearch_b200._lib import lib
     x = oracle.synthetic_rows(0, 5000, 128, seed=11)
-    index = ts.TheoremIndex(128, 10, dtype="bf16")
+    ts.set_tunable("store.no_vmm", no_vmm)
+    try:
+        index = ts.TheoremIndex(128, 10, dtype="bf16")
+    finally:
+        ts.set_tunable("store.no_vmm", 0)
+    assert int(lib.ts_index_grows_in_place(index.handle)) == 1 - no_vmm
+    ptr0 = lib.ts_index_data(index.handle)
     for lo in range(0, 5000, 700):
         index.add(torch.from_numpy(x[lo:lo + 700]).cuda())
     assert len(index) == 5000 and index.capacity >= 5000
+    if not no_vmm:
+        assert lib.ts_index_data(index.handle) == ptr0        # grown in place
+        index.reserve(3_000_000)                              # 768 MB more address space backed on demand
+        assert lib.ts_index_data(index.handle) == ptr0 and index.capacity == 3_000_000
     fresh = ts.build_index(x)
     q = torch.from_numpy(oracle.synthetic_queries(4, 128))
     s0, i0 = fresh.search(q, 10)

@@ -175,18 +175,19 @@ int ts_index_create(ts_index** out, int device, int dim, int dtype, int64_t capa
     ix->dtype = dtype;
     ix->capacity = capacity;
     size_t bytes = (size_t)std::max<int64_t>(capacity, 1) * ix->row_bytes();
-    e = cudaMalloc(&ix->data, bytes);
-    if (e != cudaSuccess) {
-        set_error("index_create: cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
-        delete ix;
-        cudaGetLastError();
-        return TS_ERR_OOM;
+    {
+        int src = row_store_create(&ix->store, device, bytes, ix->row_bytes());
+        if (src != TS_OK) {
+            delete ix;
+            return src;
+        }
+        ix->data = row_store_ptr(ix->store);
     }
     e = cudaMalloc(&ix->max_norm2, sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(ix->max_norm2, 0, sizeof(float));
     if (e != cudaSuccess) {
         set_error("index_create: cudaMalloc failed: %s", cudaGetErrorString(e));
-        cudaFree(ix->data);
+        row_store_destroy(ix->store);
         delete ix;
         cudaGetLastError();
         return TS_ERR_OOM;
@@ -198,7 +199,7 @@ int ts_index_create(ts_index** out, int device, int dim, int dtype, int64_t capa
 void ts_index_destroy(ts_index* ix) {
     if (!ix) return;
     DeviceGuard g(ix->device);
-    cudaFree(ix->data);
+    row_store_destroy(ix->store);
     cudaFree(ix->max_norm2);
     cudaFree(ix->ids);
     cudaFree(ix->centroids);
@@ -314,6 +315,7 @@ int ts_index_dtype(const ts_index* ix) { return ix ? ix->dtype : -1; }
 int ts_index_device(const ts_index* ix) { return ix ? ix->device : -1; }
 const void* ts_index_data(const ts_index* ix) { return ix ? ix->data : nullptr; }
 size_t ts_index_row_bytes(const ts_index* ix) { return ix ? ix->row_bytes() : 0; }
+int ts_index_grows_in_place(const ts_index* ix) { return ix ? (row_store_is_vmm(ix->store) ? 1 : 0) : -1; }
 
 int ts_index_get_rows(const ts_index* ix, int64_t first, int64_t n, float* out, void* stream) {
     TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "index_get_rows: index is NULL");
@@ -905,6 +907,7 @@ static int* tunable_slot(const char* name) {
     if (!strcmp(name, "ivf.fuse_rescore")) return &t.ivf_fuse_rescore;
     if (!strcmp(name, "xchg.debug_no_flag")) return &t.xchg_debug_no_flag;
     if (!strcmp(name, "scan.timeline")) return &t.scan_timeline;
+    if (!strcmp(name, "store.no_vmm")) return &t.store_no_vmm;
     if (!strcmp(name, "ivf.group_min_lists")) return &t.ivf_group_min_lists;
     return nullptr;
 }

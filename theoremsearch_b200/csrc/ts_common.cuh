@@ -100,6 +100,7 @@ struct Tunables {
     int ivf_fuse_rescore = 1;   // small IVF batches: the list scan's last CTA re-scores its candidates (no separate K4c launch)
     int ivf_select_warp = 1;    // K4d candidate selection: 1 = warp-per-query register select, 0 = CTA-per-query smem select
     int scan_timeline = 0;      // 1 = K2 CTAs record %globaltimer stamps per phase (ts_debug_scan_timeline)
+    int store_no_vmm = 0;       // 1 = plain cudaMalloc row stores (copy on grow) instead of virtual-memory mapping
     int xchg_debug_no_flag = 0; // test hook: the sharded exchange does not raise its own flag, so its wait times out
     int ivf_group_mma = 3;      // K4d scoring: 3 / 4 = tcgen05 kind::f8f6f4 (e4m3 rows straight into the tensor cores, two-term
                                 // e4m3 queries) with 16 / 8 queries per group; 1 / 2 = legacy mma.sync f16 variant with 8 / 16;
@@ -331,6 +332,9 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
 }  // namespace ts
 
 // ---------------------------------------------------------------------------- handles
+namespace ts {
+struct RowStore;
+}
 struct ts_index {
     int device = 0;
     int dim = 0;          // logical embedding dimension
@@ -338,7 +342,8 @@ struct ts_index {
     int dtype = TS_BF16;  // storage dtype of `data`
     int64_t capacity = 0;
     int64_t size = 0;
-    void* data = nullptr;     // [capacity, dim_pad] of dtype
+    void* data = nullptr;     // [capacity, dim_pad] of dtype (== row_store_ptr(store))
+    ts::RowStore* store = nullptr;   // owns `data`: a reserved address range, physical memory mapped as the index grows
     int64_t* ids = nullptr;   // [capacity] caller ids; valid only when has_ids
     bool has_ids = false;
     float* max_norm2 = nullptr;  // device scalar: max squared L2 norm over stored (quantised) rows
@@ -446,6 +451,13 @@ struct ts_ctx {
 
 // internal kernel entry points (one per .cu)
 namespace ts {
+// growable row store (vmm_store.cu): virtual-memory mapped, grows in place
+struct RowStore;
+int row_store_create(RowStore** out, int device, size_t bytes, size_t row_bytes);
+void row_store_destroy(RowStore* st);
+void* row_store_ptr(const RowStore* st);
+bool row_store_is_vmm(const RowStore* st);
+int row_store_reserve(RowStore* st, size_t bytes, size_t used);
 // IVF upkeep after rows were replaced in place (device list of corpus rows) and/or appended ([app_first,
 // app_first + app_n)): tombstones, overflow lists, automatic re-pack (k4_ivf.cu). No-op unless lists are built.
 int ivf_apply_mutation(ts_index* ix, const uint32_t* replaced_rows, int64_t n_replaced, int64_t app_first,

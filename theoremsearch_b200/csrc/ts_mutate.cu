@@ -46,15 +46,17 @@ static int regrow(T** buf, size_t used, size_t count) {
     return TS_OK;
 }
 
-// The new row store is allocated beside the old one and the rows copied across (device to device, ~3 ms per 10 GB):
-// growth needs the old and the new allocation to be resident at the same time.
+// The row store grows IN PLACE: more physical memory is mapped behind the rows in the index's reserved address range
+// (vmm_store.cu) — no row is copied, no second allocation is needed. The small side tables (ids, list positions) are
+// re-allocated and copied.
 int index_reserve(ts_index* ix, int64_t capacity) {
     if (capacity <= ix->capacity) return TS_OK;
     TS_REQUIRE(capacity < (int64_t)0xFFFFFFFFll, TS_ERR_UNSUPPORTED, "index_reserve: capacity %lld exceeds 2^32-2 rows",
                (long long)capacity);
     TS_CHECK_CUDA(cudaDeviceSynchronize());
-    int rc = regrow((uint8_t**)&ix->data, (size_t)ix->size * ix->row_bytes(), (size_t)capacity * ix->row_bytes());
+    int rc = row_store_reserve(ix->store, (size_t)capacity * ix->row_bytes(), (size_t)ix->size * ix->row_bytes());
     if (rc) return rc;
+    ix->data = row_store_ptr(ix->store);
     if (ix->has_ids && (rc = regrow(&ix->ids, (size_t)ix->size, (size_t)capacity))) return rc;
     if (ix->pos_of_row != nullptr && (rc = regrow(&ix->pos_of_row, (size_t)ix->size, (size_t)capacity))) return rc;
     ix->capacity = capacity;
