@@ -141,6 +141,7 @@ int row_store_create(RowStore** out, int device, size_t bytes, size_t row_bytes)
 void row_store_destroy(RowStore* st) {
     if (!st) return;
     if (st->vmm) {
+        cudaDeviceSynchronize();   // cudaFree waits for the device by itself, cuMemUnmap does not
         const VmmApi& api = vmm_api();
         CUdeviceptr at = (CUdeviceptr)st->base;
         for (auto& c : st->chunks) {
