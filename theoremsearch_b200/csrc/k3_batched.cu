@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(1024) build_fix_list_kernel(const int* __restr
 // walked with float4 loads against a float threshold, candidates go through a register-resident WarpSelect — no
 // shared memory, no barriers, no CTA sorts. 4096 queries x 16384 scores: 0.97 ms with the CTA-per-query kernel below.
 template <int KPL>
-__global__ void __launch_bounds__(256) dense_select_warp_kernel(const float* __restrict__ dense, int64_t stride, int64_t n_rows,
+__global__ void __launch_bounds__(256, 4) dense_select_warp_kernel(const float* __restrict__ dense, int64_t stride, int64_t n_rows,
                                                                 int nq, int kp, uint64_t* __restrict__ cand, size_t cand_stride,
                                                                 uint32_t* __restrict__ overflow) {
     const int lane = threadIdx.x & 31;

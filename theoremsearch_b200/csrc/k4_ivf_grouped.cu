@@ -864,7 +864,7 @@ ivf_grouped_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const Groupe
 // threshold, candidates go through a register-resident WarpSelect (warp_select_run) — no shared memory, no barriers, no
 // CTA sorts; 4096 queries run as 4096 independent warps. 0.93 ms -> see profiles/launches_ivf_batch_r2*.csv.
 template <int KPL>
-__global__ void __launch_bounds__(256) ivf_select_warp_kernel(const float* __restrict__ scores,
+__global__ void __launch_bounds__(256, 4) ivf_select_warp_kernel(const float* __restrict__ scores,
                                                               const unsigned long long* __restrict__ pair_off,
                                                               const uint32_t* __restrict__ pair_len,
                                                               const uint32_t* __restrict__ pair_pos0, int nq, int nprobe, int k,
