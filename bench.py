@@ -345,6 +345,9 @@ def main():
     ap.add_argument("--reference-sample-rows", type=int, default=0,
                     help="reference arm: time a row sample of this size instead of the full corpus (0 = full corpus)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stream-chain", action="store_true",
+                    help="N = 1: plain one-kernel searches instead of the scan + finishing kernel chained by programmatic "
+                         "dependent launch (queries are resident and uploaded beforehand either way)")
     ap.add_argument("--no-extras", action="store_true", help="skip the configs[2] / configs[4] sections (N = 1)")
     ap.add_argument("--batch-nq", type=int, default=4096)
     ap.add_argument("--batch-k", type=int, default=100)
@@ -362,6 +365,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": f"configs[1]: single-query exact top-{args.k} over {args.rows}x{args.dim} bf16",
+              "device_stream": ("one kernel per query (ts_search)" if args.no_stream_chain else
+                                "per query a scan kernel + a finishing kernel chained by programmatic dependent launch; queries "
+                                "uploaded beforehand (independent=True), so consecutive scans overlap their tails"),
               "rows": args.rows, "dim": args.dim, "k": args.k,
               "sharding": f"row-sharded x{world}" if world > 1 else "single GPU",
               "arithmetic": "bf16 corpus rows, fp32 query, fp32 products and accumulation",
@@ -421,7 +427,7 @@ def main():
     def one_step_device(i):
         q = queries[i:i + 1]
         if sharded is None:
-            return index.search(q, args.k)
+            return index.search(q, args.k, independent=not args.no_stream_chain)
         if peer:
             return sharded.search(q, args.k, **form)
         return sharded.search(q, args.k)

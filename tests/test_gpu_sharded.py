@@ -65,6 +65,26 @@ def test_stream_of_independent_searches_overlaps_and_stays_exact(ts):
     sh.close()
 
 
+def test_single_gpu_stream_chain_equals_plain_search_with_caller_ids_and_mask(ts):
+    """`TheoremIndex.search(..., independent=True)`: the sharded path's kernel chain on one GPU (a world of one)."""
+    n, d = 60_000, 512
+    x = oracle.synthetic_rows(0, n, d, seed=12)
+    ids = np.arange(n, dtype=np.int64) * 5 + 7
+    index = ts.build_index(x, ids=ids)
+    q = torch.from_numpy(oracle.synthetic_queries(40, d)).cuda()
+    allow = np.random.default_rng(0).random(n) < 0.4
+    mask = ts.pack_allow_mask(allow, index.device)
+    torch.cuda.synchronize()
+    for k, m in ((10, None), (100, None), (10, mask)):
+        outs = [index.search(q[i:i + 1], k, allow_mask=m, independent=True) for i in range(40)]
+        torch.cuda.synchronize()
+        for i, (s, idv) in enumerate(outs):
+            s0, i0 = index.search(q[i:i + 1], k, allow_mask=m)
+            assert torch.equal(s, s0) and torch.equal(idv, i0), (k, i)
+    assert (outs[0][1] % 5 == 2).all()                       # caller ids, not row positions
+    index.close()
+
+
 def test_fused_exchange_rebases_rows_and_maps_ids(ts):
     """A 'shard' that starts at global row 5000: fused results carry global rows / caller ids."""
     from theoremsearch_b200.sharded import ShardedIndex

@@ -747,6 +747,7 @@ static int search_sharded_impl(ts_index* ix, ts_xchg* x, const void* queries, in
     SearchWs w = carve_ws(ix, nq, k, workspace);
     TS_REQUIRE(workspace_bytes >= w.bytes, TS_ERR_CAPACITY, "search_sharded: workspace %zu < %zu bytes", workspace_bytes,
                w.bytes);
+    if (id_map == nullptr && x->world == 1 && shard_base == 0 && ix->has_ids) id_map = ix->ids;   // a world of one: the index's own ids
     XchgDev xd;
     xd.peer_slots = x->d_peer_slots;
     xd.peer_flags = x->d_peer_flags;

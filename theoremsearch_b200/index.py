@@ -69,6 +69,9 @@ class TheoremIndex:
         for ctx in self._ctx.values():
             lib.ts_ctx_destroy(ctx)
         self._ctx.clear()
+        if getattr(self, "_xchg1", None) is not None:
+            lib.ts_xchg_destroy(self._xchg1)
+            self._xchg1 = None
         if getattr(self, "_h", None):
             lib.ts_index_destroy(self._h)
             self._h = None
@@ -214,11 +217,42 @@ class TheoremIndex:
             q = q.to(torch.float32)
         return q.to(self.device).contiguous()
 
-    def search(self, queries, k: int, normalize: bool = True, allow_mask: Optional[torch.Tensor] = None):
+    def _stream_exchange(self, k: int):
+        """A world-of-one exchange handle: gives a single GPU the sharded path's kernel chain (scan + finishing kernel
+        linked by programmatic dependent launch), so that back-to-back searches overlap their tails."""
+        h = getattr(self, "_xchg1", None)
+        if h is None or self._xchg1_k < k:
+            if h is not None:
+                lib.ts_xchg_destroy(h)
+            h = C.c_void_p()
+            self._xchg1_k = max(int(k), 32)
+            check(lib.ts_xchg_create(C.byref(h), self.device.index, 1, 0, 1, self._xchg1_k))
+            check(lib.ts_xchg_connect(h, None))
+            self._xchg1 = h
+        return h
+
+    def search(self, queries, k: int, normalize: bool = True, allow_mask: Optional[torch.Tensor] = None,
+               independent: bool = False):
         """Exact top-k on device tensors. Returns (scores float32 [nq, k], ids int64 [nq, k]),
-        score descending, ties -> lower row; padded with (-inf, -1)."""
+        score descending, ties -> lower row; padded with (-inf, -1).
+
+        ``independent=True`` (single queries): a promise that ``queries`` / ``allow_mask`` are not written by the
+        kernel enqueued just before this call on the current stream (e.g. the queries were uploaded earlier). The
+        search then runs as a scan kernel plus a finishing kernel chained by programmatic dependent launch, and the
+        scan of the NEXT such search starts on every SM the moment this one's scan CTA retires: a stream of searches
+        runs at the streaming rate of the scan, without launch gaps or merge tails between queries."""
         q = self._prep_queries(queries)
         nq = q.shape[0]
+        if independent and nq == 1 and k <= _lib.TS_MAX_K and nq < _lib.get_tunable("batch.min_nq"):
+            scores = torch.empty((1, k), dtype=torch.float32, device=self.device)
+            ids = torch.empty((1, k), dtype=torch.int64, device=self.device)
+            ws = self._workspace(1, k)
+            check(lib.ts_search_sharded(self._h, self._stream_exchange(k), q.data_ptr(), _TORCH_TO_TS[q.dtype], 1, int(k),
+                                        int(normalize), self._mask_ptr(allow_mask), 0, None, scores.data_ptr(),
+                                        ids.data_ptr(), ws.data_ptr(), ws.numel(), _lib.TS_SHARDED_INDEPENDENT,
+                                        _stream_ptr(self.device)))
+            q.record_stream(torch.cuda.current_stream(self.device))
+            return scores, ids
         scores = torch.empty((nq, k), dtype=torch.float32, device=self.device)
         ids = torch.empty((nq, k), dtype=torch.int64, device=self.device)
         ws = self._workspace(nq, k)
