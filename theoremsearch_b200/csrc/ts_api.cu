@@ -672,6 +672,7 @@ int ts_xchg_handle(const ts_xchg* x, void* out_handle) {
 
 int ts_xchg_connect(ts_xchg* x, const void* all_handles) {
     TS_REQUIRE(x != nullptr && (all_handles != nullptr || x->world == 1), TS_ERR_BAD_ARG, "xchg_connect: NULL argument");
+    TS_REQUIRE(!x->connected, TS_ERR_STATE, "xchg_connect: the peers are already mapped");
     DeviceGuard g(x->device);
     TS_REQUIRE(g.ok, TS_ERR_CUDA, "xchg_connect: cannot select CUDA device %d", x->device);
     for (int r = 0; r < x->world; ++r) {
@@ -761,7 +762,8 @@ static int search_sharded_impl(ts_index* ix, ts_xchg* x, const void* queries, in
     xd.rank = x->rank;
     xd.max_nq = x->max_nq;
     xd.max_k = x->max_k;
-    xd.seq = ++x->seq;
+    xd.seq = x->seq + 1u;      // committed (x->seq) only once the search is enqueued: a failed call must not leave this
+                               // rank one sequence number ahead of its peers
     xd.base = shard_base;
     xd.timeout_ns = x->timeout_ns;
     xd.debug_no_flag = tunables().xchg_debug_no_flag;
@@ -782,8 +784,10 @@ static int search_sharded_impl(ts_index* ix, ts_xchg* x, const void* queries, in
         f.ring_need = 0;
         f.done_flag = done_flag;
         f.done_value = done_value;
-        return launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, w.part_keys, w.nparts, s,
-                                nullptr, nullptr, nullptr, nullptr, &f);
+        int rc1 = launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, w.part_keys, w.nparts, s,
+                                   nullptr, nullptr, nullptr, nullptr, &f);
+        if (rc1 == TS_OK) x->seq = xd.seq;
+        return rc1;
     }
     // two kernels chained by programmatic dependent launch: the scan writes its per-CTA lists, the exchange
     // kernel (resident early, asleep until the scan completes) merges, exchanges and writes the result while
@@ -808,6 +812,7 @@ static int search_sharded_impl(ts_index* ix, ts_xchg* x, const void* queries, in
     int rc = launch_scan_topk(ix, ix->data, ix->dtype, ix->size, w.q_f32, nq, k, allow_mask, part, w.nparts, s,
                               nullptr, nullptr, nullptr, nullptr, &f);
     if (rc) return rc;
+    x->seq = xd.seq;
     return launch_xchg_finish(part, w.nparts, nq, k, xd, id_map, out_scores, out_ids, s, done_flag, done_value);
 }
 
@@ -829,25 +834,37 @@ int ts_search_sharded_host(ts_index* ix, ts_xchg* x, const float* queries, int n
     TS_REQUIRE(queries && out_scores && out_ids, TS_ERR_BAD_ARG, "search_sharded_host: NULL buffer");
     DeviceGuard g(ix->device);
     TS_REQUIRE(g.ok, TS_ERR_CUDA, "search_sharded_host: cannot select CUDA device %d", ix->device);
-    if (x->stream == nullptr || x->host_dim != ix->dim) {   // first call: stream, pinned staging, device buffers
-        TS_REQUIRE(x->stream == nullptr, TS_ERR_BAD_ARG, "search_sharded_host: the exchange was set up for dim %d", x->host_dim);
+    if (x->host_dim != ix->dim) {   // first call: stream, pinned staging, device buffers
+        TS_REQUIRE(x->host_dim == 0, TS_ERR_BAD_ARG, "search_sharded_host: the exchange was set up for dim %d", x->host_dim);
         const size_t qb = (size_t)x->max_nq * ix->dim * sizeof(float);
         const size_t sb = (size_t)x->max_nq * x->max_k * sizeof(float);
         const size_t ib = (size_t)x->max_nq * x->max_k * sizeof(int64_t);
         x->workspace_bytes = carve_ws(ix, x->max_nq, x->max_k, nullptr).bytes;
-        TS_CHECK_CUDA(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
-        TS_CHECK_CUDA(cudaMallocHost(&x->h_queries, qb));
-        TS_CHECK_CUDA(cudaHostAlloc((void**)&x->h_scores, sb, cudaHostAllocMapped));
-        TS_CHECK_CUDA(cudaHostAlloc((void**)&x->h_ids, ib, cudaHostAllocMapped));
-        TS_CHECK_CUDA(cudaHostAlloc((void**)&x->h_done, sizeof(uint32_t), cudaHostAllocMapped));
+        cudaError_t e = x->stream ? cudaSuccess : cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking);
+        auto host = [&](void** p, size_t bytes, unsigned fl) {   // an earlier attempt may have got part of the way
+            if (e == cudaSuccess && *p == nullptr) e = cudaHostAlloc(p, bytes, fl);
+        };
+        auto dev = [&](void** p, size_t bytes) {
+            if (e == cudaSuccess && *p == nullptr) e = cudaMalloc(p, bytes);
+        };
+        host((void**)&x->h_queries, qb, cudaHostAllocDefault);
+        host((void**)&x->h_scores, sb, cudaHostAllocMapped);
+        host((void**)&x->h_ids, ib, cudaHostAllocMapped);
+        host((void**)&x->h_done, sizeof(uint32_t), cudaHostAllocMapped);
+        if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&x->m_scores, x->h_scores, 0);
+        if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&x->m_ids, x->h_ids, 0);
+        if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&x->m_done, x->h_done, 0);
+        dev((void**)&x->d_queries, qb);
+        dev((void**)&x->d_scores, sb);
+        dev((void**)&x->d_ids, ib);
+        dev((void**)&x->workspace, x->workspace_bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("search_sharded_host: staging allocation failed: %s", cudaGetErrorString(e));
+            return e == cudaErrorMemoryAllocation ? TS_ERR_OOM : TS_ERR_CUDA;
+        }
         *x->h_done = 0u;
-        TS_CHECK_CUDA(cudaHostGetDevicePointer((void**)&x->m_scores, x->h_scores, 0));
-        TS_CHECK_CUDA(cudaHostGetDevicePointer((void**)&x->m_ids, x->h_ids, 0));
-        TS_CHECK_CUDA(cudaHostGetDevicePointer((void**)&x->m_done, x->h_done, 0));
-        TS_CHECK_CUDA(cudaMalloc(&x->d_queries, qb));
-        TS_CHECK_CUDA(cudaMalloc(&x->d_scores, sb));
-        TS_CHECK_CUDA(cudaMalloc(&x->d_ids, ib));
-        TS_CHECK_CUDA(cudaMalloc(&x->workspace, x->workspace_bytes));
+        x->done_seq = 0u;
         x->host_dim = ix->dim;
     }
     const size_t qb = (size_t)nq * ix->dim * sizeof(float);

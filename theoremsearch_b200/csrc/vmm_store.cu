@@ -25,11 +25,8 @@ struct VmmApi {
     bool ok = false;
 };
 
-static const VmmApi& vmm_api() {
-    static VmmApi api;
-    static bool tried = false;
-    if (tried) return api;
-    tried = true;
+static VmmApi vmm_resolve() {
+    VmmApi api;
     auto get = [](const char* name, void** fn) {
         cudaDriverEntryPointQueryResult q;
         return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess &&
@@ -40,6 +37,11 @@ static const VmmApi& vmm_api() {
              get("cuMemMap", (void**)&api.map) && get("cuMemUnmap", (void**)&api.unmap) &&
              get("cuMemSetAccess", (void**)&api.access) && get("cuMemGetAllocationGranularity", (void**)&api.gran);
     if (!api.ok) cudaGetLastError();
+    return api;
+}
+
+static const VmmApi& vmm_api() {
+    static const VmmApi api = vmm_resolve();   // resolved once; initialisation of a local static is thread-safe
     return api;
 }
 
