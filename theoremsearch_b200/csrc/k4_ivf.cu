@@ -1068,9 +1068,8 @@ static void ivf_free_lists(ts_index* ix) {
     ix->list_rows = nullptr;
     ix->list_data = nullptr;
     ix->list_scales = nullptr;
-    cudaFree(ix->pos_of_row);
+    side_table_destroy(&ix->pos_store, &ix->pos_of_row);
     cudaFree(ix->ovf_set);
-    ix->pos_of_row = nullptr;
     ix->ovf_set = nullptr;
     ix->list_cap = ix->built_n = ix->ovf_n = ix->ivf_dead = ix->ovf_cap = 0;
     ix->ivf_built = false;
@@ -1427,7 +1426,7 @@ int ts_ivf_build(ts_index* ix, int list_dtype, void* stream) {
     if ((rc = tmp.get(&assign, (size_t)n)) || (rc = tmp.get(&sorted_assign, (size_t)n)) || (rc = tmp.get(&iota, (size_t)n)))
         return rc;
     TS_CHECK_CUDA(cudaMalloc(&ix->list_offsets, (2 * (size_t)ix->nlist + 1) * sizeof(int64_t)));
-    TS_CHECK_CUDA(cudaMalloc(&ix->pos_of_row, std::max<size_t>((size_t)ix->capacity, 1) * sizeof(uint32_t)));
+    if ((rc = side_table_create(&ix->pos_store, &ix->pos_of_row, ix->device, ix->capacity))) return rc;
     TS_CHECK_CUDA(cudaMalloc(&ix->list_rows, std::max<size_t>((size_t)n, 1) * sizeof(uint32_t)));
     TS_CHECK_CUDA(cudaMalloc(&ix->list_data, std::max<size_t>((size_t)n, 1) * lrow));
     if (list_dtype == TS_FP8_E4M3)

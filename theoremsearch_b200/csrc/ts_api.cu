@@ -201,7 +201,7 @@ void ts_index_destroy(ts_index* ix) {
     DeviceGuard g(ix->device);
     row_store_destroy(ix->store);
     cudaFree(ix->max_norm2);
-    cudaFree(ix->ids);
+    side_table_destroy(&ix->ids_store, &ix->ids);
     cudaFree(ix->centroids);
     cudaFree(ix->centroids_bf16);
     cudaFree(ix->list_offsets);
@@ -209,7 +209,7 @@ void ts_index_destroy(ts_index* ix) {
     cudaFree(ix->list_data);
     cudaFree(ix->list_scales);
     cudaFree(ix->centroid_max_norm2);
-    cudaFree(ix->pos_of_row);
+    side_table_destroy(&ix->pos_store, &ix->pos_of_row);
     cudaFree(ix->ovf_set);
     delete ix->id_map_host;
     delete ix;
@@ -235,7 +235,8 @@ int ts_index_add(ts_index* ix, const void* rows, int src_dtype, int64_t n, int n
     }
     if (ids != nullptr && !ix->has_ids) {
         // first explicit ids: materialise the id table, rows added so far keep id = row
-        TS_CHECK_CUDA(cudaMalloc(&ix->ids, (size_t)std::max<int64_t>(ix->capacity, 1) * sizeof(int64_t)));
+        int irc = side_table_create(&ix->ids_store, &ix->ids, ix->device, ix->capacity);
+        if (irc) return irc;
         if (ix->size > 0) {
             iota_ids_kernel<<<256, 256, 0, s>>>(ix->ids, 0, ix->size);
             TS_LAUNCH_CHECK();
@@ -398,7 +399,8 @@ int ts_index_append_raw_host(ts_index* ix, const void* rows, int64_t n, const in
         if (grc) return grc;
     }
     if (ids != nullptr && !ix->has_ids) {
-        TS_CHECK_CUDA(cudaMalloc(&ix->ids, (size_t)std::max<int64_t>(ix->capacity, 1) * sizeof(int64_t)));
+        int irc = side_table_create(&ix->ids_store, &ix->ids, ix->device, ix->capacity);
+        if (irc) return irc;
         if (ix->size > 0) {
             iota_ids_kernel<<<256, 256>>>(ix->ids, 0, ix->size);
             TS_LAUNCH_CHECK();

@@ -344,6 +344,8 @@ struct ts_index {
     int64_t size = 0;
     void* data = nullptr;     // [capacity, dim_pad] of dtype (== row_store_ptr(store))
     ts::RowStore* store = nullptr;   // owns `data`: a reserved address range, physical memory mapped as the index grows
+    ts::RowStore* ids_store = nullptr;   // owns `ids`
+    ts::RowStore* pos_store = nullptr;   // owns `pos_of_row`
     int64_t* ids = nullptr;   // [capacity] caller ids; valid only when has_ids
     bool has_ids = false;
     float* max_norm2 = nullptr;  // device scalar: max squared L2 norm over stored (quantised) rows
@@ -458,6 +460,25 @@ void row_store_destroy(RowStore* st);
 void* row_store_ptr(const RowStore* st);
 bool row_store_is_vmm(const RowStore* st);
 int row_store_reserve(RowStore* st, size_t bytes, size_t used);
+// the side tables that grow with the index (caller ids, IVF row positions) live in row stores of their own
+template <typename T>
+inline int side_table_create(RowStore** st, T** table, int device, int64_t capacity) {
+    int rc = row_store_create(st, device, (size_t)(capacity > 0 ? capacity : 1) * sizeof(T), sizeof(T));
+    if (rc == 0) *table = static_cast<T*>(row_store_ptr(*st));
+    return rc;
+}
+template <typename T>
+inline int side_table_reserve(RowStore* st, T** table, int64_t used, int64_t capacity) {
+    int rc = row_store_reserve(st, (size_t)capacity * sizeof(T), (size_t)used * sizeof(T));
+    if (rc == 0) *table = static_cast<T*>(row_store_ptr(st));
+    return rc;
+}
+template <typename T>
+inline void side_table_destroy(RowStore** st, T** table) {
+    row_store_destroy(*st);
+    *st = nullptr;
+    *table = nullptr;
+}
 // IVF upkeep after rows were replaced in place (device list of corpus rows) and/or appended ([app_first,
 // app_first + app_n)): tombstones, overflow lists, automatic re-pack (k4_ivf.cu). No-op unless lists are built.
 int ivf_apply_mutation(ts_index* ix, const uint32_t* replaced_rows, int64_t n_replaced, int64_t app_first,

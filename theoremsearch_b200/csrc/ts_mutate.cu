@@ -24,31 +24,8 @@ __global__ void scatter_ids_kernel(const int64_t* __restrict__ ids, const int64_
         if (dst_rows[i] >= 0) table[dst_rows[i]] = ids[i];
 }
 
-template <typename T>
-static int regrow(T** buf, size_t used, size_t count) {
-    T* fresh = nullptr;
-    cudaError_t e = cudaMalloc(&fresh, std::max<size_t>(count, 1) * sizeof(T));
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        set_error("index_reserve: cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
-        return TS_ERR_OOM;
-    }
-    if (*buf != nullptr && used > 0) {
-        e = cudaMemcpy(fresh, *buf, used * sizeof(T), cudaMemcpyDeviceToDevice);
-        if (e != cudaSuccess) {
-            cudaFree(fresh);
-            set_error("index_reserve: device copy failed: %s", cudaGetErrorString(e));
-            return TS_ERR_CUDA;
-        }
-    }
-    cudaFree(*buf);
-    *buf = fresh;
-    return TS_OK;
-}
-
-// The row store grows IN PLACE: more physical memory is mapped behind the rows in the index's reserved address range
-// (vmm_store.cu) — no row is copied, no second allocation is needed. The small side tables (ids, list positions) are
-// re-allocated and copied.
+// The row store and the side tables (ids, list positions) grow IN PLACE: more physical memory is mapped behind the
+// data in each one's reserved address range (vmm_store.cu) — nothing is copied, no second allocation is needed.
 int index_reserve(ts_index* ix, int64_t capacity) {
     if (capacity <= ix->capacity) return TS_OK;
     TS_REQUIRE(capacity < (int64_t)0xFFFFFFFFll, TS_ERR_UNSUPPORTED, "index_reserve: capacity %lld exceeds 2^32-2 rows",
@@ -57,8 +34,8 @@ int index_reserve(ts_index* ix, int64_t capacity) {
     int rc = row_store_reserve(ix->store, (size_t)capacity * ix->row_bytes(), (size_t)ix->size * ix->row_bytes());
     if (rc) return rc;
     ix->data = row_store_ptr(ix->store);
-    if (ix->has_ids && (rc = regrow(&ix->ids, (size_t)ix->size, (size_t)capacity))) return rc;
-    if (ix->pos_of_row != nullptr && (rc = regrow(&ix->pos_of_row, (size_t)ix->size, (size_t)capacity))) return rc;
+    if (ix->has_ids && (rc = side_table_reserve(ix->ids_store, &ix->ids, ix->size, capacity))) return rc;
+    if (ix->pos_of_row != nullptr && (rc = side_table_reserve(ix->pos_store, &ix->pos_of_row, ix->size, capacity))) return rc;
     ix->capacity = capacity;
     return TS_OK;
 }
@@ -74,7 +51,8 @@ int index_make_room(ts_index* ix, int64_t extra) {
 
 static int ensure_id_table(ts_index* ix, cudaStream_t s) {
     if (ix->has_ids) return TS_OK;
-    TS_CHECK_CUDA(cudaMalloc(&ix->ids, (size_t)std::max<int64_t>(ix->capacity, 1) * sizeof(int64_t)));
+    int rc = side_table_create(&ix->ids_store, &ix->ids, ix->device, ix->capacity);
+    if (rc) return rc;
     if (ix->size > 0) {
         iota_ids2_kernel<<<256, 256, 0, s>>>(ix->ids, 0, ix->size);
         TS_LAUNCH_CHECK();
