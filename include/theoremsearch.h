@@ -344,6 +344,37 @@ TS_API int ts_ivf_get_lists(const ts_index* index, int64_t* offsets_out, int64_t
 TS_API int ts_ivf_get_list_data(const ts_index* index, int64_t first, int64_t n, float* out,
                                 void* stream);
 
+/* ---- evaluation metrics from the batched top-k, on the device (K6) -------------------- */
+/* Replaces compare_embeddings.py:55-92 `evaluate_retrieval`'s six metrics — precision_at_k :95, hit_at_k :120,
+ * mrr_at_k :143, ndcg_at_k :216, err_at_k :257, q_measure_at_k :315 — each of which argsorts the full [Q, N]
+ * similarity matrix on the host. Here they are computed from the [Q, k] ids a batched ts_search left in device
+ * memory; six doubles come back. */
+typedef struct ts_eval ts_eval;   /* the relevance judgements (the reference's `qrels`) resident on one GPU */
+
+/* qrels as CSR over HOST arrays: query q judges docs[offsets[q] .. offsets[q+1]) with relevances rels[...], in the
+ * order the reference's {doc: relevance} dict would iterate (the "correct" document of a query is the FIRST one of
+ * relevance exactly 1, compare_embeddings.py:111). A query may judge nothing. max_k (1..64): the largest k nDCG
+ * will be asked for when some query judges more than max_k documents. TS_ERR_BAD_ARG on a negative doc, a
+ * non-finite relevance or a doc judged twice by one query. */
+TS_API int ts_eval_create(ts_eval** out, int device, int nq, const int64_t* offsets, const int64_t* docs,
+                          const double* rels, int max_k);
+TS_API void ts_eval_destroy(ts_eval* ev);
+TS_API int ts_eval_num_queries(const ts_eval* ev);
+/* Largest relevance judged anywhere (0 if nothing is judged): the default `max_rel` of ERR / Q-measure. */
+TS_API double ts_eval_max_relevance(const ts_eval* ev);
+/* First query that has no document of relevance exactly 1 (precision / hit / MRR are undefined for it: the
+ * reference's `next(...)` raises StopIteration there), or -1. */
+TS_API int64_t ts_eval_first_query_without_correct_doc(const ts_eval* ev);
+
+/* ranked: DEVICE int64 [nq, stride], the first `width` entries of a row are doc ids best first, -1 = padding
+ * (skipped; ranks count valid entries). k6: HOST int[6], the cut of precision, hit, MRR, nDCG, ERR, Q-measure in
+ * that order (<= 0: no cut). gain_exp: nDCG gain 2^rel - 1 (1) or rel (0). max_rel: normaliser 2^max_rel of the
+ * ERR / Q-measure gains, < 0 = the table's largest relevance. out_means: DEVICE double[6], the metrics averaged
+ * over the nq queries, same order; out_per_query: DEVICE double[nq, 6] or NULL. Enqueues two kernels on `stream`;
+ * does not synchronise. */
+TS_API int ts_eval_rankings(ts_eval* ev, const int64_t* ranked, int64_t stride, int width, const int* k6,
+                            int gain_exp, double max_rel, double* out_means, double* out_per_query, void* stream);
+
 /* ---- tuning / diagnostics (not part of the drop-in surface) -------------------------- */
 
 /* Set an internal tunable by name (e.g. "scan.ctas_per_sm", "scan.stages"); returns

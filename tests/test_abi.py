@@ -65,6 +65,10 @@ def test_no_gpu_calls_fail_loudly_not_silently():
     h = ctypes.c_void_p()
     rc = ts._lib.lib.ts_index_create(ctypes.byref(h), 0, 1024, ts._lib.TS_BF16, 10)
     assert rc == -2 and "no CPU fallback" in ts._lib.last_error()
+    import numpy as np
+    offsets, docs, rels = np.array([0, 1], np.int64), np.array([3], np.int64), np.array([1.0])
+    rc = ts._lib.lib.ts_eval_create(ctypes.byref(h), 0, 1, offsets.ctypes.data, docs.ctypes.data, rels.ctypes.data, 8)
+    assert rc == -2 and "no CPU fallback" in ts._lib.last_error()      # K6 has no host path behind the ABI either
 
 
 def test_key_packing_matches_oracle():

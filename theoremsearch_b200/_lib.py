@@ -105,6 +105,12 @@ SIGNATURES = {
     "ts_ivf_search_host": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "ts_ivf_nlist": (_i, [_p]),
     "ts_ivf_list_sizes": (_i, [_p, _p, _p]),
+    "ts_eval_create": (_i, [C.POINTER(_p), _i, _i, _p, _p, _p, _i]),
+    "ts_eval_destroy": (None, [_p]),
+    "ts_eval_num_queries": (_i, [_p]),
+    "ts_eval_max_relevance": (C.c_double, [_p]),
+    "ts_eval_first_query_without_correct_doc": (_i64, [_p]),
+    "ts_eval_rankings": (_i, [_p, _p, _i64, _i, _p, _i, C.c_double, _p, _p, _p]),
     "ts_set_tunable": (_i, [C.c_char_p, _i]),
     "ts_get_tunable": (_i, [C.c_char_p, C.POINTER(_i)]),
     "ts_debug_last_batched_fixups": (_i, []),
