@@ -22,7 +22,8 @@ Metric: queries/sec (exact top-10) of the single-query scan over a 10M x 1024 bf
 * `parity_check`: an untimed block — planted rows come back first, the host-buffer path equals the device
               path, and at N > 1 the three exchange forms agree bit for bit on every rank.
 * `batched` / `ivf` (N = 1): BASELINE.json configs[2] (4096 queries x top-100 over the same corpus, K3) and
-              configs[4] (IVF-Flat fp8, nlist 16384, recall@10 vs exact and q/s per nprobe) with clocks.
+              configs[4] (IVF-Flat fp8, nlist 16384, recall@10 vs exact and q/s per nprobe) with clocks;
+              `batched.evaluation`: the six compare_embeddings metrics from that batch's ids on the GPU (K6).
 * `cpu_baseline` / `--impl reference`: the reference's CPU path (util.cos_sim + argsort,
   test_app.py:76-77) restated in oracle/oracle.py, on the host's cores. The reference arm runs it on the
   FULL 10M x 1024 fp32 corpus (41 GB; `--reference-sample-rows R` selects a row sample instead and says so
@@ -251,7 +252,28 @@ def batched_section(ts, index, args, dev, clocks, peaks):
         same &= bool(torch.equal(s1[0], s[j]) and torch.equal(i1[0], ids[j]))
     flops = 2.0 * nq * len(index) * args.dim
     tf = flops / (ms * 1e-3) / 1e12
+    # the consumer of the reference's batched path (compare_embeddings.py:69-92): six metrics from the ids where K3
+    # left them (K6). Query j's correct document is planted at rank j % 10 + 1, so Hit@5 / MRR@5 are known exactly.
+    from theoremsearch_b200 import metrics
+    host = ids[:, :10].cpu().numpy()
+    qrels = {j: {int(host[j, j % 10]): 1.0} for j in range(nq)}
+    table = metrics.JudgedTable(qrels, nq, dev, max_k=10)
+    cuts = {"precision": 1, "hit": 5, "mrr": 5, "ndcg": 5, "err": 5, "q_measure": 5}
+    got = table.evaluate(ids, cuts)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        table.evaluate(ids, cuts)
+    e1.record()
+    torch.cuda.synchronize()
+    eval_ms = e0.elapsed_time(e1) / 10
+    table.close()
+    ranks = np.arange(nq) % 10 + 1
+    want_hit, want_mrr = float(np.mean(ranks <= 5)), float(np.mean(np.where(ranks <= 5, 1.0 / ranks, 0.0)))
+    evaluation = {"ms_incl_d2h_of_6_doubles": eval_ms, "metrics": got,
+                  "planted_ranks_recovered": bool(abs(got["hit"] - want_hit) < 1e-12 and abs(got["mrr"] - want_mrr) < 1e-12)}
     return {"workload": f"configs[2]: {nq} queries x top-{k} over {len(index)}x{args.dim} bf16 (K3)",
+            "evaluation": evaluation,
             "ms": ms, "queries_per_s": nq / (ms * 1e-3), "tflops": tf,
             "frac_burst": tf / peaks["bf16_tflops"],
             "frac_sustained": tf / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
