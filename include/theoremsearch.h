@@ -131,6 +131,19 @@ TS_API int ts_index_upsert(ts_index* index, const void* rows, int src_dtype, int
 TS_API int ts_index_upsert_host(ts_index* index, const void* rows, int src_dtype, int64_t n, int normalize,
                                 const int64_t* ids_host, int64_t* n_replaced);
 
+/* DELETE by id. Replaces the cascade of `DELETE FROM theorem WHERE paper_id = ANY(%s)`
+ * (ec2/parse_arxiv_papers/__main__.py:271-274; theorem_slogan and theorem_embedding_qwen reference theorem
+ * ON DELETE CASCADE, rds_schema.sql:35,46,51) on the corpus table. ids: HOST int64[n]; ids that are not stored
+ * (or repeated) match nothing. The store stays dense: the LAST rows move into the freed slots, so ts_index_size
+ * drops by the number deleted and row positions (the bit positions of an allow mask, the order of exact score
+ * ties) change for the moved rows — moved_from / moved_to (HOST int64[n] each, or NULL) receive the
+ * n_moved_out <= n relocations (old row -> new row) for callers that keep row-aligned side tables. Built IVF
+ * lists stay valid (entries of deleted rows are tombstoned, entries of moved rows renamed; re-packed past 10 %
+ * churn; deleting the last row drops the lists, the centroids stay). Enqueues on `stream` and synchronises it
+ * before returning. */
+TS_API int ts_index_delete(ts_index* index, const int64_t* ids, int64_t n, int64_t* n_deleted_out,
+                           int64_t* moved_from, int64_t* moved_to, int64_t* n_moved_out, void* stream);
+
 TS_API int64_t ts_index_size(const ts_index* index);     /* rows added so far */
 TS_API int64_t ts_index_capacity(const ts_index* index);
 TS_API int ts_index_dim(const ts_index* index);

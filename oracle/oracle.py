@@ -222,6 +222,17 @@ def upsert_rows(table: dict, ids: Sequence[int], rows: np.ndarray) -> int:
     return len(hit)
 
 
+def delete_rows(table: dict, ids: Sequence[int]) -> int:
+    """``DELETE FROM theorem WHERE paper_id = ANY(%s)`` (ec2/parse_arxiv_papers/__main__.py:271-274) reaches the
+    embedding table through ``ON DELETE CASCADE`` (rds_schema.sql:35,46,51): the rows of the named ids vanish, ids
+    that are not stored match nothing.  ``table``: {id: row}.  Returns how many rows were deleted."""
+    gone = 0
+    for i in ids:
+        if table.pop(int(i), None) is not None:
+            gone += 1
+    return gone
+
+
 # --------------------------------------------------------------------------------------
 # reference call shapes
 # --------------------------------------------------------------------------------------

@@ -204,3 +204,133 @@ def test_fp8_scan_copy_follows_added_rows(ts):
     s_e, i_e = index.search(q, 10)
     assert float(s[0]) == float(s_e[0, 0])                       # re-scored exactly
     assert len(set(i.tolist()) & set(i_e[0].tolist())) >= 9      # e4m3 candidate selection: recall, not identity
+
+
+# ------------------------------------------------------------------------------------------------ delete by id
+def _same_search(ts, index, table, dim, k=10, nq=7):
+    """Exact search over `index` == the oracle over the table's rows (as stored: normalised, bf16), ids and scores."""
+    ids_all = np.fromiter(table.keys(), dtype=np.int64, count=len(table))
+    rows_all = np.stack(list(table.values()))
+    stored = oracle.bf16_round(oracle.normalize_f64(rows_all))
+    q = oracle.synthetic_queries(nq, dim)
+    o_s, o_i = oracle.exact_search(oracle.normalize_f64(q), stored, k, ids=ids_all)
+    for qq, lo in ((torch.from_numpy(q), 0), (torch.from_numpy(q[2:3]), 2)):     # K3 and K2
+        s, i = index.search(qq, k)
+        assert np.array_equal(i.cpu().numpy(), o_i[lo:lo + qq.shape[0]])
+        assert np.max(np.abs(s.cpu().numpy() - o_s[lo:lo + qq.shape[0]])) < 1e-5
+
+
+@pytest.mark.parametrize("with_ids", [True, False])
+def test_delete_by_id_equals_the_oracle_table(ts, with_ids):
+    """ec2/parse_arxiv_papers/__main__.py:271-274 + ON DELETE CASCADE (rds_schema.sql:35,46,51): rows vanish by id;
+    unknown and repeated ids match nothing; the store stays dense; deletes, upserts and adds interleave."""
+    dim, n0 = 192, 3000
+    rng = np.random.default_rng(17)
+    x0 = rng.standard_normal((n0, dim)).astype(np.float32)
+    ids0 = (np.arange(n0, dtype=np.int64) * 7 + 11) if with_ids else np.arange(n0, dtype=np.int64)
+    table = {}
+    oracle.upsert_rows(table, ids0, x0)
+    index = ts.build_index(x0, ids=ids0 if with_ids else None)
+    # scattered rows, a run at the very end (no row has to move for those), an unknown id and a repeated one
+    victims = np.concatenate([rng.choice(ids0[:-50], size=400, replace=False), ids0[-20:], [10**12], ids0[-1:]])
+    want = oracle.delete_rows(table, victims)
+    got, moves = index.delete(victims, return_moves=True)
+    assert got == want == 420 and len(index) == n0 - 420 == len(table)
+    assert moves.shape[1] == 2 and len(moves) <= 400
+    assert (moves[:, 0] >= len(index)).all() and (moves[:, 1] < len(index)).all()      # tail rows filled the holes
+    assert len(set(moves[:, 1].tolist())) == len(moves)
+    _same_search(ts, index, table, dim)
+    gone = set(int(v) for v in victims)
+    _, ids_now = index.search(torch.from_numpy(oracle.synthetic_queries(1, dim)), 1000)
+    assert not (set(ids_now[0].tolist()) & gone) and len(set(ids_now[0].tolist())) == 1000
+    assert index.delete(victims) == 0                                                  # already gone: matches nothing
+    # interleave: upsert (replace + append, one of them a deleted id coming back), delete again, add
+    back = int(victims[0])
+    up_ids = np.array([int(ids0[5]) if int(ids0[5]) in table else int(next(iter(table))), back, 10**9 + 1], dtype=np.int64)
+    up_rows = rng.standard_normal((3, dim)).astype(np.float32)
+    assert index.upsert(up_rows, up_ids) == oracle.upsert_rows(table, up_ids, up_rows)
+    assert index.delete([10**9 + 1, int(next(iter(table)))]) == oracle.delete_rows(table, [10**9 + 1, int(next(iter(table)))])
+    _same_search(ts, index, table, dim)
+    # everything goes, then the index fills again
+    assert index.delete(list(table.keys())) == len(table)
+    table.clear()
+    assert len(index) == 0
+    new_ids = np.arange(5000, 5300, dtype=np.int64)
+    new_rows = rng.standard_normal((300, dim)).astype(np.float32)
+    index.upsert(new_rows, new_ids)
+    oracle.upsert_rows(table, new_ids, new_rows)
+    _same_search(ts, index, table, dim)
+
+
+@pytest.mark.parametrize("list_dtype", ["bf16", "fp8"])
+def test_ivf_lists_stay_valid_across_deletes(ts, list_dtype):
+    """Deleted rows' list entries are tombstoned, moved rows' entries renamed, overflow rows filtered: the IVF search
+    over the mutated lists equals the one over freshly packed lists of the surviving table (same centroids)."""
+    dim, n0, nlist = 256, 30_000, 48
+    rng = np.random.default_rng(23)
+    x0 = oracle.synthetic_rows(0, n0, dim, seed=51)
+    ids0 = np.arange(n0, dtype=np.int64) * 2 + 1
+    table = {}
+    oracle.upsert_rows(table, ids0, x0)
+    index = ts.build_index(x0, ids=ids0)
+    index.ivf_train(nlist, n_sample=15_000, iters=4, seed=0)
+    index.ivf_build(list_dtype)
+    # some rows into the overflow first (replacements and appends), then deletes that hit main lists AND overflow
+    up_ids = np.concatenate([rng.choice(ids0, size=300, replace=False), np.arange(10**6, 10**6 + 200)]).astype(np.int64)
+    up_rows = rng.standard_normal((500, dim)).astype(np.float32)
+    oracle.upsert_rows(table, up_ids, up_rows)
+    index.upsert(torch.from_numpy(up_rows).cuda(), up_ids)
+    ovf0, dead0 = index.ivf_pending()
+    assert ovf0 == 500 and dead0 == 300
+    victims = np.concatenate([rng.choice(ids0, size=600, replace=False), up_ids[:50], up_ids[-60:]])
+    assert index.delete(victims) == oracle.delete_rows(table, victims)
+    ovf1, dead1 = index.ivf_pending()
+    assert ovf1 < ovf0 and dead1 > dead0 and len(index) == len(table)
+    with pytest.raises(ts.TheoremSearchError):
+        index.ivf_lists()                                       # not exportable until the re-pack
+    fresh, ids_all, rows_all = _rebuild(ts, table, dim)
+    fresh.ivf_set_centroids(index.ivf_centroids())
+    fresh.ivf_build(list_dtype)
+    q = torch.from_numpy(oracle.synthetic_queries(33, dim))
+    s_e, i_e = index.search(q, 10)
+    s_x, i_x = fresh.search(q, 10)
+    assert torch.equal(s_e, s_x) and torch.equal(i_e, i_x)      # same table, different row order: no exact ties here
+    if list_dtype == "bf16":
+        for qq, se, ie in ((q, s_e, i_e), (q[:1], s_e[:1], i_e[:1])):
+            s_a, i_a = index.ivf_search(qq, 10, nprobe=nlist, rescore_k=10)
+            assert torch.equal(se, s_a) and torch.equal(ie, i_a)
+    for qq in (q, q[:1]):
+        s_m, i_m = index.ivf_search(qq, 10, nprobe=8, rescore_k=100)
+        s_f, i_f = fresh.ivf_search(qq, 10, nprobe=8, rescore_k=100)
+        assert torch.equal(s_m, s_f) and torch.equal(i_m, i_f)
+    # a row that moved is still found under its own content
+    _, moves = index.delete([int(ids_all[3])], return_moves=True)
+    oracle.delete_rows(table, [int(ids_all[3])])
+    if len(moves):
+        moved_row = index.get_rows(int(moves[0, 1]), 1)
+        s1, i1 = index.ivf_search(moved_row, 1, nprobe=8, rescore_k=20, normalize=False)
+        s2, i2 = index.search(moved_row, 1, normalize=False)
+        assert torch.equal(i1, i2) and torch.equal(s1, s2)
+    index.ivf_repack()
+    assert index.ivf_pending() == (0, 0)
+    off, rows = index.ivf_lists()
+    assert sorted(rows.cpu().tolist()) == list(range(len(index)))
+    # heavy deletion goes through the automatic re-pack
+    many = list(table.keys())[: len(table) // 5]
+    assert index.delete(many) == oracle.delete_rows(table, many)
+    assert index.ivf_pending() == (0, 0) and len(index) == len(table)
+    fresh2, _, _ = _rebuild(ts, table, dim)
+    s_a, i_a = index.ivf_search(q, 10, nprobe=nlist, rescore_k=100)
+    s_b, i_b = fresh2.search(q, 10)
+    assert oracle.recall_at_k(i_a.cpu().numpy(), i_b.cpu().numpy()) >= (1.0 if list_dtype == "bf16" else 0.97)
+
+
+def test_fp8_scan_copy_follows_deletes(ts):
+    x = oracle.synthetic_rows(0, 20_000, 256, seed=61)
+    index = ts.build_index(x, dtype="fp8")
+    index.delete(np.arange(100, 600))
+    assert index.fp8_scan_ready and len(index) == 19_500
+    s, i = ts.cos_sim_topk(torch.from_numpy(x[19_999]), index, 5)       # the last row moved into a hole: still id 19999
+    assert int(i[0]) == 19_999
+    s2, i2 = ts.cos_sim_topk(torch.from_numpy(x[300]), index, 5)        # a deleted row is not found any more
+    assert 300 not in i2.tolist()

@@ -57,6 +57,7 @@ SIGNATURES = {
     "ts_index_grows_in_place": (_i, [_p]),
     "ts_index_upsert": (_i, [_p, _p, _i, _i64, _i, _p, _p, _p]),
     "ts_index_upsert_host": (_i, [_p, _p, _i, _i64, _i, _p, _p]),
+    "ts_index_delete": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p]),
     "ts_ivf_pending": (_i, [_p, _p, _p]),
     "ts_ivf_repack": (_i, [_p, _p]),
     "ts_index_size": (_i64, [_p]),

@@ -1071,7 +1071,7 @@ static void ivf_free_lists(ts_index* ix) {
     side_table_destroy(&ix->pos_store, &ix->pos_of_row);
     cudaFree(ix->ovf_set);
     ix->ovf_set = nullptr;
-    ix->list_cap = ix->built_n = ix->ovf_n = ix->ivf_dead = ix->ovf_cap = 0;
+    ix->list_cap = ix->built_n = ix->ovf_n = ix->ivf_dead = ix->ovf_cap = ix->ivf_moved = 0;
     ix->ivf_built = false;
 }
 static void ivf_free_centroids(ts_index* ix) {
@@ -1217,6 +1217,71 @@ static int grow_buffer(T** buf, size_t old_count, size_t new_count) {
     return TS_OK;
 }
 
+// ovf_set[0, m) holds the corpus rows that live in the overflow lists (any order): sort them, file them under the
+// existing centroids, quantise them behind the main lists and publish the overflow offsets.
+static int ivf_rebuild_overflow(ts_index* ix, int64_t m, TempBufs& tmp, cudaStream_t s) {
+    int rc;
+    if (m == 0) {
+        if (ix->ovf_n > 0) {     // the overflow emptied (deletes): every overflow list is [built_n, built_n)
+            int64_t* zeros = nullptr;
+            if ((rc = tmp.get(&zeros, (size_t)ix->nlist + 1))) return rc;
+            TS_CHECK_CUDA(cudaMemsetAsync(zeros, 0, ((size_t)ix->nlist + 1) * sizeof(int64_t), s));
+            overflow_offsets_kernel<<<(ix->nlist + 1 + 255) / 256, 256, 0, s>>>(zeros, ix->nlist, ix->built_n, ix->list_offsets);
+            TS_LAUNCH_CHECK();
+            TS_CHECK_CUDA(cudaStreamSynchronize(s));
+            ix->ovf_n = 0;
+        }
+        return TS_OK;
+    }
+    TS_REQUIRE(m < (int64_t)1 << 31, TS_ERR_UNSUPPORTED, "ivf: more than 2^31-1 overflow rows");
+    // 2. the overflow set in ascending row order (so rows ascend inside every overflow list, like the main lists)
+    uint32_t* sorted_set = nullptr;
+    if ((rc = tmp.get(&sorted_set, (size_t)m))) return rc;
+    {
+        size_t tbytes = 0;
+        TS_CHECK_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tbytes, ix->ovf_set, sorted_set, (int)m, 0, 32, s));
+        uint8_t* t = nullptr;
+        if ((rc = tmp.get(&t, tbytes))) return rc;
+        TS_CHECK_CUDA(cub::DeviceRadixSort::SortKeys(t, tbytes, ix->ovf_set, sorted_set, (int)m, 0, 32, s));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        TS_CHECK_CUDA(cudaMemcpyAsync(ix->ovf_set, sorted_set, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    }
+    // 3. file them under the existing centroids: gather -> K4a -> (list, row) order
+    uint8_t* rows = nullptr;
+    uint32_t *assign = nullptr, *sorted_assign = nullptr, *iota = nullptr, *members = nullptr;
+    int64_t* offsets = nullptr;
+    if ((rc = tmp.get(&rows, (size_t)m * ix->row_bytes())) || (rc = tmp.get(&assign, (size_t)m)) ||
+        (rc = tmp.get(&sorted_assign, (size_t)m)) || (rc = tmp.get(&iota, (size_t)m)) || (rc = tmp.get(&members, (size_t)m)) ||
+        (rc = tmp.get(&offsets, (size_t)ix->nlist + 1)))
+        return rc;
+    const int gblocks = (int)std::min<int64_t>((m + 7) / 8, 148 * 16);
+    gather_rows_kernel<<<gblocks, 256, 0, s>>>((const uint8_t*)ix->data, (uint32_t)ix->row_bytes(), ix->ovf_set, m, rows);
+    TS_LAUNCH_CHECK();
+    rc = launch_assign(ix->device, rows, m, ix->row_bytes(), ix->centroids_bf16, ix->nlist, ix->dim_pad, assign, nullptr, s);
+    if (rc) return rc;
+    rc = sort_by_list(assign, m, ix->nlist, sorted_assign, iota, members, offsets, tmp, s);
+    if (rc) return rc;
+    overflow_rows_kernel<<<(int)std::min<int64_t>((m + 255) / 256, 1024), 256, 0, s>>>(ix->ovf_set, members, m, ix->built_n,
+                                                                                      ix->list_rows, ix->pos_of_row);
+    TS_LAUNCH_CHECK();
+    if (ix->list_dtype == TS_BF16)
+        gather_quantize_kernel<2><<<gblocks, 256, 0, s>>>((const uint8_t*)ix->data, (uint32_t)ix->row_bytes(),
+                                                          ix->list_rows + ix->built_n, m, ix->dim_pad, ix->list_row_bytes,
+                                                          (uint8_t*)ix->list_data + (size_t)ix->built_n * ix->list_row_bytes,
+                                                          nullptr);
+    else
+        gather_quantize_kernel<1><<<gblocks, 256, 0, s>>>((const uint8_t*)ix->data, (uint32_t)ix->row_bytes(),
+                                                          ix->list_rows + ix->built_n, m, ix->dim_pad, ix->list_row_bytes,
+                                                          (uint8_t*)ix->list_data + (size_t)ix->built_n * ix->list_row_bytes,
+                                                          ix->list_scales + ix->built_n);
+    TS_LAUNCH_CHECK();
+    overflow_offsets_kernel<<<(ix->nlist + 1 + 255) / 256, 256, 0, s>>>(offsets, ix->nlist, ix->built_n, ix->list_offsets);
+    TS_LAUNCH_CHECK();
+    TS_CHECK_CUDA(cudaStreamSynchronize(s));   // temporaries are freed on return
+    ix->ovf_n = m;
+    return TS_OK;
+}
+
 void ivf_free_all(ts_index* ix) {
     ivf_free_lists(ix);
     ivf_free_centroids(ix);
@@ -1268,54 +1333,65 @@ int ivf_apply_mutation(ts_index* ix, const uint32_t* replaced_rows, int64_t n_re
         TS_LAUNCH_CHECK();
         m += app_n;
     }
-    if (m == 0) return TS_OK;
-    TS_REQUIRE(m < (int64_t)1 << 31, TS_ERR_UNSUPPORTED, "ivf: more than 2^31-1 overflow rows");
-    // 2. the overflow set in ascending row order (so rows ascend inside every overflow list, like the main lists)
-    uint32_t* sorted_set = nullptr;
-    if ((rc = tmp.get(&sorted_set, (size_t)m))) return rc;
-    {
-        size_t tbytes = 0;
-        TS_CHECK_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tbytes, ix->ovf_set, sorted_set, (int)m, 0, 32, s));
-        uint8_t* t = nullptr;
-        if ((rc = tmp.get(&t, tbytes))) return rc;
-        TS_CHECK_CUDA(cub::DeviceRadixSort::SortKeys(t, tbytes, ix->ovf_set, sorted_set, (int)m, 0, 32, s));
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        TS_CHECK_CUDA(cudaMemcpyAsync(ix->ovf_set, sorted_set, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    return ivf_rebuild_overflow(ix, m, tmp, s);
+}
+
+// ---- delete by id (ts_index_delete) -------------------------------------------------------------------------
+// The row store is compacted: deleted rows vanish and the last rows move into the freed slots. remap[old row] is the
+// row's new position (itself for most rows) or TS_DEAD_ROW for a deleted row.
+__global__ void remap_main_lists_kernel(uint32_t* __restrict__ list_rows, int64_t built_n, const uint32_t* __restrict__ remap,
+                                        uint32_t* __restrict__ pos_of_row, unsigned int* __restrict__ died) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < built_n; p += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t row = list_rows[p];
+        if (row == TS_DEAD_ROW) continue;
+        const uint32_t now = remap[row];
+        if (now == row) continue;
+        list_rows[p] = now;                       // a deleted row's entry becomes a tombstone
+        if (now == TS_DEAD_ROW) atomicAdd(died, 1u);
+        else pos_of_row[now] = (uint32_t)p;
     }
-    // 3. file them under the existing centroids: gather -> K4a -> (list, row) order
-    uint8_t* rows = nullptr;
-    uint32_t *assign = nullptr, *sorted_assign = nullptr, *iota = nullptr, *members = nullptr;
-    int64_t* offsets = nullptr;
-    if ((rc = tmp.get(&rows, (size_t)m * ix->row_bytes())) || (rc = tmp.get(&assign, (size_t)m)) ||
-        (rc = tmp.get(&sorted_assign, (size_t)m)) || (rc = tmp.get(&iota, (size_t)m)) || (rc = tmp.get(&members, (size_t)m)) ||
-        (rc = tmp.get(&offsets, (size_t)ix->nlist + 1)))
-        return rc;
-    const int gblocks = (int)std::min<int64_t>((m + 7) / 8, 148 * 16);
-    gather_rows_kernel<<<gblocks, 256, 0, s>>>((const uint8_t*)ix->data, (uint32_t)ix->row_bytes(), ix->ovf_set, m, rows);
+}
+__global__ void remap_overflow_set_kernel(const uint32_t* __restrict__ in, int64_t m, const uint32_t* __restrict__ remap,
+                                          uint32_t* __restrict__ out, unsigned int* __restrict__ kept) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t now = remap[in[i]];
+        if (now != TS_DEAD_ROW) out[atomicAdd(kept, 1u)] = now;
+    }
+}
+
+// ix->size and the rows are already the compacted ones. Main-list entries of deleted rows are tombstoned and those
+// of moved rows renamed in place; the overflow set is filtered / renamed and its lists rebuilt (O(overflow)).
+int ivf_apply_delete(ts_index* ix, const uint32_t* remap, int64_t n_deleted, cudaStream_t s) {
+    if (!ix->ivf_built || n_deleted == 0) return TS_OK;
+    if (ix->size == 0) {          // nothing left to list: the centroids stay, the lists go (ts_ivf_build after the next add)
+        TS_CHECK_CUDA(cudaStreamSynchronize(s));
+        ivf_free_lists(ix);
+        return TS_OK;
+    }
+    const int64_t churn = ix->ivf_dead + ix->ovf_n + n_deleted;
+    if (churn > std::max<int64_t>(4096, ix->size / 10)) return ts_ivf_build(ix, ix->list_dtype, s);
+    TempBufs tmp;
+    int rc;
+    unsigned int* counters = nullptr;     // [0] main-list entries that died, [1] overflow rows kept
+    uint32_t* kept_set = nullptr;
+    if ((rc = tmp.get(&counters, 2)) || (rc = tmp.get(&kept_set, (size_t)ix->ovf_n))) return rc;
+    TS_CHECK_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), s));
+    remap_main_lists_kernel<<<(int)std::min<int64_t>((ix->built_n + 255) / 256, 148 * 8), 256, 0, s>>>(
+        ix->list_rows, ix->built_n, remap, ix->pos_of_row, counters);
     TS_LAUNCH_CHECK();
-    rc = launch_assign(ix->device, rows, m, ix->row_bytes(), ix->centroids_bf16, ix->nlist, ix->dim_pad, assign, nullptr, s);
-    if (rc) return rc;
-    rc = sort_by_list(assign, m, ix->nlist, sorted_assign, iota, members, offsets, tmp, s);
-    if (rc) return rc;
-    overflow_rows_kernel<<<(int)std::min<int64_t>((m + 255) / 256, 1024), 256, 0, s>>>(ix->ovf_set, members, m, ix->built_n,
-                                                                                      ix->list_rows, ix->pos_of_row);
-    TS_LAUNCH_CHECK();
-    if (ix->list_dtype == TS_BF16)
-        gather_quantize_kernel<2><<<gblocks, 256, 0, s>>>((const uint8_t*)ix->data, (uint32_t)ix->row_bytes(),
-                                                          ix->list_rows + ix->built_n, m, ix->dim_pad, ix->list_row_bytes,
-                                                          (uint8_t*)ix->list_data + (size_t)ix->built_n * ix->list_row_bytes,
-                                                          nullptr);
-    else
-        gather_quantize_kernel<1><<<gblocks, 256, 0, s>>>((const uint8_t*)ix->data, (uint32_t)ix->row_bytes(),
-                                                          ix->list_rows + ix->built_n, m, ix->dim_pad, ix->list_row_bytes,
-                                                          (uint8_t*)ix->list_data + (size_t)ix->built_n * ix->list_row_bytes,
-                                                          ix->list_scales + ix->built_n);
-    TS_LAUNCH_CHECK();
-    overflow_offsets_kernel<<<(ix->nlist + 1 + 255) / 256, 256, 0, s>>>(offsets, ix->nlist, ix->built_n, ix->list_offsets);
-    TS_LAUNCH_CHECK();
-    TS_CHECK_CUDA(cudaStreamSynchronize(s));   // temporaries are freed on return
-    ix->ovf_n = m;
-    return TS_OK;
+    if (ix->ovf_n > 0) {
+        remap_overflow_set_kernel<<<(int)std::min<int64_t>((ix->ovf_n + 255) / 256, 1024), 256, 0, s>>>(
+            ix->ovf_set, ix->ovf_n, remap, kept_set, counters + 1);
+        TS_LAUNCH_CHECK();
+    }
+    unsigned int h[2] = {0, 0};
+    TS_CHECK_CUDA(cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, s));
+    TS_CHECK_CUDA(cudaStreamSynchronize(s));
+    ix->ivf_dead += h[0];
+    ix->ivf_moved += n_deleted;
+    if (ix->ovf_n == 0) return TS_OK;
+    TS_CHECK_CUDA(cudaMemcpyAsync(ix->ovf_set, kept_set, (size_t)h[1] * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    return ivf_rebuild_overflow(ix, (int64_t)h[1], tmp, s);
 }
 
 }  // namespace ts
@@ -1502,9 +1578,9 @@ int ts_ivf_list_sizes(const ts_index* ix, int64_t* out, void* stream) {
 int ts_ivf_get_lists(const ts_index* ix, int64_t* offsets_out, int64_t* rows_out, void* stream) {
     TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "ivf_get_lists: index is NULL");
     TS_REQUIRE(ix->ivf_built, TS_ERR_STATE, "ivf_get_lists: lists are not built (call ts_ivf_build)");
-    TS_REQUIRE(ix->ovf_n == 0 && ix->ivf_dead == 0, TS_ERR_STATE,
-               "ivf_get_lists: rows were added or replaced since the build (%lld in overflow lists, %lld tombstones); "
-               "call ts_ivf_repack first", (long long)ix->ovf_n, (long long)ix->ivf_dead);
+    TS_REQUIRE(ix->ovf_n == 0 && ix->ivf_dead == 0 && ix->ivf_moved == 0, TS_ERR_STATE,
+               "ivf_get_lists: rows were added, replaced or deleted since the build (%lld in overflow lists, %lld "
+               "tombstones); call ts_ivf_repack first", (long long)ix->ovf_n, (long long)ix->ivf_dead);
     DeviceGuard g(ix->device);
     TS_REQUIRE(g.ok, TS_ERR_CUDA, "ivf_get_lists: cannot select CUDA device %d", ix->device);
     cudaStream_t s = (cudaStream_t)stream;

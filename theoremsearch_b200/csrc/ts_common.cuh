@@ -371,6 +371,7 @@ struct ts_index {
     int64_t list_cap = 0;            // rows the list arrays (list_rows / list_data / list_scales) can hold
     int64_t built_n = 0;
     int64_t ovf_n = 0;
+    int64_t ivf_moved = 0;           // deletes since the build: list entries were renamed in place (rows no longer ascend)
     int64_t ivf_dead = 0;            // tombstoned positions among the main lists
     uint32_t* pos_of_row = nullptr;  // [capacity] list position of every corpus row
     uint32_t* ovf_set = nullptr;     // [ovf_cap] corpus rows filed in the overflow lists, ascending
@@ -483,6 +484,8 @@ inline void side_table_destroy(RowStore** st, T** table) {
 // app_first + app_n)): tombstones, overflow lists, automatic re-pack (k4_ivf.cu). No-op unless lists are built.
 int ivf_apply_mutation(ts_index* ix, const uint32_t* replaced_rows, int64_t n_replaced, int64_t app_first,
                        int64_t app_n, cudaStream_t s);
+// after ts_index_delete compacted the rows: remap[old row] = new row or TS_DEAD_ROW (device, one entry per old row)
+int ivf_apply_delete(ts_index* ix, const uint32_t* remap, int64_t n_deleted, cudaStream_t s);
 void ivf_free_all(ts_index* ix);
 // grow the row capacity (data, ids, pos_of_row); synchronises the device
 int index_reserve(ts_index* ix, int64_t capacity);

@@ -24,6 +24,28 @@ __global__ void scatter_ids_kernel(const int64_t* __restrict__ ids, const int64_
         if (dst_rows[i] >= 0) table[dst_rows[i]] = ids[i];
 }
 
+// delete by id: the last rows move into the freed slots (one warp per row, 16-byte chunks), their ids with them
+__global__ void relocate_rows_kernel(uint8_t* __restrict__ data, uint32_t row_bytes, const int64_t* __restrict__ from,
+                                     const int64_t* __restrict__ to, int64_t n, int64_t* __restrict__ ids) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += (int64_t)gridDim.x * 8) {
+        const uint8_t* src = data + (size_t)from[i] * row_bytes;
+        uint8_t* dst = data + (size_t)to[i] * row_bytes;
+        for (uint32_t off = lane * 16u; off < row_bytes; off += 512u)
+            *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(src + off);
+        if (lane == 0) ids[to[i]] = ids[from[i]];
+    }
+}
+__global__ void identity_remap_kernel(uint32_t* remap, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        remap[i] = (uint32_t)i;
+}
+__global__ void scatter_remap_kernel(uint32_t* __restrict__ remap, const int64_t* __restrict__ rows,
+                                     const int64_t* __restrict__ now, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        remap[rows[i]] = now ? (uint32_t)now[i] : TS_DEAD_ROW;
+}
+
 // The row store and the side tables (ids, list positions) grow IN PLACE: more physical memory is mapped behind the
 // data in each one's reserved address range (vmm_store.cu) — nothing is copied, no second allocation is needed.
 int index_reserve(ts_index* ix, int64_t capacity) {
@@ -190,6 +212,115 @@ int ts_index_upsert(ts_index* ix, const void* rows, int src_dtype, int64_t n, in
         return rc;
     }
     if (n_replaced_out) *n_replaced_out = (int64_t)replaced.size();
+    return TS_OK;
+}
+
+// DELETE: the reference re-parses a paper with `DELETE FROM theorem WHERE paper_id = ANY(%s)`
+// (ec2/parse_arxiv_papers/__main__.py:271-274); theorem_slogan and theorem_embedding_qwen reference it
+// ON DELETE CASCADE (rds_schema.sql:35,46,51), so the embedding rows of those slogans vanish from the corpus table.
+int ts_index_delete(ts_index* ix, const int64_t* ids_host, int64_t n, int64_t* n_deleted_out, int64_t* moved_from,
+                    int64_t* moved_to, int64_t* n_moved_out, void* stream) {
+    TS_REQUIRE(ix != nullptr, TS_ERR_BAD_ARG, "index_delete: index is NULL");
+    TS_REQUIRE(n >= 0 && (n == 0 || ids_host != nullptr), TS_ERR_BAD_ARG, "index_delete: n=%lld / ids", (long long)n);
+    if (n_deleted_out) *n_deleted_out = 0;
+    if (n_moved_out) *n_moved_out = 0;
+    if (n == 0 || ix->size == 0) return TS_OK;
+    DeviceGuard g(ix->device);
+    TS_REQUIRE(g.ok, TS_ERR_CUDA, "index_delete: cannot select CUDA device %d", ix->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = ensure_host_id_map(ix);
+    if (rc) return rc;
+    auto& map = *ix->id_map_host;
+    std::vector<int64_t> dead;                       // stored rows to delete; an id that is not stored matches nothing
+    for (int64_t i = 0; i < n; ++i) {
+        auto it = map.find(ids_host[i]);
+        if (it == map.end()) continue;               // unknown id, or a repeat of one already taken
+        dead.push_back(it->second);
+        map.erase(it);
+    }
+    if (dead.empty()) return TS_OK;
+    auto rollback = [&]() { ix->id_map_valid = false; };   // the map was edited optimistically
+    std::sort(dead.begin(), dead.end());
+    const int64_t d = (int64_t)dead.size(), old_size = ix->size, new_size = old_size - d;
+    // rows >= new_size that survive move into the deleted slots < new_size (same count on both sides)
+    std::vector<int64_t> from, to;
+    {
+        size_t tail = std::lower_bound(dead.begin(), dead.end(), new_size) - dead.begin();   // dead[tail..) lie in the tail
+        size_t hole = 0;
+        for (int64_t r = new_size; r < old_size; ++r) {
+            if (tail < dead.size() && dead[tail] == r) {
+                ++tail;
+                continue;
+            }
+            from.push_back(r);
+            to.push_back(dead[hole++]);
+        }
+    }
+    const int64_t m = (int64_t)from.size();
+    if ((rc = ensure_id_table(ix, s))) {             // positions stop being ids once rows move
+        rollback();
+        return rc;
+    }
+    std::vector<int64_t> tail_ids((size_t)(old_size - new_size));
+    cudaError_t e = cudaMemcpyAsync(tail_ids.data(), ix->ids + new_size, tail_ids.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    int64_t *d_from = nullptr, *d_to = nullptr, *d_dead = nullptr;
+    uint32_t* d_remap = nullptr;
+    if (e == cudaSuccess && m > 0) {
+        e = cudaMalloc(&d_from, (size_t)m * sizeof(int64_t));
+        if (e == cudaSuccess) e = cudaMalloc(&d_to, (size_t)m * sizeof(int64_t));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_from, from.data(), (size_t)m * sizeof(int64_t), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_to, to.data(), (size_t)m * sizeof(int64_t), cudaMemcpyHostToDevice, s);
+    }
+    if (e == cudaSuccess && ix->ivf_built) {
+        // the lists name rows by position: old position -> new position / deleted, consumed by ivf_apply_delete
+        e = cudaMalloc(&d_remap, (size_t)old_size * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&d_dead, (size_t)d * sizeof(int64_t));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_dead, dead.data(), (size_t)d * sizeof(int64_t), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) {
+            identity_remap_kernel<<<1024, 256, 0, s>>>(d_remap, old_size);
+            scatter_remap_kernel<<<(int)std::min<int64_t>((d + 255) / 256, 1024), 256, 0, s>>>(d_remap, d_dead, nullptr, d);
+            if (m > 0) scatter_remap_kernel<<<(int)std::min<int64_t>((m + 255) / 256, 1024), 256, 0, s>>>(d_remap, d_from, d_to, m);
+            g_launches.fetch_add(m > 0 ? 3 : 2, std::memory_order_relaxed);
+            e = cudaGetLastError();
+        }
+    }
+    rc = TS_OK;
+    if (e != cudaSuccess) {
+        set_error("index_delete: staging failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        rc = e == cudaErrorMemoryAllocation ? TS_ERR_OOM : TS_ERR_CUDA;
+    }
+    if (rc == TS_OK && m > 0) {
+        relocate_rows_kernel<<<(int)std::min<int64_t>((m + 7) / 8, 148 * 16), 256, 0, s>>>(
+            (uint8_t*)ix->data, (uint32_t)ix->row_bytes(), d_from, d_to, m, ix->ids);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (cudaGetLastError() != cudaSuccess) rc = TS_ERR_CUDA;
+    }
+    if (rc == TS_OK) {
+        ix->size = new_size;
+        for (int64_t i = 0; i < m; ++i) map[tail_ids[(size_t)(from[(size_t)i] - new_size)]] = to[(size_t)i];
+        rc = ivf_apply_delete(ix, d_remap, d, s);
+    }
+    if (cudaStreamSynchronize(s) != cudaSuccess && rc == TS_OK) {
+        set_error("index_delete: kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = TS_ERR_CUDA;
+    }
+    cudaFree(d_from);
+    cudaFree(d_to);
+    cudaFree(d_dead);
+    cudaFree(d_remap);
+    if (rc != TS_OK) {
+        rollback();
+        return rc;
+    }
+    if (n_deleted_out) *n_deleted_out = d;
+    if (n_moved_out) *n_moved_out = m;
+    if (moved_from && moved_to)
+        for (int64_t i = 0; i < m; ++i) {
+            moved_from[i] = from[(size_t)i];
+            moved_to[i] = to[(size_t)i];
+        }
     return TS_OK;
 }
 

@@ -185,6 +185,25 @@ class TheoremIndex:
         check(lib.ts_index_upsert_host(self._h, ptr, code, n, int(normalize), id_arr.ctypes.data, C.byref(replaced)))
         return int(replaced.value)
 
+    def delete(self, ids, return_moves: bool = False):
+        """``DELETE`` by id — what the cascade of the reference's re-parse does to the corpus table
+        (``DELETE FROM theorem WHERE paper_id = ANY(%s)``, ec2/parse_arxiv_papers/__main__.py:271-274;
+        ``ON DELETE CASCADE`` down to theorem_embedding_qwen, rds_schema.sql:35,46,51). Ids that are not stored
+        match nothing. The store stays dense: the last rows move into the freed slots. Returns the number of rows
+        deleted; with ``return_moves=True`` also the relocations as an int64 [m, 2] array of (old row, new row)
+        for callers that keep row-aligned side tables (``TheoremStore``, allow masks). Built IVF lists stay valid."""
+        id_arr = np.ascontiguousarray(np.asarray(ids.cpu() if isinstance(ids, torch.Tensor) else ids, dtype=np.int64)).reshape(-1)
+        n = int(id_arr.shape[0])
+        deleted, moved = C.c_int64(0), C.c_int64(0)
+        src = np.empty(max(n, 1), dtype=np.int64)
+        dst = np.empty(max(n, 1), dtype=np.int64)
+        check(lib.ts_index_delete(self._h, id_arr.ctypes.data, n, C.byref(deleted), src.ctypes.data, dst.ctypes.data,
+                                  C.byref(moved), _stream_ptr(self.device)))
+        if return_moves:
+            m = int(moved.value)
+            return int(deleted.value), np.stack([src[:m], dst[:m]], axis=1)
+        return int(deleted.value)
+
     def get_rows(self, first: int = 0, n: Optional[int] = None) -> torch.Tensor:
         """Stored rows dequantised to fp32 (device tensor) — the oracle's 'same inputs'."""
         n = len(self) - first if n is None else n
