@@ -69,9 +69,9 @@ class TheoremIndex:
         for ctx in self._ctx.values():
             lib.ts_ctx_destroy(ctx)
         self._ctx.clear()
-        if getattr(self, "_xchg1", None) is not None:
-            lib.ts_xchg_destroy(self._xchg1)
-            self._xchg1 = None
+        for h, _k in getattr(self, "_xchg1", {}).values():
+            lib.ts_xchg_destroy(h)
+        self._xchg1 = {}
         if getattr(self, "_h", None):
             lib.ts_index_destroy(self._h)
             self._h = None
@@ -239,15 +239,26 @@ class TheoremIndex:
     def _stream_exchange(self, k: int):
         """A world-of-one exchange handle: gives a single GPU the sharded path's kernel chain (scan + finishing kernel
         linked by programmatic dependent launch), so that back-to-back searches overlap their tails."""
-        h = getattr(self, "_xchg1", None)
-        if h is None or self._xchg1_k < k:
+        # one handle per (host thread, stream): the handle numbers its searches and chains them in that order
+        table = self.__dict__.setdefault("_xchg1", {})
+        key = (threading.get_ident(), _stream_ptr(self.device))
+        h, cap = table.get(key, (None, 0))
+        if h is None or cap < k:
             if h is not None:
+                torch.cuda.current_stream(self.device).synchronize()
                 lib.ts_xchg_destroy(h)
-            h = C.c_void_p()
-            self._xchg1_k = max(int(k), 32)
-            check(lib.ts_xchg_create(C.byref(h), self.device.index, 1, 0, 1, self._xchg1_k))
+            h, cap = C.c_void_p(), max(int(k), 32)
+            check(lib.ts_xchg_create(C.byref(h), self.device.index, 1, 0, 1, cap))
             check(lib.ts_xchg_connect(h, None))
-            self._xchg1 = h
+            with self._lock:
+                # threads come and go (one script thread per Streamlit rerun): drop the handles of threads that exited
+                alive = {t.ident for t in threading.enumerate()}
+                doomed = [table.pop(kk) for kk in [kk for kk in table if kk[0] not in alive]]
+                table[key] = (h, cap)
+            if doomed:
+                torch.cuda.synchronize(self.device)
+                for old_h, _ in doomed:
+                    lib.ts_xchg_destroy(old_h)
         return h
 
     def search(self, queries, k: int, normalize: bool = True, allow_mask: Optional[torch.Tensor] = None,
