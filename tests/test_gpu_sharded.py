@@ -85,6 +85,40 @@ def test_single_gpu_stream_chain_equals_plain_search_with_caller_ids_and_mask(ts
     index.close()
 
 
+def test_stream_chains_of_two_host_threads_do_not_interfere(ts):
+    """Each (host thread, stream) chains its own searches through its own exchange handle."""
+    import threading
+    n, d = 40_000, 256
+    index = ts.build_index(oracle.synthetic_rows(0, n, d, seed=14))
+    q = torch.from_numpy(oracle.synthetic_queries(64, d)).cuda()
+    want = [index.search(q[i:i + 1], 10) for i in range(64)]
+    torch.cuda.synchronize()
+    got, errors = {}, []
+
+    def worker(t):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                outs = [index.search(q[i:i + 1], 10, independent=True) for i in range(t, 64, 2) for _ in range(3)]
+                stream.synchronize()
+            got[t] = outs
+        except Exception as e:                                  # surfaced by the assert below
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    assert len(index._xchg1) == 2
+    for t in range(2):
+        for j, (s, i) in enumerate(got[t]):
+            s0, i0 = want[t + 2 * (j // 3)]
+            assert torch.equal(s, s0) and torch.equal(i, i0)
+    index.close()
+
+
 def test_fused_exchange_rebases_rows_and_maps_ids(ts):
     """A 'shard' that starts at global row 5000: fused results carry global rows / caller ids."""
     from theoremsearch_b200.sharded import ShardedIndex
