@@ -92,7 +92,8 @@ TS_API void ts_index_destroy(ts_index* index);
  * `F.normalize` inside sentence_transformers.util.cos_sim (test_app.py:76) and
  * `model.encode(..., normalize_embeddings=True)` (ec2/generate_embeddings/embeddings.py:27,35).
  * `ids` (device int64[n]) are the caller's row keys (slogan_id / theorem_id,
- * rds_schema.sql:22,34); NULL = the row's position in the index.  Kernel K1. */
+ * rds_schema.sql:22,34); NULL = the row's position in the index — after a ts_index_delete, one past
+ * the largest position ever occupied, like a SERIAL column: ids are not handed out twice.  Kernel K1. */
 TS_API int ts_index_add(ts_index* index, const void* rows, int src_dtype, int64_t n,
                         int normalize, const int64_t* ids, void* stream);
 

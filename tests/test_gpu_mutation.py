@@ -334,3 +334,82 @@ def test_fp8_scan_copy_follows_deletes(ts):
     assert int(i[0]) == 19_999
     s2, i2 = ts.cos_sim_topk(torch.from_numpy(x[300]), index, 5)        # a deleted row is not found any more
     assert 300 not in i2.tolist()
+
+
+def test_rows_added_without_ids_after_a_delete_get_fresh_ids(ts):
+    """No ids = the row's position; a delete shrinks the positions but ids are not handed out twice (SERIAL-like)."""
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((50, 64)).astype(np.float32)
+    index = ts.build_index(x)
+    assert index.delete([3, 10]) == 2 and len(index) == 48
+    y = rng.standard_normal((4, 64)).astype(np.float32)
+    index.add(torch.from_numpy(y).cuda())                       # device path
+    index.add(y[:1] * 2.0 + 1.0)                                # host path
+    assert len(index) == 53
+    _, ids = index.search(torch.from_numpy(x[:1]), 53)
+    got = sorted(ids[0].tolist())
+    assert got == sorted(set(range(50)) - {3, 10}) + [50, 51, 52, 53, 54]
+    s, i = index.search(torch.from_numpy(y), 1)
+    assert i[:, 0].tolist() == [50, 51, 52, 53]
+    s, i = index.search(torch.from_numpy(x[49:50]), 1)          # row 49 moved into a freed slot, still id 49
+    assert int(i[0, 0]) == 49
+
+
+@pytest.mark.parametrize("seed,dtype", [(0, "bf16"), (1, "bf16"), (2, "f32")])
+def test_random_interleaving_of_upserts_deletes_and_adds(ts, seed, dtype):
+    """A writer's life: random upsert / delete / add batches; after every few operations the index must equal the
+    oracle's table — exact search (K2 and K3) and, on bf16 rows, the IVF search with every list probed (overflow
+    lists, tombstones, renamed entries and the automatic re-pack all occur along the way)."""
+    dim, nlist = 64, 8
+    rng = np.random.default_rng(100 + seed)
+    table = {}
+    ids0 = np.arange(0, 4000, 2, dtype=np.int64)
+    x0 = rng.standard_normal((len(ids0), dim)).astype(np.float32)
+    oracle.upsert_rows(table, ids0, x0)
+    index = ts.build_index(x0, ids=ids0, dtype=dtype)
+    ivf = dtype == "bf16"
+    if ivf:
+        index.ivf_train(nlist, iters=3, seed=0)
+        index.ivf_build("bf16")
+    fresh_id = 10**6
+    states = set()
+    for step in range(36):
+        op = rng.integers(0, 3)
+        if op == 0:                                             # upsert: existing and new ids mixed
+            ids = rng.integers(0, 6000, size=int(rng.integers(1, 260))).astype(np.int64)
+            rows = rng.standard_normal((len(ids), dim)).astype(np.float32)
+            assert index.upsert(rows if step % 2 else torch.from_numpy(rows).cuda(), ids) == oracle.upsert_rows(table, ids, rows)
+        elif op == 1 and len(table) > 600:                      # delete: stored ids, unknown ids, repeats
+            stored = np.fromiter(table.keys(), dtype=np.int64, count=len(table))
+            ids = np.concatenate([rng.choice(stored, size=int(rng.integers(1, 300)), replace=False),
+                                  rng.integers(7000, 8000, size=5)])
+            ids = np.concatenate([ids, ids[:3]])
+            assert index.delete(ids) == oracle.delete_rows(table, ids)
+        else:                                                   # add: fresh ids
+            n = int(rng.integers(1, 200))
+            ids = np.arange(fresh_id, fresh_id + n, dtype=np.int64)
+            fresh_id += n
+            rows = rng.standard_normal((n, dim)).astype(np.float32)
+            index.add(torch.from_numpy(rows).cuda(), ids=ids)
+            oracle.upsert_rows(table, ids, rows)
+        assert len(index) == len(table)
+        if ivf:
+            states.add(tuple(v > 0 for v in index.ivf_pending()))
+        if step % 4 == 3 or step == 35:
+            ids_all = np.fromiter(table.keys(), dtype=np.int64, count=len(table))
+            rows_all = oracle.normalize_f64(np.stack(list(table.values())))
+            stored_rows = oracle.bf16_round(rows_all) if dtype == "bf16" else rows_all.astype(np.float32).astype(np.float64)
+            q = oracle.synthetic_queries(5, dim, seed=step)
+            o_s, o_i = oracle.exact_search(oracle.normalize_f64(q), stored_rows, 10, ids=ids_all)
+            qt = torch.from_numpy(q)
+            s3, i3 = index.search(qt, 10)
+            s2, i2 = index.search(qt[:1], 10)
+            assert np.array_equal(i3.cpu().numpy(), o_i) and np.array_equal(i2.cpu().numpy(), o_i[:1]), step
+            assert np.max(np.abs(s3.cpu().numpy() - o_s)) < 1e-5
+            if ivf:
+                s_a, i_a = index.ivf_search(qt, 10, nprobe=nlist, rescore_k=10)
+                assert torch.equal(i_a, i3) and torch.equal(s_a, s3), step
+                s_b, i_b = index.ivf_search(qt[:1], 10, nprobe=nlist, rescore_k=10)
+                assert torch.equal(i_b, i3[:1]) and torch.equal(s_b, s3[:1]), step
+    if ivf:
+        assert (True, True) in states                            # overflow rows and tombstones were live together

@@ -248,8 +248,12 @@ int ts_index_add(ts_index* ix, const void* rows, int src_dtype, int64_t n, int n
             TS_CHECK_CUDA(cudaMemcpyAsync(ix->ids + ix->size, ids, (size_t)n * sizeof(int64_t),
                                           cudaMemcpyDeviceToDevice, s));
         } else {
-            iota_ids_kernel<<<256, 256, 0, s>>>(ix->ids + ix->size, ix->size, n);
+            // no ids given: the rows are numbered on from the largest position ever used (after a delete the row
+            // positions shrink; ids are not handed out twice)
+            const int64_t auto_first = std::max(ix->auto_next, ix->size);
+            iota_ids_kernel<<<256, 256, 0, s>>>(ix->ids + ix->size, auto_first, n);
             TS_LAUNCH_CHECK();
+            ix->auto_next = auto_first + n;
         }
     }
     void* dst = (char*)ix->data + (size_t)ix->size * ix->row_bytes();
@@ -258,6 +262,7 @@ int ts_index_add(ts_index* ix, const void* rows, int src_dtype, int64_t n, int n
     if (rc) return rc;
     const int64_t first = ix->size;
     ix->size += n;
+    ix->auto_next = std::max(ix->auto_next, ix->size);
     ix->id_map_valid = false;
     // built IVF lists stay valid: the new rows are filed in overflow lists (re-packed once they reach a tenth of the corpus)
     return ivf_apply_mutation(ix, nullptr, 0, first, n, s);
@@ -413,8 +418,10 @@ int ts_index_append_raw_host(ts_index* ix, const void* rows, int64_t n, const in
         if (ids != nullptr) {
             TS_CHECK_CUDA(cudaMemcpy(ix->ids + ix->size, ids, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice));
         } else {
-            iota_ids_kernel<<<256, 256>>>(ix->ids + ix->size, ix->size, n);
+            const int64_t auto_first = std::max(ix->auto_next, ix->size);
+            iota_ids_kernel<<<256, 256>>>(ix->ids + ix->size, auto_first, n);
             TS_LAUNCH_CHECK();
+            ix->auto_next = auto_first + n;
         }
     }
     int rc = launch_max_norm2(dst, ix->dtype, n, ix->dim_pad, ix->max_norm2, nullptr);
@@ -422,6 +429,7 @@ int ts_index_append_raw_host(ts_index* ix, const void* rows, int64_t n, const in
     TS_CHECK_CUDA(cudaDeviceSynchronize());
     const int64_t first = ix->size;
     ix->size += n;
+    ix->auto_next = std::max(ix->auto_next, ix->size);
     ix->id_map_valid = false;
     return ivf_apply_mutation(ix, nullptr, 0, first, n, nullptr);
 }

@@ -345,6 +345,8 @@ struct ts_index {
     void* data = nullptr;     // [capacity, dim_pad] of dtype (== row_store_ptr(store))
     ts::RowStore* store = nullptr;   // owns `data`: a reserved address range, physical memory mapped as the index grows
     ts::RowStore* ids_store = nullptr;   // owns `ids`
+    int64_t auto_next = 0;           // id of the next row added WITHOUT an id: one past the largest row position ever
+                                     // occupied (a SERIAL column: positions shrink on delete, this never does)
     ts::RowStore* pos_store = nullptr;   // owns `pos_of_row`
     int64_t* ids = nullptr;   // [capacity] caller ids; valid only when has_ids
     bool has_ids = false;

@@ -198,6 +198,7 @@ int ts_index_upsert(ts_index* ix, const void* rows, int src_dtype, int64_t n, in
     const int64_t old_size = ix->size;
     if (rc == TS_OK) {
         ix->size += n_new;
+        ix->auto_next = std::max(ix->auto_next, ix->size);
         rc = ivf_apply_mutation(ix, d_replaced, (int64_t)replaced.size(), old_size, n_new, s);
     }
     if (cudaStreamSynchronize(s) != cudaSuccess && rc == TS_OK) {
