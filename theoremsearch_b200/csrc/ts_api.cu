@@ -430,6 +430,8 @@ int ts_index_append_raw_host(ts_index* ix, const void* rows, int64_t n, const in
     const int64_t first = ix->size;
     ix->size += n;
     ix->auto_next = std::max(ix->auto_next, ix->size);
+    if (ids != nullptr)          // a reloaded index keeps numbering id-less rows past its largest stored id
+        for (int64_t i = 0; i < n; ++i) ix->auto_next = std::max(ix->auto_next, ids[i] + 1);
     ix->id_map_valid = false;
     return ivf_apply_mutation(ix, nullptr, 0, first, n, nullptr);
 }
