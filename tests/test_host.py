@@ -344,3 +344,49 @@ def test_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert abs(d["ms_per_step"] * d["value"] - 1000.0) < 1e-6
+
+
+def test_host_metrics_on_random_graded_judgements_match_the_oracle():
+    """The array-arithmetic (host) evaluation of a ranking against the oracle's per-query loops: graded relevances,
+    rows padded with -1, unjudged queries, every cut."""
+    from theoremsearch_b200 import metrics
+    rng = np.random.default_rng(4)
+    nq, n_docs, width = 120, 300, 12
+    ranked = np.stack([rng.permutation(n_docs)[:width] for _ in range(nq)]).astype(np.int64)
+    for q in np.flatnonzero(rng.random(nq) < 0.2):
+        ranked[q, rng.integers(1, width):] = -1
+    qrels = {}
+    for q in range(nq):
+        pool = np.concatenate([ranked[q][ranked[q] >= 0], rng.integers(0, n_docs, size=20)])
+        docs = list(dict.fromkeys(int(d) for d in rng.permutation(pool)))[: int(rng.integers(1, 25))]
+        rels = rng.choice([0.0, 0.5, 2.0, 3.0], size=len(docs)).tolist()
+        rels[int(rng.integers(0, len(docs)))] = 1.0
+        qrels[q] = dict(zip(docs, rels))
+    for k in (1, 3, 5, 10, 12):
+        assert metrics.precision_at_k(ranked, qrels, k) == pytest.approx(oracle.precision_at_k(ranked, qrels, k), abs=1e-12)
+        assert metrics.hit_at_k(ranked, qrels, k) == pytest.approx(oracle.hit_at_k(ranked, qrels, k), abs=1e-12)
+        assert metrics.mrr_at_k(ranked, qrels, k) == pytest.approx(oracle.mrr_at_k(ranked, qrels, k), abs=1e-12)
+        assert metrics.ndcg_at_k(ranked, qrels, k) == pytest.approx(oracle.ndcg_at_k(ranked, qrels, k), abs=1e-12)
+        assert metrics.ndcg_at_k(ranked, qrels, k, gain="linear") == pytest.approx(
+            oracle.ndcg_at_k(ranked, qrels, k, gain="linear"), abs=1e-12)
+        for max_rel in (None, 4.0):
+            assert metrics.err_at_k(ranked, qrels, k, max_rel) == pytest.approx(oracle.err_at_k(ranked, qrels, k, max_rel), abs=1e-12)
+            assert metrics.q_measure_at_k(ranked, qrels, k, max_rel) == pytest.approx(
+                oracle.q_measure_at_k(ranked, qrels, k, max_rel), abs=1e-12)
+    assert metrics.mrr_at_k(ranked, qrels, None) == pytest.approx(oracle.mrr_at_k(ranked, qrels, None), abs=1e-12)
+    some = {q: v for q, v in qrels.items() if q % 5}                 # every fifth query unjudged
+    for k in (3, 10):
+        assert metrics.ndcg_at_k(ranked, some, k) == pytest.approx(oracle.ndcg_at_k(ranked, some, k), abs=1e-12)
+        assert metrics.err_at_k(ranked, some, k) == pytest.approx(oracle.err_at_k(ranked, some, k), abs=1e-12)
+        assert metrics.q_measure_at_k(ranked, some, k) == pytest.approx(oracle.q_measure_at_k(ranked, some, k), abs=1e-12)
+
+
+def test_oracle_table_writes():
+    """oracle.upsert_rows / delete_rows: the dict model of the reference's writer statements."""
+    t = {}
+    assert oracle.upsert_rows(t, [5, 7, 5], np.array([[1.0], [2.0], [3.0]], np.float32)) == 0
+    assert list(t) == [5, 7] and float(t[5][0]) == 3.0                # a repeated id keeps its last row, first place
+    assert oracle.upsert_rows(t, [7, 9], np.array([[4.0], [5.0]], np.float32)) == 1
+    assert list(t) == [5, 7, 9] and float(t[7][0]) == 4.0
+    assert oracle.delete_rows(t, [7, 7, 100]) == 1 and list(t) == [5, 9]
+    assert oracle.delete_rows(t, []) == 0
