@@ -150,13 +150,21 @@ def kernel_launches() -> int:
     return int(lib.ts_kernel_launches())
 
 
+_tunables: dict[str, int] = {}      # values read or set through this module (every writer goes through set_tunable)
+
+
 def set_tunable(name: str, value: int) -> None:
     check(lib.ts_set_tunable(name.encode(), int(value)))
+    _tunables[name] = int(value)
 
 
 def get_tunable(name: str) -> int:
+    cached = _tunables.get(name)
+    if cached is not None:          # on the per-query path (ShardedIndex.search): no FFI call for a constant
+        return cached
     v = _i(0)
     check(lib.ts_get_tunable(name.encode(), C.byref(v)))
+    _tunables[name] = v.value
     return v.value
 
 

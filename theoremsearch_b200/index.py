@@ -62,6 +62,7 @@ class TheoremIndex:
         self._h = h
         self._ws: dict[tuple, torch.Tensor] = {}
         self._ctx: dict[tuple, C.c_void_p] = {}
+        self._ctx_timing: dict[int, bool] = {}
         self._lock = threading.Lock()
 
     # -------------------------------------------------------------------------------- lifecycle
@@ -69,6 +70,7 @@ class TheoremIndex:
         for ctx in self._ctx.values():
             lib.ts_ctx_destroy(ctx)
         self._ctx.clear()
+        self._ctx_timing.clear()
         for h, _k in getattr(self, "_xchg1", {}).values():
             lib.ts_xchg_destroy(h)
         self._xchg1 = {}
@@ -334,6 +336,7 @@ class TheoremIndex:
                      if key[0] not in alive or (key[0] == tid and key[1] <= nq and key[2] <= k)]
             doomed = [self._ctx.pop(key) for key in stale]
         for ctx in doomed:          # no live thread can be inside a call on these
+            self._ctx_timing.pop(ctx.value, None)
             lib.ts_ctx_destroy(ctx)
         ctx = C.c_void_p()
         check(lib.ts_ctx_create(C.byref(ctx), self._h, nq, k))
@@ -353,7 +356,9 @@ class TheoremIndex:
             raise _lib.TheoremSearchError(-1, f"queries must be [nq, {self.dim}], got {q.shape}")
         nq = q.shape[0]
         ctx = self._get_ctx(nq, k)
-        check(lib.ts_ctx_set_timing(ctx, 1 if timing else 0))
+        if self._ctx_timing.get(ctx.value, False) != bool(timing):      # not an FFI call per query
+            check(lib.ts_ctx_set_timing(ctx, 1 if timing else 0))
+            self._ctx_timing[ctx.value] = bool(timing)
         scores = np.empty((nq, k), dtype=np.float32)
         ids = np.empty((nq, k), dtype=np.int64)
         check(lib.ts_search_host(ctx, q.ctypes.data, nq, int(k), int(normalize), self._mask_ptr(allow_mask),
